@@ -1,0 +1,104 @@
+"""oracle/xsi_ref.py -- TEST INFRASTRUCTURE ONLY.
+
+ctypes door onto oracle/_ref/libxsi_ref.so: the UNMODIFIED reference (XsiFactoryExt writer and
+Accessor reader) compiled by oracle/Makefile from /root/reference, driven by oracle/ref_shim.cpp.
+Only tests/, __graft_entry__.smoke() and bench.py's reference / cpu_baseline legs may import this.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+REF_SO = os.path.join(_HERE, "_ref", "libxsi_ref.so")
+REF_CLI = os.path.join(_HERE, "_ref", "xsqueezeit_ref")
+
+_lib = None
+
+
+def available():
+    return os.path.exists(REF_SO)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        L = ctypes.CDLL(REF_SO)
+        L.xsi_ref_encode_file.restype = ctypes.c_int
+        L.xsi_ref_encode_file.argtypes = [
+            ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+            ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
+            ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
+        L.xsi_ref_accessor_open.restype = ctypes.c_void_p
+        L.xsi_ref_accessor_open.argtypes = [ctypes.c_char_p]
+        L.xsi_ref_hap_samples.restype = ctypes.c_uint64
+        L.xsi_ref_hap_samples.argtypes = [ctypes.c_void_p]
+        L.xsi_ref_fill_genotype_array.restype = ctypes.c_uint64
+        L.xsi_ref_fill_genotype_array.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
+                                                  ctypes.c_uint64, ctypes.c_uint64]
+        L.xsi_ref_allele_counts.restype = ctypes.c_uint64
+        L.xsi_ref_allele_counts.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
+        L.xsi_ref_accessor_close.restype = None
+        L.xsi_ref_accessor_close.argtypes = [ctypes.c_void_p]
+        _lib = L
+    return _lib
+
+
+def encode_file(path, gt, rec_off, ngt, n_allele, n_samples, block_len, mac_threshold,
+                default_phased, zstd=False, zstd_level=7, sample_names=None):
+    """Run the reference writer on in-memory rows. gt: int32 flat, rec_off: uint64 row starts."""
+    gt = np.ascontiguousarray(gt, dtype=np.int32)
+    rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
+    ngt = np.ascontiguousarray(ngt, dtype=np.int32)
+    n_allele = np.ascontiguousarray(n_allele, dtype=np.int32)
+    blob = None
+    if sample_names is not None:
+        blob = b"".join(s.encode() + b"\0" for s in sample_names)
+    rc = lib().xsi_ref_encode_file(path.encode(), gt.ctypes.data, rec_off.ctypes.data, ngt.ctypes.data,
+                                   n_allele.ctypes.data, len(ngt), n_samples, block_len, mac_threshold,
+                                   int(default_phased), int(zstd), zstd_level, 1, blob)
+    if rc != 0:
+        raise RuntimeError("reference encode failed rc=%d" % rc)
+
+
+class RefAccessor:
+    """The reference Accessor (accessor.hpp:31-124) on an .xsi file."""
+
+    def __init__(self, path):
+        self.h = lib().xsi_ref_accessor_open(path.encode())
+        if not self.h:
+            raise RuntimeError("reference Accessor failed to open " + path)
+        self.hap_samples = int(lib().xsi_ref_hap_samples(self.h))
+
+    def fill_genotype_array(self, n_alleles, position, out=None):
+        if out is None:
+            out = np.empty(self.hap_samples, dtype=np.int32)
+        n = lib().xsi_ref_fill_genotype_array(self.h, out.ctypes.data, out.size, n_alleles, position)
+        if n == 2**64 - 1:
+            raise RuntimeError("reference fill_genotype_array threw")
+        return out, int(n)
+
+    def allele_counts(self):
+        buf = np.zeros(256, dtype=np.uint64)
+        n = lib().xsi_ref_allele_counts(self.h, buf.ctypes.data, buf.size)
+        return buf[:n].copy()
+
+    def close(self):
+        if self.h:
+            lib().xsi_ref_accessor_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+
+def load_gtdump(prefix):
+    """Read oracle/gtdump.c output: returns (n_samples, n_allele[int32], ngt[int32], gt[int32 flat], names)."""
+    meta = np.fromfile(prefix + ".meta", dtype=np.uint8)
+    magic, n_samples = np.frombuffer(meta[:8], dtype=np.uint32)
+    assert magic == 0x31445447
+    n_records = int(np.frombuffer(meta[8:16], dtype=np.uint64)[0])
+    m = np.frombuffer(meta[16:16 + 8 * n_records], dtype=np.uint32).reshape(n_records, 2)
+    gt = np.fromfile(prefix + ".gt", dtype=np.int32)
+    names = [l.rstrip("\n") for l in open(prefix + ".samples")]
+    return int(n_samples), m[:, 0].astype(np.int32), m[:, 1].astype(np.int32), gt, names
