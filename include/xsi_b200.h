@@ -1,0 +1,136 @@
+/* include/xsi_b200.h -- C ABI of the B200-native xSqueezeIt genotype encode/decode path.
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int return codes, no C++ or torch
+ * types, no exceptions across the boundary.  Every entry point names the reference interface
+ * (rwk-unil/xSqueezeIt @55ad8c7, paths under /root/reference) it replaces.  INTEGRATION.md
+ * shows the reference-side binding a maintainer would add.
+ *
+ * There is NO CPU fallback: every call that does genotype work needs a CUDA device and fails
+ * with XSI_E_CUDA when there is none.
+ *
+ * Genotype values use the htslib int32 encoding of bcf_get_genotypes (htslib/htslib/vcf.h:892-898,
+ * 1324,1329): (allele+1)<<1 | phased, 0/1 = missing, INT32_MIN = bcf_int32_missing,
+ * INT32_MIN+1 = bcf_int32_vector_end.  gt_elem_bytes = 1 takes the raw BCF FORMAT/GT int8
+ * payload instead (same encoding, 0x80 = missing, 0x81 = vector end; bcf_fmt_t.p, vcf.h:152-158).
+ */
+#ifndef XSI_B200_H
+#define XSI_B200_H
+#include <stddef.h>
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum {
+    XSI_OK = 0,
+    XSI_E_CUDA = -1,        /* no device / CUDA runtime error (see xsi_last_error) */
+    XSI_E_ARG = -2,         /* bad argument */
+    XSI_E_ALLELE = -3,      /* reference: throw "Unknown allele error !"  (gt_block.hpp:259-265) */
+    XSI_E_PLOIDY = -4,      /* reference: "Ploidy higher than 2 is not yet supported" (gt_compressor_new.hpp:118-120) */
+    XSI_E_UNSUPPORTED = -5, /* shapes the reference itself cannot round-trip (e.g. 32768..65535 samples) */
+    XSI_E_FORMAT = -6,      /* malformed .xsi / GT block */
+    XSI_E_NOMEM = -7,
+    XSI_E_IO = -8,
+    XSI_E_ZSTD = -9,        /* libzstd not loadable / (de)compression error */
+};
+
+typedef struct xsi_ctx xsi_ctx; /* one per (thread, device); owns a CUDA stream and scratch pools */
+
+int  xsi_create(int device, xsi_ctx** out);
+void xsi_destroy(xsi_ctx* ctx);
+const char* xsi_last_error(const xsi_ctx* ctx); /* never NULL */
+const char* xsi_version(void);
+/* CUDA stream of the context as a cudaStream_t cast to void* (for event timing by the caller) */
+void* xsi_stream(xsi_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+uint64_t xsi_kernel_launches(const xsi_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * ENCODE  -- replaces GtBlock<A_T,uint16_t>::encode_line + write_to_stream
+ *            (include/gt_block.hpp:185-204,279-406), i.e. the IWritableBCFLineEncoder the
+ *            reference registers under KEY_GT_ENTRY (include/xsi_factory.hpp:419-433),
+ *            for a batch of whole blocks at a time.
+ * ------------------------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t n_records;        /* records in this batch; blocks are cut every block_len records          */
+    uint32_t n_samples;        /* bcf_hdr_nsamples                                                          */
+    uint32_t block_len;        /* --variant-block-length (xsqueezeit.hpp:113, default 8192)                 */
+    uint64_t mac_threshold;    /* (size_t)((double)N_HAPS*MAF), gt_compressor_new.hpp:98-99                 */
+    int32_t  default_phasing;  /* seek_default_phased, xcf.cpp:811-836                                      */
+    int32_t  gt_elem_bytes;    /* 4: int32 rows (bcf_get_genotypes); 1: raw BCF int8 rows                   */
+    int32_t  gt_on_device;     /* 0: gt is host memory (copied H2D inside the call); 1: device pointer      */
+    int32_t  reserved;
+    const void*     gt;        /* rows back to back: row r starts at element sum(ploidy[0..r))*n_samples    */
+    const uint32_t* n_allele;  /* host, per record: bcf1_t::n_allele                                        */
+    const uint8_t*  ploidy;    /* host, per record: ngt / n_samples (1 or 2); NULL = all 2                  */
+} xsi_encode_desc;
+
+/* Asynchronous part: uploads (if needed), runs every encode kernel on the context stream.  */
+int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* desc);
+/* Waits, brings the encoded sections back and assembles the byte-exact GT blocks.
+ * n_blocks_out blocks; block b is blocks_out[b] .. +sizes_out[b] (memory owned by ctx, valid
+ * until the next xsi_encode_launch on this ctx).  Each is exactly what the reference's
+ * GtBlock::write_to_stream writes: [u32 -1][u32 n][dictionary][sections].                   */
+int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint8_t* const** blocks_out,
+                       const uint64_t** sizes_out);
+/* Per-block payload byte counts of the last launch, available without assembling (what a
+ * multi-GPU writer all-gathers to build the global offset table).  Valid after collect.    */
+int xsi_encode_block_sizes(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint64_t** sizes_out);
+/* max ploidy seen in the last batch (header.ploidy, xsi_factory.hpp:548) */
+int xsi_encode_max_ploidy(const xsi_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * DECODE  -- replaces DecompressPointerGTBlock<A_T,uint16_t> (seek + fill_genotype_array_advance,
+ *            include/accessor_internals_new.hpp:154-384) behind AccessorInternals::fill_genotype_array
+ *            (include/accessor_internals.hpp:399-413).
+ * ------------------------------------------------------------------------------------------ */
+/* Stage 1: upload the GT blocks (host pointers to the [u32 -1][n][dict].. payloads, i.e. what
+ * set_gt_block_ptr yields, accessor_internals_new.hpp:830-843), expand every WAH line and undo
+ * the PBWT order on the device.  num_samples / aet_bytes come from header_t
+ * (include/compression.hpp:40-104).  Replaces any previously loaded set.                    */
+int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks,
+                           const uint64_t* sizes, uint64_t num_samples, int32_t aet_bytes);
+/* Stage 2: materialise records. Record i is the one whose first binary line is line_offset[i]
+ * (the low 15 bits of BM) in loaded block block_index[i] (index into the loaded set), with
+ * n_alleles[i] alleles.  Row i is written at out + i*out_stride (int32 elements); entries
+ * past the returned length are left untouched.  out_on_device: 1 = device pointer.
+ * n_filled[i] (host, may be NULL) receives what fill_genotype_array returns
+ * (CURRENT_N_HAPS: num_samples for an all-haploid line, else 2*num_samples).
+ * allele_counts (host, may be NULL): row i holds n_alleles[i] counts at allele_counts + i*counts_stride
+ * (AccessorInternals::get_allele_counts).                                                    */
+int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                       const uint32_t* n_alleles, int32_t* out, uint64_t out_stride, int32_t out_on_device,
+                       uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride);
+/* Blocks until everything queued on the context stream is done. */
+int xsi_sync(xsi_ctx* ctx);
+
+/* ------------------------------------------------------------------------------------------
+ * Host container layer (no GPU work by itself): the .xsi file, byte-compatible with
+ * XsiFactoryExt (include/xsi_factory.hpp:435-639) and readable like Accessor (include/accessor.hpp).
+ * ------------------------------------------------------------------------------------------ */
+typedef struct xsi_writer xsi_writer;
+/* sample_names: n_samples NUL-terminated strings back to back. zstd_level used when zstd_on. */
+int xsi_writer_open(const char* path, uint32_t n_samples, const char* sample_names, uint32_t block_len,
+                    uint64_t mac_threshold, int32_t default_phasing, int32_t zstd_on, int32_t zstd_level,
+                    xsi_writer** out);
+/* Appends finished GT blocks (from xsi_encode_collect) in order; n_records / n_variants are the
+ * BCF lines and sum(n_allele-1) they cover (xsi_factory.hpp:518-519).                          */
+int xsi_writer_add_blocks(xsi_writer* w, uint32_t n_blocks, const uint8_t* const* blocks, const uint64_t* sizes,
+                          uint64_t n_records, uint64_t n_variants);
+/* finalize_file (xsi_factory.hpp:543-606): index, sample names, header rewrite. */
+int xsi_writer_close(xsi_writer* w, int32_t max_ploidy);
+
+typedef struct xsi_reader xsi_reader;
+int  xsi_reader_open(const char* path, xsi_reader** out); /* mmap + header checks (accessor.cpp:26-82) */
+void xsi_reader_close(xsi_reader* r);
+int  xsi_reader_info(const xsi_reader* r, uint64_t* num_samples, uint64_t* hap_samples, uint32_t* ploidy,
+                     uint32_t* aet_bytes, uint32_t* n_blocks, uint32_t* block_len, uint64_t* xcf_entries,
+                     uint64_t* num_variants, int32_t* zstd, uint64_t* rare_threshold, int32_t* default_phased);
+const char* xsi_reader_sample_name(const xsi_reader* r, uint64_t i);
+/* GT block payload of block b (inflated into reader-owned memory when the file is zstd'ed). */
+int xsi_reader_gt_block(xsi_reader* r, uint32_t b, const uint8_t** ptr, uint64_t* size);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XSI_B200_H */

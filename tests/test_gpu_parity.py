@@ -1,0 +1,240 @@
+"""GPU parity tests (run with -m gpu on the B200 box): the CUDA path, called through the C ABI
+(include/xsi_b200.h via xsqueezeit_b200.Context / Compressor / Accessor), against the oracle
+(oracle/xsi_oracle.c, itself pinned to the reference in test_oracle_golden.py) and against the
+committed golden .xsi files produced by the unmodified reference.  Bit-exact everywhere."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import synth
+import xsi_oracle as xo
+
+pytestmark = pytest.mark.gpu
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+MAN = json.load(open(os.path.join(G, "manifest.json")))
+SMALL = sorted(k for k in MAN if k != "chr20_small")
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import xsqueezeit_b200 as xb
+    c = xb.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_encode(ctx, tmp_path, ds, block_len, maf, names=None, elem=4, zstd=False, blocks_per_batch=8):
+    import xsqueezeit_b200 as xb
+    comp = xb.Compressor(ctx, maf=maf, reset_sort_block_length=block_len, zstd_compression_on=zstd,
+                         blocks_per_batch=blocks_per_batch)
+    p = str(tmp_path / "gpu.xsi")
+    gt = ds["gt"]
+    if elem == 1:
+        g8 = gt.astype(np.int64)
+        g8 = np.where(gt == synth.I32_MISSING, -128, np.where(gt == synth.EOV, -127, g8)).astype(np.int8)
+        gt = g8
+    comp.compress_to_file(p, gt, ds["ngt"], ds["n_allele"], ds["n_samples"], sample_names=names, gt_elem_bytes=elem)
+    return p
+
+
+def oracle_image(ds, block_len, maf, names=None):
+    gt, ngt, nal, ns = ds["gt"], ds["ngt"], ds["n_allele"], ds["n_samples"]
+    off = xo.row_offsets(ngt)
+    dp = xo.default_phased(gt, off, ngt, ns)
+    thr = xo.mac_threshold(ns, int(ngt[0]) // ns, maf)
+    return xo.encode(gt, off, ngt, nal, ns, block_len, thr, dp, names)
+
+
+def check_decode(ctx, path, image, n_allele, block_len, one_by_one=False):
+    import xsqueezeit_b200 as xb
+    acc = xb.Accessor(path, ctx)
+    rd = xo.Reader(image)
+    pos = xo.bm_positions(n_allele, block_len)
+    assert np.array_equal(pos, xb.bm_positions(n_allele, block_len))
+    if one_by_one:
+        for r in range(len(n_allele)):
+            a, na = acc.fill_genotype_array(int(n_allele[r]), int(pos[r]))
+            b, nb = rd.fill_genotype_array(int(n_allele[r]), int(pos[r]))
+            assert na == nb and np.array_equal(a[:na], b[:nb]), r
+            assert np.array_equal(acc.get_allele_counts(), rd.allele_counts()), r
+    else:
+        out, filled, counts = acc.fill_genotype_arrays(n_allele, pos, want_counts=True)
+        for r in range(len(n_allele)):
+            b, nb = rd.fill_genotype_array(int(n_allele[r]), int(pos[r]))
+            assert filled[r] == nb and np.array_equal(out[r, :nb], b[:nb]), r
+            assert np.array_equal(counts[r, :int(n_allele[r])], rd.allele_counts()), r
+    acc.close()
+
+
+def roundtrip(ctx, tmp_path, ds, block_len, maf, elem=4, one_by_one=False, blocks_per_batch=8):
+    p = gpu_encode(ctx, tmp_path, ds, block_len, maf, elem=elem, blocks_per_batch=blocks_per_batch)
+    img = oracle_image(ds, block_len, maf)
+    got = open(p, "rb").read()
+    assert len(got) == len(img)
+    assert got == img
+    check_decode(ctx, p, img, ds["n_allele"], block_len, one_by_one=one_by_one)
+
+
+# ---- golden fixtures written by the unmodified reference --------------------------------------
+@pytest.mark.parametrize("name", SMALL)
+def test_golden_small_fixture(ctx, tmp_path, name):
+    d = np.load(os.path.join(G, name + ".npz"))
+    ds = dict(gt=d["gt"], ngt=d["ngt"], n_allele=d["n_allele"], n_samples=int(d["n_samples"]))
+    names = [str(x) for x in d["names"]]
+    p = gpu_encode(ctx, tmp_path, ds, int(d["block_len"]), float(d["maf"]), names=names)
+    got = open(p, "rb").read()
+    gold = open(os.path.join(G, name + ".xsi"), "rb").read()
+    assert hashlib.sha256(got).hexdigest() == MAN[name]["xsi_sha256"]
+    assert got == gold
+    # decode the REFERENCE's file and compare with the reference Accessor's own output
+    import xsqueezeit_b200 as xb
+    acc = xb.Accessor(os.path.join(G, name + ".xsi"), ctx)
+    pos = xb.bm_positions(d["n_allele"], int(d["block_len"]))
+    out, filled, _ = acc.fill_genotype_arrays(d["n_allele"], pos)
+    dec = np.concatenate([out[i, :filled[i]] for i in range(len(pos))])
+    assert list(filled) == list(d["ref_decoded_ngt"])
+    assert np.array_equal(dec, d["ref_decoded"])
+    assert acc.get_sample_list() == names
+
+
+def test_golden_chr20_small(ctx, tmp_path):
+    import xsqueezeit_b200 as xb
+    man = MAN["chr20_small"]
+    d = np.load(os.path.join(G, "chr20_small_meta.npz"))
+    ns, nal, ngt = int(d["n_samples"]), d["n_allele"].astype(np.uint32), d["ngt"]
+    names = [str(x) for x in d["names"]]
+    gold_path = os.path.join(G, "chr20_small_default.xsi")
+    acc = xb.Accessor(gold_path, ctx)
+    pos = xb.bm_positions(nal, 8192)
+    out, filled, _ = acc.fill_genotype_arrays(nal, pos)
+    assert (filled == ngt).all()
+    gt = np.ascontiguousarray(out[:, :2 * ns]).reshape(-1)
+    # == bcf_get_genotypes on the original BCF == reference Accessor decode
+    assert hashlib.sha256(gt.tobytes()).hexdigest() == man["gt_sha256"]
+    ds = dict(gt=gt, ngt=ngt, n_allele=nal, n_samples=ns)
+    for key, o in man["options"].items():
+        argv = o["argv"]
+        maf = float(argv[argv.index("--maf") + 1]) if "--maf" in argv else 0.001
+        bl = int(argv[argv.index("--variant-block-length") + 1]) if "--variant-block-length" in argv else 8192
+        p = gpu_encode(ctx, tmp_path, ds, bl, maf, names=names)
+        got = open(p, "rb").read()
+        assert len(got) == o["xsi_size"], key
+        assert hashlib.sha256(got).hexdigest() == o["xsi_sha256"], key
+
+
+# ---- seeded synthetic matrices against the oracle -----------------------------------------------
+def test_biallelic_ld(ctx, tmp_path):
+    roundtrip(ctx, tmp_path, synth.make_dataset(700, 301, seed=1), 256, 0.01, one_by_one=True)
+
+
+def test_int8_input_equals_int32(ctx, tmp_path):
+    ds = synth.make_dataset(500, 333, seed=11, missing=0.01, haploid_samples=0.3, unphased=0.02)
+    roundtrip(ctx, tmp_path, ds, 128, 0.01, elem=1)
+
+
+def test_multiallelic_missing_eov_unphased(ctx, tmp_path):
+    ds = synth.make_dataset(600, 257, seed=2, max_alt=4, multi_frac=0.2, missing=0.01, unphased=0.02, haploid_samples=0.4)
+    roundtrip(ctx, tmp_path, ds, 128, 0.02)
+    roundtrip(ctx, tmp_path, ds, 8192, 0.3)
+
+
+def test_many_alleles(ctx, tmp_path):
+    ds = synth.make_dataset(120, 200, seed=12, max_alt=9, multi_frac=0.5)
+    roundtrip(ctx, tmp_path, ds, 50, 0.02)
+
+
+def test_negated_sparse_and_int32_missing(ctx, tmp_path):
+    ds = synth.make_dataset(200, 100, seed=3)
+    gt = ds["gt"].reshape(200, 200)
+    gt[5, :] = synth.encode_gt(np.ones(200, np.int8))
+    gt[6, :] = synth.encode_gt(np.ones(200, np.int8))
+    gt[6, 17] = synth.encode_gt(np.zeros(1, np.int8))[0]
+    gt[7, 3] = synth.I32_MISSING
+    gt[8, 0::2] = 0
+    ds["gt"] = np.ascontiguousarray(gt.reshape(-1))
+    roundtrip(ctx, tmp_path, ds, 64, 0.05, one_by_one=True)
+
+
+def test_unphased_default(ctx, tmp_path):
+    roundtrip(ctx, tmp_path, synth.make_dataset(300, 64, seed=4, phased=0, unphased=0.03, missing=0.01), 100, 0.01)
+
+
+def test_all_haploid_records(ctx, tmp_path):
+    rng = np.random.default_rng(6)
+    ns, nrec = 90, 150
+    al = (rng.random((nrec, ns)) < rng.uniform(0.0, 0.6, size=(nrec, 1))).astype(np.int8)
+    ds = dict(gt=np.ascontiguousarray(synth.encode_gt(al, 0).reshape(-1)), ngt=np.full(nrec, ns, np.int32),
+              n_allele=np.full(nrec, 2, np.int32), n_samples=ns)
+    roundtrip(ctx, tmp_path, ds, 40, 0.05)
+
+
+def test_mixed_ploidy_records(ctx, tmp_path):
+    rng = np.random.default_rng(7)
+    ns = 1200
+    rows, ngt = [], []
+    for r in range(200):
+        p = 1 if r % 7 == 3 else 2
+        al = (rng.random(ns * p) < 0.3).astype(np.int8)
+        rows.append(synth.encode_gt(al, 1 if p == 2 else 0))
+        ngt.append(ns * p)
+    ds = dict(gt=np.concatenate(rows).astype(np.int32), ngt=np.array(ngt, np.int32), n_allele=np.full(200, 2, np.int32),
+              n_samples=ns)
+    roundtrip(ctx, tmp_path, ds, 64, 0.01)
+
+
+def test_ragged_last_block_and_single_record(ctx, tmp_path):
+    roundtrip(ctx, tmp_path, synth.make_dataset(1, 17, seed=8), 8192, 0.0)
+    roundtrip(ctx, tmp_path, synth.make_dataset(257, 1000, seed=9), 128, 0.001, blocks_per_batch=1)
+
+
+def test_kgp_shape_blocks(ctx, tmp_path):
+    # 1KGP3 shape: 2,504 samples, two full 8192-record blocks + a partial one would be 100M genotypes;
+    # 3000 records in blocks of 1024 keeps the oracle in seconds and still crosses batch boundaries
+    ds = synth.make_dataset(3000, 2504, seed=13, n_founders=128)
+    roundtrip(ctx, tmp_path, ds, 1024, 0.001, blocks_per_batch=2)
+
+
+def test_hrc_shape_uint16_limit(ctx, tmp_path):
+    # HRC shape: 32,488 samples = 64,976 haplotypes (uint16 permutation in shared memory)
+    ds = synth.make_dataset(160, 32488, seed=14, n_founders=128, fmin=0.0005)
+    roundtrip(ctx, tmp_path, ds, 64, 0.001)
+
+
+def test_max_uint16_samples(ctx, tmp_path):
+    ds = synth.make_dataset(40, 32767, seed=15, n_founders=64, fmin=0.001)
+    roundtrip(ctx, tmp_path, ds, 16, 0.001)
+
+
+def test_uint32_index_path(ctx, tmp_path):
+    ds = synth.make_dataset(12, 66000, seed=5, n_founders=16, fmin=0.001)
+    roundtrip(ctx, tmp_path, ds, 5, 0.001)
+
+
+def test_zstd_layer_roundtrip(ctx, tmp_path):
+    import xsqueezeit_b200 as xb
+    ds = synth.make_dataset(400, 150, seed=16, missing=0.01)
+    p = gpu_encode(ctx, tmp_path, ds, 100, 0.01, zstd=True)
+    img = oracle_image(ds, 100, 0.01)
+    acc = xb.Accessor(p, ctx)
+    assert acc.zstd
+    acc.close()
+    check_decode(ctx, p, img, ds["n_allele"], 100)
+
+
+def test_error_codes(ctx):
+    import xsqueezeit_b200 as xb
+    gt = synth.encode_gt(np.zeros((4, 20), np.int8)).reshape(-1).copy()
+    gt[5] = synth.encode_gt(np.array([3], np.int8))[0]  # allele 3 with n_allele 2
+    with pytest.raises(xb.XsiError) as e:
+        ctx.encode_launch(gt, [2, 2, 2, 2], 10, 8192, 0, 1)
+    assert e.value.code == -3
+    with pytest.raises(xb.XsiError) as e:
+        ctx.encode_launch(np.zeros(30, np.int32), [2], 10, 8192, 0, 1, ploidy=[3])
+    assert e.value.code == -4
+    with pytest.raises(xb.XsiError) as e:
+        ctx.encode_launch(np.zeros(2 * 40000, np.int32), [2], 40000, 8192, 0, 1)
+    assert e.value.code == -5

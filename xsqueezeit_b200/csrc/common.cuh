@@ -1,0 +1,72 @@
+// common.cuh -- shared device helpers for the sm_100a genotype kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define XSI_FULL 0xFFFFFFFFu
+#define XSI_I32_MISSING ((int32_t)0x80000000)     // bcf_int32_missing, htslib/vcf.h:1324
+#define XSI_I32_VECTOR_END ((int32_t)0x80000001)  // bcf_int32_vector_end, htslib/vcf.h:1329
+
+// line_flags bits (one byte per binary line)
+#define LF_WAH 1u      // line is PBWT+WAH encoded (else sparse)            gt_block.hpp:299-303
+#define LF_NEGATED 2u  // sparse line lists allele==0 carriers, MSB set    gt_block.hpp:318-324
+#define LF_HAPLOID 4u  // line belongs to an all-haploid record (ngt == n_samples)
+// rec_flags bits (one byte per BCF record)
+#define RF_MISSING 1u
+#define RF_EOV 2u
+#define RF_PHASE 4u
+#define RF_HAPLOID 8u
+
+namespace xsi {
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+    uint32_t m;
+    asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+    return m;
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP) -------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy; bytes % 16 == 0, both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- genotype value helpers (htslib/vcf.h:892-898) ------------------------------------------
+template <int ELEM>
+__device__ __forceinline__ int32_t load_gt(const void* base, uint64_t idx) {
+    if (ELEM == 4) {
+        return __ldg(reinterpret_cast<const int32_t*>(base) + idx);
+    } else {
+        int32_t b = (int32_t)__ldg(reinterpret_cast<const signed char*>(base) + idx);
+        // raw BCF int8: 0x80 = missing, 0x81 = end of vector (vcf.h bcf_int8_missing / bcf_int8_vector_end)
+        return b == -128 ? XSI_I32_MISSING : (b == -127 ? XSI_I32_VECTOR_END : b);
+    }
+}
+__device__ __forceinline__ bool gt_is_missing(int32_t v) { return ((v >> 1) == 0) || v == XSI_I32_MISSING; }
+
+}  // namespace xsi

@@ -1,0 +1,634 @@
+// decode_kernels.cuh -- sm_100a kernels of the decode path.
+//
+//   D0 wah_tile_sum / wah_tile_base / wah_find_lines   where does every WAH line start in its matrix
+//                        (the reference finds out by walking: wah2_extract consumes words until >= N bits,
+//                        include/wah.hpp:177-223; here: prefix sum of the group length of every word)
+//   D1 wah_expand        WAH2-16 words -> bit-row (+ popcount), one warp per line   (wah.hpp:177-235)
+//   D2 pbwt_unpermute    per block, sequential over its WAH lines: x[a[j]] = y[j], a <- stable partition
+//                        (accessor_internals_new.hpp:221-231, 548-589; gt_block.hpp:124-136)
+//   D3 sparse_index      start of every sparse / missing / end-of-vector list (accessor_internals_new.hpp:639-653)
+//   D4 compose_records   bit-rows + sparse lists + overlays -> int32 genotype rows
+//                        (fill_genotype_array_advance, accessor_internals_new.hpp:198-384); HBM-bound, 4 B/genotype
+#pragma once
+#include "common.cuh"
+
+namespace xsi {
+
+// dline_flags bits (one byte per binary line of the loaded set)
+#define DL_WAH 1u
+#define DL_HAPLOID 2u
+#define DL_MISSING 4u
+#define DL_EOV 8u
+#define DL_PHASE 16u
+
+struct DecSeg {       // one WAH matrix (GT lines or phase lines) of one block
+    uint64_t byte_off;  // in blob
+    uint32_t n_words;
+    uint32_t job0, njobs;
+    uint32_t tile0;     // first tile of this segment
+};
+struct DecBlock {
+    uint64_t blob_off;
+    uint64_t sparse_off, miss_off, eov_off;  // byte offsets in blob of the matrices (or ~0)
+    uint32_t line0, n_lines;                  // binary lines (global index base)
+    uint32_t wah0, n_wah;                     // GT WAH jobs
+    uint32_t sp0, n_sp, ms0, n_ms, ev0, n_ev; // ordinals of sparse / missing / eov lists
+    uint32_t default_phasing, pad;
+};
+
+struct DecDev {
+    const uint8_t* blob;
+    const DecSeg* segs; uint32_t nseg;
+    const DecBlock* blocks; uint32_t nb;
+    const uint32_t* tile_seg;   // [ntiles]
+    const uint32_t* tile_word0; // [ntiles]
+    uint32_t ntiles;
+    uint32_t* tile_sum;         // [ntiles] groups in tile, then exclusive base within the segment
+    const uint32_t* job_gcum;   // [NJ] groups before this line within its segment
+    const uint32_t* job_nbits;  // [NJ]
+    const uint32_t* job_seg;    // [NJ]
+    uint32_t* job_word0;        // [NJ] word index within the segment (0xFFFFFFFF = not found)
+    uint32_t* job_ones;         // [NJ]
+    uint32_t NJ;
+    uint32_t* rows;             // [NJ][WS] expanded rows; GT rows become natural order after D2
+    uint32_t WS;
+    uint32_t n_samples;         // header.num_samples
+    uint32_t aet;               // 2 or 4
+    const uint8_t* dline_flags; // [Lt]
+    const uint32_t* dline_ord;  // [Lt] WAH job ordinal (DL_WAH) or sparse list ordinal
+    const uint32_t* dline_mord; // [Lt] ordinal of the missing list (if DL_MISSING)
+    const uint32_t* dline_eord; // [Lt]
+    const uint32_t* dline_pord; // [Lt] job ordinal of the phase row (if DL_PHASE)
+    uint64_t* sp_off;           // [nsp] entry offset of each sparse list within its matrix
+    uint64_t* ms_off;           // [nms]
+    uint64_t* ev_off;           // [nev]
+    uint32_t* err;              // device error word
+};
+#define DERR_WAH_STREAM 1u   // a WAH line does not start on a word boundary / wrong total
+#define DERR_INDEX 2u
+
+constexpr int D0_TILE = 2048;
+constexpr int D0_THREADS = 256;
+
+__device__ __forceinline__ uint32_t wah_word_groups(uint32_t w) { return (w & 0x8000u) ? (w & 0x3FFFu) : 1u; }
+
+__global__ void __launch_bounds__(D0_THREADS) wah_tile_sum_kernel(DecDev d) {
+    __shared__ uint32_t s_sum;
+    const uint32_t t = blockIdx.x;
+    const DecSeg sg = d.segs[d.tile_seg[t]];
+    const uint16_t* w = reinterpret_cast<const uint16_t*>(d.blob + sg.byte_off);
+    const uint32_t w0 = d.tile_word0[t], w1 = min(sg.n_words, w0 + D0_TILE);
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    uint32_t acc = 0;
+    for (uint32_t i = w0 + threadIdx.x; i < w1; i += D0_THREADS) acc += wah_word_groups(w[i]);
+    acc = __reduce_add_sync(XSI_FULL, acc);
+    if (lane_id() == 0) atomicAdd(&s_sum, acc);
+    __syncthreads();
+    if (threadIdx.x == 0) d.tile_sum[t] = s_sum;
+}
+
+// one warp per segment: exclusive scan of its tile sums
+__global__ void __launch_bounds__(128) wah_tile_base_kernel(DecDev d, uint32_t* seg_total) {
+    const uint32_t s = blockIdx.x * 4 + (threadIdx.x >> 5);
+    if (s >= d.nseg) return;
+    const uint32_t lane = lane_id();
+    const DecSeg sg = d.segs[s];
+    const uint32_t nt = (sg.n_words + D0_TILE - 1) / D0_TILE;
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < nt; b += 32) {
+        const uint32_t i = b + lane;
+        const uint32_t v = i < nt ? d.tile_sum[sg.tile0 + i] : 0u;
+        uint32_t incl = v;
+#pragma unroll
+        for (int q = 1; q < 32; q <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, q); if (lane >= (uint32_t)q) incl += o; }
+        if (i < nt) d.tile_sum[sg.tile0 + i] = carry + incl - v;
+        carry += __shfl_sync(XSI_FULL, incl, 31);
+    }
+    if (lane == 0) seg_total[s] = carry;
+}
+
+// per tile: local scan, then locate the lines that start inside this tile
+__global__ void __launch_bounds__(D0_THREADS) wah_find_lines_kernel(DecDev d) {
+    __shared__ uint32_t s_g[D0_TILE + 1];
+    __shared__ uint32_t s_w[D0_THREADS / 32];
+    const uint32_t t = blockIdx.x;
+    const DecSeg sg = d.segs[d.tile_seg[t]];
+    const uint16_t* w = reinterpret_cast<const uint16_t*>(d.blob + sg.byte_off);
+    const uint32_t w0 = d.tile_word0[t], w1 = min(sg.n_words, w0 + D0_TILE);
+    const uint32_t n = w1 - w0;
+    const uint32_t base = d.tile_sum[t];
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    constexpr int PER = D0_TILE / D0_THREADS;  // 8 consecutive words per thread
+    uint32_t v[PER], tot = 0;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { const uint32_t i = tid * PER + q; v[q] = i < n ? wah_word_groups(w[w0 + i]) : 0u; tot += v[q]; }
+    uint32_t incl = tot;
+#pragma unroll
+    for (int q = 1; q < 32; q <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, q); if (lane >= (uint32_t)q) incl += o; }
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t wbase = 0;
+    for (uint32_t q = 0; q < warp; ++q) wbase += s_w[q];
+    uint32_t ex = base + wbase + incl - tot;
+#pragma unroll
+    for (int q = 0; q < PER; ++q) { s_g[tid * PER + q] = ex; ex += v[q]; }
+    if (tid == D0_THREADS - 1) s_g[D0_TILE] = ex;
+    __syncthreads();
+    const uint32_t g_lo = base, g_hi = s_g[D0_TILE];  // groups [g_lo, g_hi) start in this tile
+    // jobs of this segment whose gcum lies in [g_lo, g_hi) (an empty tile range finds nothing)
+    const uint32_t* gc = d.job_gcum + sg.job0;
+    uint32_t lo = 0, hi = sg.njobs;
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (gc[m] < g_lo) lo = m + 1; else hi = m; }
+    const uint32_t j_lo = lo;
+    hi = sg.njobs;
+    while (lo < hi) { const uint32_t m = (lo + hi) >> 1; if (gc[m] < g_hi) lo = m + 1; else hi = m; }
+    const uint32_t j_hi = lo;
+    for (uint32_t j = j_lo + tid; j < j_hi; j += D0_THREADS) {
+        const uint32_t target = gc[j];
+        uint32_t a = 0, b = n;  // first word with s_g >= target
+        while (a < b) { const uint32_t m = (a + b) >> 1; if (s_g[m] < target) a = m + 1; else b = m; }
+        if (a < n && s_g[a] == target) d.job_word0[sg.job0 + j] = w0 + a;
+        else atomicOr(d.err, DERR_WAH_STREAM);
+    }
+}
+
+// =============================================================================================
+// D1: expand one WAH line per warp into a bit-row
+// =============================================================================================
+// dynamic smem per warp: g15[Gpad] (u16) | tog[Tpad] (u32)
+__global__ void wah_expand_kernel(DecDev d, uint32_t warps_per_cta, uint32_t Gpad, uint32_t Tpad) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t wi = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t job = blockIdx.x * warps_per_cta + wi;
+    if (job >= d.NJ) return;
+    uint16_t* g15 = reinterpret_cast<uint16_t*>(smem_raw + (size_t)wi * (Gpad * 2 + Tpad * 4));
+    uint32_t* tog = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(g15) + Gpad * 2);
+    const DecSeg sg = d.segs[d.job_seg[job]];
+    const uint16_t* w = reinterpret_cast<const uint16_t*>(d.blob + sg.byte_off);
+    const uint32_t nbits = d.job_nbits[job];
+    const uint32_t G = (nbits + 14) / 15;
+    const uint32_t ws = d.job_word0[job];
+    const uint32_t we = (job + 1 < sg.job0 + sg.njobs) ? d.job_word0[job + 1] : sg.n_words;
+    uint32_t* out = d.rows + (size_t)job * d.WS;
+    if (ws == 0xFFFFFFFFu || we == 0xFFFFFFFFu || we < ws) {
+        if (lane == 0) atomicOr(d.err, DERR_WAH_STREAM);
+        for (uint32_t m = lane; m < d.WS; m += 32) out[m] = 0;
+        return;
+    }
+    for (uint32_t i = lane; i < Gpad; i += 32) g15[i] = 0;
+    for (uint32_t i = lane; i < Tpad; i += 32) tog[i] = 0;
+    __syncwarp();
+    uint32_t gbase = 0;
+    for (uint32_t b = ws; b < we; b += 32) {
+        const uint32_t i = b + lane;
+        const uint32_t word = i < we ? w[i] : 0u;
+        const uint32_t ng = i < we ? wah_word_groups(word) : 0u;
+        uint32_t incl = ng;
+#pragma unroll
+        for (int q = 1; q < 32; q <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, q); if (lane >= (uint32_t)q) incl += o; }
+        const uint32_t gs = gbase + incl - ng;
+        if (i < we) {
+            if (!(word & 0x8000u)) { if (gs < G) g15[gs] = (uint16_t)word; }
+            else if ((word & 0x4000u) && ng) {  // run of all-one groups: toggle marks, filled by the prefix-xor below
+                const uint32_t s0 = min(gs, G), e0 = min(gs + ng, G);
+                atomicXor(&tog[s0 >> 5], 1u << (s0 & 31));
+                atomicXor(&tog[e0 >> 5], 1u << (e0 & 31));
+            }
+        }
+        gbase += __shfl_sync(XSI_FULL, incl, 31);
+    }
+    if (gbase != G && lane == 0) atomicOr(d.err, DERR_WAH_STREAM);
+    __syncwarp();
+    // prefix-xor over the toggle bits -> bit g set iff group g lies inside a ones-run
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < Tpad; b += 32) {
+        const uint32_t i = b + lane;
+        uint32_t tw = i < Tpad ? tog[i] : 0u;
+        tw ^= tw << 1; tw ^= tw << 2; tw ^= tw << 4; tw ^= tw << 8; tw ^= tw << 16;
+        const uint32_t pm = __ballot_sync(XSI_FULL, tw >> 31);
+        const uint32_t cin = (__popc(pm & lanemask_lt()) & 1u) ^ carry;
+        if (cin) tw = ~tw;
+        if (i < Tpad) tog[i] = tw;
+        carry ^= (__popc(pm) & 1u);
+    }
+    __syncwarp();
+    uint32_t ones = 0;
+    const uint32_t nwords = (nbits + 31) >> 5;
+    for (uint32_t m = lane; m < d.WS; m += 32) {
+        uint32_t o = 0;
+        if (m < nwords) {
+            const uint32_t b0 = m * 32, g0 = b0 / 15, sh = b0 - g0 * 15;
+            uint64_t acc = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t g = g0 + q;
+                uint32_t val = 0;
+                if (g < G) val = ((tog[g >> 5] >> (g & 31)) & 1u) ? 0x7FFFu : g15[g];
+                acc |= (uint64_t)val << (15 * q);
+            }
+            o = (uint32_t)(acc >> sh);
+            if (m == nwords - 1 && (nbits & 31)) o &= (1u << (nbits & 31)) - 1u;
+        }
+        out[m] = o;
+        ones += __popc(o);
+    }
+    ones = __reduce_add_sync(XSI_FULL, ones);
+    if (lane == 0) d.job_ones[job] = ones;
+}
+
+// =============================================================================================
+// D2: undo the PBWT order, a[] in shared memory as uint16 (2*num_samples <= 65536)
+// =============================================================================================
+// dynamic smem: a[N] u16 | ybuf[2][WS] | xb[N+32] u8 | zc[64] | mbar[2]
+template <int WPW, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) pbwt_unpermute_smem_kernel(DecDev d, const uint8_t* __restrict__ job_hap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t S = d.n_samples, N = 2 * S;
+    const uint32_t W = (N + 31) >> 5, WS = d.WS;
+    const uint32_t a_bytes = ((N * 2 + 15) / 16) * 16;
+    uint16_t* a = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* ybuf = reinterpret_cast<uint32_t*>(smem_raw + a_bytes);
+    uint8_t* xb = reinterpret_cast<uint8_t*>(ybuf + 2 * WS);
+    const uint32_t xb_bytes = ((N + 32 + 15) / 16) * 16;
+    uint32_t* zc = reinterpret_cast<uint32_t*>(xb + xb_bytes);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(zc + 64);
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, NW = blockDim.x >> 5;
+    const DecBlock blk = d.blocks[blockIdx.x];
+    const uint32_t nwah = blk.n_wah, row_bytes = WS * 4;
+    for (uint32_t i = tid; i < N; i += blockDim.x) a[i] = (uint16_t)i;
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+    __syncthreads();
+    if (nwah == 0) return;
+    if (tid == 0) { mbar_expect_tx(&mbar[0], row_bytes); bulk_g2s(ybuf, d.rows + (size_t)blk.wah0 * WS, row_bytes, &mbar[0]); }
+    uint32_t par0 = 0, par1 = 0;
+    const uint32_t w0 = warp * WPW, ltm = lanemask_lt();
+    for (uint32_t k = 0; k < nwah; ++k) {
+        const uint32_t cur = k & 1, job = blk.wah0 + k;
+        const bool hap = job_hap[job] != 0;
+        if (k + 1 < nwah && tid == 0) {
+            mbar_expect_tx(&mbar[cur ^ 1], row_bytes);
+            bulk_g2s(ybuf + (cur ^ 1) * WS, d.rows + (size_t)(job + 1) * WS, row_bytes, &mbar[cur ^ 1]);
+        }
+        if (cur == 0) { mbar_wait(&mbar[0], par0); par0 ^= 1; } else { mbar_wait(&mbar[1], par1); par1 ^= 1; }
+        uint32_t* yrow = ybuf + cur * WS;
+        uint32_t* grow = d.rows + (size_t)job * WS;
+        uint32_t av[WPW / 2 > 0 ? WPW / 2 : 1];
+        uint32_t zeros = 0, evens = 0;
+        if (!hap) {
+            // ---- A: x[a[j]] = y[j] ----
+#pragma unroll
+            for (int q = 0; q < WPW; ++q) {
+                const uint32_t widx = w0 + q, j = widx * 32 + lane;
+                const bool valid = j < N;
+                const uint32_t aj = valid ? a[j] : 0u;
+                if (q & 1) av[q >> 1] |= aj << 16; else av[q >> 1] = aj;
+                const uint32_t yk = widx < W ? yrow[widx] : 0u;
+                if (valid) xb[aj] = (uint8_t)((yk >> lane) & 1u);
+                zeros += __popc(~yk & __ballot_sync(XSI_FULL, valid));
+            }
+        } else {
+            // haploid line: y is over a1 = even entries of a (interfaces.hpp:318-333); x[sample] = y[rank among evens]
+#pragma unroll
+            for (int q = 0; q < WPW; ++q) {
+                const uint32_t widx = w0 + q, j = widx * 32 + lane;
+                const bool valid = j < N;
+                const uint32_t aj = valid ? a[j] : 0u;
+                if (q & 1) av[q >> 1] |= aj << 16; else av[q >> 1] = aj;
+                evens += __popc(__ballot_sync(XSI_FULL, valid && !(aj & 1u)));
+            }
+            if (lane == 0) zc[32 + warp] = evens;
+            __syncthreads();
+            const uint32_t ev = lane < NW ? zc[32 + lane] : 0u;
+            uint32_t ebase = __reduce_add_sync(XSI_FULL, lane < warp ? ev : 0u);
+#pragma unroll
+            for (int q = 0; q < WPW; ++q) {
+                const uint32_t widx = w0 + q, j = widx * 32 + lane;
+                const bool valid = j < N;
+                const uint32_t aj = (q & 1) ? (av[q >> 1] >> 16) : (av[q >> 1] & 0xFFFFu);
+                const bool even = valid && !(aj & 1u);
+                const uint32_t ek = __ballot_sync(XSI_FULL, even);
+                if (even) {
+                    const uint32_t i = ebase + __popc(ek & ltm);
+                    xb[aj >> 1] = i < S ? (uint8_t)((yrow[i >> 5] >> (i & 31)) & 1u) : (uint8_t)0;
+                }
+                ebase += __popc(ek);
+            }
+            __syncthreads();
+            // y2[j] = x[a[j]/2] for all j, kept in ybuf (the consumed row) for the partition below
+            __syncthreads();
+#pragma unroll
+            for (int q = 0; q < WPW; ++q) {
+                const uint32_t widx = w0 + q, j = widx * 32 + lane;
+                const bool valid = j < N;
+                const uint32_t aj = (q & 1) ? (av[q >> 1] >> 16) : (av[q >> 1] & 0xFFFFu);
+                const uint32_t bit = valid ? xb[aj >> 1] : 0u;
+                const uint32_t yk = __ballot_sync(XSI_FULL, bit);
+                zeros += __popc(~yk & __ballot_sync(XSI_FULL, valid));
+                if (widx < WS && lane == 0) yrow[widx] = yk;
+            }
+        }
+        if (lane == 0) zc[warp] = zeros;
+        __syncthreads();  // #1
+        // ---- natural-order row back to global (in place) ----
+        {
+            const uint32_t nx = hap ? S : N;
+            const uint32_t nxw = (nx + 31) >> 5;
+            for (uint32_t m = warp; m * 32 < WS; m += NW) {  // 32 words per warp-iteration
+                uint32_t keep = 0;
+                for (uint32_t s = 0; s < 32; ++s) {
+                    const uint32_t widx = m * 32 + s;
+                    if (widx >= nxw) break;
+                    const uint32_t i = widx * 32 + lane;
+                    const uint32_t bw = __ballot_sync(XSI_FULL, i < nx && xb[i]);
+                    if (lane == s) keep = bw;
+                }
+                const uint32_t widx = m * 32 + lane;
+                if (widx < WS) grow[widx] = keep;
+            }
+        }
+        // ---- B/C: stable partition of a by y ----
+        const uint32_t zv = lane < NW ? zc[lane] : 0u;
+        const uint32_t Z = __reduce_add_sync(XSI_FULL, zv);
+        uint32_t zbase = __reduce_add_sync(XSI_FULL, lane < warp ? zv : 0u);
+        uint32_t obase = Z + (min(w0 * 32, N) - zbase);
+#pragma unroll
+        for (int q = 0; q < WPW; ++q) {
+            const uint32_t widx = w0 + q, j = widx * 32 + lane;
+            const bool valid = j < N;
+            const uint32_t vm = __ballot_sync(XSI_FULL, valid);
+            const uint32_t yk = (widx < W ? yrow[widx] : 0u) & vm;
+            const uint32_t nz = ~yk & vm;
+            const uint32_t bit = (yk >> lane) & 1u;
+            const uint32_t aj = (q & 1) ? (av[q >> 1] >> 16) : (av[q >> 1] & 0xFFFFu);
+            const uint32_t dest = bit ? obase + __popc(yk & ltm) : zbase + __popc(nz & ltm);
+            if (valid) a[dest] = (uint16_t)aj;
+            zbase += __popc(nz);
+            obase += __popc(yk);
+        }
+        if (hap) fence_proxy_async();
+        __syncthreads();  // #2
+    }
+}
+
+// generic fallback for > 65536 haplotypes: a[] and x[] in global memory
+__global__ void __launch_bounds__(1024, 1) pbwt_unpermute_gmem_kernel(DecDev d, const uint8_t* __restrict__ job_hap,
+                                                                      uint32_t* a_pool, uint8_t* x_pool) {
+    __shared__ uint32_t zc[64];
+    const uint32_t S = d.n_samples, N = 2 * S;
+    const uint32_t W = (N + 31) >> 5, WS = d.WS;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, NW = blockDim.x >> 5;
+    const DecBlock blk = d.blocks[blockIdx.x];
+    uint32_t* abuf[2] = {a_pool + (size_t)blockIdx.x * 2 * N, a_pool + (size_t)blockIdx.x * 2 * N + N};
+    uint8_t* xb = x_pool + (size_t)blockIdx.x * (N + 32);
+    uint32_t* y2 = a_pool + (size_t)gridDim.x * 2 * N + (size_t)blockIdx.x * WS;
+    for (uint32_t i = tid; i < N; i += blockDim.x) abuf[0][i] = i;
+    __syncthreads();
+    const uint32_t wpw = (W + NW - 1) / NW;
+    const uint32_t w0 = warp * wpw, w1 = min(W, w0 + wpw), ltm = lanemask_lt();
+    uint32_t cur = 0;
+    for (uint32_t k = 0; k < blk.n_wah; ++k) {
+        const uint32_t job = blk.wah0 + k;
+        const bool hap = job_hap[job] != 0;
+        uint32_t* row = d.rows + (size_t)job * WS;
+        const uint32_t* a = abuf[cur];
+        uint32_t* an = abuf[cur ^ 1];
+        uint32_t zeros = 0, evens = 0;
+        if (!hap) {
+            for (uint32_t widx = w0; widx < w1; ++widx) {
+                const uint32_t j = widx * 32 + lane;
+                const bool valid = j < N;
+                const uint32_t yk = row[widx];
+                if (valid) xb[a[j]] = (uint8_t)((yk >> lane) & 1u);
+                zeros += __popc(~yk & __ballot_sync(XSI_FULL, valid));
+                if (lane == 0) y2[widx] = yk;
+            }
+        } else {
+            for (uint32_t widx = w0; widx < w1; ++widx) {
+                const uint32_t j = widx * 32 + lane;
+                evens += __popc(__ballot_sync(XSI_FULL, j < N && !(a[j] & 1u)));
+            }
+            if (lane == 0) zc[32 + warp] = evens;
+            __syncthreads();
+            const uint32_t ev = lane < NW ? zc[32 + lane] : 0u;
+            uint32_t ebase = __reduce_add_sync(XSI_FULL, lane < warp ? ev : 0u);
+            for (uint32_t widx = w0; widx < w1; ++widx) {
+                const uint32_t j = widx * 32 + lane;
+                const bool even = j < N && !(a[j] & 1u);
+                const uint32_t ek = __ballot_sync(XSI_FULL, even);
+                if (even) { const uint32_t i = ebase + __popc(ek & ltm); xb[a[j] >> 1] = i < S ? (uint8_t)((row[i >> 5] >> (i & 31)) & 1u) : (uint8_t)0; }
+                ebase += __popc(ek);
+            }
+            __syncthreads();
+            for (uint32_t widx = w0; widx < w1; ++widx) {
+                const uint32_t j = widx * 32 + lane;
+                const bool valid = j < N;
+                const uint32_t yk = __ballot_sync(XSI_FULL, valid && xb[a[j] >> 1]);
+                zeros += __popc(~yk & __ballot_sync(XSI_FULL, valid));
+                if (lane == 0) y2[widx] = yk;
+            }
+        }
+        if (lane == 0) zc[warp] = zeros;
+        __syncthreads();
+        const uint32_t nx = hap ? S : N, nxw = (nx + 31) >> 5;
+        for (uint32_t widx = warp; widx < WS; widx += NW) {
+            const uint32_t i = widx * 32 + lane;
+            const uint32_t bw = (widx < nxw) ? __ballot_sync(XSI_FULL, i < nx && xb[i]) : 0u;
+            if (lane == 0) row[widx] = bw;
+        }
+        const uint32_t zv = lane < NW ? zc[lane] : 0u;
+        const uint32_t Z = __reduce_add_sync(XSI_FULL, zv);
+        uint32_t zbase = __reduce_add_sync(XSI_FULL, lane < warp ? zv : 0u);
+        uint32_t obase = Z + (min(w0 * 32, N) - zbase);
+        for (uint32_t widx = w0; widx < w1; ++widx) {
+            const uint32_t j = widx * 32 + lane;
+            const bool valid = j < N;
+            const uint32_t vm = __ballot_sync(XSI_FULL, valid);
+            const uint32_t yk = y2[widx] & vm, nz = ~yk & vm;
+            const uint32_t bit = (yk >> lane) & 1u;
+            const uint32_t dest = bit ? obase + __popc(yk & ltm) : zbase + __popc(nz & ltm);
+            if (valid) an[dest] = a[j];
+            zbase += __popc(nz);
+            obase += __popc(yk);
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+}
+
+// =============================================================================================
+// D3: start offsets of the variable-length index lists (one thread per matrix)
+// =============================================================================================
+__global__ void sparse_index_kernel(DecDev d) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= d.nb * 3) return;
+    const DecBlock blk = d.blocks[t / 3];
+    const uint32_t kind = t % 3;
+    const uint64_t moff = kind == 0 ? blk.sparse_off : kind == 1 ? blk.miss_off : blk.eov_off;
+    const uint32_t n = kind == 0 ? blk.n_sp : kind == 1 ? blk.n_ms : blk.n_ev;
+    uint64_t* off = kind == 0 ? d.sp_off + blk.sp0 : kind == 1 ? d.ms_off + blk.ms0 : d.ev_off + blk.ev0;
+    if (!n) return;
+    if (moff == ~0ull) { atomicOr(d.err, DERR_INDEX); return; }
+    uint64_t e = 0;
+    if (d.aet == 2) {
+        const uint16_t* m = reinterpret_cast<const uint16_t*>(d.blob + moff);
+        for (uint32_t i = 0; i < n; ++i) { off[i] = e; e += 1 + (m[e] & 0x7FFFu); }
+    } else {
+        const uint8_t* m = d.blob + moff;  // only 2-byte aligned in the file: assemble from halves
+        for (uint32_t i = 0; i < n; ++i) {
+            off[i] = e;
+            const uint16_t* h = reinterpret_cast<const uint16_t*>(m + e * 4);
+            const uint32_t c = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+            e += 1 + (c & 0x7FFFFFFFu);
+        }
+    }
+}
+
+// =============================================================================================
+// D4: compose genotype rows
+// =============================================================================================
+struct ReqDev {
+    const uint32_t* blk;       // [n] loaded-block index
+    const uint32_t* line;      // [n] first binary line within the block
+    const uint32_t* nall;      // [n]
+    uint32_t n;
+    int32_t* out; uint64_t out_stride;
+    uint32_t* filled;          // [n]
+    uint32_t* counts; uint32_t counts_stride;  // [n][counts_stride]
+    uint8_t* scratch;          // [grid][2][Npad]  allele code / phase-by-index flag (general path)
+    uint32_t Npad;
+};
+
+__device__ __forceinline__ uint32_t rd_entry(const uint8_t* m, uint64_t e, uint32_t aet) {
+    if (aet == 2) return reinterpret_cast<const uint16_t*>(m)[e];
+    const uint16_t* h = reinterpret_cast<const uint16_t*>(m + e * 4);
+    return (uint32_t)h[0] | ((uint32_t)h[1] << 16);
+}
+
+constexpr int D4_THREADS = 256;
+constexpr uint8_t CODE_MISSING = 254, CODE_EOV = 255;
+
+__global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, ReqDev q) {
+    const uint32_t tid = threadIdx.x;
+    const uint32_t S = d.n_samples, NH = 2 * S;
+    const uint32_t msb = d.aet == 2 ? 0x8000u : 0x80000000u;
+    for (uint32_t ri = blockIdx.x; ri < q.n; ri += gridDim.x) {
+        const DecBlock blk = d.blocks[q.blk[ri]];
+        const uint32_t nall = q.nall[ri];
+        const uint32_t gl0 = blk.line0 + q.line[ri];
+        const uint8_t f0 = d.dline_flags[gl0];
+        const uint32_t n = (f0 & DL_HAPLOID) ? S : NH;
+        const int32_t DP = (int32_t)(blk.default_phasing & 1u);
+        int32_t* out = q.out + (size_t)ri * q.out_stride;
+        uint32_t* cnts = q.counts ? q.counts + (size_t)ri * q.counts_stride : nullptr;
+        const uint8_t* spm = d.blob + blk.sparse_off;
+        const bool weird = (f0 & (DL_MISSING | DL_EOV | DL_PHASE)) != 0;
+        if (tid == 0 && q.filled) q.filled[ri] = n;
+
+        if (nall == 2 && !weird) {
+            // -------- fast path: one ALT, no overlays --------
+            if (f0 & DL_WAH) {
+                const uint32_t job = d.dline_ord[gl0];
+                const uint32_t* row = d.rows + (size_t)job * d.WS;
+                const bool hap = (f0 & DL_HAPLOID) != 0;
+                for (uint32_t i4 = tid * 4; i4 < n; i4 += D4_THREADS * 4) {
+                    const uint32_t bits = row[i4 >> 5] >> (i4 & 31);
+                    int32_t v[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) v[k] = (int32_t)((((bits >> k) & 1u) + 1u) << 1) | (hap ? 0 : ((int32_t)((i4 + k) & 1u) & DP));
+                    if (i4 + 3 < n && ((reinterpret_cast<uintptr_t>(out + i4) & 15) == 0)) *reinterpret_cast<int4*>(out + i4) = make_int4(v[0], v[1], v[2], v[3]);
+                    else for (int k = 0; k < 4; ++k) if (i4 + k < n) out[i4 + k] = v[k];
+                }
+                if (cnts && tid == 0) { const uint32_t ones = d.job_ones[job]; cnts[1] = ones; cnts[0] = n - ones; }
+            } else {
+                const uint64_t e0 = d.sp_off[d.dline_ord[gl0]];
+                const uint32_t hdr = rd_entry(spm, e0, d.aet);
+                const bool neg = (hdr & msb) != 0;
+                const uint32_t cnt = hdr & ~msb;
+                const int32_t dflt = neg ? 4 : 2, spv = neg ? 2 : 4;  // bcf_gt_unphased(1) = 4, (0) = 2
+                for (uint32_t i = tid; i < n; i += D4_THREADS) out[i] = dflt | ((int32_t)(i & 1u) & DP);
+                __syncthreads();
+                for (uint32_t k = tid; k < cnt; k += D4_THREADS) {
+                    const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet);
+                    if (i < q.out_stride) out[i] = spv | ((int32_t)(i & 1u) & DP);
+                }
+                if (cnts && tid == 0) { const uint32_t ones = neg ? n - cnt : cnt; cnts[1] = ones; cnts[0] = n - ones; }
+            }
+            __syncthreads();
+            continue;
+        }
+
+        // -------- general path (accessor_internals_new.hpp:207-384) --------
+        uint8_t* val = q.scratch + (size_t)blockIdx.x * 2 * q.Npad;
+        uint8_t* pf = val + q.Npad;
+        uint32_t total_alt = 0;
+        for (uint32_t alt = 1; alt < nall; ++alt) {
+            const uint32_t gl = gl0 + alt - 1;
+            const uint8_t fl = d.dline_flags[gl];
+            const bool hapl = (fl & DL_HAPLOID) != 0;
+            uint32_t ones;
+            if (fl & DL_WAH) {
+                const uint32_t job = d.dline_ord[gl];
+                const uint32_t* row = d.rows + (size_t)job * d.WS;
+                ones = d.job_ones[job];
+                if (alt == 1) {
+                    for (uint32_t i = tid; i < n; i += D4_THREADS) { val[i] = (uint8_t)((row[i >> 5] >> (i & 31)) & 1u); pf[i] = hapl ? 0 : 1; }
+                } else {
+                    const uint8_t code = hapl ? (uint8_t)1 : (uint8_t)alt;  // sic: haploid WAH ALT>=2 writes allele 1 (:269)
+                    for (uint32_t i = tid; i < n; i += D4_THREADS)
+                        if ((row[i >> 5] >> (i & 31)) & 1u) { val[i] = code; pf[i] = hapl ? 0 : 1; }
+                }
+            } else {
+                const uint64_t e0 = d.sp_off[d.dline_ord[gl]];
+                const uint32_t hdr = rd_entry(spm, e0, d.aet);
+                const bool neg = (hdr & msb) != 0;
+                const uint32_t cnt = hdr & ~msb;
+                ones = neg ? n - cnt : cnt;
+                if (alt == 1) {
+                    for (uint32_t i = tid; i < n; i += D4_THREADS) { val[i] = neg ? 1 : 0; pf[i] = 1; }
+                    __syncthreads();
+                    for (uint32_t k = tid; k < cnt; k += D4_THREADS) { const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet); if (i < q.Npad) { val[i] = neg ? 0 : 1; pf[i] = 1; } }
+                } else if (neg) {
+                    for (uint32_t i = tid; i < n; i += D4_THREADS) if (val[i] == 0) { val[i] = (uint8_t)alt; pf[i] = 1; }
+                    __syncthreads();
+                    for (uint32_t k = tid; k < cnt; k += D4_THREADS) { const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet); if (i < q.Npad && val[i] == (uint8_t)alt) { val[i] = 0; pf[i] = 1; } }
+                } else {
+                    for (uint32_t k = tid; k < cnt; k += D4_THREADS) { const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet); if (i < q.Npad) { val[i] = (uint8_t)alt; pf[i] = 1; } }
+                }
+            }
+            if (cnts && tid == 0) cnts[alt] = ones;
+            total_alt += ones;
+            __syncthreads();
+        }
+        uint32_t n_missing = 0, n_eov = 0;
+        if (f0 & DL_MISSING) {
+            const uint8_t* mm = d.blob + blk.miss_off;
+            const uint64_t e0 = d.ms_off[d.dline_mord[gl0]];
+            n_missing = rd_entry(mm, e0, d.aet) & ~msb;
+            for (uint32_t k = tid; k < n_missing; k += D4_THREADS) { const uint32_t i = rd_entry(mm, e0 + 1 + k, d.aet); if (i < q.Npad) { val[i] = CODE_MISSING; pf[i] = 1; } }
+            __syncthreads();
+        }
+        if (f0 & DL_EOV) {
+            const uint8_t* mm = d.blob + blk.eov_off;
+            const uint64_t e0 = d.ev_off[d.dline_eord[gl0]];
+            n_eov = rd_entry(mm, e0, d.aet) & ~msb;
+            for (uint32_t k = tid; k < n_eov; k += D4_THREADS) { const uint32_t i = rd_entry(mm, e0 + 1 + k, d.aet); if (i < q.Npad) val[i] = CODE_EOV; }
+            __syncthreads();
+        }
+        const uint32_t* prow = (f0 & DL_PHASE) ? d.rows + (size_t)d.dline_pord[gl0] * d.WS : nullptr;
+        for (uint32_t i = tid; i < n; i += D4_THREADS) {
+            const uint8_t c = val[i];
+            int32_t v;
+            if (c == CODE_EOV) v = XSI_I32_VECTOR_END;
+            else {
+                v = (c == CODE_MISSING ? 0 : (int32_t)(((uint32_t)c + 1u) << 1)) | ((int32_t)(pf[i] & i & 1u) & DP);
+                if (prow && ((prow[i >> 5] >> (i & 31)) & 1u)) v ^= (int32_t)(i & 1u);
+            }
+            out[i] = v;
+        }
+        if (cnts && tid == 0) cnts[0] = n - (total_alt + n_missing + n_eov);
+        __syncthreads();
+    }
+}
+
+}  // namespace xsi

@@ -1,0 +1,619 @@
+// encode_kernels.cuh -- sm_100a kernels of the encode path.
+//
+//   E1 scan_rows        gt rows -> per-ALT bit-rows (natural order), counts, flags, WAH/sparse decision
+//                        replaces GtBlock::scan_genotypes + the decision in encode_line
+//                        (reference include/gt_block.hpp:207-269, 292-329); HBM-bound, 4 B/genotype
+//   E2 build_wah_lists  per block: ordered list of the lines that are PBWT+WAH encoded
+//   E3 pbwt_permute     per block, sequential over its WAH lines: y[j] = bit[a[j]], a <- stable
+//                        partition of a by y  (wah.hpp:506-578 gather + internal_gt_record.hpp:32-59)
+//   E4 wah_encode_rows  bit-row -> WAH2-16 words (wah.hpp:376-429 process_wah_word rules), warp per line
+//   E5 sparse_emit      bit-row -> [count|MSB][ascending indices]  (block.hpp:54-99)
+//   E6 pack_wah         gather the per-line WAH words into the contiguous per-block matrix
+//   scan_u32            exclusive prefix sums for the output offsets
+#pragma once
+#include "common.cuh"
+
+namespace xsi {
+
+struct EncDev {
+    const void* gt;
+    const uint64_t* rec_goff;     // [R] element offset of the row
+    const uint32_t* rec_ngt;      // [R]
+    const uint32_t* rec_nallele;  // [R]
+    const uint32_t* rec_line0;    // [R] first binary line (batch-global)
+    const uint32_t* line_rec;     // [L]
+    const uint32_t* blk_line0;    // [nb+1]
+    uint32_t n_samples, R, L, nb;
+    uint32_t WS;     // words per bit-row (multiple of 4)
+    uint32_t SLOTW;  // u16 words per WAH slot
+    uint32_t aux_cap, phase_cap;
+    uint64_t mac_thr;
+    int32_t default_phasing;
+    uint32_t* bitrows;  // [L][WS]
+    uint32_t* auxrows;  // [aux_cap][WS]   missing / end-of-vector rows
+    uint32_t* phrows;   // [phase_cap][WS] non-default-phase rows
+    uint32_t* counters; // [0] aux rows used, [1] phase rows used, [2] error bits
+    int32_t* rec_aux;   // [R][3] slot of missing / eov / phase row, -1 = none
+    uint32_t* line_cnt;       // [L] carriers of the line's ALT allele
+    uint8_t* line_flags;      // [L]
+    uint32_t* line_sparse_n;  // [L] A_T entries of the sparse line incl. header (0 for WAH lines)
+    uint32_t* line_wah_n;     // [L] WAH words (0 for sparse lines)
+    uint8_t* rec_flags;       // [R]
+    uint32_t* rec_miss_n;     // [R] entries incl. header, 0 if none
+    uint32_t* rec_eov_n;      // [R]
+    uint32_t* rec_phase_n;    // [R] WAH words of the phase line
+    uint32_t* wah_list;       // [L] per block (at blk_line0[b]) the WAH lines in order
+    uint32_t* blk_nwah;       // [nb]
+    uint16_t* wahslots;       // [L][SLOTW]
+    uint16_t* phslots;        // [phase_cap][SLOTW]
+};
+
+#define ERR_ALLELE 1u
+#define ERR_AUX_OVERFLOW 2u
+#define ERR_PHASE_OVERFLOW 4u
+
+// =============================================================================================
+// E1
+// =============================================================================================
+constexpr int E1_THREADS = 256;
+constexpr int E1_WARPS = E1_THREADS / 32;
+constexpr int E1_MAXALLELE = 256;
+
+// one predicate row: kind 0 allele==key, 1 missing, 2 end-of-vector, 3 non-default phase
+template <int ELEM, int KIND>
+__device__ __forceinline__ void emit_pred_row(const void* gt, uint64_t goff, uint32_t ngt, uint32_t WS, int32_t key,
+                                              uint32_t* __restrict__ dst) {
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t nwords = (ngt + 31) >> 5, nchunks = (WS + 31) >> 5;
+    for (uint32_t c = warp; c < nchunks; c += E1_WARPS) {
+        uint32_t keep = 0;
+#pragma unroll 4
+        for (uint32_t s = 0; s < 32; ++s) {
+            const uint32_t widx = c * 32 + s;
+            if (widx >= nwords) break;
+            const uint32_t i = widx * 32 + lane;
+            bool pred = false;
+            if (i < ngt) {
+                const int32_t v = load_gt<ELEM>(gt, goff + i);
+                if (KIND == 0) pred = ((v >> 1) - 1) == key;
+                else if (KIND == 1) pred = gt_is_missing(v);
+                else if (KIND == 2) pred = (v == XSI_I32_VECTOR_END);
+                else pred = (i & 1) && ((v & 1) != key);
+            }
+            const uint32_t b = __ballot_sync(XSI_FULL, pred);
+            if (lane == s) keep = b;
+        }
+        const uint32_t w = c * 32 + lane;
+        if (w < WS) dst[w] = keep;
+    }
+}
+
+template <int ELEM>
+__global__ void __launch_bounds__(E1_THREADS) scan_rows_kernel(EncDev p) {
+    __shared__ uint32_t s_cnt[E1_MAXALLELE];
+    __shared__ uint8_t s_lflag[E1_MAXALLELE];
+    __shared__ uint32_t s_misc[4];  // nmiss, neov, phase bits, err
+    __shared__ int32_t s_slot[3];
+    const uint32_t r = blockIdx.x;
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+    const uint32_t ngt = p.rec_ngt[r], n_allele = p.rec_nallele[r], line0 = p.rec_line0[r];
+    const uint64_t goff = p.rec_goff[r];
+    const uint32_t P = p.n_samples ? ngt / p.n_samples : 0;
+    const uint32_t nwords = (ngt + 31) >> 5, nchunks = (p.WS + 31) >> 5;
+    const uint32_t dpmask = p.default_phasing ? 0xFFFFFFFFu : 0u;
+    const int32_t filler = 2 | (p.default_phasing & 1);  // REF with default phase: matches nothing
+    for (uint32_t i = threadIdx.x; i < E1_MAXALLELE; i += E1_THREADS) { s_cnt[i] = 0; s_lflag[i] = 0; }
+    if (threadIdx.x < 4) s_misc[threadIdx.x] = 0;
+    if (threadIdx.x < 3) s_slot[threadIdx.x] = -1;
+    __syncthreads();
+
+    uint32_t w_nmiss = 0, w_neov = 0, w_phase = 0, w_err = 0;
+    uint32_t alt0 = 1;
+    do {
+        const uint32_t nal = n_allele > alt0 ? min(4u, n_allele - alt0) : 0u;
+        uint32_t wc0 = 0, wc1 = 0, wc2 = 0, wc3 = 0;
+        for (uint32_t c = warp; c < nchunks; c += E1_WARPS) {
+            uint32_t k0 = 0, k1 = 0, k2 = 0, k3 = 0;
+#pragma unroll 8
+            for (uint32_t s = 0; s < 32; ++s) {
+                const uint32_t widx = c * 32 + s;
+                if (widx >= nwords) break;
+                const uint32_t i = widx * 32 + lane;
+                const bool valid = i < ngt;
+                const int32_t v = valid ? load_gt<ELEM>(p.gt, goff + i) : filler;
+                const int32_t h = v >> 1;
+                if (alt0 == 1) {
+                    const bool bad = (uint32_t)(h - 1) >= n_allele;  // missing / EOV / unknown allele
+                    if (__any_sync(XSI_FULL, bad)) {
+                        const bool miss = gt_is_missing(v);
+                        const bool eov = (v == XSI_I32_VECTOR_END);
+                        w_nmiss += __popc(__ballot_sync(XSI_FULL, miss));
+                        w_neov += __popc(__ballot_sync(XSI_FULL, eov));
+                        w_err |= __any_sync(XSI_FULL, bad && !miss && !eov) ? 1u : 0u;
+                    }
+                    if (P == 2) w_phase |= (__ballot_sync(XSI_FULL, v & 1) ^ dpmask) & 0xAAAAAAAAu;
+                }
+                if (nal > 0) { const uint32_t b = __ballot_sync(XSI_FULL, h == (int32_t)(alt0 + 1)); wc0 += __popc(b); if (lane == s) k0 = b; }
+                if (nal > 1) { const uint32_t b = __ballot_sync(XSI_FULL, h == (int32_t)(alt0 + 2)); wc1 += __popc(b); if (lane == s) k1 = b; }
+                if (nal > 2) { const uint32_t b = __ballot_sync(XSI_FULL, h == (int32_t)(alt0 + 3)); wc2 += __popc(b); if (lane == s) k2 = b; }
+                if (nal > 3) { const uint32_t b = __ballot_sync(XSI_FULL, h == (int32_t)(alt0 + 4)); wc3 += __popc(b); if (lane == s) k3 = b; }
+            }
+            const uint32_t w = c * 32 + lane;
+            if (w < p.WS) {
+                uint32_t* row = p.bitrows + (size_t)(line0 + alt0 - 1) * p.WS + w;
+                if (nal > 0) row[0] = k0;
+                if (nal > 1) row[(size_t)p.WS] = k1;
+                if (nal > 2) row[(size_t)p.WS * 2] = k2;
+                if (nal > 3) row[(size_t)p.WS * 3] = k3;
+            }
+        }
+        if (lane == 0) {
+            if (nal > 0) atomicAdd(&s_cnt[alt0], wc0);
+            if (nal > 1) atomicAdd(&s_cnt[alt0 + 1], wc1);
+            if (nal > 2) atomicAdd(&s_cnt[alt0 + 2], wc2);
+            if (nal > 3) atomicAdd(&s_cnt[alt0 + 3], wc3);
+        }
+        alt0 += 4;
+    } while (alt0 < n_allele);
+    if (lane == 0) {
+        if (w_nmiss) atomicAdd(&s_misc[0], w_nmiss);
+        if (w_neov) atomicAdd(&s_misc[1], w_neov);
+        if (w_phase) atomicOr(&s_misc[2], w_phase);
+        if (w_err) atomicOr(&s_misc[3], 1u);
+    }
+    __syncthreads();
+
+    // ---- per-record decisions (gt_block.hpp:292-338) ----
+    if (threadIdx.x == 0) {
+        const uint32_t nmiss = s_misc[0], neov = s_misc[1];
+        uint8_t rf = 0;
+        if (nmiss) rf |= RF_MISSING;
+        if (neov) rf |= RF_EOV;
+        if (s_misc[2]) rf |= RF_PHASE;
+        if (P == 1) rf |= RF_HAPLOID;
+        if (s_misc[3]) atomicOr(&p.counters[2], ERR_ALLELE);
+        uint32_t sum_alt = 0;
+        for (uint32_t a = 1; a < n_allele; ++a) sum_alt += s_cnt[a];
+        const uint32_t cnt0 = ngt - sum_alt - nmiss - neov;
+        for (uint32_t a = 1; a < n_allele; ++a) {
+            const uint32_t c = s_cnt[a];
+            const uint32_t mac = min(c, ngt - c);
+            const uint32_t line = line0 + a - 1;
+            uint8_t lf = (P == 1) ? LF_HAPLOID : 0;
+            uint32_t sn = 0;
+            if ((uint64_t)mac > p.mac_thr) lf |= LF_WAH;
+            else if (c == mac) sn = c + 1;
+            else { lf |= LF_NEGATED; sn = cnt0 + 1; }
+            p.line_cnt[line] = c;
+            p.line_flags[line] = lf;
+            p.line_sparse_n[line] = sn;
+            p.line_wah_n[line] = 0;
+            s_lflag[a] = lf;
+        }
+        p.rec_flags[r] = rf;
+        p.rec_miss_n[r] = nmiss ? nmiss + 1 : 0;
+        p.rec_eov_n[r] = neov ? neov + 1 : 0;
+        p.rec_phase_n[r] = 0;
+        if (nmiss) { const uint32_t s = atomicAdd(&p.counters[0], 1u); if (s < p.aux_cap) s_slot[0] = (int32_t)s; else atomicOr(&p.counters[2], ERR_AUX_OVERFLOW); }
+        if (neov) { const uint32_t s = atomicAdd(&p.counters[0], 1u); if (s < p.aux_cap) s_slot[1] = (int32_t)s; else atomicOr(&p.counters[2], ERR_AUX_OVERFLOW); }
+        if (rf & RF_PHASE) { const uint32_t s = atomicAdd(&p.counters[1], 1u); if (s < p.phase_cap) s_slot[2] = (int32_t)s; else atomicOr(&p.counters[2], ERR_PHASE_OVERFLOW); }
+        p.rec_aux[r * 3 + 0] = s_slot[0];
+        p.rec_aux[r * 3 + 1] = s_slot[1];
+        p.rec_aux[r * 3 + 2] = s_slot[2];
+    }
+    __syncthreads();
+    // ---- rare second passes over the (L2-hot) row ----
+    for (uint32_t a = 1; a < n_allele; ++a)
+        if (s_lflag[a] & LF_NEGATED)  // negated sparse lists REF carriers (block.hpp:59-65 with sparse_allele 0)
+            emit_pred_row<ELEM, 0>(p.gt, goff, ngt, p.WS, 0, p.bitrows + (size_t)(line0 + a - 1) * p.WS);
+    if (s_slot[0] >= 0) emit_pred_row<ELEM, 1>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[0] * p.WS);
+    if (s_slot[1] >= 0) emit_pred_row<ELEM, 2>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[1] * p.WS);
+    if (s_slot[2] >= 0) emit_pred_row<ELEM, 3>(p.gt, goff, ngt, p.WS, p.default_phasing, p.phrows + (size_t)s_slot[2] * p.WS);
+}
+
+// =============================================================================================
+// E2: ordered list of WAH lines per block
+// =============================================================================================
+__global__ void __launch_bounds__(32) build_wah_lists_kernel(EncDev p) {
+    const uint32_t b = blockIdx.x, lane = lane_id();
+    const uint32_t l0 = p.blk_line0[b], l1 = p.blk_line0[b + 1];
+    uint32_t n = 0;
+    for (uint32_t base = l0; base < l1; base += 32) {
+        const uint32_t l = base + lane;
+        const bool w = l < l1 && (p.line_flags[l] & LF_WAH);
+        const uint32_t m = __ballot_sync(XSI_FULL, w);
+        // bit 31 carries the haploid flag so the sequential kernel needs no extra load per line
+        if (w) p.wah_list[l0 + n + __popc(m & lanemask_lt())] = l | ((p.line_flags[l] & LF_HAPLOID) ? 0x80000000u : 0u);
+        n += __popc(m);
+    }
+    if (lane == 0) p.blk_nwah[b] = n;
+}
+
+// =============================================================================================
+// E3: PBWT permute, a[] resident in shared memory as uint16 (2*n_samples <= 65536)
+// =============================================================================================
+// dynamic smem layout (bytes): a[2*NHpad] | row[2][WS*4] | ybuf[WS*4] | ebuf[WS*4] | zc[64*4] | mbar[2*8]
+template <int WPW, int MAXT>
+__global__ void __launch_bounds__(MAXT, 1) pbwt_permute_smem_kernel(EncDev p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t N = 2 * p.n_samples;  // a.size(), gt_block.hpp:171
+    const uint32_t W = (N + 31) >> 5;
+    const uint32_t WS = p.WS;
+    const uint32_t a_bytes = ((N * 2 + 15) / 16) * 16;
+    uint16_t* a = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* rowbuf = reinterpret_cast<uint32_t*>(smem_raw + a_bytes);
+    uint32_t* ybuf = rowbuf + 2 * WS;
+    uint32_t* ebuf = ybuf + WS;
+    uint32_t* zc = ebuf + WS;  // [0..31] zeros per warp, [32..63] evens per warp
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(zc + 64);
+
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, NW = blockDim.x >> 5;
+    const uint32_t b = blockIdx.x;
+    const uint32_t l0 = p.blk_line0[b];
+    const uint32_t nwah = p.blk_nwah[b];
+    const uint32_t* list = p.wah_list + l0;
+    const uint32_t row_bytes = WS * 4;
+
+    for (uint32_t i = tid; i < N; i += blockDim.x) a[i] = (uint16_t)i;  // iota, gt_block.hpp:179
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+    __syncthreads();
+    if (nwah == 0) return;
+    uint32_t par0 = 0, par1 = 0;
+    if (tid == 0) {
+        mbar_expect_tx(&mbar[0], row_bytes);
+        bulk_g2s(rowbuf, p.bitrows + (size_t)(list[0] & 0x7FFFFFFFu) * WS, row_bytes, &mbar[0]);
+    }
+    const uint32_t w0 = warp * WPW;
+    const uint32_t ltm = lanemask_lt();
+    uint32_t line_next = nwah > 1 ? list[1] : 0;
+
+    for (uint32_t k = 0; k < nwah; ++k) {
+        const uint32_t cur = k & 1;
+        const uint32_t entry = (k == 0) ? list[0] : line_next;
+        const uint32_t line = entry & 0x7FFFFFFFu;
+        const bool hap = (entry >> 31) != 0;
+        // prefetch: row of line k+1 into the other buffer, id of line k+2
+        if (k + 1 < nwah) {
+            if (tid == 0) {
+                mbar_expect_tx(&mbar[cur ^ 1], row_bytes);
+                bulk_g2s(rowbuf + (cur ^ 1) * WS, p.bitrows + (size_t)(line_next & 0x7FFFFFFFu) * WS, row_bytes, &mbar[cur ^ 1]);
+            }
+            line_next = (k + 2 < nwah) ? list[k + 2] : 0;
+        }
+        if (cur == 0) { mbar_wait(&mbar[0], par0); par0 ^= 1; } else { mbar_wait(&mbar[1], par1); par1 ^= 1; }
+        const uint32_t* row = rowbuf + cur * WS;
+
+        // ---- phase A: gather y through a, count zeros ----
+        uint32_t av[WPW / 2 > 0 ? WPW / 2 : 1];
+        uint32_t zeros = 0, evens = 0;
+#pragma unroll
+        for (int q = 0; q < WPW; ++q) {
+            const uint32_t widx = w0 + q;
+            const uint32_t j = widx * 32 + lane;
+            const bool valid = j < N;
+            const uint32_t aj = valid ? a[j] : 0u;
+            if (q & 1) av[q >> 1] |= aj << 16; else av[q >> 1] = aj;
+            const uint32_t gi = hap ? (aj >> 1) : aj;
+            const uint32_t bit = valid ? ((row[gi >> 5] >> (gi & 31)) & 1u) : 0u;
+            const uint32_t yk = __ballot_sync(XSI_FULL, bit);
+            const uint32_t vm = __ballot_sync(XSI_FULL, valid);
+            zeros += __popc(~yk & vm);
+            if (widx < WS && lane == 0) ybuf[widx] = yk;
+            if (hap) {
+                const uint32_t ek = __ballot_sync(XSI_FULL, valid && !(aj & 1u));
+                evens += __popc(ek);
+                if (widx < WS && lane == 0) ebuf[widx] = ek;
+            }
+        }
+        if (lane == 0) { zc[warp] = zeros; zc[32 + warp] = evens; }
+        __syncthreads();  // #1: all reads of a[] and row[] done, ybuf / zc complete
+
+        // ---- phase B: offsets ----
+        const uint32_t zv = lane < NW ? zc[lane] : 0u;
+        const uint32_t Z = __reduce_add_sync(XSI_FULL, zv);
+        uint32_t zbase = __reduce_add_sync(XSI_FULL, lane < warp ? zv : 0u);
+        const uint32_t pos0 = min(w0 * 32, N);
+        uint32_t obase = Z + (pos0 - zbase);
+        uint32_t* grow = p.bitrows + (size_t)line * WS;
+        uint32_t ebase = 0;
+        uint32_t* obuf = rowbuf + cur * WS;  // haploid path reuses the consumed row buffer
+        if (!hap) {
+            for (uint32_t i = tid; i < WS; i += blockDim.x) grow[i] = i < W ? ybuf[i] : 0u;  // permuted row, in place
+        } else {
+            const uint32_t ev = lane < NW ? zc[32 + lane] : 0u;
+            ebase = __reduce_add_sync(XSI_FULL, lane < warp ? ev : 0u);
+            for (uint32_t i = tid; i < WS; i += blockDim.x) obuf[i] = 0u;
+            __syncthreads();
+        }
+        // ---- phase C: stable partition of a by y (zeros first) ----
+#pragma unroll
+        for (int q = 0; q < WPW; ++q) {
+            const uint32_t widx = w0 + q;
+            const uint32_t j = widx * 32 + lane;
+            const bool valid = j < N;
+            const uint32_t yk = widx < WS ? ybuf[widx] : 0u;
+            const uint32_t vm = __ballot_sync(XSI_FULL, valid);
+            const uint32_t nz = ~yk & vm;
+            const uint32_t bit = (yk >> lane) & 1u;
+            const uint32_t aj = (q & 1) ? (av[q >> 1] >> 16) : (av[q >> 1] & 0xFFFFu);
+            const uint32_t dest = bit ? obase + __popc(yk & ltm) : zbase + __popc(nz & ltm);
+            if (valid) a[dest] = (uint16_t)aj;
+            zbase += __popc(nz);
+            obase += __popc(yk);
+            if (hap) {  // WAH row of a haploid line is y over a1 = even entries of a (interfaces.hpp:318-333)
+                const uint32_t ek = widx < WS ? ebuf[widx] : 0u;
+                if (((ek >> lane) & 1u) && bit) {
+                    const uint32_t pp = ebase + __popc(ek & ltm);
+                    atomicOr(&obuf[pp >> 5], 1u << (pp & 31));
+                }
+                ebase += __popc(ek);
+            }
+        }
+        __syncthreads();  // #2: a[] updated
+        if (hap) {
+            for (uint32_t i = tid; i < WS; i += blockDim.x) grow[i] = obuf[i];
+            fence_proxy_async();
+            __syncthreads();
+        }
+    }
+}
+
+// generic fallback for > 65536 haplotypes: a[] ping-pongs in global memory (L2 resident)
+__global__ void __launch_bounds__(1024, 1) pbwt_permute_gmem_kernel(EncDev p, uint32_t* a_pool) {
+    __shared__ uint32_t zc[64];
+    __shared__ uint32_t s_tot[2];
+    const uint32_t N = 2 * p.n_samples;
+    const uint32_t W = (N + 31) >> 5, WS = p.WS;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, NW = blockDim.x >> 5;
+    const uint32_t b = blockIdx.x;
+    const uint32_t l0 = p.blk_line0[b], nwah = p.blk_nwah[b];
+    const uint32_t* list = p.wah_list + l0;
+    uint32_t* abuf[2] = {a_pool + (size_t)b * 2 * N, a_pool + (size_t)b * 2 * N + N};
+    uint32_t* ytmp = a_pool + (size_t)gridDim.x * 2 * N + (size_t)b * 2 * WS;  // y words, then even masks
+    for (uint32_t i = tid; i < N; i += blockDim.x) abuf[0][i] = i;
+    __syncthreads();
+    const uint32_t wpw = (W + NW - 1) / NW;
+    const uint32_t w0 = warp * wpw, w1 = min(W, w0 + wpw);
+    const uint32_t ltm = lanemask_lt();
+    uint32_t cur = 0;
+    for (uint32_t k = 0; k < nwah; ++k) {
+        const uint32_t line = list[k] & 0x7FFFFFFFu;
+        const bool hap = (list[k] >> 31) != 0;
+        uint32_t* row = p.bitrows + (size_t)line * WS;
+        const uint32_t* a = abuf[cur];
+        uint32_t* an = abuf[cur ^ 1];
+        uint32_t zeros = 0, evens = 0;
+        for (uint32_t widx = w0; widx < w1; ++widx) {
+            const uint32_t j = widx * 32 + lane;
+            const bool valid = j < N;
+            const uint32_t aj = valid ? a[j] : 0u;
+            const uint32_t gi = hap ? (aj >> 1) : aj;
+            const uint32_t bit = valid ? ((row[gi >> 5] >> (gi & 31)) & 1u) : 0u;
+            const uint32_t yk = __ballot_sync(XSI_FULL, bit);
+            const uint32_t vm = __ballot_sync(XSI_FULL, valid);
+            zeros += __popc(~yk & vm);
+            const uint32_t ek = __ballot_sync(XSI_FULL, valid && !(aj & 1u));
+            evens += __popc(ek);
+            if (lane == 0) { ytmp[widx] = yk; ytmp[WS + widx] = ek; }
+        }
+        if (lane == 0) { zc[warp] = zeros; zc[32 + warp] = evens; }
+        __syncthreads();
+        const uint32_t zv = lane < NW ? zc[lane] : 0u;
+        const uint32_t Z = __reduce_add_sync(XSI_FULL, zv);
+        uint32_t zbase = __reduce_add_sync(XSI_FULL, lane < warp ? zv : 0u);
+        const uint32_t ev = lane < NW ? zc[32 + lane] : 0u;
+        uint32_t ebase = __reduce_add_sync(XSI_FULL, lane < warp ? ev : 0u);
+        uint32_t obase = Z + (min(w0 * 32, N) - zbase);
+        // the natural row has been fully consumed: overwrite it with the permuted row
+        if (!hap) { for (uint32_t i = tid; i < WS; i += blockDim.x) row[i] = i < W ? ytmp[i] : 0u; }
+        else { for (uint32_t i = tid; i < WS; i += blockDim.x) row[i] = 0u; }
+        __syncthreads();
+        for (uint32_t widx = w0; widx < w1; ++widx) {
+            const uint32_t j = widx * 32 + lane;
+            const bool valid = j < N;
+            const uint32_t yk = ytmp[widx];
+            const uint32_t vm = __ballot_sync(XSI_FULL, valid);
+            const uint32_t nz = ~yk & vm;
+            const uint32_t bit = (yk >> lane) & 1u;
+            const uint32_t dest = bit ? obase + __popc(yk & ltm) : zbase + __popc(nz & ltm);
+            if (valid) an[dest] = a[j];
+            zbase += __popc(nz);
+            obase += __popc(yk);
+            if (hap) {
+                const uint32_t ek = ytmp[WS + widx];
+                if (((ek >> lane) & 1u) && bit) { const uint32_t pp = ebase + __popc(ek & ltm); atomicOr(&row[pp >> 5], 1u << (pp & 31)); }
+                ebase += __popc(ek);
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    (void)s_tot;
+}
+
+// =============================================================================================
+// E4: WAH2-16 encode of bit-rows, one warp per row
+// =============================================================================================
+// Rules (wah.hpp:376-429,568-573): 15-bit groups LSB first; all-zero / all-one groups are
+// counted into 0x8000|n / 0xC000|n words, n <= 16383 (a saturated counter is emitted as
+// 0xBFFF / 0xFFFF and counting restarts); anything else is a literal; the tail is zero padded.
+__device__ __forceinline__ uint32_t wah_encode_row_warp(const uint32_t* __restrict__ row, uint32_t WS, uint32_t nbits,
+                                                        uint16_t* __restrict__ out) {
+    const uint32_t lane = lane_id();
+    const uint32_t G = (nbits + 14) / 15;
+    const uint32_t iters = (G + 31) >> 5;
+    uint32_t heads_base = 0, carry_type = 3, carry_len = 0;
+    const uint32_t le = lanemask_lt() | (1u << lane);
+    for (uint32_t it = 0; it < iters; ++it) {
+        const uint32_t wi = it * 15 + lane;
+        const uint32_t wv = (lane < 16 && wi < WS) ? row[wi] : 0u;
+        const uint32_t bitpos = 15 * lane;
+        const uint32_t lo = __shfl_sync(XSI_FULL, wv, bitpos >> 5);
+        const uint32_t hi = __shfl_sync(XSI_FULL, wv, (bitpos >> 5) + 1);
+        const uint32_t grp = __funnelshift_r(lo, hi, bitpos & 31) & 0x7FFFu;
+        const uint32_t nextgrp = __shfl_sync(XSI_FULL, wv, 15) & 0x7FFFu;
+        const uint32_t g = it * 32 + lane;
+        const bool valid = g < G;
+        const uint32_t type = !valid ? 3u : (grp == 0 ? 0u : (grp == 0x7FFFu ? 1u : 2u));
+        const uint32_t nexttype = ((it + 1) * 32 < G) ? (nextgrp == 0 ? 0u : (nextgrp == 0x7FFFu ? 1u : 2u)) : 3u;
+        uint32_t prevtype = __shfl_up_sync(XSI_FULL, type, 1);
+        if (lane == 0) prevtype = carry_type;
+        uint32_t succtype = __shfl_down_sync(XSI_FULL, type, 1);
+        if (lane == 31) succtype = nexttype;
+        const bool h0 = valid && (type == 2 || type != prevtype);
+        const uint32_t H0 = __ballot_sync(XSI_FULL, h0);
+        const uint32_t hb = H0 & le;
+        const uint32_t offset = hb ? lane - (31 - __clz(hb)) : carry_len + lane;  // groups since the run's natural start
+        const bool h1 = valid && type < 2 && offset > 0 && (offset % 16383u) == 0;
+        const uint32_t H = H0 | __ballot_sync(XSI_FULL, h1);
+        const uint32_t idx = heads_base + __popc(H & le) - 1;
+        if (valid) {
+            if (type == 2) out[idx] = (uint16_t)grp;
+            else if (succtype != type || ((offset + 1) % 16383u) == 0)
+                out[idx] = (uint16_t)(0x8000u | (type << 14) | ((offset % 16383u) + 1));
+        }
+        heads_base += __popc(H);
+        const uint32_t t31 = __shfl_sync(XSI_FULL, type, 31);
+        const uint32_t o31 = __shfl_sync(XSI_FULL, offset, 31);
+        carry_type = t31;
+        carry_len = t31 < 2 ? o31 + 1 : 0;
+    }
+    return heads_base;
+}
+
+constexpr int E4_WARPS = 4;
+__global__ void __launch_bounds__(E4_WARPS * 32) wah_encode_rows_kernel(EncDev p) {
+    const uint32_t job = blockIdx.x * E4_WARPS + (threadIdx.x >> 5);
+    if (job < p.L) {
+        if (!(p.line_flags[job] & LF_WAH)) return;
+        const uint32_t n = wah_encode_row_warp(p.bitrows + (size_t)job * p.WS, p.WS, p.rec_ngt[p.line_rec[job]],
+                                               p.wahslots + (size_t)job * p.SLOTW);
+        if (lane_id() == 0) p.line_wah_n[job] = n;
+    } else if (job < p.L + p.R) {
+        const uint32_t r = job - p.L;
+        const int32_t slot = p.rec_aux[r * 3 + 2];
+        if (slot < 0) return;
+        const uint32_t n = wah_encode_row_warp(p.phrows + (size_t)slot * p.WS, p.WS, p.rec_ngt[r],
+                                               p.phslots + (size_t)slot * p.SLOTW);
+        if (lane_id() == 0) p.rec_phase_n[r] = n;
+    }
+}
+
+// =============================================================================================
+// exclusive scan of u32 -> u64 (single CTA per array; arrays are at most a few million entries)
+// =============================================================================================
+struct ScanJob { const uint32_t* in; uint64_t* out; uint32_t n; uint32_t pad; };  // out has n+1 entries
+constexpr int SCAN_THREADS = 1024;
+__global__ void __launch_bounds__(SCAN_THREADS) scan_u32_kernel(const ScanJob* jobs) {
+    __shared__ uint64_t s_warp[32];
+    __shared__ uint64_t s_carry;
+    const ScanJob j = jobs[blockIdx.x];
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < j.n; base += SCAN_THREADS * 4) {
+        const uint32_t i0 = base + tid * 4;
+        uint32_t v[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) v[q] = (i0 + q < j.n) ? j.in[i0 + q] : 0u;
+        uint64_t t = (uint64_t)v[0] + v[1] + v[2] + v[3];
+        uint64_t incl = t;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(XSI_FULL, incl, d); if (lane >= (uint32_t)d) incl += o; }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint64_t w = s_warp[lane], wi = w;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(XSI_FULL, wi, d); if (lane >= (uint32_t)d) wi += o; }
+            s_warp[lane] = wi - w;  // exclusive
+        }
+        __syncthreads();
+        uint64_t ex = s_carry + s_warp[warp] + (incl - t);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { if (i0 + q < j.n) j.out[i0 + q] = ex; ex += v[q]; }
+        __syncthreads();
+        if (tid == SCAN_THREADS - 1) s_carry = ex;
+        __syncthreads();
+    }
+    if (tid == 0) j.out[j.n] = s_carry;
+}
+
+// =============================================================================================
+// E5: sparse index lists.  job < L: GT sparse line; L..L+R: missing list; L+R..L+2R: EOV list
+// =============================================================================================
+struct EmitDev {
+    const uint64_t* line_sparse_off;  // [L+1] in A_T entries
+    const uint64_t* rec_miss_off;     // [R+1]
+    const uint64_t* rec_eov_off;      // [R+1]
+    const uint64_t* line_wah_off;     // [L+1] in u16 words
+    const uint64_t* rec_phase_off;    // [R+1]
+    void* out_sparse; void* out_miss; void* out_eov;
+    uint16_t* out_wah; uint16_t* out_phase;
+};
+
+template <typename AT>
+__device__ __forceinline__ void sparse_emit_row_warp(const uint32_t* __restrict__ row, uint32_t nbits, AT* __restrict__ out,
+                                                     bool negated) {
+    const uint32_t lane = lane_id();
+    const uint32_t nwords = (nbits + 31) >> 5;
+    uint32_t base = 0;
+    for (uint32_t w0 = 0; w0 < nwords; w0 += 32) {
+        const uint32_t wi = w0 + lane;
+        uint32_t w = wi < nwords ? row[wi] : 0u;
+        if (wi == nwords - 1 && (nbits & 31)) w &= (1u << (nbits & 31)) - 1u;
+        const uint32_t c = __popc(w);
+        uint32_t incl = c;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, d); if (lane >= (uint32_t)d) incl += o; }
+        uint32_t pos = base + incl - c;
+        while (w) { const uint32_t bpos = __ffs(w) - 1; w &= w - 1; out[1 + pos++] = (AT)(wi * 32 + bpos); }
+        base += __shfl_sync(XSI_FULL, incl, 31);
+    }
+    if (lane == 0) out[0] = (AT)(base | (negated ? ((AT)1 << (sizeof(AT) * 8 - 1)) : (AT)0));
+}
+
+constexpr int E5_WARPS = 4;
+template <typename AT>
+__global__ void __launch_bounds__(E5_WARPS * 32) sparse_emit_kernel(EncDev p, EmitDev e) {
+    const uint32_t job = blockIdx.x * E5_WARPS + (threadIdx.x >> 5);
+    if (job < p.L) {
+        const uint8_t lf = p.line_flags[job];
+        if (lf & LF_WAH) return;
+        sparse_emit_row_warp<AT>(p.bitrows + (size_t)job * p.WS, p.rec_ngt[p.line_rec[job]],
+                                 reinterpret_cast<AT*>(e.out_sparse) + e.line_sparse_off[job], (lf & LF_NEGATED) != 0);
+    } else if (job < p.L + 2 * p.R) {
+        const uint32_t kind = (job - p.L) / p.R;  // 0 missing, 1 eov
+        const uint32_t r = (job - p.L) - kind * p.R;
+        const int32_t slot = p.rec_aux[r * 3 + kind];
+        if (slot < 0) return;
+        AT* out = kind == 0 ? reinterpret_cast<AT*>(e.out_miss) + e.rec_miss_off[r]
+                            : reinterpret_cast<AT*>(e.out_eov) + e.rec_eov_off[r];
+        sparse_emit_row_warp<AT>(p.auxrows + (size_t)slot * p.WS, p.rec_ngt[r], out, false);
+    }
+}
+
+// =============================================================================================
+// E6: pack the WAH words of every line / phase line into the contiguous matrices
+// =============================================================================================
+constexpr int E6_WARPS = 4;
+__global__ void __launch_bounds__(E6_WARPS * 32) pack_wah_kernel(EncDev p, EmitDev e) {
+    const uint32_t job = blockIdx.x * E6_WARPS + (threadIdx.x >> 5);
+    const uint32_t lane = lane_id();
+    const uint16_t* src; uint16_t* dst; uint32_t n;
+    if (job < p.L) {
+        n = p.line_wah_n[job];
+        if (!n) return;
+        src = p.wahslots + (size_t)job * p.SLOTW;
+        dst = e.out_wah + e.line_wah_off[job];
+    } else if (job < p.L + p.R) {
+        const uint32_t r = job - p.L;
+        n = p.rec_phase_n[r];
+        if (!n) return;
+        src = p.phslots + (size_t)p.rec_aux[r * 3 + 2] * p.SLOTW;
+        dst = e.out_phase + e.rec_phase_off[r];
+    } else return;
+    for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
+}
+
+}  // namespace xsi

@@ -1,0 +1,896 @@
+// xsi_b200.cu -- CUDA context behind include/xsi_b200.h: buffer pools, kernel launches, and the
+// host-side assembly of byte-exact GT blocks.  No CPU fallback lives here: every genotype
+// operation is a kernel from encode_kernels.cuh / decode_kernels.cuh.
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/xsi_b200.h"
+#include "decode_kernels.cuh"
+#include "encode_kernels.cuh"
+#include "host_util.hpp"
+
+using namespace xsi;
+
+namespace {
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr; cap = 0;
+        size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) { want = bytes; e = cudaMalloc(&p, want); }
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFree(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+struct PinBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr; cap = 0;
+        const size_t want = bytes + bytes / 8 + 256;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() { if (p) cudaFreeHost(p); p = nullptr; cap = 0; }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+template <typename T>
+size_t vec_bytes(const std::vector<T>& v) { return v.size() * sizeof(T); }
+
+}  // namespace
+
+struct xsi_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr, stream2 = nullptr;
+    cudaEvent_t ev_side = nullptr;
+    std::string err = "";
+    uint64_t launches = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+
+    // ---------------- encode ----------------
+    struct {
+        bool launched = false;
+        uint64_t R = 0, L = 0;
+        uint32_t nb = 0, n_samples = 0, block_len = 0, WS = 0, SLOTW = 0, aet = 2;
+        int32_t default_phasing = 0;
+        int max_ploidy = 0;
+        uint32_t aux_cap = 0, phase_cap = 0;
+        std::vector<uint32_t> h_nallele, h_ngt, h_line0, h_line_rec, h_blk_line0, h_blk_rec0;
+        std::vector<uint64_t> h_goff;
+        DevBuf gt, tables, bitrows, auxrows, phrows, counters, rec_aux, line_u32, line_flags, rec_u32, rec_flags,
+            wah_list, blk_nwah, wahslots, phslots, offs, scanjobs, out_wah, out_sparse, out_miss, out_eov, out_phase,
+            a_pool;
+        PinBuf h_small, h_offs, h_out, h_flags;
+        uint64_t tot_sparse = 0, tot_miss = 0, tot_eov = 0, tot_wah = 0, tot_phase = 0;
+        std::vector<std::vector<uint8_t>> blocks;
+        std::vector<const uint8_t*> block_ptrs;
+        std::vector<uint64_t> block_sizes;
+        bool collected = false;
+    } enc;
+
+    // ---------------- decode ----------------
+    struct {
+        bool loaded = false;
+        uint32_t nb = 0, n_samples = 0, aet = 2, WS = 0, NJ = 0, n_gt_jobs = 0;
+        uint64_t Lt = 0;
+        std::vector<DecBlock> h_blocks;
+        std::vector<uint32_t> h_bin_lines;
+        DevBuf blob, meta, rows, job_u32, job_hap, tile_u32, dline, lists, err, a_pool, x_pool, req, out, scratch, counts,
+            seg_total;
+        PinBuf h_stage;
+        DecDev dev;
+    } dec;
+};
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (call);                                                                  \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__);                        \
+            return XSI_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+#define CKL()                                                                                      \
+    do {                                                                                           \
+        ctx->launches++;                                                                           \
+        cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ != cudaSuccess) {                                                                  \
+            ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e__);                   \
+            return XSI_E_CUDA;                                                                     \
+        }                                                                                          \
+    } while (0)
+
+extern "C" const char* xsi_version(void) { return "xsi-b200 0.1 (sm_100a)"; }
+
+extern "C" int xsi_create(int device, xsi_ctx** out) {
+    if (!out) return XSI_E_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return XSI_E_CUDA;
+    xsi_ctx* ctx = new xsi_ctx();
+    ctx->device = device;
+    if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return XSI_E_CUDA; }
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming) != cudaSuccess) {
+        delete ctx;
+        return XSI_E_CUDA;
+    }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) {
+        ctx->sm_count = prop.multiProcessorCount;
+        ctx->smem_optin = prop.sharedMemPerBlockOptin;
+    }
+    *out = ctx;
+    return XSI_OK;
+}
+
+extern "C" void xsi_destroy(xsi_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    cudaStreamSynchronize(ctx->stream2);
+    auto& e = ctx->enc;
+    for (DevBuf* b : {&e.gt, &e.tables, &e.bitrows, &e.auxrows, &e.phrows, &e.counters, &e.rec_aux, &e.line_u32,
+                      &e.line_flags, &e.rec_u32, &e.rec_flags, &e.wah_list, &e.blk_nwah, &e.wahslots, &e.phslots,
+                      &e.offs, &e.scanjobs, &e.out_wah, &e.out_sparse, &e.out_miss, &e.out_eov, &e.out_phase, &e.a_pool})
+        b->release();
+    for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags}) b->release();
+    auto& d = ctx->dec;
+    for (DevBuf* b : {&d.blob, &d.meta, &d.rows, &d.job_u32, &d.job_hap, &d.tile_u32, &d.dline, &d.lists, &d.err,
+                      &d.a_pool, &d.x_pool, &d.req, &d.out, &d.scratch, &d.counts, &d.seg_total})
+        b->release();
+    d.h_stage.release();
+    cudaEventDestroy(ctx->ev_side);
+    cudaStreamDestroy(ctx->stream);
+    cudaStreamDestroy(ctx->stream2);
+    delete ctx;
+}
+
+extern "C" const char* xsi_last_error(const xsi_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+extern "C" void* xsi_stream(xsi_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" uint64_t xsi_kernel_launches(const xsi_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int xsi_sync(xsi_ctx* ctx) {
+    if (!ctx) return XSI_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return XSI_OK;
+}
+
+// =================================================================================================
+// ENCODE
+// =================================================================================================
+namespace {
+
+// words-per-warp of the sequential PBWT kernels: smallest power of two that covers the row with
+// <= 32 warps; XSI_PBWT_WPW overrides it (tuning).  WPW 128 runs 512 threads with 128 registers.
+int choose_wpw(uint32_t W) {
+    int wpw = 2;
+    while ((W + wpw - 1) / wpw > 32) wpw *= 2;
+    if (const char* s = getenv("XSI_PBWT_WPW")) {
+        const int v = atoi(s);
+        if ((v == 2 || v == 4 || v == 8 || v == 16 || v == 32 || v == 64 || v == 128) && (W + v - 1) / v <= (v == 128 ? 16u : 32u)) wpw = v;
+    }
+    return wpw;
+}
+
+template <int WPW, int MAXT>
+int launch_permute(xsi_ctx* ctx, const EncDev& p, uint32_t NW, size_t smem) {
+    CK(cudaFuncSetAttribute(pbwt_permute_smem_kernel<WPW, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pbwt_permute_smem_kernel<WPW, MAXT><<<p.nb, NW * 32, smem, ctx->stream>>>(p);
+    CKL();
+    return XSI_OK;
+}
+
+int run_permute(xsi_ctx* ctx, const EncDev& p) {
+    const uint32_t N = 2 * p.n_samples;
+    const uint32_t W = (N + 31) / 32;
+    const size_t smem = ((size_t)N * 2 + 15) / 16 * 16 + (size_t)4 * p.WS * 4 + 64 * 4 + 16;
+    if (N <= 65536 && smem <= ctx->smem_optin) {
+        const int wpw = choose_wpw(W);
+        const uint32_t NW = (W + wpw - 1) / wpw;
+        switch (wpw) {
+            case 2: return launch_permute<2, 1024>(ctx, p, NW, smem);
+            case 4: return launch_permute<4, 1024>(ctx, p, NW, smem);
+            case 8: return launch_permute<8, 1024>(ctx, p, NW, smem);
+            case 16: return launch_permute<16, 1024>(ctx, p, NW, smem);
+            case 32: return launch_permute<32, 1024>(ctx, p, NW, smem);
+            case 64: return launch_permute<64, 1024>(ctx, p, NW, smem);
+            default: return launch_permute<128, 512>(ctx, p, NW, smem);
+        }
+    }
+    // > 65536 haplotypes: a[] lives in global memory (two uint32 copies per block + y / even-mask words)
+    auto& e = ctx->enc;
+    CK(e.a_pool.ensure(((size_t)p.nb * 2 * N + (size_t)p.nb * 2 * p.WS) * 4));
+    pbwt_permute_gmem_kernel<<<p.nb, 1024, 0, ctx->stream>>>(p, e.a_pool.as<uint32_t>());
+    CKL();
+    return XSI_OK;
+}
+
+}  // namespace
+
+extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
+    if (!ctx || !d) return XSI_E_ARG;
+    auto& e = ctx->enc;
+    e.launched = false; e.collected = false;
+    if (!d->gt || !d->n_allele || d->n_records == 0 || d->n_samples == 0 || d->block_len == 0) { ctx->err = "bad encode descriptor"; return XSI_E_ARG; }
+    if (d->gt_elem_bytes != 4 && d->gt_elem_bytes != 1) { ctx->err = "gt_elem_bytes must be 1 or 4"; return XSI_E_ARG; }
+    if (d->n_records >= (1ull << 31)) { ctx->err = "batch too large"; return XSI_E_ARG; }
+    if (d->n_samples > 32767 && d->n_samples <= 65535) {
+        ctx->err = "32768..65535 samples: the reference pairs a uint16 permutation with >65535 haplotypes (xsi_factory.hpp:425 vs gt_compressor_new.hpp:182)";
+        return XSI_E_UNSUPPORTED;
+    }
+    CK(cudaSetDevice(ctx->device));
+    const uint64_t R = d->n_records;
+    const uint32_t S = d->n_samples;
+    e.R = R; e.n_samples = S; e.block_len = d->block_len; e.default_phasing = d->default_phasing ? 1 : 0;
+    e.aet = S <= 65535 ? 2 : 4;
+    e.nb = (uint32_t)((R + d->block_len - 1) / d->block_len);
+    // ---- host tables ----
+    e.h_nallele.assign(d->n_allele, d->n_allele + R);
+    e.h_ngt.resize(R); e.h_line0.resize(R); e.h_goff.resize(R);
+    e.h_blk_line0.assign(e.nb + 1, 0); e.h_blk_rec0.assign(e.nb + 1, 0);
+    uint64_t goff = 0, L = 0;
+    e.max_ploidy = 0;
+    for (uint64_t r = 0; r < R; ++r) {
+        const uint32_t pl = d->ploidy ? d->ploidy[r] : 2;
+        if (pl > 2) { ctx->err = "Ploidy higher than 2 is not yet supported"; return XSI_E_PLOIDY; }
+        if (pl == 0) { ctx->err = "record with ploidy 0"; return XSI_E_ARG; }
+        if (e.h_nallele[r] < 1 || e.h_nallele[r] > (uint32_t)E1_MAXALLELE) { ctx->err = "n_allele out of range (1..256)"; return XSI_E_UNSUPPORTED; }
+        if ((int)pl > e.max_ploidy) e.max_ploidy = (int)pl;
+        if (r % d->block_len == 0) { e.h_blk_line0[r / d->block_len] = (uint32_t)L; e.h_blk_rec0[r / d->block_len] = (uint32_t)r; }
+        e.h_ngt[r] = S * pl;
+        e.h_goff[r] = goff;
+        e.h_line0[r] = (uint32_t)L;
+        goff += (uint64_t)S * pl;
+        L += e.h_nallele[r] - 1;
+        if (L >= (1ull << 31)) { ctx->err = "too many binary lines in batch"; return XSI_E_ARG; }
+    }
+    e.h_blk_line0[e.nb] = (uint32_t)L; e.h_blk_rec0[e.nb] = (uint32_t)R;
+    for (uint32_t b = 0; b < e.nb; ++b)
+        if (e.h_blk_line0[b + 1] - e.h_blk_line0[b] >= 32768) { ctx->err = "block with >= 32768 binary lines (BM offset is 15 bits)"; return XSI_E_UNSUPPORTED; }
+    e.L = L;
+    e.h_line_rec.resize(L ? L : 1);
+    for (uint64_t r = 0; r < R; ++r) for (uint32_t a = 1; a < e.h_nallele[r]; ++a) e.h_line_rec[e.h_line0[r] + a - 1] = (uint32_t)r;
+    const uint32_t N2 = 2 * S;
+    e.WS = ((N2 + 31) / 32 + 3) / 4 * 4;
+    e.SLOTW = ((N2 + 14) / 15 + 2 + 7) / 8 * 8;
+    const uint64_t Lp = L ? L : 1;
+
+    // ---- device buffers ----
+    const size_t gt_bytes = goff * (size_t)d->gt_elem_bytes;
+    const void* dgt = d->gt;
+    if (!d->gt_on_device) {
+        CK(e.gt.ensure(gt_bytes));
+        CK(cudaMemcpyAsync(e.gt.p, d->gt, gt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        dgt = e.gt.p;
+    }
+    // tables: goff[R] u64 | ngt[R] | nallele[R] | line0[R] | line_rec[L] | blk_line0[nb+1]
+    const size_t t_goff = 0, t_ngt = t_goff + R * 8, t_nal = t_ngt + R * 4, t_l0 = t_nal + R * 4, t_lr = t_l0 + R * 4,
+                 t_bl = t_lr + Lp * 4, t_end = t_bl + (e.nb + 1) * 4;
+    CK(e.tables.ensure(t_end));
+    CK(e.h_small.ensure(t_end));
+    {
+        uint8_t* h = e.h_small.as<uint8_t>();
+        memcpy(h + t_goff, e.h_goff.data(), R * 8);
+        memcpy(h + t_ngt, e.h_ngt.data(), R * 4);
+        memcpy(h + t_nal, e.h_nallele.data(), R * 4);
+        memcpy(h + t_l0, e.h_line0.data(), R * 4);
+        memcpy(h + t_lr, e.h_line_rec.data(), Lp * 4);
+        memcpy(h + t_bl, e.h_blk_line0.data(), (e.nb + 1) * 4);
+        CK(cudaMemcpyAsync(e.tables.p, h, t_end, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    CK(e.bitrows.ensure(Lp * e.WS * 4));
+    CK(e.wahslots.ensure(Lp * e.SLOTW * 2));
+    CK(e.counters.ensure(16));
+    CK(e.rec_aux.ensure(R * 3 * 4));
+    CK(e.line_u32.ensure(Lp * 3 * 4));  // cnt | sparse_n | wah_n
+    CK(e.line_flags.ensure(Lp));
+    CK(e.rec_u32.ensure(R * 3 * 4));    // miss_n | eov_n | phase_n
+    CK(e.rec_flags.ensure(R));
+    CK(e.wah_list.ensure(Lp * 4));
+    CK(e.blk_nwah.ensure(e.nb * 4));
+    // offsets: line_sparse_off[L+1] | rec_miss_off[R+1] | rec_eov_off[R+1] | line_wah_off[L+1] | rec_phase_off[R+1]
+    const size_t o_sp = 0, o_ms = o_sp + (L + 1) * 8, o_ev = o_ms + (R + 1) * 8, o_wh = o_ev + (R + 1) * 8,
+                 o_ph = o_wh + (L + 1) * 8, o_end = o_ph + (R + 1) * 8;
+    CK(e.offs.ensure(o_end));
+    CK(e.scanjobs.ensure(8 * sizeof(ScanJob)));
+    if (e.aux_cap == 0) e.aux_cap = (uint32_t)std::max<uint64_t>(256, R / 16);
+    if (e.phase_cap == 0) e.phase_cap = (uint32_t)std::max<uint64_t>(256, R / 16);
+
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        CK(e.auxrows.ensure((size_t)e.aux_cap * e.WS * 4));
+        CK(e.phrows.ensure((size_t)e.phase_cap * e.WS * 4));
+        CK(e.phslots.ensure((size_t)e.phase_cap * e.SLOTW * 2));
+        EncDev p;
+        uint8_t* tb = e.tables.as<uint8_t>();
+        p.gt = dgt;
+        p.rec_goff = reinterpret_cast<const uint64_t*>(tb + t_goff);
+        p.rec_ngt = reinterpret_cast<const uint32_t*>(tb + t_ngt);
+        p.rec_nallele = reinterpret_cast<const uint32_t*>(tb + t_nal);
+        p.rec_line0 = reinterpret_cast<const uint32_t*>(tb + t_l0);
+        p.line_rec = reinterpret_cast<const uint32_t*>(tb + t_lr);
+        p.blk_line0 = reinterpret_cast<const uint32_t*>(tb + t_bl);
+        p.n_samples = S; p.R = (uint32_t)R; p.L = (uint32_t)L; p.nb = e.nb;
+        p.WS = e.WS; p.SLOTW = e.SLOTW; p.aux_cap = e.aux_cap; p.phase_cap = e.phase_cap;
+        p.mac_thr = d->mac_threshold; p.default_phasing = e.default_phasing;
+        p.bitrows = e.bitrows.as<uint32_t>(); p.auxrows = e.auxrows.as<uint32_t>(); p.phrows = e.phrows.as<uint32_t>();
+        p.counters = e.counters.as<uint32_t>(); p.rec_aux = e.rec_aux.as<int32_t>();
+        p.line_cnt = e.line_u32.as<uint32_t>(); p.line_sparse_n = p.line_cnt + Lp; p.line_wah_n = p.line_sparse_n + Lp;
+        p.line_flags = e.line_flags.as<uint8_t>();
+        p.rec_miss_n = e.rec_u32.as<uint32_t>(); p.rec_eov_n = p.rec_miss_n + R; p.rec_phase_n = p.rec_eov_n + R;
+        p.rec_flags = e.rec_flags.as<uint8_t>();
+        p.wah_list = e.wah_list.as<uint32_t>(); p.blk_nwah = e.blk_nwah.as<uint32_t>();
+        p.wahslots = e.wahslots.as<uint16_t>(); p.phslots = e.phslots.as<uint16_t>();
+
+        CK(cudaMemsetAsync(e.counters.p, 0, 16, ctx->stream));
+        if (d->gt_elem_bytes == 4) scan_rows_kernel<4><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
+        else scan_rows_kernel<1><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
+        CKL();
+        if (L) {
+            build_wah_lists_kernel<<<e.nb, 32, 0, ctx->stream>>>(p);
+            CKL();
+            int rc = run_permute(ctx, p);
+            if (rc) return rc;
+        }
+        {
+            const uint64_t jobs = L + R;
+            wah_encode_rows_kernel<<<(uint32_t)((jobs + E4_WARPS - 1) / E4_WARPS), E4_WARPS * 32, 0, ctx->stream>>>(p);
+            CKL();
+        }
+        uint8_t* ob = e.offs.as<uint8_t>();
+        ScanJob jobs[5] = {{p.line_sparse_n, reinterpret_cast<uint64_t*>(ob + o_sp), (uint32_t)L, 0},
+                           {p.rec_miss_n, reinterpret_cast<uint64_t*>(ob + o_ms), (uint32_t)R, 0},
+                           {p.rec_eov_n, reinterpret_cast<uint64_t*>(ob + o_ev), (uint32_t)R, 0},
+                           {p.line_wah_n, reinterpret_cast<uint64_t*>(ob + o_wh), (uint32_t)L, 0},
+                           {p.rec_phase_n, reinterpret_cast<uint64_t*>(ob + o_ph), (uint32_t)R, 0}};
+        CK(cudaMemcpyAsync(e.scanjobs.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice, ctx->stream));
+        scan_u32_kernel<<<5, SCAN_THREADS, 0, ctx->stream>>>(e.scanjobs.as<ScanJob>());
+        CKL();
+        // totals + counters back, then size the outputs
+        CK(e.h_offs.ensure(o_end + 64));
+        uint8_t* ho = e.h_offs.as<uint8_t>();
+        CK(cudaMemcpyAsync(ho, e.offs.p, o_end, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ho + o_end, e.counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const uint32_t* cnt = reinterpret_cast<const uint32_t*>(ho + o_end);
+        if (cnt[2] & ERR_ALLELE) { ctx->err = "Unknown allele error !"; return XSI_E_ALLELE; }
+        if (cnt[2] & (ERR_AUX_OVERFLOW | ERR_PHASE_OVERFLOW)) {
+            e.aux_cap = std::max(e.aux_cap, cnt[0] + cnt[0] / 8 + 16);
+            e.phase_cap = std::max(e.phase_cap, cnt[1] + cnt[1] / 8 + 16);
+            continue;  // rerun the batch with big enough row pools
+        }
+        e.tot_sparse = reinterpret_cast<const uint64_t*>(ho + o_sp)[L];
+        e.tot_miss = reinterpret_cast<const uint64_t*>(ho + o_ms)[R];
+        e.tot_eov = reinterpret_cast<const uint64_t*>(ho + o_ev)[R];
+        e.tot_wah = reinterpret_cast<const uint64_t*>(ho + o_wh)[L];
+        e.tot_phase = reinterpret_cast<const uint64_t*>(ho + o_ph)[R];
+        CK(e.out_sparse.ensure(e.tot_sparse * e.aet + 16));
+        CK(e.out_miss.ensure(e.tot_miss * e.aet + 16));
+        CK(e.out_eov.ensure(e.tot_eov * e.aet + 16));
+        CK(e.out_wah.ensure(e.tot_wah * 2 + 16));
+        CK(e.out_phase.ensure(e.tot_phase * 2 + 16));
+        EmitDev em;
+        em.line_sparse_off = reinterpret_cast<const uint64_t*>(ob + o_sp);
+        em.rec_miss_off = reinterpret_cast<const uint64_t*>(ob + o_ms);
+        em.rec_eov_off = reinterpret_cast<const uint64_t*>(ob + o_ev);
+        em.line_wah_off = reinterpret_cast<const uint64_t*>(ob + o_wh);
+        em.rec_phase_off = reinterpret_cast<const uint64_t*>(ob + o_ph);
+        em.out_sparse = e.out_sparse.p; em.out_miss = e.out_miss.p; em.out_eov = e.out_eov.p;
+        em.out_wah = e.out_wah.as<uint16_t>(); em.out_phase = e.out_phase.as<uint16_t>();
+        {
+            const uint64_t jobs5 = L + 2 * R;
+            const uint32_t grid = (uint32_t)((jobs5 + E5_WARPS - 1) / E5_WARPS);
+            if (e.aet == 2) sparse_emit_kernel<uint16_t><<<grid, E5_WARPS * 32, 0, ctx->stream>>>(p, em);
+            else sparse_emit_kernel<uint32_t><<<grid, E5_WARPS * 32, 0, ctx->stream>>>(p, em);
+            CKL();
+            const uint64_t jobs6 = L + R;
+            pack_wah_kernel<<<(uint32_t)((jobs6 + E6_WARPS - 1) / E6_WARPS), E6_WARPS * 32, 0, ctx->stream>>>(p, em);
+            CKL();
+        }
+        // ---- results back to pinned host memory (async; collect() waits) ----
+        const size_t b_sp = 0, b_ms = b_sp + e.tot_sparse * e.aet, b_ev = b_ms + e.tot_miss * e.aet,
+                     b_wh = (b_ev + e.tot_eov * e.aet + 1) / 2 * 2, b_ph = b_wh + e.tot_wah * 2, b_end = b_ph + e.tot_phase * 2;
+        CK(e.h_out.ensure(b_end + 16));
+        uint8_t* hb = e.h_out.as<uint8_t>();
+        if (e.tot_sparse) CK(cudaMemcpyAsync(hb + b_sp, e.out_sparse.p, e.tot_sparse * e.aet, cudaMemcpyDeviceToHost, ctx->stream));
+        if (e.tot_miss) CK(cudaMemcpyAsync(hb + b_ms, e.out_miss.p, e.tot_miss * e.aet, cudaMemcpyDeviceToHost, ctx->stream));
+        if (e.tot_eov) CK(cudaMemcpyAsync(hb + b_ev, e.out_eov.p, e.tot_eov * e.aet, cudaMemcpyDeviceToHost, ctx->stream));
+        if (e.tot_wah) CK(cudaMemcpyAsync(hb + b_wh, e.out_wah.p, e.tot_wah * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        if (e.tot_phase) CK(cudaMemcpyAsync(hb + b_ph, e.out_phase.p, e.tot_phase * 2, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(e.h_flags.ensure(Lp + R + 16));
+        CK(cudaMemcpyAsync(e.h_flags.p, e.line_flags.p, Lp, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(e.h_flags.as<uint8_t>() + Lp, e.rec_flags.p, R, cudaMemcpyDeviceToHost, ctx->stream));
+        e.launched = true;
+        return XSI_OK;
+    }
+    ctx->err = "row pool overflow persisted";
+    return XSI_E_NOMEM;
+}
+
+extern "C" int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint8_t* const** blocks_out,
+                                  const uint64_t** sizes_out) {
+    if (!ctx) return XSI_E_ARG;
+    auto& e = ctx->enc;
+    if (!e.launched) { ctx->err = "xsi_encode_collect without a successful xsi_encode_launch"; return XSI_E_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint64_t R = e.R, L = e.L, Lp = L ? L : 1;
+    const size_t o_sp = 0, o_ms = o_sp + (L + 1) * 8, o_ev = o_ms + (R + 1) * 8, o_wh = o_ev + (R + 1) * 8, o_ph = o_wh + (L + 1) * 8;
+    const uint8_t* ho = e.h_offs.as<uint8_t>();
+    const uint64_t* off_sp = reinterpret_cast<const uint64_t*>(ho + o_sp);
+    const uint64_t* off_ms = reinterpret_cast<const uint64_t*>(ho + o_ms);
+    const uint64_t* off_ev = reinterpret_cast<const uint64_t*>(ho + o_ev);
+    const uint64_t* off_wh = reinterpret_cast<const uint64_t*>(ho + o_wh);
+    const uint64_t* off_ph = reinterpret_cast<const uint64_t*>(ho + o_ph);
+    const size_t b_sp = 0, b_ms = b_sp + e.tot_sparse * e.aet, b_ev = b_ms + e.tot_miss * e.aet,
+                 b_wh = (b_ev + e.tot_eov * e.aet + 1) / 2 * 2, b_ph = b_wh + e.tot_wah * 2;
+    const uint8_t* hb = e.h_out.as<uint8_t>();
+    const uint8_t* lflags = e.h_flags.as<uint8_t>();
+    const uint8_t* rflags = lflags + Lp;
+
+    e.blocks.assign(e.nb, {});
+    e.block_ptrs.assign(e.nb, nullptr);
+    e.block_sizes.assign(e.nb, 0);
+    for (uint32_t b = 0; b < e.nb; ++b) {
+        const uint32_t r0 = e.h_blk_rec0[b], r1 = e.h_blk_rec0[b + 1], l0 = e.h_blk_line0[b], l1 = e.h_blk_line0[b + 1];
+        const uint32_t nrec = r1 - r0, nlines = l1 - l0;
+        bool any_missing = false, any_eov = false, any_phase = false, any_hap = false;
+        uint32_t max_pl = 1;  // gt_block.hpp:168
+        std::vector<uint8_t> v_wah(nlines), v_miss(nlines, 0), v_eov(nlines, 0), v_phase(nlines, 0), v_hap(nrec, 0);
+        for (uint32_t l = l0; l < l1; ++l) v_wah[l - l0] = (lflags[l] & LF_WAH) ? 1 : 0;
+        for (uint32_t r = r0; r < r1; ++r) {
+            const uint8_t f = rflags[r];
+            const uint32_t pl = e.h_ngt[r] / e.n_samples;
+            max_pl = std::max(max_pl, pl);
+            if (f & RF_HAPLOID) { any_hap = true; v_hap[r - r0] = 1; }
+            any_missing |= (f & RF_MISSING) != 0; any_eov |= (f & RF_EOV) != 0; any_phase |= (f & RF_PHASE) != 0;
+            // re-index record flags to the record's first binary line (gt_block.hpp:650-666)
+            const uint32_t bl = e.h_line0[r] - l0;
+            if (bl < nlines) {
+                if (f & RF_MISSING) v_miss[bl] = 1;
+                if (f & RF_EOV) v_eov[bl] = 1;
+                if (f & RF_PHASE) v_phase[bl] = 1;
+            }
+        }
+        // dictionary, insertion sequence of GtBlock::fill_dictionary (gt_block.hpp:464-510)
+        RefDictOrder ord;
+        std::map<uint32_t, uint32_t> val;
+        auto ins = [&](uint32_t k, uint32_t v) { ord.insert(k); val[k] = v; };
+        ins(KEY_BCF_LINES, nrec); ins(KEY_BINARY_LINES, nlines); ins(KEY_MAX_LINE_PLOIDY, max_pl);
+        ins(KEY_DEFAULT_PHASING, (uint32_t)e.default_phasing); ins(KEY_WEIRDNESS_STRATEGY, WS_SPARSE);
+        ins(KEY_LINE_SORT, VAL_UNDEFINED); ins(KEY_LINE_SELECT, VAL_UNDEFINED); ins(KEY_MATRIX_WAH, VAL_UNDEFINED);
+        ins(KEY_MATRIX_SPARSE, VAL_UNDEFINED);
+        if (any_missing) { ins(KEY_LINE_MISSING, VAL_UNDEFINED); ins(KEY_MATRIX_MISSING, VAL_UNDEFINED); ins(KEY_MATRIX_MISSING_SPARSE, VAL_UNDEFINED); }
+        if (any_eov) { ins(KEY_LINE_END_OF_VECTORS, VAL_UNDEFINED); ins(KEY_MATRIX_END_OF_VECTORS, VAL_UNDEFINED); ins(KEY_MATRIX_END_OF_VECTORS_SPARSE, VAL_UNDEFINED); }
+        if (any_phase) { ins(KEY_LINE_NON_UNIFORM_PHASING, VAL_UNDEFINED); ins(KEY_MATRIX_NON_UNIFORM_PHASING, VAL_UNDEFINED); }
+        if (any_hap) ins(KEY_LINE_HAPLOID, VAL_UNDEFINED);
+        const std::vector<uint32_t> order = ord.order();
+
+        std::vector<uint8_t>& out = e.blocks[b];
+        const uint64_t wah_bytes = (off_wh[l1] - off_wh[l0]) * 2, sp_bytes = (off_sp[l1] - off_sp[l0]) * e.aet;
+        const uint64_t ms_bytes = (off_ms[r1] - off_ms[r0]) * e.aet, ev_bytes = (off_ev[r1] - off_ev[r0]) * e.aet;
+        const uint64_t ph_bytes = (off_ph[r1] - off_ph[r0]) * 2;
+        out.reserve(8 + order.size() * 8 + wah_bytes + sp_bytes + ms_bytes + ev_bytes + ph_bytes + nlines + 64);
+        put_u32(out, 0xFFFFFFFFu);
+        put_u32(out, (uint32_t)order.size());
+        const size_t dict_at = out.size();
+        out.resize(out.size() + order.size() * 8);
+        // write_writables, gt_block.hpp:512-647
+        val[KEY_LINE_SORT] = val[KEY_LINE_SELECT] = (uint32_t)out.size();
+        wah16_encode_bools(v_wah, out);
+        val[KEY_MATRIX_WAH] = (uint32_t)out.size();
+        out.insert(out.end(), hb + b_wh + off_wh[l0] * 2, hb + b_wh + off_wh[l1] * 2);
+        val[KEY_MATRIX_SPARSE] = (uint32_t)out.size();
+        out.insert(out.end(), hb + b_sp + off_sp[l0] * e.aet, hb + b_sp + off_sp[l1] * e.aet);
+        if (any_missing) {
+            val[KEY_LINE_MISSING] = (uint32_t)out.size();
+            wah16_encode_bools(v_miss, out);
+            val[KEY_MATRIX_MISSING_SPARSE] = (uint32_t)out.size();
+            out.insert(out.end(), hb + b_ms + off_ms[r0] * e.aet, hb + b_ms + off_ms[r1] * e.aet);
+        }
+        if (any_eov) {
+            val[KEY_LINE_END_OF_VECTORS] = (uint32_t)out.size();
+            wah16_encode_bools(v_eov, out);
+            val[KEY_MATRIX_END_OF_VECTORS_SPARSE] = (uint32_t)out.size();
+            out.insert(out.end(), hb + b_ev + off_ev[r0] * e.aet, hb + b_ev + off_ev[r1] * e.aet);
+        }
+        if (any_phase) {
+            val[KEY_LINE_NON_UNIFORM_PHASING] = (uint32_t)out.size();
+            wah16_encode_bools(v_phase, out);
+            val[KEY_MATRIX_NON_UNIFORM_PHASING] = (uint32_t)out.size();
+            out.insert(out.end(), hb + b_ph + off_ph[r0] * 2, hb + b_ph + off_ph[r1] * 2);
+        }
+        if (any_hap) {
+            val[KEY_LINE_HAPLOID] = (uint32_t)out.size();
+            wah16_encode_bools(v_hap, out);  // one bit per BCF line, gt_block.hpp:219-224,639-642
+        }
+        for (size_t i = 0; i < order.size(); ++i) {
+            memcpy(out.data() + dict_at + 8 * i, &order[i], 4);
+            const uint32_t v = val[order[i]];
+            memcpy(out.data() + dict_at + 8 * i + 4, &v, 4);
+        }
+        e.block_ptrs[b] = out.data();
+        e.block_sizes[b] = out.size();
+    }
+    e.collected = true;
+    if (n_blocks_out) *n_blocks_out = e.nb;
+    if (blocks_out) *blocks_out = e.block_ptrs.data();
+    if (sizes_out) *sizes_out = e.block_sizes.data();
+    return XSI_OK;
+}
+
+extern "C" int xsi_encode_block_sizes(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint64_t** sizes_out) {
+    if (!ctx || !ctx->enc.collected) return XSI_E_ARG;
+    if (n_blocks_out) *n_blocks_out = ctx->enc.nb;
+    if (sizes_out) *sizes_out = ctx->enc.block_sizes.data();
+    return XSI_OK;
+}
+extern "C" int xsi_encode_max_ploidy(const xsi_ctx* ctx) { return ctx ? ctx->enc.max_ploidy : 0; }
+
+// =================================================================================================
+// DECODE
+// =================================================================================================
+namespace {
+
+struct ParsedBlock {
+    std::map<uint32_t, uint32_t> dict;
+    uint32_t bcf_lines = 0, bin_lines = 0, default_phasing = 0;
+    std::vector<uint8_t> is_wah, has_missing, has_eov, has_phase, haploid;
+    bool p_missing = false, p_eov = false, p_phase = false;
+};
+
+// end of the section that starts at `off`: the next larger dictionary offset, else the block end
+uint64_t section_end(const ParsedBlock& pb, uint32_t off, uint64_t size) {
+    uint64_t end = size;
+    for (const auto& kv : pb.dict)
+        if (kv.first >= 0x10 && kv.second != VAL_UNDEFINED && kv.second > off && kv.second < end) end = kv.second;
+    return end;
+}
+
+int parse_block(xsi_ctx* ctx, const uint8_t* p, uint64_t size, ParsedBlock& pb) {
+    if (size < 8 || rd_u32(p) != 0xFFFFFFFFu) { ctx->err = "GT block: missing dictionary marker"; return XSI_E_FORMAT; }
+    const uint32_t n = rd_u32(p + 4);
+    if (8 + (uint64_t)n * 8 > size) { ctx->err = "GT block: truncated dictionary"; return XSI_E_FORMAT; }
+    for (uint32_t i = 0; i < n; ++i) pb.dict[rd_u32(p + 8 + 8 * (size_t)i)] = rd_u32(p + 12 + 8 * (size_t)i);
+    auto need = [&](uint32_t k, uint32_t& v) { auto it = pb.dict.find(k); if (it == pb.dict.end()) return false; v = it->second; return true; };
+    uint32_t dp = 0, ws = 0;
+    if (!need(KEY_BCF_LINES, pb.bcf_lines) || !need(KEY_BINARY_LINES, pb.bin_lines) || !need(KEY_DEFAULT_PHASING, dp)) { ctx->err = "GT block: required key missing"; return XSI_E_FORMAT; }
+    pb.default_phasing = dp == 1 ? 1 : 0;  // accessor_internals_new.hpp:77-81
+    if (!need(KEY_WEIRDNESS_STRATEGY, ws) || ws != WS_SPARSE) { ctx->err = "GT block: only the sparse missing/EOV strategy is supported (file written with --wah-encode-missing?)"; return XSI_E_UNSUPPORTED; }
+    auto vec = [&](uint32_t key, std::vector<uint8_t>& v, bool& present) {
+        present = false;
+        auto it = pb.dict.find(key);
+        if (it == pb.dict.end() || it->second == VAL_UNDEFINED || it->second >= size) return;
+        wah16_decode_bools(p + it->second, p + size, pb.bin_lines, v);  // accessor_internals_new.hpp:591-604
+        present = true;
+    };
+    bool pw = false, ps = false, ph = false;
+    vec(KEY_LINE_SELECT, pb.is_wah, pw);
+    if (!pw) { ctx->err = "GT block: no LINE_SELECT vector"; return XSI_E_FORMAT; }
+    std::vector<uint8_t> sort;
+    vec(KEY_LINE_SORT, sort, ps);
+    if (ps && sort != pb.is_wah) { ctx->err = "GT block: LINE_SORT differs from LINE_SELECT (not produced by the v5 writer)"; return XSI_E_UNSUPPORTED; }
+    vec(KEY_LINE_MISSING, pb.has_missing, pb.p_missing);
+    vec(KEY_LINE_END_OF_VECTORS, pb.has_eov, pb.p_eov);
+    vec(KEY_LINE_NON_UNIFORM_PHASING, pb.has_phase, pb.p_phase);
+    vec(KEY_LINE_HAPLOID, pb.haploid, ph);  // read per BINARY line although written per BCF line (reference quirk)
+    if (!ph) pb.haploid.assign(pb.bin_lines, 0);
+    if (!pb.p_missing) pb.has_missing.assign(pb.bin_lines, 0);
+    if (!pb.p_eov) pb.has_eov.assign(pb.bin_lines, 0);
+    if (!pb.p_phase) pb.has_phase.assign(pb.bin_lines, 0);
+    return XSI_OK;
+}
+
+template <int WPW, int MAXT>
+int launch_unpermute(xsi_ctx* ctx, const DecDev& dd, const uint8_t* job_hap, uint32_t NW, size_t smem) {
+    CK(cudaFuncSetAttribute(pbwt_unpermute_smem_kernel<WPW, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    pbwt_unpermute_smem_kernel<WPW, MAXT><<<dd.nb, NW * 32, smem, ctx->stream>>>(dd, job_hap);
+    CKL();
+    return XSI_OK;
+}
+
+}  // namespace
+
+extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks,
+                                      const uint64_t* sizes, uint64_t num_samples, int32_t aet_bytes) {
+    if (!ctx || !gt_blocks || !sizes || n_blocks == 0) return XSI_E_ARG;
+    if (aet_bytes != 2 && aet_bytes != 4) { ctx->err = "Unsupported access type"; return XSI_E_ARG; }
+    if (num_samples == 0 || num_samples >= (1ull << 30)) { ctx->err = "bad num_samples"; return XSI_E_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    auto& d = ctx->dec;
+    d.loaded = false;
+    const uint32_t S = (uint32_t)num_samples, N = 2 * S;
+    d.n_samples = S; d.aet = (uint32_t)aet_bytes; d.nb = n_blocks;
+    d.WS = ((N + 31) / 32 + 3) / 4 * 4;
+
+    std::vector<ParsedBlock> pbs(n_blocks);
+    std::vector<DecBlock> blocks(n_blocks);
+    std::vector<DecSeg> segs;
+    std::vector<uint32_t> job_gcum, job_nbits, job_seg, tile_seg, tile_word0;
+    std::vector<uint8_t> job_hap;
+    std::vector<uint64_t> blob_off(n_blocks);
+    uint64_t blob_size = 0, Lt = 0;
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        int rc = parse_block(ctx, gt_blocks[b], sizes[b], pbs[b]);
+        if (rc) return rc;
+        blob_off[b] = blob_size;
+        blob_size += (sizes[b] + 15) / 16 * 16;
+        Lt += pbs[b].bin_lines;
+    }
+    d.Lt = Lt;
+    std::vector<uint8_t> dl_flags(Lt ? Lt : 1, 0);
+    std::vector<uint32_t> dl_ord(Lt ? Lt : 1, 0), dl_mord(Lt ? Lt : 1, 0), dl_eord(Lt ? Lt : 1, 0), dl_pord(Lt ? Lt : 1, 0);
+    // pass 1: GT WAH jobs of every block (contiguous per block), lists ordinals
+    uint32_t njobs = 0, nsp = 0, nms = 0, nev = 0;
+    uint64_t line_base = 0;
+    struct PhaseTmp { uint32_t b; uint32_t gl; uint32_t nbits; };
+    std::vector<PhaseTmp> phase_lines;
+    auto add_tiles = [&](uint32_t seg_index, uint32_t n_words) {
+        for (uint32_t w = 0; w < n_words; w += D0_TILE) { tile_seg.push_back(seg_index); tile_word0.push_back(w); }
+    };
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        const ParsedBlock& pb = pbs[b];
+        DecBlock& bk = blocks[b];
+        memset(&bk, 0, sizeof(bk));
+        bk.blob_off = blob_off[b];
+        bk.line0 = (uint32_t)line_base; bk.n_lines = pb.bin_lines;
+        bk.default_phasing = pb.default_phasing;
+        auto moff = [&](uint32_t key) -> uint64_t {
+            auto it = pb.dict.find(key);
+            if (it == pb.dict.end() || it->second == VAL_UNDEFINED || it->second >= sizes[b]) return ~0ull;
+            return blob_off[b] + it->second;
+        };
+        bk.sparse_off = moff(KEY_MATRIX_SPARSE); bk.miss_off = moff(KEY_MATRIX_MISSING_SPARSE); bk.eov_off = moff(KEY_MATRIX_END_OF_VECTORS_SPARSE);
+        bk.wah0 = njobs; bk.sp0 = nsp; bk.ms0 = nms; bk.ev0 = nev;
+        uint32_t gc = 0;
+        const uint32_t seg_index = (uint32_t)segs.size();
+        for (uint32_t l = 0; l < pb.bin_lines; ++l) {
+            const uint64_t gl = line_base + l;
+            uint8_t f = 0;
+            const bool hap = pb.haploid[l] != 0;
+            if (hap) f |= DL_HAPLOID;
+            if (pb.is_wah[l]) {
+                f |= DL_WAH;
+                dl_ord[gl] = njobs++;
+                const uint32_t nbits = hap ? S : N;
+                job_gcum.push_back(gc); job_nbits.push_back(nbits); job_seg.push_back(seg_index); job_hap.push_back(hap ? 1 : 0);
+                gc += (nbits + 14) / 15;
+            } else {
+                dl_ord[gl] = nsp++;
+            }
+            if (pb.has_missing[l]) { f |= DL_MISSING; dl_mord[gl] = nms++; }
+            if (pb.has_eov[l]) { f |= DL_EOV; dl_eord[gl] = nev++; }
+            if (pb.has_phase[l]) { f |= DL_PHASE; phase_lines.push_back({b, (uint32_t)gl, hap ? S : N}); }
+            dl_flags[gl] = f;
+        }
+        bk.n_wah = njobs - bk.wah0; bk.n_sp = nsp - bk.sp0; bk.n_ms = nms - bk.ms0; bk.n_ev = nev - bk.ev0;
+        if (bk.n_wah) {
+            auto it = pb.dict.find(KEY_MATRIX_WAH);
+            if (it == pb.dict.end() || it->second == VAL_UNDEFINED || it->second >= sizes[b]) { ctx->err = "GT block: WAH lines without a WAH matrix"; return XSI_E_FORMAT; }
+            DecSeg sg;
+            sg.byte_off = blob_off[b] + it->second;
+            sg.n_words = (uint32_t)((section_end(pb, it->second, sizes[b]) - it->second) / 2);
+            sg.job0 = bk.wah0; sg.njobs = bk.n_wah; sg.tile0 = (uint32_t)tile_seg.size();
+            add_tiles(seg_index, sg.n_words);
+            segs.push_back(sg);
+        }
+        if ((bk.n_sp && bk.sparse_off == ~0ull) || (bk.n_ms && bk.miss_off == ~0ull) || (bk.n_ev && bk.eov_off == ~0ull)) { ctx->err = "GT block: index lists without their matrix"; return XSI_E_FORMAT; }
+        line_base += pb.bin_lines;
+    }
+    d.n_gt_jobs = njobs;
+    // pass 2: phase lines are extra expand-only jobs after all GT jobs, one segment per block
+    {
+        size_t i = 0;
+        while (i < phase_lines.size()) {
+            const uint32_t b = phase_lines[i].b;
+            const ParsedBlock& pb = pbs[b];
+            auto it = pb.dict.find(KEY_MATRIX_NON_UNIFORM_PHASING);
+            if (it == pb.dict.end() || it->second == VAL_UNDEFINED || it->second >= sizes[b]) { ctx->err = "GT block: phase lines without their matrix"; return XSI_E_FORMAT; }
+            DecSeg sg;
+            const uint32_t seg_index = (uint32_t)segs.size();
+            sg.byte_off = blob_off[b] + it->second;
+            sg.n_words = (uint32_t)((section_end(pb, it->second, sizes[b]) - it->second) / 2);
+            sg.job0 = njobs; sg.tile0 = (uint32_t)tile_seg.size();
+            uint32_t gc = 0;
+            while (i < phase_lines.size() && phase_lines[i].b == b) {
+                dl_pord[phase_lines[i].gl] = njobs++;
+                job_gcum.push_back(gc); job_nbits.push_back(phase_lines[i].nbits); job_seg.push_back(seg_index); job_hap.push_back(0);
+                gc += (phase_lines[i].nbits + 14) / 15;
+                ++i;
+            }
+            sg.njobs = njobs - sg.job0;
+            add_tiles(seg_index, sg.n_words);
+            segs.push_back(sg);
+        }
+    }
+    d.NJ = njobs;
+    d.h_blocks = blocks;
+    d.h_bin_lines.resize(n_blocks);
+    for (uint32_t b = 0; b < n_blocks; ++b) d.h_bin_lines[b] = pbs[b].bin_lines;
+
+    // ---- upload ----
+    CK(d.blob.ensure(blob_size + 64));
+    for (uint32_t b = 0; b < n_blocks; ++b)
+        CK(cudaMemcpyAsync(d.blob.as<uint8_t>() + blob_off[b], gt_blocks[b], sizes[b], cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t NJp = njobs ? njobs : 1, ntiles = (uint32_t)tile_seg.size(), nseg = (uint32_t)segs.size();
+    // meta: blocks | segs
+    const size_t m_blk = 0, m_seg = m_blk + sizeof(DecBlock) * n_blocks, m_end = m_seg + sizeof(DecSeg) * (nseg ? nseg : 1);
+    CK(d.meta.ensure(m_end));
+    CK(cudaMemcpyAsync(d.meta.as<uint8_t>() + m_blk, blocks.data(), sizeof(DecBlock) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
+    if (nseg) CK(cudaMemcpyAsync(d.meta.as<uint8_t>() + m_seg, segs.data(), sizeof(DecSeg) * nseg, cudaMemcpyHostToDevice, ctx->stream));
+    // job arrays: gcum | nbits | seg | word0 | ones
+    CK(d.job_u32.ensure((size_t)NJp * 5 * 4));
+    uint32_t* ju = d.job_u32.as<uint32_t>();
+    if (njobs) {
+        CK(cudaMemcpyAsync(ju, job_gcum.data(), njobs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ju + NJp, job_nbits.data(), njobs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ju + 2 * NJp, job_seg.data(), njobs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemsetAsync(ju + 3 * NJp, 0xFF, (size_t)njobs * 4, ctx->stream));
+    }
+    CK(d.job_hap.ensure(NJp));
+    if (njobs) CK(cudaMemcpyAsync(d.job_hap.p, job_hap.data(), njobs, cudaMemcpyHostToDevice, ctx->stream));
+    const uint32_t ntp = ntiles ? ntiles : 1;
+    CK(d.tile_u32.ensure((size_t)ntp * 3 * 4));
+    uint32_t* tu = d.tile_u32.as<uint32_t>();
+    if (ntiles) {
+        CK(cudaMemcpyAsync(tu, tile_seg.data(), ntiles * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(tu + ntp, tile_word0.data(), ntiles * 4, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const uint64_t Ltp = Lt ? Lt : 1;
+    CK(d.dline.ensure(Ltp * 17));
+    uint8_t* dlb = d.dline.as<uint8_t>();
+    CK(cudaMemcpyAsync(dlb, dl_ord.data(), Ltp * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dlb + Ltp * 4, dl_mord.data(), Ltp * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dlb + Ltp * 8, dl_eord.data(), Ltp * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dlb + Ltp * 12, dl_pord.data(), Ltp * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dlb + Ltp * 16, dl_flags.data(), Ltp, cudaMemcpyHostToDevice, ctx->stream));
+    CK(d.lists.ensure(((size_t)nsp + nms + nev + 3) * 8));
+    CK(d.err.ensure(16));
+    CK(cudaMemsetAsync(d.err.p, 0, 16, ctx->stream));
+    CK(d.rows.ensure((size_t)NJp * d.WS * 4));
+    CK(d.seg_total.ensure((size_t)(nseg ? nseg : 1) * 4));
+
+    DecDev& dd = d.dev;
+    dd.blob = d.blob.as<uint8_t>();
+    dd.segs = reinterpret_cast<const DecSeg*>(d.meta.as<uint8_t>() + m_seg); dd.nseg = nseg;
+    dd.blocks = reinterpret_cast<const DecBlock*>(d.meta.as<uint8_t>() + m_blk); dd.nb = n_blocks;
+    dd.tile_seg = tu; dd.tile_word0 = tu + ntp; dd.tile_sum = tu + 2 * ntp; dd.ntiles = ntiles;
+    dd.job_gcum = ju; dd.job_nbits = ju + NJp; dd.job_seg = ju + 2 * NJp; dd.job_word0 = ju + 3 * NJp; dd.job_ones = ju + 4 * NJp;
+    dd.NJ = njobs; dd.rows = d.rows.as<uint32_t>(); dd.WS = d.WS; dd.n_samples = S; dd.aet = d.aet;
+    dd.dline_ord = reinterpret_cast<const uint32_t*>(dlb); dd.dline_mord = reinterpret_cast<const uint32_t*>(dlb + Ltp * 4);
+    dd.dline_eord = reinterpret_cast<const uint32_t*>(dlb + Ltp * 8); dd.dline_pord = reinterpret_cast<const uint32_t*>(dlb + Ltp * 12);
+    dd.dline_flags = dlb + Ltp * 16;
+    dd.sp_off = d.lists.as<uint64_t>(); dd.ms_off = dd.sp_off + nsp + 1; dd.ev_off = dd.ms_off + nms + 1;
+    dd.err = d.err.as<uint32_t>();
+
+    // ---- kernels ----
+    if (nsp + nms + nev) {
+        sparse_index_kernel<<<(n_blocks * 3 + 63) / 64, 64, 0, ctx->stream>>>(dd);
+        CKL();
+    }
+    if (njobs) {
+        wah_tile_sum_kernel<<<ntiles, D0_THREADS, 0, ctx->stream>>>(dd);
+        CKL();
+        wah_tile_base_kernel<<<(nseg + 3) / 4, 128, 0, ctx->stream>>>(dd, d.seg_total.as<uint32_t>());
+        CKL();
+        wah_find_lines_kernel<<<ntiles, D0_THREADS, 0, ctx->stream>>>(dd);
+        CKL();
+        const uint32_t G = (N + 14) / 15;
+        const uint32_t Gpad = (G + 4 + 7) / 8 * 8, Tpad = (G + 1 + 31) / 32 + 1;
+        const size_t per_warp = (size_t)Gpad * 2 + (size_t)Tpad * 4;
+        uint32_t wpc = (uint32_t)std::min<size_t>(4, std::max<size_t>(1, (ctx->smem_optin - 1024) / per_warp));
+        if (per_warp > ctx->smem_optin) { ctx->err = "haplotype count too large for the WAH expand kernel"; return XSI_E_UNSUPPORTED; }
+        const size_t smem = per_warp * wpc;
+        CK(cudaFuncSetAttribute(wah_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        wah_expand_kernel<<<(njobs + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(dd, wpc, Gpad, Tpad);
+        CKL();
+        if (d.n_gt_jobs) {
+            const uint32_t W = (N + 31) / 32;
+            const size_t smem2 = ((size_t)N * 2 + 15) / 16 * 16 + (size_t)2 * d.WS * 4 + ((size_t)N + 32 + 15) / 16 * 16 + 64 * 4 + 16;
+            if (N <= 65536 && smem2 <= ctx->smem_optin) {
+                const int wpw = choose_wpw(W);
+                const uint32_t NW = (W + wpw - 1) / wpw;
+                const uint8_t* jh = d.job_hap.as<uint8_t>();
+                int rc;
+                switch (wpw) {
+                    case 2: rc = launch_unpermute<2, 1024>(ctx, dd, jh, NW, smem2); break;
+                    case 4: rc = launch_unpermute<4, 1024>(ctx, dd, jh, NW, smem2); break;
+                    case 8: rc = launch_unpermute<8, 1024>(ctx, dd, jh, NW, smem2); break;
+                    case 16: rc = launch_unpermute<16, 1024>(ctx, dd, jh, NW, smem2); break;
+                    case 32: rc = launch_unpermute<32, 1024>(ctx, dd, jh, NW, smem2); break;
+                    case 64: rc = launch_unpermute<64, 1024>(ctx, dd, jh, NW, smem2); break;
+                    default: rc = launch_unpermute<128, 512>(ctx, dd, jh, NW, smem2); break;
+                }
+                if (rc) return rc;
+            } else {
+                CK(d.a_pool.ensure(((size_t)n_blocks * 2 * N + (size_t)n_blocks * d.WS) * 4));
+                CK(d.x_pool.ensure((size_t)n_blocks * (N + 32)));
+                pbwt_unpermute_gmem_kernel<<<n_blocks, 1024, 0, ctx->stream>>>(dd, d.job_hap.as<uint8_t>(), d.a_pool.as<uint32_t>(), d.x_pool.as<uint8_t>());
+                CKL();
+            }
+        }
+    }
+    uint32_t herr = 0;
+    CK(cudaMemcpyAsync(&herr, d.err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (herr) { ctx->err = "malformed WAH / index stream in GT block (device check)"; return XSI_E_FORMAT; }
+    d.loaded = true;
+    return XSI_OK;
+}
+
+extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                                  const uint32_t* n_alleles, int32_t* out, uint64_t out_stride, int32_t out_on_device,
+                                  uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
+    if (!ctx || !block_index || !line_offset || !n_alleles || !out) return XSI_E_ARG;
+    auto& d = ctx->dec;
+    if (!d.loaded) { ctx->err = "xsi_decode_records without loaded blocks"; return XSI_E_ARG; }
+    if (n == 0) return XSI_OK;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t N = 2 * d.n_samples;
+    if (out_stride < N) { ctx->err = "out_stride smaller than 2*num_samples"; return XSI_E_ARG; }
+    uint32_t max_all = 2;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (block_index[i] >= d.nb) { ctx->err = "block index out of range"; return XSI_E_ARG; }
+        if (n_alleles[i] < 2 || n_alleles[i] > 254) { ctx->err = "n_alleles out of range (2..254)"; return XSI_E_UNSUPPORTED; }
+        if ((uint64_t)line_offset[i] + n_alleles[i] - 1 > d.h_bin_lines[block_index[i]]) { ctx->err = "record runs past the end of its block"; return XSI_E_ARG; }
+        max_all = std::max(max_all, n_alleles[i]);
+    }
+    const bool want_counts = allele_counts != nullptr;
+    if (want_counts && counts_stride < max_all) { ctx->err = "counts_stride too small"; return XSI_E_ARG; }
+    // chunk so that the staging buffers stay bounded
+    const uint64_t row_bytes = out_stride * 4;
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (1ull << 30) / row_bytes));
+    const uint32_t Npad = (N + 63) / 64 * 64;
+    for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
+        const uint64_t cn = std::min(chunk, n - c0);
+        CK(d.req.ensure(cn * 4 * 4));
+        uint32_t* rq = d.req.as<uint32_t>();
+        CK(cudaMemcpyAsync(rq, block_index + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(rq + cn, line_offset + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(rq + 2 * cn, n_alleles + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        const uint32_t grid = (uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * 8);
+        CK(d.scratch.ensure((size_t)grid * 2 * Npad));
+        ReqDev q;
+        q.blk = rq; q.line = rq + cn; q.nall = rq + 2 * cn; q.n = (uint32_t)cn;
+        q.filled = rq + 3 * cn;
+        q.out_stride = out_stride;
+        if (out_on_device) q.out = out + c0 * out_stride;
+        else { CK(d.out.ensure(cn * row_bytes)); q.out = d.out.as<int32_t>(); }
+        q.counts = nullptr; q.counts_stride = counts_stride;
+        if (want_counts) { CK(d.counts.ensure(cn * counts_stride * 4)); q.counts = d.counts.as<uint32_t>(); }
+        q.scratch = d.scratch.as<uint8_t>(); q.Npad = Npad;
+        compose_records_kernel<<<grid, D4_THREADS, 0, ctx->stream>>>(d.dev, q);
+        CKL();
+        if (!out_on_device) CK(cudaMemcpyAsync(out + c0 * out_stride, q.out, cn * row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if (n_filled) CK(cudaMemcpyAsync(n_filled + c0, q.filled, cn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (want_counts) {
+            CK(d.h_stage.ensure(cn * counts_stride * 4));
+            CK(cudaMemcpyAsync(d.h_stage.p, q.counts, cn * counts_stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+            const uint32_t* hc = d.h_stage.as<uint32_t>();
+            for (uint64_t i = 0; i < cn; ++i)
+                for (uint32_t k = 0; k < n_alleles[c0 + i]; ++k) allele_counts[(c0 + i) * counts_stride + k] = hc[i * counts_stride + k];
+        } else if (!out_on_device || n_filled || c0 + chunk < n) {
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+    }
+    return XSI_OK;
+}
