@@ -45,6 +45,12 @@ void* xsi_stream(xsi_ctx* ctx);
 /* number of kernels this context has launched so far (bench.py's gpu_launches) */
 uint64_t xsi_kernel_launches(const xsi_ctx* ctx);
 
+/* Per-kernel timing with CUDA events on the context stream (measurement aid, off by default).
+ * xsi_profile_read waits for the stream and returns "name launches total_ms\n" lines for
+ * everything launched since the previous read (string owned by ctx).                          */
+int xsi_profile(xsi_ctx* ctx, int on);
+const char* xsi_profile_read(xsi_ctx* ctx);
+
 /* ------------------------------------------------------------------------------------------
  * ENCODE  -- replaces GtBlock<A_T,uint16_t>::encode_line + write_to_stream
  *            (include/gt_block.hpp:185-204,279-406), i.e. the IWritableBCFLineEncoder the

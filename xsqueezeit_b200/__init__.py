@@ -64,6 +64,10 @@ def lib():
     L.xsi_kernel_launches.argtypes = [vp]
     L.xsi_sync.restype = i32
     L.xsi_sync.argtypes = [vp]
+    L.xsi_profile.restype = i32
+    L.xsi_profile.argtypes = [vp, i32]
+    L.xsi_profile_read.restype = ctypes.c_char_p
+    L.xsi_profile_read.argtypes = [vp]
     L.xsi_encode_launch.restype = i32
     L.xsi_encode_launch.argtypes = [vp, P(_EncodeDesc)]
     L.xsi_encode_collect.restype = i32
@@ -142,6 +146,17 @@ class Context:
 
     def sync(self):
         self._check(self._L.xsi_sync(self.h))
+
+    def profile(self, on=True):
+        self._L.xsi_profile(self.h, 1 if on else 0)
+
+    def profile_read(self):
+        """{kernel: (launches, total_ms)} since the previous read (CUDA events on the ctx stream)."""
+        out = {}
+        for line in self._L.xsi_profile_read(self.h).decode().splitlines():
+            n, c, ms = line.split()
+            out[n] = (int(c), float(ms))
+        return out
 
     # ---- encode --------------------------------------------------------------------------
     def encode_launch(self, gt, n_allele, n_samples, block_len, mac_threshold, default_phasing, ploidy=None,

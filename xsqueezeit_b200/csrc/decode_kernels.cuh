@@ -188,7 +188,8 @@ __global__ void wah_expand_kernel(DecDev d, uint32_t warps_per_cta, uint32_t Gpa
 #pragma unroll
         for (int q = 1; q < 32; q <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, q); if (lane >= (uint32_t)q) incl += o; }
         const uint32_t gs = gbase + incl - ng;
-        if (i < we) {
+        // the last line of a matrix may be followed by alignment bytes: words past G groups are not ours
+        if (i < we && gs < G) {
             if (!(word & 0x8000u)) { if (gs < G) g15[gs] = (uint16_t)word; }
             else if ((word & 0x4000u) && ng) {  // run of all-one groups: toggle marks, filled by the prefix-xor below
                 const uint32_t s0 = min(gs, G), e0 = min(gs + ng, G);
@@ -196,7 +197,9 @@ __global__ void wah_expand_kernel(DecDev d, uint32_t warps_per_cta, uint32_t Gpa
                 atomicXor(&tog[e0 >> 5], 1u << (e0 & 31));
             }
         }
-        gbase += __shfl_sync(XSI_FULL, incl, 31);
+        const uint32_t endg = (i < we && gs < G) ? gs + ng : 0u;  // end of the last word that starts inside the line
+        gbase = max(gbase, __reduce_max_sync(XSI_FULL, endg));
+        if (gbase >= G) break;
     }
     if (gbase != G && lane == 0) atomicOr(d.err, DERR_WAH_STREAM);
     __syncwarp();
@@ -257,7 +260,7 @@ __global__ void __launch_bounds__(MAXT, 1) pbwt_unpermute_smem_kernel(DecDev d, 
     const DecBlock blk = d.blocks[blockIdx.x];
     const uint32_t nwah = blk.n_wah, row_bytes = WS * 4;
     for (uint32_t i = tid; i < N; i += blockDim.x) a[i] = (uint16_t)i;
-    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_proxy_async(); }
     __syncthreads();
     if (nwah == 0) return;
     if (tid == 0) { mbar_expect_tx(&mbar[0], row_bytes); bulk_g2s(ybuf, d.rows + (size_t)blk.wah0 * WS, row_bytes, &mbar[0]); }

@@ -255,7 +255,7 @@ __global__ void __launch_bounds__(MAXT, 1) pbwt_permute_smem_kernel(EncDev p) {
     const uint32_t row_bytes = WS * 4;
 
     for (uint32_t i = tid; i < N; i += blockDim.x) a[i] = (uint16_t)i;  // iota, gt_block.hpp:179
-    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); }
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_proxy_async(); }
     __syncthreads();
     if (nwah == 0) return;
     uint32_t par0 = 0, par1 = 0;
@@ -265,21 +265,22 @@ __global__ void __launch_bounds__(MAXT, 1) pbwt_permute_smem_kernel(EncDev p) {
     }
     const uint32_t w0 = warp * WPW;
     const uint32_t ltm = lanemask_lt();
-    uint32_t line_next = nwah > 1 ? list[1] : 0;
+    uint32_t entry_cur = list[0], entry_next = nwah > 1 ? list[1] : 0;
 
     for (uint32_t k = 0; k < nwah; ++k) {
         const uint32_t cur = k & 1;
-        const uint32_t entry = (k == 0) ? list[0] : line_next;
+        const uint32_t entry = entry_cur;
         const uint32_t line = entry & 0x7FFFFFFFu;
         const bool hap = (entry >> 31) != 0;
         // prefetch: row of line k+1 into the other buffer, id of line k+2
         if (k + 1 < nwah) {
             if (tid == 0) {
                 mbar_expect_tx(&mbar[cur ^ 1], row_bytes);
-                bulk_g2s(rowbuf + (cur ^ 1) * WS, p.bitrows + (size_t)(line_next & 0x7FFFFFFFu) * WS, row_bytes, &mbar[cur ^ 1]);
+                bulk_g2s(rowbuf + (cur ^ 1) * WS, p.bitrows + (size_t)(entry_next & 0x7FFFFFFFu) * WS, row_bytes, &mbar[cur ^ 1]);
             }
-            line_next = (k + 2 < nwah) ? list[k + 2] : 0;
         }
+        entry_cur = entry_next;
+        entry_next = (k + 2 < nwah) ? list[k + 2] : 0;
         if (cur == 0) { mbar_wait(&mbar[0], par0); par0 ^= 1; } else { mbar_wait(&mbar[1], par1); par1 ^= 1; }
         const uint32_t* row = rowbuf + cur * WS;
 

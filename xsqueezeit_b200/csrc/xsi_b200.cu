@@ -63,6 +63,11 @@ struct xsi_ctx {
     uint64_t launches = 0;
     int sm_count = 148;
     size_t smem_optin = 0;
+    // optional per-kernel timing (CUDA events on the launching stream)
+    bool profile = false;
+    struct Span { const char* name; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::string profile_text;
 
     // ---------------- encode ----------------
     struct {
@@ -107,6 +112,15 @@ struct xsi_ctx {
             return XSI_E_CUDA;                                                                     \
         }                                                                                          \
     } while (0)
+// PROF(name) { launch; }  brackets a launch with events when profiling is on
+struct ProfScope {
+    xsi_ctx* c; bool on; cudaEvent_t a = nullptr, b = nullptr; const char* name;
+    ProfScope(xsi_ctx* ctx, const char* n) : c(ctx), on(ctx->profile), name(n) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+    }
+    ~ProfScope() { if (on) { cudaEventRecord(b, c->stream); c->spans.push_back({name, a, b}); } }
+};
+#define PROF(name) ProfScope prof_scope__(ctx, name)
 #define CKL()                                                                                      \
     do {                                                                                           \
         ctx->launches++;                                                                           \
@@ -167,6 +181,36 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
 extern "C" const char* xsi_last_error(const xsi_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" void* xsi_stream(xsi_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
 extern "C" uint64_t xsi_kernel_launches(const xsi_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int xsi_profile(xsi_ctx* ctx, int on) {
+    if (!ctx) return XSI_E_ARG;
+    ctx->profile = on != 0;
+    return XSI_OK;
+}
+// "name count total_ms\n" per kernel since the last read; clears the record
+extern "C" const char* xsi_profile_read(xsi_ctx* ctx) {
+    if (!ctx) return "";
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    std::map<std::string, std::pair<int, double>> agg;
+    std::vector<std::string> order;
+    for (auto& sp : ctx->spans) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, sp.a, sp.b);
+        if (!agg.count(sp.name)) order.push_back(sp.name);
+        agg[sp.name].first++;
+        agg[sp.name].second += ms;
+        cudaEventDestroy(sp.a);
+        cudaEventDestroy(sp.b);
+    }
+    ctx->spans.clear();
+    ctx->profile_text.clear();
+    char line[256];
+    for (auto& n : order) {
+        snprintf(line, sizeof line, "%s %d %.6f\n", n.c_str(), agg[n].first, agg[n].second);
+        ctx->profile_text += line;
+    }
+    return ctx->profile_text.c_str();
+}
 extern "C" int xsi_sync(xsi_ctx* ctx) {
     if (!ctx) return XSI_E_ARG;
     CK(cudaSetDevice(ctx->device));
@@ -194,7 +238,7 @@ int choose_wpw(uint32_t W) {
 template <int WPW, int MAXT>
 int launch_permute(xsi_ctx* ctx, const EncDev& p, uint32_t NW, size_t smem) {
     CK(cudaFuncSetAttribute(pbwt_permute_smem_kernel<WPW, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pbwt_permute_smem_kernel<WPW, MAXT><<<p.nb, NW * 32, smem, ctx->stream>>>(p);
+    { PROF("pbwt_permute"); pbwt_permute_smem_kernel<WPW, MAXT><<<p.nb, NW * 32, smem, ctx->stream>>>(p); }
     CKL();
     return XSI_OK;
 }
@@ -219,7 +263,7 @@ int run_permute(xsi_ctx* ctx, const EncDev& p) {
     // > 65536 haplotypes: a[] lives in global memory (two uint32 copies per block + y / even-mask words)
     auto& e = ctx->enc;
     CK(e.a_pool.ensure(((size_t)p.nb * 2 * N + (size_t)p.nb * 2 * p.WS) * 4));
-    pbwt_permute_gmem_kernel<<<p.nb, 1024, 0, ctx->stream>>>(p, e.a_pool.as<uint32_t>());
+    { PROF("pbwt_permute"); pbwt_permute_gmem_kernel<<<p.nb, 1024, 0, ctx->stream>>>(p, e.a_pool.as<uint32_t>()); }
     CKL();
     return XSI_OK;
 }
@@ -341,18 +385,21 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         p.wahslots = e.wahslots.as<uint16_t>(); p.phslots = e.phslots.as<uint16_t>();
 
         CK(cudaMemsetAsync(e.counters.p, 0, 16, ctx->stream));
-        if (d->gt_elem_bytes == 4) scan_rows_kernel<4><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
-        else scan_rows_kernel<1><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
+        {
+            PROF("scan_rows");
+            if (d->gt_elem_bytes == 4) scan_rows_kernel<4><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
+            else scan_rows_kernel<1><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
+        }
         CKL();
         if (L) {
-            build_wah_lists_kernel<<<e.nb, 32, 0, ctx->stream>>>(p);
+            { PROF("build_wah_lists"); build_wah_lists_kernel<<<e.nb, 32, 0, ctx->stream>>>(p); }
             CKL();
             int rc = run_permute(ctx, p);
             if (rc) return rc;
         }
         {
             const uint64_t jobs = L + R;
-            wah_encode_rows_kernel<<<(uint32_t)((jobs + E4_WARPS - 1) / E4_WARPS), E4_WARPS * 32, 0, ctx->stream>>>(p);
+            { PROF("wah_encode_rows"); wah_encode_rows_kernel<<<(uint32_t)((jobs + E4_WARPS - 1) / E4_WARPS), E4_WARPS * 32, 0, ctx->stream>>>(p); }
             CKL();
         }
         uint8_t* ob = e.offs.as<uint8_t>();
@@ -362,7 +409,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
                            {p.line_wah_n, reinterpret_cast<uint64_t*>(ob + o_wh), (uint32_t)L, 0},
                            {p.rec_phase_n, reinterpret_cast<uint64_t*>(ob + o_ph), (uint32_t)R, 0}};
         CK(cudaMemcpyAsync(e.scanjobs.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice, ctx->stream));
-        scan_u32_kernel<<<5, SCAN_THREADS, 0, ctx->stream>>>(e.scanjobs.as<ScanJob>());
+        { PROF("scan_u32"); scan_u32_kernel<<<5, SCAN_THREADS, 0, ctx->stream>>>(e.scanjobs.as<ScanJob>()); }
         CKL();
         // totals + counters back, then size the outputs
         CK(e.h_offs.ensure(o_end + 64));
@@ -398,11 +445,14 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         {
             const uint64_t jobs5 = L + 2 * R;
             const uint32_t grid = (uint32_t)((jobs5 + E5_WARPS - 1) / E5_WARPS);
-            if (e.aet == 2) sparse_emit_kernel<uint16_t><<<grid, E5_WARPS * 32, 0, ctx->stream>>>(p, em);
-            else sparse_emit_kernel<uint32_t><<<grid, E5_WARPS * 32, 0, ctx->stream>>>(p, em);
+            {
+                PROF("sparse_emit");
+                if (e.aet == 2) sparse_emit_kernel<uint16_t><<<grid, E5_WARPS * 32, 0, ctx->stream>>>(p, em);
+                else sparse_emit_kernel<uint32_t><<<grid, E5_WARPS * 32, 0, ctx->stream>>>(p, em);
+            }
             CKL();
             const uint64_t jobs6 = L + R;
-            pack_wah_kernel<<<(uint32_t)((jobs6 + E6_WARPS - 1) / E6_WARPS), E6_WARPS * 32, 0, ctx->stream>>>(p, em);
+            { PROF("pack_wah"); pack_wah_kernel<<<(uint32_t)((jobs6 + E6_WARPS - 1) / E6_WARPS), E6_WARPS * 32, 0, ctx->stream>>>(p, em); }
             CKL();
         }
         // ---- results back to pinned host memory (async; collect() waits) ----
@@ -602,7 +652,7 @@ int parse_block(xsi_ctx* ctx, const uint8_t* p, uint64_t size, ParsedBlock& pb) 
 template <int WPW, int MAXT>
 int launch_unpermute(xsi_ctx* ctx, const DecDev& dd, const uint8_t* job_hap, uint32_t NW, size_t smem) {
     CK(cudaFuncSetAttribute(pbwt_unpermute_smem_kernel<WPW, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    pbwt_unpermute_smem_kernel<WPW, MAXT><<<dd.nb, NW * 32, smem, ctx->stream>>>(dd, job_hap);
+    { PROF("pbwt_unpermute"); pbwt_unpermute_smem_kernel<WPW, MAXT><<<dd.nb, NW * 32, smem, ctx->stream>>>(dd, job_hap); }
     CKL();
     return XSI_OK;
 }
@@ -783,15 +833,15 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
 
     // ---- kernels ----
     if (nsp + nms + nev) {
-        sparse_index_kernel<<<(n_blocks * 3 + 63) / 64, 64, 0, ctx->stream>>>(dd);
+        { PROF("sparse_index"); sparse_index_kernel<<<(n_blocks * 3 + 63) / 64, 64, 0, ctx->stream>>>(dd); }
         CKL();
     }
     if (njobs) {
-        wah_tile_sum_kernel<<<ntiles, D0_THREADS, 0, ctx->stream>>>(dd);
+        { PROF("wah_tile_sum"); wah_tile_sum_kernel<<<ntiles, D0_THREADS, 0, ctx->stream>>>(dd); }
         CKL();
-        wah_tile_base_kernel<<<(nseg + 3) / 4, 128, 0, ctx->stream>>>(dd, d.seg_total.as<uint32_t>());
+        { PROF("wah_tile_base"); wah_tile_base_kernel<<<(nseg + 3) / 4, 128, 0, ctx->stream>>>(dd, d.seg_total.as<uint32_t>()); }
         CKL();
-        wah_find_lines_kernel<<<ntiles, D0_THREADS, 0, ctx->stream>>>(dd);
+        { PROF("wah_find_lines"); wah_find_lines_kernel<<<ntiles, D0_THREADS, 0, ctx->stream>>>(dd); }
         CKL();
         const uint32_t G = (N + 14) / 15;
         const uint32_t Gpad = (G + 4 + 7) / 8 * 8, Tpad = (G + 1 + 31) / 32 + 1;
@@ -800,7 +850,7 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
         if (per_warp > ctx->smem_optin) { ctx->err = "haplotype count too large for the WAH expand kernel"; return XSI_E_UNSUPPORTED; }
         const size_t smem = per_warp * wpc;
         CK(cudaFuncSetAttribute(wah_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        wah_expand_kernel<<<(njobs + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(dd, wpc, Gpad, Tpad);
+        { PROF("wah_expand"); wah_expand_kernel<<<(njobs + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(dd, wpc, Gpad, Tpad); }
         CKL();
         if (d.n_gt_jobs) {
             const uint32_t W = (N + 31) / 32;
@@ -823,7 +873,7 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
             } else {
                 CK(d.a_pool.ensure(((size_t)n_blocks * 2 * N + (size_t)n_blocks * d.WS) * 4));
                 CK(d.x_pool.ensure((size_t)n_blocks * (N + 32)));
-                pbwt_unpermute_gmem_kernel<<<n_blocks, 1024, 0, ctx->stream>>>(dd, d.job_hap.as<uint8_t>(), d.a_pool.as<uint32_t>(), d.x_pool.as<uint8_t>());
+                { PROF("pbwt_unpermute"); pbwt_unpermute_gmem_kernel<<<n_blocks, 1024, 0, ctx->stream>>>(dd, d.job_hap.as<uint8_t>(), d.a_pool.as<uint32_t>(), d.x_pool.as<uint8_t>()); }
                 CKL();
             }
         }
@@ -877,7 +927,7 @@ extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* bloc
         q.counts = nullptr; q.counts_stride = counts_stride;
         if (want_counts) { CK(d.counts.ensure(cn * counts_stride * 4)); q.counts = d.counts.as<uint32_t>(); }
         q.scratch = d.scratch.as<uint8_t>(); q.Npad = Npad;
-        compose_records_kernel<<<grid, D4_THREADS, 0, ctx->stream>>>(d.dev, q);
+        { PROF("compose_records"); compose_records_kernel<<<grid, D4_THREADS, 0, ctx->stream>>>(d.dev, q); }
         CKL();
         if (!out_on_device) CK(cudaMemcpyAsync(out + c0 * out_stride, q.out, cn * row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (n_filled) CK(cudaMemcpyAsync(n_filled + c0, q.filled, cn * 4, cudaMemcpyDeviceToHost, ctx->stream));
