@@ -84,6 +84,9 @@ int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint8_t* cons
 int xsi_encode_block_sizes(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint64_t** sizes_out);
 /* max ploidy seen in the last batch (header.ploidy, xsi_factory.hpp:548) */
 int xsi_encode_max_ploidy(const xsi_ctx* ctx);
+/* Line statistics of the last collected batch: binary lines (KEY_BINARY_LINES summed over the
+ * blocks) and how many of them were PBWT+WAH encoded (the rest are sparse).  Valid after collect. */
+int xsi_encode_line_counts(const xsi_ctx* ctx, uint64_t* n_binary_lines, uint64_t* n_wah_lines);
 
 /* ------------------------------------------------------------------------------------------
  * DECODE  -- replaces DecompressPointerGTBlock<A_T,uint16_t> (seek + fill_genotype_array_advance,

@@ -76,6 +76,8 @@ def lib():
     L.xsi_encode_block_sizes.argtypes = [vp, P(u32), P(P(u64))]
     L.xsi_encode_max_ploidy.restype = i32
     L.xsi_encode_max_ploidy.argtypes = [vp]
+    L.xsi_encode_line_counts.restype = i32
+    L.xsi_encode_line_counts.argtypes = [vp, P(u64), P(u64)]
     L.xsi_decode_load_blocks.restype = i32
     L.xsi_decode_load_blocks.argtypes = [vp, u32, P(vp), P(u64), u64, i32]
     L.xsi_decode_records.restype = i32
@@ -196,6 +198,12 @@ class Context:
     @property
     def encode_max_ploidy(self):
         return int(self._L.xsi_encode_max_ploidy(self.h))
+
+    def encode_line_counts(self):
+        """(binary lines, PBWT+WAH lines) of the last collected batch."""
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self._L.xsi_encode_line_counts(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
 
     # ---- decode --------------------------------------------------------------------------
     def decode_load_blocks(self, blocks, num_samples, aet_bytes):

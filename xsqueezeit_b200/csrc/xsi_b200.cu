@@ -88,6 +88,7 @@ struct xsi_ctx {
         std::vector<const uint8_t*> block_ptrs;
         std::vector<uint64_t> block_sizes;
         bool collected = false;
+        uint64_t n_wah_lines = 0;
     } enc;
 
     // ---------------- decode ----------------
@@ -496,6 +497,8 @@ extern "C" int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const ui
     const uint8_t* lflags = e.h_flags.as<uint8_t>();
     const uint8_t* rflags = lflags + Lp;
 
+    e.n_wah_lines = 0;
+    for (uint64_t l = 0; l < L; ++l) e.n_wah_lines += (lflags[l] & LF_WAH) ? 1 : 0;
     e.blocks.assign(e.nb, {});
     e.block_ptrs.assign(e.nb, nullptr);
     e.block_sizes.assign(e.nb, 0);
@@ -594,6 +597,12 @@ extern "C" int xsi_encode_block_sizes(xsi_ctx* ctx, uint32_t* n_blocks_out, cons
     return XSI_OK;
 }
 extern "C" int xsi_encode_max_ploidy(const xsi_ctx* ctx) { return ctx ? ctx->enc.max_ploidy : 0; }
+extern "C" int xsi_encode_line_counts(const xsi_ctx* ctx, uint64_t* n_binary_lines, uint64_t* n_wah_lines) {
+    if (!ctx || !ctx->enc.collected) return XSI_E_ARG;
+    if (n_binary_lines) *n_binary_lines = ctx->enc.L;
+    if (n_wah_lines) *n_wah_lines = ctx->enc.n_wah_lines;
+    return XSI_OK;
+}
 
 // =================================================================================================
 // DECODE
