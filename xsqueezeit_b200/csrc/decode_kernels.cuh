@@ -52,6 +52,9 @@ struct DecDev {
     uint32_t NJ;
     uint32_t* rows;             // [NJ][WS] expanded rows; GT rows become natural order after D2
     uint32_t WS;
+    uint32_t* tabs;             // [n_gt_jobs][TW] or NULL: per 16 positions (zeros before << 16 | y bits), then at
+                                // [2*WS] the line's total zeros; TW = 2*WS + 4; for D2 v2
+    uint32_t TW, n_gt_jobs;
     uint32_t n_samples;         // header.num_samples
     uint32_t aet;               // 2 or 4
     const uint8_t* dline_flags; // [Lt]
@@ -218,7 +221,10 @@ __global__ void wah_expand_kernel(DecDev d, uint32_t warps_per_cta, uint32_t Gpa
     __syncwarp();
     uint32_t ones = 0;
     const uint32_t nwords = (nbits + 31) >> 5;
-    for (uint32_t m = lane; m < d.WS; m += 32) {
+    uint32_t* tab = (d.tabs && job < d.n_gt_jobs) ? d.tabs + (size_t)job * d.TW : nullptr;
+    uint32_t zcarry = 0;
+    for (uint32_t m0 = 0; m0 < d.WS; m0 += 32) {
+        const uint32_t m = m0 + lane;
         uint32_t o = 0;
         if (m < nwords) {
             const uint32_t b0 = m * 32, g0 = b0 / 15, sh = b0 - g0 * 15;
@@ -233,10 +239,23 @@ __global__ void wah_expand_kernel(DecDev d, uint32_t warps_per_cta, uint32_t Gpa
             o = (uint32_t)(acc >> sh);
             if (m == nwords - 1 && (nbits & 31)) o &= (1u << (nbits & 31)) - 1u;
         }
-        out[m] = o;
+        if (m < d.WS) out[m] = o;
         ones += __popc(o);
+        if (tab) {  // zeros before every 16-position chunk (positions past nbits are never looked up)
+            const uint32_t nz = 32u - __popc(o);
+            uint32_t incl = nz;
+#pragma unroll
+            for (int q = 1; q < 32; q <<= 1) { const uint32_t t = __shfl_up_sync(XSI_FULL, incl, q); if (lane >= (uint32_t)q) incl += t; }
+            const uint32_t zp = zcarry + incl - nz;
+            if (2 * m + 1 < d.TW) {
+                *reinterpret_cast<uint2*>(tab + 2 * m) =
+                    make_uint2((zp << 16) | (o & 0xFFFFu), ((zp + 16u - __popc(o & 0xFFFFu)) << 16) | (o >> 16));
+            }
+            zcarry += __shfl_sync(XSI_FULL, incl, 31);
+        }
     }
     ones = __reduce_add_sync(XSI_FULL, ones);
+    if (tab && lane == 0) tab[2 * d.WS] = nbits - ones;  // Z, total zeros of the line
     if (lane == 0) d.job_ones[job] = ones;
 }
 
@@ -371,6 +390,90 @@ __global__ void __launch_bounds__(MAXT, 1) pbwt_unpermute_smem_kernel(DecDev d, 
         }
         if (hap) fence_proxy_async();
         __syncthreads();  // #2
+    }
+}
+
+// =============================================================================================
+// D2 v2: undo the PBWT order without any block-wide barrier (diploid lines only; a batch with an
+// all-haploid line uses the kernel above).  State is the INVERSE permutation pos[i] = current
+// position of haplotype i, so every haplotype is independent given the line's table
+//   T[c] = (zeros in positions [0,16c)) << 16 | y bits of positions [16c, 16c+16)
+// (written by wah_expand):   j = pos[i];  x[i] = y[j];  pos[i] = y[j] ? Z + j - zb(j) : zb(j)
+// That makes the grid (block, haplotype slice): each CTA owns 32*warps words of haplotypes and
+// streams the tables through a TMA ring guarded by full/empty mbarriers.
+// dynamic smem: pos[nwarps*1024] u16 | ring[D][TW] u32 | full[D], empty[D] u64
+// =============================================================================================
+constexpr int D2_STAGES = 4;
+__global__ void __launch_bounds__(1024) pbwt_unpermute_v2_kernel(DecDev d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t N = 2 * d.n_samples, TW = d.TW, WS = d.WS;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, NWARP = blockDim.x >> 5;
+    uint16_t* pos = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + (size_t)NWARP * 2048);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)D2_STAGES * TW);
+    uint64_t* empty = full + D2_STAGES;
+    const DecBlock blk = d.blocks[blockIdx.x];
+    const uint32_t nwah = blk.n_wah;
+    const uint32_t word0 = (blockIdx.y * NWARP + warp) * 32;  // first natural-order word of this warp
+    const uint32_t i0 = word0 * 32;
+    const uint32_t tab_bytes = TW * 4;
+    if (tid == 0) {
+        for (int s = 0; s < D2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
+        fence_proxy_async();
+    }
+    for (uint32_t q = 0; q < 32; ++q) pos[warp * 1024 + q * 32 + lane] = (uint16_t)(i0 + q * 32 + lane);
+    __syncthreads();
+    if (nwah == 0 || blockIdx.y * NWARP * 32 >= WS) return;
+    const uint32_t* tabs = d.tabs + (size_t)blk.wah0 * TW;
+    if (tid == 0) {
+        for (uint32_t k = 0; k < (uint32_t)(D2_STAGES - 1) && k < nwah; ++k) {
+            mbar_expect_tx(&full[k], tab_bytes);
+            bulk_g2s(ring + (size_t)k * TW, tabs + (size_t)k * TW, tab_bytes, &full[k]);
+        }
+    }
+    const bool checked = i0 + 1024 > N;
+    uint16_t* mypos = pos + warp * 1024 + lane;
+    for (uint32_t k = 0; k < nwah; ++k) {
+        const uint32_t st = k % D2_STAGES, use = k / D2_STAGES;
+        if (tid == 0 && k + D2_STAGES - 1 < nwah) {  // refill the stage line k-1 used
+            const uint32_t kn = k + D2_STAGES - 1, sn = kn % D2_STAGES, un = kn / D2_STAGES;
+            if (un > 0) mbar_wait(&empty[sn], (un - 1) & 1u);
+            mbar_expect_tx(&full[sn], tab_bytes);
+            bulk_g2s(ring + (size_t)sn * TW, tabs + (size_t)kn * TW, tab_bytes, &full[sn]);
+        }
+        mbar_wait(&full[st], use & 1u);
+        const uint32_t* T = ring + (size_t)st * TW;
+        const uint32_t job = blk.wah0 + k;
+        const uint32_t Z = T[2 * WS];
+        uint32_t xkeep = 0;
+        if (!checked) {
+#pragma unroll 8
+            for (uint32_t q = 0; q < 32; ++q) {
+                const uint32_t j = mypos[q * 32];
+                const uint32_t e = T[j >> 4];
+                const uint32_t s = j & 15u;
+                const uint32_t zb = (e >> 16) + __popc(~e & ((1u << s) - 1u));
+                const uint32_t bit = (e >> s) & 1u;
+                mypos[q * 32] = (uint16_t)(bit ? Z + j - zb : zb);
+                const uint32_t xw = __ballot_sync(XSI_FULL, bit);
+                if (lane == q) xkeep = xw;
+            }
+        } else {
+            for (uint32_t q = 0; q < 32; ++q) {
+                const bool valid = i0 + q * 32 + lane < N;
+                const uint32_t j = valid ? mypos[q * 32] : 0u;
+                const uint32_t e = T[j >> 4];
+                const uint32_t s = j & 15u;
+                const uint32_t zb = (e >> 16) + __popc(~e & ((1u << s) - 1u));
+                const uint32_t bit = valid ? ((e >> s) & 1u) : 0u;
+                if (valid) mypos[q * 32] = (uint16_t)(bit ? Z + j - zb : zb);
+                const uint32_t xw = __ballot_sync(XSI_FULL, bit);
+                if (lane == q) xkeep = xw;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (word0 + lane < WS) d.rows[(size_t)job * WS + word0 + lane] = xkeep;  // natural-order row, in place
     }
 }
 

@@ -359,6 +359,130 @@ __global__ void __launch_bounds__(MAXT, 1) pbwt_permute_smem_kernel(EncDev p) {
     }
 }
 
+// =============================================================================================
+// E3 v2: PBWT permute, diploid lines only (the launch falls back to the kernel above when the
+// batch holds an all-haploid record).  Same contract, ~4x fewer instructions per line:
+//   A  y[j] = row[a[j]] by ballot, the warp's y words stay in registers (lane q keeps word q)
+//   A' per-warp exclusive zero counts -> ytab[word] = {y, zeros before the word inside the warp}
+//   C  dest(j) = y[j] ? Z + j - zb(j) : zb(j),  zb(j) = zeros before j;  a[dest] = a[j]
+// Two block barriers per line.  Positions >= N of the last warp are treated as ones, so they
+// stay where they are; only that warp runs the checked variant of the loops.
+// dynamic smem (bytes): a[Npad*2] | row[2][WS*4] | ytab[RW*8] | zc[32*4] | mbar[2*8]
+// =============================================================================================
+template <int WPW, bool CHECK>
+__device__ __forceinline__ void permute_gather_v2(const uint16_t* __restrict__ a, const uint32_t* __restrict__ row,
+                                                  uint2* __restrict__ ytab, uint32_t* __restrict__ zc,
+                                                  uint32_t* __restrict__ grow, uint32_t (&av)[(WPW + 1) / 2], uint32_t N,
+                                                  uint32_t WS, uint32_t w0, uint32_t lane, uint32_t warp) {
+    constexpr int KQ = (WPW + 31) / 32;
+    uint32_t ykeep[KQ];
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) ykeep[k] = 0;
+    // ---- A: gather ----
+#pragma unroll
+    for (int q = 0; q < WPW; ++q) {
+        const uint32_t j = (w0 + q) * 32 + lane;
+        const uint32_t aj = a[j];
+        if (q & 1) av[q >> 1] |= aj << 16; else av[q >> 1] = aj;
+        uint32_t bit;
+        if (CHECK) {
+            const bool valid = j < N;
+            const uint32_t gi = valid ? aj : 0u;
+            bit = valid ? ((row[gi >> 5] >> (gi & 31)) & 1u) : 1u;
+        } else {
+            bit = (row[aj >> 5] >> (aj & 31)) & 1u;
+        }
+        const uint32_t yk = __ballot_sync(XSI_FULL, bit);
+        if (lane == (uint32_t)(q & 31)) ykeep[q >> 5] = yk;
+    }
+    // ---- A': zero prefix per word inside the warp, permuted row to global ----
+    uint32_t carry = 0;
+#pragma unroll
+    for (int k = 0; k < KQ; ++k) {
+        const bool mine = (k * 32 + (int)lane) < WPW;
+        const uint32_t widx = w0 + k * 32 + lane;
+        const uint32_t nz = mine ? __popc(~ykeep[k]) : 0u;
+        uint32_t incl = nz;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, d); if (lane >= (uint32_t)d) incl += o; }
+        if (mine) {
+            ytab[widx] = make_uint2(ykeep[k], carry + incl - nz);
+            if (widx < WS) {
+                uint32_t yo = ykeep[k];
+                if (CHECK) {
+                    const uint32_t b0 = widx * 32;
+                    yo = b0 + 32 <= N ? yo : (b0 >= N ? 0u : (yo & ((1u << (N - b0)) - 1u)));
+                }
+                grow[widx] = yo;
+            }
+        }
+        carry += __shfl_sync(XSI_FULL, incl, 31);
+    }
+    if (lane == 0) zc[warp] = carry;
+}
+
+template <int WPW>
+__global__ void __launch_bounds__(1024, 1) pbwt_permute_v2_kernel(EncDev p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t N = 2 * p.n_samples;
+    const uint32_t WS = p.WS;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, NW = blockDim.x >> 5;
+    const uint32_t RW = NW * WPW, Npad = RW * 32;
+    uint16_t* a = reinterpret_cast<uint16_t*>(smem_raw);
+    uint32_t* rowbuf = reinterpret_cast<uint32_t*>(smem_raw + (size_t)Npad * 2);
+    uint2* ytab = reinterpret_cast<uint2*>(rowbuf + 2 * WS);
+    uint32_t* zc = reinterpret_cast<uint32_t*>(ytab + RW);
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(zc + 32);
+    const uint32_t b = blockIdx.x;
+    const uint32_t l0 = p.blk_line0[b], nwah = p.blk_nwah[b];
+    const uint32_t* list = p.wah_list + l0;
+    const uint32_t row_bytes = WS * 4;
+    for (uint32_t i = tid; i < Npad; i += blockDim.x) a[i] = (uint16_t)i;  // iota, gt_block.hpp:179
+    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_proxy_async(); }
+    __syncthreads();
+    if (nwah == 0) return;
+    if (tid == 0) {
+        mbar_expect_tx(&mbar[0], row_bytes);
+        bulk_g2s(rowbuf, p.bitrows + (size_t)(list[0] & 0x7FFFFFFFu) * WS, row_bytes, &mbar[0]);
+    }
+    const uint32_t w0 = warp * WPW, ltm = lanemask_lt(), lanebit = 1u << lane;
+    const bool checked = (w0 + WPW) * 32 > N;
+    uint32_t entry_cur = list[0], entry_next = nwah > 1 ? list[1] : 0;
+    uint32_t par0 = 0, par1 = 0;
+    for (uint32_t k = 0; k < nwah; ++k) {
+        const uint32_t cur = k & 1;
+        const uint32_t line = entry_cur & 0x7FFFFFFFu;
+        if (k + 1 < nwah && tid == 0) {
+            mbar_expect_tx(&mbar[cur ^ 1], row_bytes);
+            bulk_g2s(rowbuf + (cur ^ 1) * WS, p.bitrows + (size_t)(entry_next & 0x7FFFFFFFu) * WS, row_bytes, &mbar[cur ^ 1]);
+        }
+        entry_cur = entry_next;
+        entry_next = (k + 2 < nwah) ? list[k + 2] : 0;
+        if (cur == 0) { mbar_wait(&mbar[0], par0); par0 ^= 1; } else { mbar_wait(&mbar[1], par1); par1 ^= 1; }
+        const uint32_t* row = rowbuf + cur * WS;
+        uint32_t* grow = p.bitrows + (size_t)line * WS;
+        uint32_t av[(WPW + 1) / 2];
+        if (checked) permute_gather_v2<WPW, true>(a, row, ytab, zc, grow, av, N, WS, w0, lane, warp);
+        else permute_gather_v2<WPW, false>(a, row, ytab, zc, grow, av, N, WS, w0, lane, warp);
+        __syncthreads();  // #1: every read of a[] and row[] is done, zc complete
+        // ---- B: block offsets ----
+        const uint32_t zv = lane < NW ? zc[lane] : 0u;
+        const uint32_t Z = __reduce_add_sync(XSI_FULL, zv);
+        const uint32_t zbase = __reduce_add_sync(XSI_FULL, lane < warp ? zv : 0u);
+        const uint32_t ocst = Z + w0 * 32 + lane;
+        // ---- C: stable partition, dest(j) = y[j] ? Z + j - zb(j) : zb(j) ----
+#pragma unroll
+        for (int q = 0; q < WPW; ++q) {
+            const uint2 t = ytab[w0 + q];
+            const uint32_t zb = zbase + t.y + __popc(~t.x & ltm);
+            const uint32_t aj = (q & 1) ? (av[q >> 1] >> 16) : (av[q >> 1] & 0xFFFFu);
+            const uint32_t dest = (t.x & lanebit) ? (ocst + q * 32 - zb) : zb;
+            a[dest] = (uint16_t)aj;
+        }
+        __syncthreads();  // #2: a[] updated
+    }
+}
+
 // generic fallback for > 65536 haplotypes: a[] ping-pongs in global memory (L2 resident)
 __global__ void __launch_bounds__(1024, 1) pbwt_permute_gmem_kernel(EncDev p, uint32_t* a_pool) {
     __shared__ uint32_t zc[64];

@@ -88,6 +88,7 @@ struct xsi_ctx {
         std::vector<const uint8_t*> block_ptrs;
         std::vector<uint64_t> block_sizes;
         bool collected = false;
+        bool any_haploid = false;
         uint64_t n_wah_lines = 0;
     } enc;
 
@@ -99,7 +100,7 @@ struct xsi_ctx {
         std::vector<DecBlock> h_blocks;
         std::vector<uint32_t> h_bin_lines;
         DevBuf blob, meta, rows, job_u32, job_hap, tile_u32, dline, lists, err, a_pool, x_pool, req, out, scratch, counts,
-            seg_total;
+            seg_total, tabs;
         PinBuf h_stage;
         DecDev dev;
     } dec;
@@ -170,7 +171,7 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
     for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags}) b->release();
     auto& d = ctx->dec;
     for (DevBuf* b : {&d.blob, &d.meta, &d.rows, &d.job_u32, &d.job_hap, &d.tile_u32, &d.dline, &d.lists, &d.err,
-                      &d.a_pool, &d.x_pool, &d.req, &d.out, &d.scratch, &d.counts, &d.seg_total})
+                      &d.a_pool, &d.x_pool, &d.req, &d.out, &d.scratch, &d.counts, &d.seg_total, &d.tabs})
         b->release();
     d.h_stage.release();
     cudaEventDestroy(ctx->ev_side);
@@ -244,9 +245,34 @@ int launch_permute(xsi_ctx* ctx, const EncDev& p, uint32_t NW, size_t smem) {
     return XSI_OK;
 }
 
+template <int WPW>
+int launch_permute_v2(xsi_ctx* ctx, const EncDev& p, uint32_t NW, size_t smem) {
+    CK(cudaFuncSetAttribute(pbwt_permute_v2_kernel<WPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    { PROF("pbwt_permute"); pbwt_permute_v2_kernel<WPW><<<p.nb, NW * 32, smem, ctx->stream>>>(p); }
+    CKL();
+    return XSI_OK;
+}
+
 int run_permute(xsi_ctx* ctx, const EncDev& p) {
     const uint32_t N = 2 * p.n_samples;
     const uint32_t W = (N + 31) / 32;
+    if (!ctx->enc.any_haploid && N <= 65534 && !getenv("XSI_PBWT_V1")) {
+        int wpw = 1;
+        while ((W + wpw - 1) / wpw > 32) wpw *= 2;
+        const uint32_t NW = (W + wpw - 1) / wpw, RW = NW * wpw;
+        const size_t smem2 = (size_t)RW * 32 * 2 + (size_t)2 * p.WS * 4 + (size_t)RW * 8 + 32 * 4 + 16;
+        if (wpw <= 64 && smem2 <= ctx->smem_optin) {
+            switch (wpw) {
+                case 1: return launch_permute_v2<1>(ctx, p, NW, smem2);
+                case 2: return launch_permute_v2<2>(ctx, p, NW, smem2);
+                case 4: return launch_permute_v2<4>(ctx, p, NW, smem2);
+                case 8: return launch_permute_v2<8>(ctx, p, NW, smem2);
+                case 16: return launch_permute_v2<16>(ctx, p, NW, smem2);
+                case 32: return launch_permute_v2<32>(ctx, p, NW, smem2);
+                default: return launch_permute_v2<64>(ctx, p, NW, smem2);
+            }
+        }
+    }
     const size_t smem = ((size_t)N * 2 + 15) / 16 * 16 + (size_t)4 * p.WS * 4 + 64 * 4 + 16;
     if (N <= 65536 && smem <= ctx->smem_optin) {
         const int wpw = choose_wpw(W);
@@ -294,12 +320,14 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
     e.h_blk_line0.assign(e.nb + 1, 0); e.h_blk_rec0.assign(e.nb + 1, 0);
     uint64_t goff = 0, L = 0;
     e.max_ploidy = 0;
+    e.any_haploid = false;
     for (uint64_t r = 0; r < R; ++r) {
         const uint32_t pl = d->ploidy ? d->ploidy[r] : 2;
         if (pl > 2) { ctx->err = "Ploidy higher than 2 is not yet supported"; return XSI_E_PLOIDY; }
         if (pl == 0) { ctx->err = "record with ploidy 0"; return XSI_E_ARG; }
         if (e.h_nallele[r] < 1 || e.h_nallele[r] > (uint32_t)E1_MAXALLELE) { ctx->err = "n_allele out of range (1..256)"; return XSI_E_UNSUPPORTED; }
         if ((int)pl > e.max_ploidy) e.max_ploidy = (int)pl;
+        if (pl == 1) e.any_haploid = true;
         if (r % d->block_len == 0) { e.h_blk_line0[r / d->block_len] = (uint32_t)L; e.h_blk_rec0[r / d->block_len] = (uint32_t)r; }
         e.h_ngt[r] = S * pl;
         e.h_goff[r] = goff;
@@ -839,6 +867,30 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     dd.dline_flags = dlb + Ltp * 16;
     dd.sp_off = d.lists.as<uint64_t>(); dd.ms_off = dd.sp_off + nsp + 1; dd.ev_off = dd.ms_off + nms + 1;
     dd.err = d.err.as<uint32_t>();
+    // D2 v2 (barrier-free, sliced over haplotypes) needs the per-line tables; all-haploid lines use v1
+    bool any_hap_job = false;
+    for (uint32_t j = 0; j < d.n_gt_jobs; ++j) any_hap_job |= job_hap[j] != 0;
+    const uint32_t TWv2 = 2 * d.WS + 4;
+    uint32_t un_warps = 0, un_slices = 0;
+    size_t un_smem = 0;
+    const bool use_v2 = d.n_gt_jobs && !any_hap_job && N <= 65534 && !getenv("XSI_PBWT_V1");
+    if (use_v2) {
+        const uint32_t Wn = (N + 31) / 32, chunks = (Wn + 31) / 32;  // 32-word (1024-haplotype) chunks
+        uint32_t target = (2 * (uint32_t)ctx->sm_count + n_blocks - 1) / n_blocks;
+        un_warps = (chunks + target - 1) / target;
+        const uint32_t min_warps = std::min<uint32_t>(chunks, 4);
+        if (un_warps < min_warps) un_warps = min_warps;
+        if (const char* sw = getenv("XSI_UNPERM_WARPS")) { const int v = atoi(sw); if (v >= 1 && v <= 32) un_warps = std::min<uint32_t>(chunks, (uint32_t)v); }
+        if (un_warps > 32) un_warps = 32;
+        un_slices = (chunks + un_warps - 1) / un_warps;
+        un_smem = (size_t)un_warps * 2048 + (size_t)D2_STAGES * TWv2 * 4 + 2 * D2_STAGES * 8;
+    }
+    const bool v2_ok = use_v2 && un_smem <= ctx->smem_optin;
+    dd.tabs = nullptr; dd.TW = TWv2; dd.n_gt_jobs = d.n_gt_jobs;
+    if (v2_ok) {
+        CK(d.tabs.ensure((size_t)d.n_gt_jobs * TWv2 * 4));
+        dd.tabs = d.tabs.as<uint32_t>();
+    }
 
     // ---- kernels ----
     if (nsp + nms + nev) {
@@ -861,7 +913,11 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
         CK(cudaFuncSetAttribute(wah_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         { PROF("wah_expand"); wah_expand_kernel<<<(njobs + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(dd, wpc, Gpad, Tpad); }
         CKL();
-        if (d.n_gt_jobs) {
+        if (v2_ok) {
+            CK(cudaFuncSetAttribute(pbwt_unpermute_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)un_smem));
+            { PROF("pbwt_unpermute"); pbwt_unpermute_v2_kernel<<<dim3(n_blocks, un_slices), un_warps * 32, un_smem, ctx->stream>>>(dd); }
+            CKL();
+        } else if (d.n_gt_jobs) {
             const uint32_t W = (N + 31) / 32;
             const size_t smem2 = ((size_t)N * 2 + 15) / 16 * 16 + (size_t)2 * d.WS * 4 + ((size_t)N + 32 + 15) / 16 * 16 + 64 * 4 + 16;
             if (N <= 65536 && smem2 <= ctx->smem_optin) {
