@@ -614,7 +614,7 @@ __device__ __forceinline__ uint32_t rd_entry(const uint8_t* m, uint64_t e, uint3
 constexpr int D4_THREADS = 256;
 constexpr uint8_t CODE_MISSING = 254, CODE_EOV = 255;
 
-__global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, ReqDev q) {
+__global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, ReqDev q, int skip_simple) {
     const uint32_t tid = threadIdx.x;
     const uint32_t S = d.n_samples, NH = 2 * S;
     const uint32_t msb = d.aet == 2 ? 0x8000u : 0x80000000u;
@@ -629,6 +629,7 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
         uint32_t* cnts = q.counts ? q.counts + (size_t)ri * q.counts_stride : nullptr;
         const uint8_t* spm = d.blob + blk.sparse_off;
         const bool weird = (f0 & (DL_MISSING | DL_EOV | DL_PHASE)) != 0;
+        if (skip_simple && nall == 2 && !weird) continue;  // written by compose_simple_kernel
         if (tid == 0 && q.filled) q.filled[ri] = n;
 
         if (nall == 2 && !weird) {
@@ -735,6 +736,103 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
         if (cnts && tid == 0) cnts[0] = n - (total_alt + n_missing + n_eov);
         __syncthreads();
     }
+}
+
+// =============================================================================================
+// D4 fast path: records with one ALT line and no missing / end-of-vector / phase overlay (the bulk
+// of any file).  Persistent CTAs build 8192-genotype int32 tiles in shared memory -- a thread
+// expands its own 32-bit word of the bit-row (WAH lines) or writes the default pattern that the
+// listed carriers then patch (sparse lines) -- and hand every tile to the TMA engine
+// (cp.async.bulk shared->global), double buffered.  Needs 16-byte aligned output rows.
+// =============================================================================================
+constexpr int D5_TILE = 8192;
+__device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N_PENDING>
+__device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N_PENDING) : "memory"); }
+template <int N_PENDING>
+__device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
+
+__global__ void __launch_bounds__(D4_THREADS, 2) compose_simple_kernel(DecDev d, ReqDev q) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // 2 tiles of D5_TILE int32
+    int32_t* tiles = reinterpret_cast<int32_t*>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const uint32_t S = d.n_samples, NH = 2 * S;
+    const uint32_t msb = d.aet == 2 ? 0x8000u : 0x80000000u;
+    const uint32_t rot = tid & 7u;
+    uint32_t buf = 0;
+    for (uint32_t ri = blockIdx.x; ri < q.n; ri += gridDim.x) {
+        if (q.nall[ri] != 2) continue;
+        const DecBlock blk = d.blocks[q.blk[ri]];
+        const uint32_t gl0 = blk.line0 + q.line[ri];
+        const uint8_t f0 = d.dline_flags[gl0];
+        if (f0 & (DL_MISSING | DL_EOV | DL_PHASE)) continue;
+        const bool hap = (f0 & DL_HAPLOID) != 0;
+        const uint32_t n = hap ? S : NH;
+        const int32_t DP = (int32_t)(blk.default_phasing & 1u);
+        int32_t* out = q.out + (size_t)ri * q.out_stride;
+        const bool wah = (f0 & DL_WAH) != 0;
+        const uint32_t ord = d.dline_ord[gl0];
+        const uint32_t* row = d.rows + (size_t)ord * d.WS;
+        const uint8_t* spm = d.blob + blk.sparse_off;
+        uint64_t e0 = 0; uint32_t cnt = 0; bool neg = false;
+        if (!wah) {
+            e0 = d.sp_off[ord];
+            const uint32_t hdr = rd_entry(spm, e0, d.aet);
+            neg = (hdr & msb) != 0; cnt = hdr & ~msb;
+        }
+        if (tid == 0) {
+            if (q.filled) q.filled[ri] = n;
+            if (q.counts) {
+                const uint32_t ones = wah ? d.job_ones[ord] : (neg ? n - cnt : cnt);
+                uint32_t* cnts = q.counts + (size_t)ri * q.counts_stride;
+                cnts[1] = ones; cnts[0] = n - ones;
+            }
+        }
+        const int32_t ph = (wah && hap) ? 0 : DP;        // phase bit of odd entries
+        const int32_t base_even = (!wah && neg) ? 4 : 2;  // value of a 0 bit: REF (or ALT for negated lists)
+        const uint32_t ntiles = (n + D5_TILE - 1) / D5_TILE;
+        for (uint32_t tt = 0; tt < ntiles; ++tt) {
+            if (tid == 0) bulk_wait_read<1>();  // the store that last used this buffer has read it
+            __syncthreads();
+            int32_t* tile = tiles + (size_t)buf * D5_TILE;
+            const uint32_t elem0 = tt * D5_TILE;
+            uint32_t w = 0;
+            if (wah) { const uint32_t wi = tt * 256 + tid; w = wi < d.WS ? row[wi] : 0u; }
+            const uint32_t wr = __funnelshift_r(w, w, 4 * rot);  // chunk k of wr = chunk (k + rot) & 7 of w
+            const int32_t ce = base_even, co = base_even | ph;
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k) {
+                const uint32_t c = (k + rot) & 7u;
+                int4 v;
+                v.x = ce + (int32_t)(((wr >> (4 * k)) & 1u) << 1);
+                v.y = co + (int32_t)(((wr >> (4 * k + 1)) & 1u) << 1);
+                v.z = ce + (int32_t)(((wr >> (4 * k + 2)) & 1u) << 1);
+                v.w = co + (int32_t)(((wr >> (4 * k + 3)) & 1u) << 1);
+                *reinterpret_cast<int4*>(tile + tid * 32 + c * 4) = v;
+            }
+            if (!wah && cnt) {
+                __syncthreads();
+                const int32_t spv = neg ? 2 : 4;
+                for (uint32_t k = tid; k < cnt; k += D4_THREADS) {
+                    const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet);
+                    const uint32_t li = i - elem0;
+                    if (li < (uint32_t)D5_TILE && i < n) tile[li] = spv | ((int32_t)(i & 1u) & DP);
+                }
+            }
+            fence_proxy_async();
+            __syncthreads();
+            if (tid == 0) {
+                const uint32_t bytes = min((uint32_t)D5_TILE, n - elem0) * 4u;
+                bulk_s2g(out + elem0, tile, bytes);
+                bulk_commit();
+            }
+            buf ^= 1u;
+        }
+    }
+    if (tid == 0) bulk_wait<0>();
 }
 
 }  // namespace xsi

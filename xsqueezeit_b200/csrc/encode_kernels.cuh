@@ -88,6 +88,61 @@ __device__ __forceinline__ void emit_pred_row(const void* gt, uint64_t goff, uin
     }
 }
 
+// Per-record decisions and the rare extra rows, shared by both scan kernels.  Expects the block's
+// s_cnt[alt] / s_misc {nmiss, neov, phase bits, err} to be complete (barrier before the call).
+template <int ELEM>
+__device__ __forceinline__ void finish_record(const EncDev& p, uint32_t r, uint32_t ngt, uint32_t n_allele, uint32_t line0,
+                                              uint64_t goff, uint32_t P, uint32_t* s_cnt, uint8_t* s_lflag,
+                                              uint32_t* s_misc, int32_t* s_slot) {
+    // ---- per-record decisions (gt_block.hpp:292-338) ----
+    if (threadIdx.x == 0) {
+        const uint32_t nmiss = s_misc[0], neov = s_misc[1];
+        uint8_t rf = 0;
+        if (nmiss) rf |= RF_MISSING;
+        if (neov) rf |= RF_EOV;
+        if (s_misc[2]) rf |= RF_PHASE;
+        if (P == 1) rf |= RF_HAPLOID;
+        if (s_misc[3]) atomicOr(&p.counters[2], ERR_ALLELE);
+        uint32_t sum_alt = 0;
+        for (uint32_t a = 1; a < n_allele; ++a) sum_alt += s_cnt[a];
+        const uint32_t cnt0 = ngt - sum_alt - nmiss - neov;
+        for (uint32_t a = 1; a < n_allele; ++a) {
+            const uint32_t c = s_cnt[a];
+            const uint32_t mac = min(c, ngt - c);
+            const uint32_t line = line0 + a - 1;
+            uint8_t lf = (P == 1) ? LF_HAPLOID : 0;
+            uint32_t sn = 0;
+            if ((uint64_t)mac > p.mac_thr) lf |= LF_WAH;
+            else if (c == mac) sn = c + 1;
+            else { lf |= LF_NEGATED; sn = cnt0 + 1; }
+            p.line_cnt[line] = c;
+            p.line_flags[line] = lf;
+            p.line_sparse_n[line] = sn;
+            p.line_wah_n[line] = 0;
+            s_lflag[a] = lf;
+        }
+        p.rec_flags[r] = rf;
+        p.rec_miss_n[r] = nmiss ? nmiss + 1 : 0;
+        p.rec_eov_n[r] = neov ? neov + 1 : 0;
+        p.rec_phase_n[r] = 0;
+        s_slot[0] = s_slot[1] = s_slot[2] = -1;
+        if (nmiss) { const uint32_t s = atomicAdd(&p.counters[0], 1u); if (s < p.aux_cap) s_slot[0] = (int32_t)s; else atomicOr(&p.counters[2], ERR_AUX_OVERFLOW); }
+        if (neov) { const uint32_t s = atomicAdd(&p.counters[0], 1u); if (s < p.aux_cap) s_slot[1] = (int32_t)s; else atomicOr(&p.counters[2], ERR_AUX_OVERFLOW); }
+        if (rf & RF_PHASE) { const uint32_t s = atomicAdd(&p.counters[1], 1u); if (s < p.phase_cap) s_slot[2] = (int32_t)s; else atomicOr(&p.counters[2], ERR_PHASE_OVERFLOW); }
+        p.rec_aux[r * 3 + 0] = s_slot[0];
+        p.rec_aux[r * 3 + 1] = s_slot[1];
+        p.rec_aux[r * 3 + 2] = s_slot[2];
+    }
+    __syncthreads();
+    // ---- rare second passes over the (L2-hot) row ----
+    for (uint32_t a = 1; a < n_allele; ++a)
+        if (s_lflag[a] & LF_NEGATED)  // negated sparse lists REF carriers (block.hpp:59-65 with sparse_allele 0)
+            emit_pred_row<ELEM, 0>(p.gt, goff, ngt, p.WS, 0, p.bitrows + (size_t)(line0 + a - 1) * p.WS);
+    if (s_slot[0] >= 0) emit_pred_row<ELEM, 1>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[0] * p.WS);
+    if (s_slot[1] >= 0) emit_pred_row<ELEM, 2>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[1] * p.WS);
+    if (s_slot[2] >= 0) emit_pred_row<ELEM, 3>(p.gt, goff, ngt, p.WS, p.default_phasing, p.phrows + (size_t)s_slot[2] * p.WS);
+}
+
 template <int ELEM>
 __global__ void __launch_bounds__(E1_THREADS) scan_rows_kernel(EncDev p) {
     __shared__ uint32_t s_cnt[E1_MAXALLELE];
@@ -163,52 +218,208 @@ __global__ void __launch_bounds__(E1_THREADS) scan_rows_kernel(EncDev p) {
     }
     __syncthreads();
 
-    // ---- per-record decisions (gt_block.hpp:292-338) ----
-    if (threadIdx.x == 0) {
-        const uint32_t nmiss = s_misc[0], neov = s_misc[1];
-        uint8_t rf = 0;
-        if (nmiss) rf |= RF_MISSING;
-        if (neov) rf |= RF_EOV;
-        if (s_misc[2]) rf |= RF_PHASE;
-        if (P == 1) rf |= RF_HAPLOID;
-        if (s_misc[3]) atomicOr(&p.counters[2], ERR_ALLELE);
-        uint32_t sum_alt = 0;
-        for (uint32_t a = 1; a < n_allele; ++a) sum_alt += s_cnt[a];
-        const uint32_t cnt0 = ngt - sum_alt - nmiss - neov;
-        for (uint32_t a = 1; a < n_allele; ++a) {
-            const uint32_t c = s_cnt[a];
-            const uint32_t mac = min(c, ngt - c);
-            const uint32_t line = line0 + a - 1;
-            uint8_t lf = (P == 1) ? LF_HAPLOID : 0;
-            uint32_t sn = 0;
-            if ((uint64_t)mac > p.mac_thr) lf |= LF_WAH;
-            else if (c == mac) sn = c + 1;
-            else { lf |= LF_NEGATED; sn = cnt0 + 1; }
-            p.line_cnt[line] = c;
-            p.line_flags[line] = lf;
-            p.line_sparse_n[line] = sn;
-            p.line_wah_n[line] = 0;
-            s_lflag[a] = lf;
-        }
-        p.rec_flags[r] = rf;
-        p.rec_miss_n[r] = nmiss ? nmiss + 1 : 0;
-        p.rec_eov_n[r] = neov ? neov + 1 : 0;
-        p.rec_phase_n[r] = 0;
-        if (nmiss) { const uint32_t s = atomicAdd(&p.counters[0], 1u); if (s < p.aux_cap) s_slot[0] = (int32_t)s; else atomicOr(&p.counters[2], ERR_AUX_OVERFLOW); }
-        if (neov) { const uint32_t s = atomicAdd(&p.counters[0], 1u); if (s < p.aux_cap) s_slot[1] = (int32_t)s; else atomicOr(&p.counters[2], ERR_AUX_OVERFLOW); }
-        if (rf & RF_PHASE) { const uint32_t s = atomicAdd(&p.counters[1], 1u); if (s < p.phase_cap) s_slot[2] = (int32_t)s; else atomicOr(&p.counters[2], ERR_PHASE_OVERFLOW); }
-        p.rec_aux[r * 3 + 0] = s_slot[0];
-        p.rec_aux[r * 3 + 1] = s_slot[1];
-        p.rec_aux[r * 3 + 2] = s_slot[2];
+    finish_record<ELEM>(p, r, ngt, n_allele, line0, goff, P, s_cnt, s_lflag, s_misc, s_slot);
+}
+
+// =============================================================================================
+// E1 v2: the same scan fed by the TMA engine.  Persistent CTAs (2 per SM) walk records
+// r = blockIdx.x, blockIdx.x + gridDim.x, ...; the row streams through a ring of 8192-genotype
+// tiles (cp.async.bulk global->shared, full/empty mbarriers) and every thread turns its own 32
+// consecutive genotypes into one word per ALT line with no cross-lane traffic: 16-byte
+// conflict-free shared loads (chunk order rotated by the thread index), compile-time bit
+// positions, one funnel shift to undo the rotation, coalesced 128-byte word stores.
+// Needs 16-byte aligned rows (host checks; otherwise scan_rows_kernel runs).
+// =============================================================================================
+constexpr int S2_TILE = 8192;   // genotypes per tile = 256 threads x 32
+constexpr int S2_STAGES = 3;
+
+template <int ELEM>
+__device__ __forceinline__ int32_t tile_value(const unsigned char* base, uint32_t i) {
+    if (ELEM == 4) return reinterpret_cast<const int32_t*>(base)[i];
+    return (int32_t)reinterpret_cast<const signed char*>(base)[i];
+}
+// classify one genotype that failed the allele range test: bit0 missing, bit1 end of vector, bit2 unknown allele
+template <int ELEM>
+__device__ __forceinline__ uint32_t classify_bad(int32_t v) {
+    const bool miss = ELEM == 4 ? gt_is_missing(v) : (((v >> 1) == 0) || v == -128);
+    const bool eov = ELEM == 4 ? (v == XSI_I32_VECTOR_END) : (v == -127);
+    return miss ? 1u : (eov ? 2u : 4u);
+}
+
+template <int ELEM>
+__global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ uint32_t s_cnt[E1_MAXALLELE];
+    __shared__ uint8_t s_lflag[E1_MAXALLELE];
+    __shared__ uint32_t s_misc[4];
+    __shared__ int32_t s_slot[3];
+    constexpr uint32_t TILE_BYTES = S2_TILE * ELEM;
+    constexpr uint32_t TBYTES = 32 * ELEM;              // bytes of one thread's 32 genotypes
+    constexpr uint32_t NCH = TBYTES / 16;               // 16-byte chunks per thread: 8 (int32) / 2 (int8)
+    constexpr uint32_t EPC = 16 / ELEM;                 // genotypes per chunk: 4 / 16
+    unsigned char* ring = smem_raw;
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)S2_STAGES * TILE_BYTES);
+    uint64_t* empty = full + S2_STAGES;
+    const uint32_t tid = threadIdx.x, lane = lane_id();
+    const uint32_t tiles_per_rec = (p.WS + 255) / 256;
+    const unsigned char* gbase = reinterpret_cast<const unsigned char*>(p.gt);
+    const uint32_t rot = ELEM == 4 ? (tid & 7u) : ((tid >> 2) & 1u);  // chunk rotation of this thread
+    if (tid == 0) {
+        for (int s = 0; s < S2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], E1_WARPS); }
+        fence_proxy_async();
     }
     __syncthreads();
-    // ---- rare second passes over the (L2-hot) row ----
-    for (uint32_t a = 1; a < n_allele; ++a)
-        if (s_lflag[a] & LF_NEGATED)  // negated sparse lists REF carriers (block.hpp:59-65 with sparse_allele 0)
-            emit_pred_row<ELEM, 0>(p.gt, goff, ngt, p.WS, 0, p.bitrows + (size_t)(line0 + a - 1) * p.WS);
-    if (s_slot[0] >= 0) emit_pred_row<ELEM, 1>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[0] * p.WS);
-    if (s_slot[1] >= 0) emit_pred_row<ELEM, 2>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[1] * p.WS);
-    if (s_slot[2] >= 0) emit_pred_row<ELEM, 3>(p.gt, goff, ngt, p.WS, p.default_phasing, p.phrows + (size_t)s_slot[2] * p.WS);
+    // ---- producer state (thread 0): next data tile to request ----
+    uint32_t pr = blockIdx.x, pt = 0, issued = 0;
+    auto produce = [&]() {
+        while (pr < p.R) {
+            const uint32_t ngt = p.rec_ngt[pr];
+            const uint32_t ndt = (ngt + S2_TILE - 1) / S2_TILE;
+            if (pt < ndt) {
+                const uint32_t st = issued % S2_STAGES, use = issued / S2_STAGES;
+                if (use > 0) mbar_wait(&empty[st], (use - 1) & 1u);
+                const uint32_t bytes = min(TILE_BYTES, (ngt - pt * S2_TILE) * ELEM);
+                mbar_expect_tx(&full[st], bytes);
+                bulk_g2s(ring + (size_t)st * TILE_BYTES, gbase + (p.rec_goff[pr] + (uint64_t)pt * S2_TILE) * ELEM, bytes, &full[st]);
+                ++issued; ++pt;
+                return;
+            }
+            pr += gridDim.x; pt = 0;
+        }
+    };
+    if (tid == 0) for (int s = 0; s < S2_STAGES - 1; ++s) produce();
+    uint32_t consumed = 0;
+    const int32_t dpx = p.default_phasing & 1;
+
+    for (uint32_t r = blockIdx.x; r < p.R; r += gridDim.x) {
+        const uint32_t ngt = p.rec_ngt[r], n_allele = p.rec_nallele[r], line0 = p.rec_line0[r];
+        const uint64_t goff = p.rec_goff[r];
+        const uint32_t P = p.n_samples ? ngt / p.n_samples : 0;
+        const uint32_t ndt = (ngt + S2_TILE - 1) / S2_TILE;
+        for (uint32_t i = tid; i < E1_MAXALLELE; i += E1_THREADS) { s_cnt[i] = 0; s_lflag[i] = 0; }
+        if (tid < 4) s_misc[tid] = 0;
+        __syncthreads();
+        uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, nmiss = 0, neov = 0, phase = 0, err = 0;
+        for (uint32_t tt = 0; tt < tiles_per_rec; ++tt) {
+            const uint32_t wi = tt * 256 + tid;
+            const uint32_t elem0 = tt * S2_TILE + tid * 32;
+            const bool data = tt < ndt;
+            uint32_t st = 0;
+            if (data) {
+                if (tid == 0) produce();  // refill the stage the previous tile released
+                st = consumed % S2_STAGES;
+                mbar_wait(&full[st], (consumed / S2_STAGES) & 1u);
+            }
+            const unsigned char* tile = ring + (size_t)st * TILE_BYTES + tid * TBYTES;
+            const uint32_t nvalid = (data && ngt > elem0) ? min(32u, ngt - elem0) : 0u;
+            for (uint32_t alt0 = 1; alt0 < n_allele || alt0 == 1; alt0 += 4) {
+                const uint32_t nal = n_allele > alt0 ? min(4u, n_allele - alt0) : 0u;
+                const int32_t key = (int32_t)alt0 + 1;  // (v >> 1) of ALT alt0
+                uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+                if (nvalid == 32) {
+#pragma unroll
+                    for (uint32_t k = 0; k < NCH; ++k) {
+                        const uint32_t c = (k + rot) & (NCH - 1);
+                        const int4 q = *reinterpret_cast<const int4*>(tile + c * 16);
+                        int32_t v[EPC];
+                        if (ELEM == 4) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+                        else {
+                            const uint32_t qq[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+                            for (uint32_t e = 0; e < EPC; ++e) v[e % EPC] = (int32_t)(int8_t)(qq[e >> 2] >> (8 * (e & 3)));
+                        }
+                        bool badc = false;
+#pragma unroll
+                        for (uint32_t e = 0; e < EPC; ++e) {
+                            const int32_t h = v[e] >> 1;
+                            const uint32_t bitv = 1u << (k * EPC + e);
+                            if (h == key) w0 |= bitv;
+                            if (nal > 1 && h == key + 1) w1 |= bitv;
+                            if (nal > 2 && h == key + 2) w2 |= bitv;
+                            if (nal > 3 && h == key + 3) w3 |= bitv;
+                            if (alt0 == 1) {
+                                badc |= (uint32_t)(h - 1) >= n_allele;
+                                if (e & 1) phase |= (uint32_t)(v[e] ^ dpx);
+                            }
+                        }
+                        if (alt0 == 1 && badc) {
+#pragma unroll
+                            for (uint32_t e = 0; e < EPC; ++e) {
+                                if ((uint32_t)((v[e] >> 1) - 1) >= n_allele) {
+                                    const uint32_t cl = classify_bad<ELEM>(v[e]);
+                                    nmiss += cl & 1u; neov += (cl >> 1) & 1u; err |= cl >> 2;
+                                }
+                            }
+                        }
+                    }
+                    // undo the chunk rotation: chunk k of w* is genotype chunk (k + rot)
+                    const uint32_t sh = rot * (EPC);
+                    w0 = __funnelshift_l(w0, w0, sh);
+                    if (nal > 1) w1 = __funnelshift_l(w1, w1, sh);
+                    if (nal > 2) w2 = __funnelshift_l(w2, w2, sh);
+                    if (nal > 3) w3 = __funnelshift_l(w3, w3, sh);
+                } else if (nvalid) {  // the one partially filled word of the row
+                    for (uint32_t e = 0; e < nvalid; ++e) {
+                        const int32_t v = tile_value<ELEM>(tile, e);
+                        const int32_t h = v >> 1;
+                        const uint32_t bitv = 1u << e;
+                        if (h == key) w0 |= bitv;
+                        if (nal > 1 && h == key + 1) w1 |= bitv;
+                        if (nal > 2 && h == key + 2) w2 |= bitv;
+                        if (nal > 3 && h == key + 3) w3 |= bitv;
+                        if (alt0 == 1) {
+                            if (e & 1) phase |= (uint32_t)(v ^ dpx);
+                            if ((uint32_t)(h - 1) >= n_allele) {
+                                const uint32_t cl = classify_bad<ELEM>(v);
+                                nmiss += cl & 1u; neov += (cl >> 1) & 1u; err |= cl >> 2;
+                            }
+                        }
+                    }
+                }
+                if (wi < p.WS) {
+                    uint32_t* row = p.bitrows + (size_t)(line0 + alt0 - 1) * p.WS + wi;
+                    if (nal > 0) row[0] = w0;
+                    if (nal > 1) row[(size_t)p.WS] = w1;
+                    if (nal > 2) row[(size_t)p.WS * 2] = w2;
+                    if (nal > 3) row[(size_t)p.WS * 3] = w3;
+                }
+                if (alt0 == 1) { c0 += __popc(w0); c1 += __popc(w1); c2 += __popc(w2); c3 += __popc(w3); }
+                else if (nal > 0) {  // rare: more than 4 ALT alleles
+                    const uint32_t a0 = __reduce_add_sync(XSI_FULL, __popc(w0)), a1 = __reduce_add_sync(XSI_FULL, __popc(w1));
+                    const uint32_t a2 = __reduce_add_sync(XSI_FULL, __popc(w2)), a3 = __reduce_add_sync(XSI_FULL, __popc(w3));
+                    if (lane == 0) {
+                        atomicAdd(&s_cnt[alt0], a0);
+                        if (nal > 1) atomicAdd(&s_cnt[alt0 + 1], a1);
+                        if (nal > 2) atomicAdd(&s_cnt[alt0 + 2], a2);
+                        if (nal > 3) atomicAdd(&s_cnt[alt0 + 3], a3);
+                    }
+                }
+            }
+            if (data) {
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&empty[st]);
+                ++consumed;
+            }
+        }
+        // ---- block totals ----
+        c0 = __reduce_add_sync(XSI_FULL, c0); c1 = __reduce_add_sync(XSI_FULL, c1);
+        c2 = __reduce_add_sync(XSI_FULL, c2); c3 = __reduce_add_sync(XSI_FULL, c3);
+        nmiss = __reduce_add_sync(XSI_FULL, nmiss); neov = __reduce_add_sync(XSI_FULL, neov);
+        phase = __reduce_or_sync(XSI_FULL, phase & 1u); err = __reduce_or_sync(XSI_FULL, err);
+        if (lane == 0) {
+            if (n_allele > 1) atomicAdd(&s_cnt[1], c0);
+            if (n_allele > 2) atomicAdd(&s_cnt[2], c1);
+            if (n_allele > 3) atomicAdd(&s_cnt[3], c2);
+            if (n_allele > 4) atomicAdd(&s_cnt[4], c3);
+            if (nmiss) atomicAdd(&s_misc[0], nmiss);
+            if (neov) atomicAdd(&s_misc[1], neov);
+            if (phase && P == 2) atomicOr(&s_misc[2], 1u);
+            if (err) atomicOr(&s_misc[3], 1u);
+        }
+        __syncthreads();
+        finish_record<ELEM>(p, r, ngt, n_allele, line0, goff, P, s_cnt, s_lflag, s_misc, s_slot);
+        __syncthreads();
+    }
 }
 
 // =============================================================================================

@@ -319,6 +319,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
     e.h_ngt.resize(R); e.h_line0.resize(R); e.h_goff.resize(R);
     e.h_blk_line0.assign(e.nb + 1, 0); e.h_blk_rec0.assign(e.nb + 1, 0);
     uint64_t goff = 0, L = 0;
+    bool rows_aligned16 = true;  // every row starts and ends on a 16-byte boundary -> TMA-fed scan
     e.max_ploidy = 0;
     e.any_haploid = false;
     for (uint64_t r = 0; r < R; ++r) {
@@ -331,6 +332,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         if (r % d->block_len == 0) { e.h_blk_line0[r / d->block_len] = (uint32_t)L; e.h_blk_rec0[r / d->block_len] = (uint32_t)r; }
         e.h_ngt[r] = S * pl;
         e.h_goff[r] = goff;
+        if ((goff * (uint64_t)d->gt_elem_bytes) % 16 || ((uint64_t)S * pl * d->gt_elem_bytes) % 16) rows_aligned16 = false;
         e.h_line0[r] = (uint32_t)L;
         goff += (uint64_t)S * pl;
         L += e.h_nallele[r] - 1;
@@ -355,6 +357,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         CK(cudaMemcpyAsync(e.gt.p, d->gt, gt_bytes, cudaMemcpyHostToDevice, ctx->stream));
         dgt = e.gt.p;
     }
+    if (reinterpret_cast<uintptr_t>(dgt) % 16) rows_aligned16 = false;
     // tables: goff[R] u64 | ngt[R] | nallele[R] | line0[R] | line_rec[L] | blk_line0[nb+1]
     const size_t t_goff = 0, t_ngt = t_goff + R * 8, t_nal = t_ngt + R * 4, t_l0 = t_nal + R * 4, t_lr = t_l0 + R * 4,
                  t_bl = t_lr + Lp * 4, t_end = t_bl + (e.nb + 1) * 4;
@@ -414,7 +417,19 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         p.wahslots = e.wahslots.as<uint16_t>(); p.phslots = e.phslots.as<uint16_t>();
 
         CK(cudaMemsetAsync(e.counters.p, 0, 16, ctx->stream));
-        {
+        if (rows_aligned16 && !getenv("XSI_SCAN_V1")) {
+            // TMA-fed persistent scan: 2 CTAs per SM, each walks records blockIdx.x, +gridDim.x, ...
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(R, (uint64_t)ctx->sm_count * 2);
+            const size_t smem = (size_t)S2_STAGES * S2_TILE * d->gt_elem_bytes + 2 * S2_STAGES * 8;
+            PROF("scan_rows");
+            if (d->gt_elem_bytes == 4) {
+                CK(cudaFuncSetAttribute(scan_rows_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                scan_rows_v2_kernel<4><<<grid, E1_THREADS, smem, ctx->stream>>>(p);
+            } else {
+                CK(cudaFuncSetAttribute(scan_rows_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                scan_rows_v2_kernel<1><<<grid, E1_THREADS, smem, ctx->stream>>>(p);
+            }
+        } else {
             PROF("scan_rows");
             if (d->gt_elem_bytes == 4) scan_rows_kernel<4><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
             else scan_rows_kernel<1><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
@@ -972,7 +987,9 @@ extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* bloc
     if (want_counts && counts_stride < max_all) { ctx->err = "counts_stride too small"; return XSI_E_ARG; }
     // chunk so that the staging buffers stay bounded
     const uint64_t row_bytes = out_stride * 4;
-    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (1ull << 30) / row_bytes));
+    // host output is staged through a bounded device buffer; device output needs no chunking
+    const uint64_t chunk = out_on_device ? std::min<uint64_t>(n, 1ull << 30)
+                                         : std::max<uint64_t>(1, std::min<uint64_t>(n, (1ull << 30) / row_bytes));
     const uint32_t Npad = (N + 63) / 64 * 64;
     for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
         const uint64_t cn = std::min(chunk, n - c0);
@@ -992,7 +1009,17 @@ extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* bloc
         q.counts = nullptr; q.counts_stride = counts_stride;
         if (want_counts) { CK(d.counts.ensure(cn * counts_stride * 4)); q.counts = d.counts.as<uint32_t>(); }
         q.scratch = d.scratch.as<uint8_t>(); q.Npad = Npad;
-        { PROF("compose_records"); compose_records_kernel<<<grid, D4_THREADS, 0, ctx->stream>>>(d.dev, q); }
+        // rows that start and end on 16-byte boundaries take the TMA-store fast path for simple records
+        const bool fast = !getenv("XSI_COMPOSE_V1") && (reinterpret_cast<uintptr_t>(q.out) % 16 == 0) && (out_stride % 4 == 0) &&
+                          (d.n_samples % 4 == 0);
+        if (fast) {
+            const size_t smem = (size_t)2 * D5_TILE * 4;
+            CK(cudaFuncSetAttribute(compose_simple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const uint32_t g2 = (uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * 2);
+            { PROF("compose_simple"); compose_simple_kernel<<<g2, D4_THREADS, smem, ctx->stream>>>(d.dev, q); }
+            CKL();
+        }
+        { PROF("compose_records"); compose_records_kernel<<<grid, D4_THREADS, 0, ctx->stream>>>(d.dev, q, fast ? 1 : 0); }
         CKL();
         if (!out_on_device) CK(cudaMemcpyAsync(out + c0 * out_stride, q.out, cn * row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (n_filled) CK(cudaMemcpyAsync(n_filled + c0, q.filled, cn * 4, cudaMemcpyDeviceToHost, ctx->stream));
