@@ -365,12 +365,18 @@ def main():
     def ev():
         return torch.cuda.Event(enable_timing=True)
 
+    host_ms = {"encode_launch": 0.0, "encode_collect": 0.0, "decode_load_blocks": 0.0, "decode_records": 0.0}
+
     def encode_step(gt_ptr, on_device, n_rec):
+        t0 = time.perf_counter()
         ctx.encode_launch(gt_ptr, nal[:n_rec], S, BL, thr, 1, gt_on_device=on_device)
+        t1 = time.perf_counter()
         n = ctypes.c_uint32()
         bp = ctypes.POINTER(ctypes.c_void_p)()
         sz = ctypes.POINTER(ctypes.c_uint64)()
         ctx._check(L.xsi_encode_collect(ctx.h, ctypes.byref(n), ctypes.byref(bp), ctypes.byref(sz)))
+        host_ms["encode_launch"] += (t1 - t0) * 1e3
+        host_ms["encode_collect"] += (time.perf_counter() - t1) * 1e3
         blocks = [(bp[i], sz[i]) for i in range(n.value)]
         if dist is not None:  # the one exchange step: per-block byte counts -> global offset table
             sizes_dev[:n.value].copy_(torch.tensor([b[1] for b in blocks], dtype=torch.int64), non_blocking=False)
@@ -379,15 +385,21 @@ def main():
         return blocks
 
     def decode_step(blocks, out_ptr, on_device, n_rec):
+        t0 = time.perf_counter()
         ctx.decode_load_blocks(blocks, S, 2)
+        t1 = time.perf_counter()
         ctx._check(L.xsi_decode_records(ctx.h, n_rec, blk[:n_rec].ctypes.data, off[:n_rec].ctypes.data,
                                         nal[:n_rec].ctypes.data, out_ptr, H, 1 if on_device else 0, None, None, 0))
         ctx.sync()
+        host_ms["decode_load_blocks"] += (t1 - t0) * 1e3
+        host_ms["decode_records"] += (time.perf_counter() - t1) * 1e3
 
     def run_leg(n_rec, gt_ptr, out_ptr, on_device, nsteps, nwarm, sampler=None):
         for _ in range(nwarm):
             decode_step(encode_step(gt_ptr, on_device, n_rec), out_ptr, on_device, n_rec)
         ctx.profile_read()
+        for k in host_ms:
+            host_ms[k] = 0.0
         launches0 = ctx.kernel_launches
         barrier()
         if sampler:
@@ -410,7 +422,8 @@ def main():
         t_dec = sum(b.elapsed_time(c) for b, c in zip(e1, e2)) / 1e3
         t_all = e0[0].elapsed_time(e2[-1]) / 1e3
         return dict(t_enc=t_enc, t_dec=t_dec, t_all=t_all, payload=payload, clocks=clocks,
-                    launches=ctx.kernel_launches - launches0, prof=ctx.profile_read(), lines=lines)
+                    launches=ctx.kernel_launches - launches0, prof=ctx.profile_read(), lines=lines,
+                    host_ms={k: v / nsteps for k, v in host_ms.items()})
 
     def maxr(x):
         if dist is None:
@@ -489,7 +502,7 @@ def main():
                            "genotypes_per_gpu_per_step": G, "input": "int32 rows resident in HBM (%.1f GB, > L2; no flush needed)" % (G * 4 / 1e9),
                            "xsi_payload_bytes_per_step": res["payload"], "binary_lines": res["lines"][0], "wah_lines": res["lines"][1], "parallelism": "blocks sharded over %d GPU(s)" % world},
                 "compress_ggts": G * world * steps / t_enc / 1e9, "decompress_ggts": G * world * steps / t_dec / 1e9,
-                "verified": verified, "roofline": roof, "kernels": kernels, "cpu_baseline": cpu, "e2e": e2e,
+                "verified": verified, "roofline": roof, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": res["launches"], "clocks": res["clocks"]}
         print(json.dumps(line))
     ctx.close()

@@ -84,7 +84,8 @@ struct xsi_ctx {
             a_pool;
         PinBuf h_small, h_offs, h_out, h_flags;
         uint64_t tot_sparse = 0, tot_miss = 0, tot_eov = 0, tot_wah = 0, tot_phase = 0;
-        std::vector<std::vector<uint8_t>> blocks;
+        PinBuf arena;                       // finished GT blocks, back to back (16-byte aligned starts)
+        std::vector<uint64_t> block_at;     // offset of every block in the arena
         std::vector<const uint8_t*> block_ptrs;
         std::vector<uint64_t> block_sizes;
         bool collected = false;
@@ -168,7 +169,7 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
                       &e.line_flags, &e.rec_u32, &e.rec_flags, &e.wah_list, &e.blk_nwah, &e.wahslots, &e.phslots,
                       &e.offs, &e.scanjobs, &e.out_wah, &e.out_sparse, &e.out_miss, &e.out_eov, &e.out_phase, &e.a_pool})
         b->release();
-    for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags}) b->release();
+    for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags, &e.arena}) b->release();
     auto& d = ctx->dec;
     for (DevBuf* b : {&d.blob, &d.meta, &d.rows, &d.job_u32, &d.job_hap, &d.tile_u32, &d.dline, &d.lists, &d.err,
                       &d.a_pool, &d.x_pool, &d.req, &d.out, &d.scratch, &d.counts, &d.seg_total, &d.tabs})
@@ -455,11 +456,14 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         CK(cudaMemcpyAsync(e.scanjobs.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice, ctx->stream));
         { PROF("scan_u32"); scan_u32_kernel<<<5, SCAN_THREADS, 0, ctx->stream>>>(e.scanjobs.as<ScanJob>()); }
         CKL();
-        // totals + counters back, then size the outputs
+        // totals + counters + flags back, then size the outputs and lay the blocks out
         CK(e.h_offs.ensure(o_end + 64));
         uint8_t* ho = e.h_offs.as<uint8_t>();
         CK(cudaMemcpyAsync(ho, e.offs.p, o_end, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaMemcpyAsync(ho + o_end, e.counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(e.h_flags.ensure(Lp + R + 16));
+        CK(cudaMemcpyAsync(e.h_flags.p, e.line_flags.p, Lp, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(e.h_flags.as<uint8_t>() + Lp, e.rec_flags.p, R, cudaMemcpyDeviceToHost, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream));
         const uint32_t* cnt = reinterpret_cast<const uint32_t*>(ho + o_end);
         if (cnt[2] & ERR_ALLELE) { ctx->err = "Unknown allele error !"; return XSI_E_ALLELE; }
@@ -499,19 +503,108 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
             { PROF("pack_wah"); pack_wah_kernel<<<(uint32_t)((jobs6 + E6_WARPS - 1) / E6_WARPS), E6_WARPS * 32, 0, ctx->stream>>>(p, em); }
             CKL();
         }
-        // ---- results back to pinned host memory (async; collect() waits) ----
-        const size_t b_sp = 0, b_ms = b_sp + e.tot_sparse * e.aet, b_ev = b_ms + e.tot_miss * e.aet,
-                     b_wh = (b_ev + e.tot_eov * e.aet + 1) / 2 * 2, b_ph = b_wh + e.tot_wah * 2, b_end = b_ph + e.tot_phase * 2;
-        CK(e.h_out.ensure(b_end + 16));
-        uint8_t* hb = e.h_out.as<uint8_t>();
-        if (e.tot_sparse) CK(cudaMemcpyAsync(hb + b_sp, e.out_sparse.p, e.tot_sparse * e.aet, cudaMemcpyDeviceToHost, ctx->stream));
-        if (e.tot_miss) CK(cudaMemcpyAsync(hb + b_ms, e.out_miss.p, e.tot_miss * e.aet, cudaMemcpyDeviceToHost, ctx->stream));
-        if (e.tot_eov) CK(cudaMemcpyAsync(hb + b_ev, e.out_eov.p, e.tot_eov * e.aet, cudaMemcpyDeviceToHost, ctx->stream));
-        if (e.tot_wah) CK(cudaMemcpyAsync(hb + b_wh, e.out_wah.p, e.tot_wah * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        if (e.tot_phase) CK(cudaMemcpyAsync(hb + b_ph, e.out_phase.p, e.tot_phase * 2, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(e.h_flags.ensure(Lp + R + 16));
-        CK(cudaMemcpyAsync(e.h_flags.p, e.line_flags.p, Lp, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(e.h_flags.as<uint8_t>() + Lp, e.rec_flags.p, R, cudaMemcpyDeviceToHost, ctx->stream));
+        // ---- while those run: lay out every GT block (dictionary, per-line bool vectors, section offsets) in the
+        //      pinned arena, then queue the device->host copies of the sections straight into their final place ----
+        {
+            const uint64_t* off_sp = reinterpret_cast<const uint64_t*>(ho + o_sp);
+            const uint64_t* off_ms = reinterpret_cast<const uint64_t*>(ho + o_ms);
+            const uint64_t* off_ev = reinterpret_cast<const uint64_t*>(ho + o_ev);
+            const uint64_t* off_wh = reinterpret_cast<const uint64_t*>(ho + o_wh);
+            const uint64_t* off_ph = reinterpret_cast<const uint64_t*>(ho + o_ph);
+            const uint8_t* lflags = e.h_flags.as<uint8_t>();
+            const uint8_t* rflags = lflags + Lp;
+            struct Copy { uint64_t dst; const void* src; uint64_t bytes; };
+            std::vector<Copy> copies;
+            std::vector<std::vector<uint8_t>> heads(e.nb);   // dictionary + first bool vector of each block
+            struct Tail { uint64_t at; std::vector<uint8_t> bytes; };
+            std::vector<Tail> tails;                          // later bool vectors (missing / eov / phase / haploid)
+            e.block_at.assign(e.nb, 0);
+            e.block_sizes.assign(e.nb, 0);
+            e.n_wah_lines = 0;
+            uint64_t arena_size = 0;
+            for (uint32_t b = 0; b < e.nb; ++b) {
+                const uint32_t r0 = e.h_blk_rec0[b], r1 = e.h_blk_rec0[b + 1], l0 = e.h_blk_line0[b], l1 = e.h_blk_line0[b + 1];
+                const uint32_t nrec = r1 - r0, nlines = l1 - l0;
+                bool any_missing = false, any_eov = false, any_phase = false, any_hap = false;
+                uint32_t max_pl = 1;  // gt_block.hpp:168
+                std::vector<uint8_t> v_wah(nlines), v_miss(nlines, 0), v_eov(nlines, 0), v_phase(nlines, 0), v_hap(nrec, 0);
+                for (uint32_t l = l0; l < l1; ++l) { v_wah[l - l0] = (lflags[l] & LF_WAH) ? 1 : 0; e.n_wah_lines += v_wah[l - l0]; }
+                for (uint32_t r = r0; r < r1; ++r) {
+                    const uint8_t f = rflags[r];
+                    const uint32_t pl = e.h_ngt[r] / e.n_samples;
+                    max_pl = std::max(max_pl, pl);
+                    if (f & RF_HAPLOID) { any_hap = true; v_hap[r - r0] = 1; }
+                    any_missing |= (f & RF_MISSING) != 0; any_eov |= (f & RF_EOV) != 0; any_phase |= (f & RF_PHASE) != 0;
+                    // re-index record flags to the record's first binary line (gt_block.hpp:650-666)
+                    const uint32_t bl = e.h_line0[r] - l0;
+                    if (bl < nlines) {
+                        if (f & RF_MISSING) v_miss[bl] = 1;
+                        if (f & RF_EOV) v_eov[bl] = 1;
+                        if (f & RF_PHASE) v_phase[bl] = 1;
+                    }
+                }
+                // dictionary, insertion sequence of GtBlock::fill_dictionary (gt_block.hpp:464-510)
+                RefDictOrder ord;
+                std::map<uint32_t, uint32_t> val;
+                auto ins = [&](uint32_t k, uint32_t v) { ord.insert(k); val[k] = v; };
+                ins(KEY_BCF_LINES, nrec); ins(KEY_BINARY_LINES, nlines); ins(KEY_MAX_LINE_PLOIDY, max_pl);
+                ins(KEY_DEFAULT_PHASING, (uint32_t)e.default_phasing); ins(KEY_WEIRDNESS_STRATEGY, WS_SPARSE);
+                ins(KEY_LINE_SORT, VAL_UNDEFINED); ins(KEY_LINE_SELECT, VAL_UNDEFINED); ins(KEY_MATRIX_WAH, VAL_UNDEFINED);
+                ins(KEY_MATRIX_SPARSE, VAL_UNDEFINED);
+                if (any_missing) { ins(KEY_LINE_MISSING, VAL_UNDEFINED); ins(KEY_MATRIX_MISSING, VAL_UNDEFINED); ins(KEY_MATRIX_MISSING_SPARSE, VAL_UNDEFINED); }
+                if (any_eov) { ins(KEY_LINE_END_OF_VECTORS, VAL_UNDEFINED); ins(KEY_MATRIX_END_OF_VECTORS, VAL_UNDEFINED); ins(KEY_MATRIX_END_OF_VECTORS_SPARSE, VAL_UNDEFINED); }
+                if (any_phase) { ins(KEY_LINE_NON_UNIFORM_PHASING, VAL_UNDEFINED); ins(KEY_MATRIX_NON_UNIFORM_PHASING, VAL_UNDEFINED); }
+                if (any_hap) ins(KEY_LINE_HAPLOID, VAL_UNDEFINED);
+                const std::vector<uint32_t> order = ord.order();
+
+                const uint64_t base = arena_size;
+                e.block_at[b] = base;
+                std::vector<uint8_t>& head = heads[b];
+                put_u32(head, 0xFFFFFFFFu);
+                put_u32(head, (uint32_t)order.size());
+                const size_t dict_at = head.size();
+                head.resize(head.size() + order.size() * 8);
+                // write_writables, gt_block.hpp:512-647
+                val[KEY_LINE_SORT] = val[KEY_LINE_SELECT] = (uint32_t)head.size();
+                wah16_encode_bools(v_wah, head);
+                uint64_t pos = head.size();  // running size of the block
+                auto section = [&](uint32_t key, const void* dev, uint64_t first, uint64_t last, uint32_t unit) {
+                    val[key] = (uint32_t)pos;
+                    const uint64_t bytes = (last - first) * unit;
+                    if (bytes) copies.push_back({base + pos, (const uint8_t*)dev + first * unit, bytes});
+                    pos += bytes;
+                };
+                auto boolvec = [&](uint32_t key, const std::vector<uint8_t>& v) {
+                    val[key] = (uint32_t)pos;
+                    Tail t; t.at = base + pos;
+                    wah16_encode_bools(v, t.bytes);
+                    pos += t.bytes.size();
+                    tails.push_back(std::move(t));
+                };
+                section(KEY_MATRIX_WAH, e.out_wah.p, off_wh[l0], off_wh[l1], 2);
+                section(KEY_MATRIX_SPARSE, e.out_sparse.p, off_sp[l0], off_sp[l1], e.aet);
+                if (any_missing) { boolvec(KEY_LINE_MISSING, v_miss); section(KEY_MATRIX_MISSING_SPARSE, e.out_miss.p, off_ms[r0], off_ms[r1], e.aet); }
+                if (any_eov) { boolvec(KEY_LINE_END_OF_VECTORS, v_eov); section(KEY_MATRIX_END_OF_VECTORS_SPARSE, e.out_eov.p, off_ev[r0], off_ev[r1], e.aet); }
+                if (any_phase) { boolvec(KEY_LINE_NON_UNIFORM_PHASING, v_phase); section(KEY_MATRIX_NON_UNIFORM_PHASING, e.out_phase.p, off_ph[r0], off_ph[r1], 2); }
+                if (any_hap) boolvec(KEY_LINE_HAPLOID, v_hap);  // one bit per BCF line, gt_block.hpp:219-224,639-642
+                for (size_t i = 0; i < order.size(); ++i) {
+                    memcpy(head.data() + dict_at + 8 * i, &order[i], 4);
+                    const uint32_t v = val[order[i]];
+                    memcpy(head.data() + dict_at + 8 * i + 4, &v, 4);
+                }
+                e.block_sizes[b] = pos;
+                arena_size = (base + pos + 15) / 16 * 16;
+            }
+            CK(e.arena.ensure(arena_size + 16));
+            uint8_t* ar = e.arena.as<uint8_t>();
+            e.block_ptrs.assign(e.nb, nullptr);
+            for (uint32_t b = 0; b < e.nb; ++b) {
+                e.block_ptrs[b] = ar + e.block_at[b];
+                memcpy(ar + e.block_at[b], heads[b].data(), heads[b].size());
+            }
+            for (const Tail& t : tails) memcpy(ar + t.at, t.bytes.data(), t.bytes.size());
+            for (const Copy& c : copies) CK(cudaMemcpyAsync(ar + c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        }
         e.launched = true;
         return XSI_OK;
     }
@@ -525,107 +618,7 @@ extern "C" int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const ui
     auto& e = ctx->enc;
     if (!e.launched) { ctx->err = "xsi_encode_collect without a successful xsi_encode_launch"; return XSI_E_ARG; }
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));
-    const uint64_t R = e.R, L = e.L, Lp = L ? L : 1;
-    const size_t o_sp = 0, o_ms = o_sp + (L + 1) * 8, o_ev = o_ms + (R + 1) * 8, o_wh = o_ev + (R + 1) * 8, o_ph = o_wh + (L + 1) * 8;
-    const uint8_t* ho = e.h_offs.as<uint8_t>();
-    const uint64_t* off_sp = reinterpret_cast<const uint64_t*>(ho + o_sp);
-    const uint64_t* off_ms = reinterpret_cast<const uint64_t*>(ho + o_ms);
-    const uint64_t* off_ev = reinterpret_cast<const uint64_t*>(ho + o_ev);
-    const uint64_t* off_wh = reinterpret_cast<const uint64_t*>(ho + o_wh);
-    const uint64_t* off_ph = reinterpret_cast<const uint64_t*>(ho + o_ph);
-    const size_t b_sp = 0, b_ms = b_sp + e.tot_sparse * e.aet, b_ev = b_ms + e.tot_miss * e.aet,
-                 b_wh = (b_ev + e.tot_eov * e.aet + 1) / 2 * 2, b_ph = b_wh + e.tot_wah * 2;
-    const uint8_t* hb = e.h_out.as<uint8_t>();
-    const uint8_t* lflags = e.h_flags.as<uint8_t>();
-    const uint8_t* rflags = lflags + Lp;
-
-    e.n_wah_lines = 0;
-    for (uint64_t l = 0; l < L; ++l) e.n_wah_lines += (lflags[l] & LF_WAH) ? 1 : 0;
-    e.blocks.assign(e.nb, {});
-    e.block_ptrs.assign(e.nb, nullptr);
-    e.block_sizes.assign(e.nb, 0);
-    for (uint32_t b = 0; b < e.nb; ++b) {
-        const uint32_t r0 = e.h_blk_rec0[b], r1 = e.h_blk_rec0[b + 1], l0 = e.h_blk_line0[b], l1 = e.h_blk_line0[b + 1];
-        const uint32_t nrec = r1 - r0, nlines = l1 - l0;
-        bool any_missing = false, any_eov = false, any_phase = false, any_hap = false;
-        uint32_t max_pl = 1;  // gt_block.hpp:168
-        std::vector<uint8_t> v_wah(nlines), v_miss(nlines, 0), v_eov(nlines, 0), v_phase(nlines, 0), v_hap(nrec, 0);
-        for (uint32_t l = l0; l < l1; ++l) v_wah[l - l0] = (lflags[l] & LF_WAH) ? 1 : 0;
-        for (uint32_t r = r0; r < r1; ++r) {
-            const uint8_t f = rflags[r];
-            const uint32_t pl = e.h_ngt[r] / e.n_samples;
-            max_pl = std::max(max_pl, pl);
-            if (f & RF_HAPLOID) { any_hap = true; v_hap[r - r0] = 1; }
-            any_missing |= (f & RF_MISSING) != 0; any_eov |= (f & RF_EOV) != 0; any_phase |= (f & RF_PHASE) != 0;
-            // re-index record flags to the record's first binary line (gt_block.hpp:650-666)
-            const uint32_t bl = e.h_line0[r] - l0;
-            if (bl < nlines) {
-                if (f & RF_MISSING) v_miss[bl] = 1;
-                if (f & RF_EOV) v_eov[bl] = 1;
-                if (f & RF_PHASE) v_phase[bl] = 1;
-            }
-        }
-        // dictionary, insertion sequence of GtBlock::fill_dictionary (gt_block.hpp:464-510)
-        RefDictOrder ord;
-        std::map<uint32_t, uint32_t> val;
-        auto ins = [&](uint32_t k, uint32_t v) { ord.insert(k); val[k] = v; };
-        ins(KEY_BCF_LINES, nrec); ins(KEY_BINARY_LINES, nlines); ins(KEY_MAX_LINE_PLOIDY, max_pl);
-        ins(KEY_DEFAULT_PHASING, (uint32_t)e.default_phasing); ins(KEY_WEIRDNESS_STRATEGY, WS_SPARSE);
-        ins(KEY_LINE_SORT, VAL_UNDEFINED); ins(KEY_LINE_SELECT, VAL_UNDEFINED); ins(KEY_MATRIX_WAH, VAL_UNDEFINED);
-        ins(KEY_MATRIX_SPARSE, VAL_UNDEFINED);
-        if (any_missing) { ins(KEY_LINE_MISSING, VAL_UNDEFINED); ins(KEY_MATRIX_MISSING, VAL_UNDEFINED); ins(KEY_MATRIX_MISSING_SPARSE, VAL_UNDEFINED); }
-        if (any_eov) { ins(KEY_LINE_END_OF_VECTORS, VAL_UNDEFINED); ins(KEY_MATRIX_END_OF_VECTORS, VAL_UNDEFINED); ins(KEY_MATRIX_END_OF_VECTORS_SPARSE, VAL_UNDEFINED); }
-        if (any_phase) { ins(KEY_LINE_NON_UNIFORM_PHASING, VAL_UNDEFINED); ins(KEY_MATRIX_NON_UNIFORM_PHASING, VAL_UNDEFINED); }
-        if (any_hap) ins(KEY_LINE_HAPLOID, VAL_UNDEFINED);
-        const std::vector<uint32_t> order = ord.order();
-
-        std::vector<uint8_t>& out = e.blocks[b];
-        const uint64_t wah_bytes = (off_wh[l1] - off_wh[l0]) * 2, sp_bytes = (off_sp[l1] - off_sp[l0]) * e.aet;
-        const uint64_t ms_bytes = (off_ms[r1] - off_ms[r0]) * e.aet, ev_bytes = (off_ev[r1] - off_ev[r0]) * e.aet;
-        const uint64_t ph_bytes = (off_ph[r1] - off_ph[r0]) * 2;
-        out.reserve(8 + order.size() * 8 + wah_bytes + sp_bytes + ms_bytes + ev_bytes + ph_bytes + nlines + 64);
-        put_u32(out, 0xFFFFFFFFu);
-        put_u32(out, (uint32_t)order.size());
-        const size_t dict_at = out.size();
-        out.resize(out.size() + order.size() * 8);
-        // write_writables, gt_block.hpp:512-647
-        val[KEY_LINE_SORT] = val[KEY_LINE_SELECT] = (uint32_t)out.size();
-        wah16_encode_bools(v_wah, out);
-        val[KEY_MATRIX_WAH] = (uint32_t)out.size();
-        out.insert(out.end(), hb + b_wh + off_wh[l0] * 2, hb + b_wh + off_wh[l1] * 2);
-        val[KEY_MATRIX_SPARSE] = (uint32_t)out.size();
-        out.insert(out.end(), hb + b_sp + off_sp[l0] * e.aet, hb + b_sp + off_sp[l1] * e.aet);
-        if (any_missing) {
-            val[KEY_LINE_MISSING] = (uint32_t)out.size();
-            wah16_encode_bools(v_miss, out);
-            val[KEY_MATRIX_MISSING_SPARSE] = (uint32_t)out.size();
-            out.insert(out.end(), hb + b_ms + off_ms[r0] * e.aet, hb + b_ms + off_ms[r1] * e.aet);
-        }
-        if (any_eov) {
-            val[KEY_LINE_END_OF_VECTORS] = (uint32_t)out.size();
-            wah16_encode_bools(v_eov, out);
-            val[KEY_MATRIX_END_OF_VECTORS_SPARSE] = (uint32_t)out.size();
-            out.insert(out.end(), hb + b_ev + off_ev[r0] * e.aet, hb + b_ev + off_ev[r1] * e.aet);
-        }
-        if (any_phase) {
-            val[KEY_LINE_NON_UNIFORM_PHASING] = (uint32_t)out.size();
-            wah16_encode_bools(v_phase, out);
-            val[KEY_MATRIX_NON_UNIFORM_PHASING] = (uint32_t)out.size();
-            out.insert(out.end(), hb + b_ph + off_ph[r0] * 2, hb + b_ph + off_ph[r1] * 2);
-        }
-        if (any_hap) {
-            val[KEY_LINE_HAPLOID] = (uint32_t)out.size();
-            wah16_encode_bools(v_hap, out);  // one bit per BCF line, gt_block.hpp:219-224,639-642
-        }
-        for (size_t i = 0; i < order.size(); ++i) {
-            memcpy(out.data() + dict_at + 8 * i, &order[i], 4);
-            const uint32_t v = val[order[i]];
-            memcpy(out.data() + dict_at + 8 * i + 4, &v, 4);
-        }
-        e.block_ptrs[b] = out.data();
-        e.block_sizes[b] = out.size();
-    }
+    CK(cudaStreamSynchronize(ctx->stream));  // the sections have landed in the arena (laid out in xsi_encode_launch)
     e.collected = true;
     if (n_blocks_out) *n_blocks_out = e.nb;
     if (blocks_out) *blocks_out = e.block_ptrs.data();
