@@ -246,6 +246,76 @@ __device__ __forceinline__ uint32_t classify_bad(int32_t v) {
     return miss ? 1u : (eov ? 2u : 4u);
 }
 
+struct ScanAcc { uint32_t nmiss, neov, phase, err; };
+
+// One thread, one tile: the thread's 32 genotypes -> one word per ALT allele key-1 .. key-1+NAL-1
+// (key = (v >> 1) of the first ALT of the group).  FIRST also runs the per-record checks
+// (missing / end of vector / unknown allele, non-default phase).  `tile` points at the thread's
+// 32 genotypes in shared memory; nvalid < 32 only for the last, partially filled word of a row.
+template <int ELEM, int NAL, bool FIRST>
+__device__ __forceinline__ void scan_words(const unsigned char* __restrict__ tile, uint32_t nvalid, uint32_t rot, int32_t key,
+                                           uint32_t n_allele, int32_t dpx, uint32_t (&w)[4], ScanAcc& acc) {
+    constexpr uint32_t NCH = 32 * ELEM / 16, EPC = 16 / ELEM;
+    if (nvalid == 32) {
+#pragma unroll
+        for (uint32_t k = 0; k < NCH; ++k) {
+            const uint32_t c = (k + rot) & (NCH - 1);
+            const int4 q = *reinterpret_cast<const int4*>(tile + c * 16);
+            int32_t v[EPC];
+            if (ELEM == 4) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+            else {
+                const uint32_t qq[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+                for (uint32_t e = 0; e < EPC; ++e) v[e] = (int32_t)(int8_t)(qq[e >> 2] >> (8 * (e & 3)));
+            }
+            bool badc = false;
+#pragma unroll
+            for (uint32_t e = 0; e < EPC; ++e) {
+                const int32_t h = v[e] >> 1;
+                const uint32_t bitv = 1u << (k * EPC + e);
+                if (h == key) w[0] |= bitv;
+                if (NAL > 1 && h == key + 1) w[1] |= bitv;
+                if (NAL > 2 && h == key + 2) w[2] |= bitv;
+                if (NAL > 3 && h == key + 3) w[3] |= bitv;
+                if (FIRST) {
+                    badc |= (uint32_t)(h - 1) >= n_allele;
+                    if (e & 1) acc.phase |= (uint32_t)(v[e] ^ dpx);
+                }
+            }
+            if (FIRST && badc) {
+#pragma unroll
+                for (uint32_t e = 0; e < EPC; ++e) {
+                    if ((uint32_t)((v[e] >> 1) - 1) >= n_allele) {
+                        const uint32_t cl = classify_bad<ELEM>(v[e]);
+                        acc.nmiss += cl & 1u; acc.neov += (cl >> 1) & 1u; acc.err |= cl >> 2;
+                    }
+                }
+            }
+        }
+        // undo the chunk rotation: chunk k of w[] is genotype chunk (k + rot)
+        const uint32_t sh = rot * EPC;
+#pragma unroll
+        for (int a = 0; a < NAL; ++a) w[a] = __funnelshift_l(w[a], w[a], sh);
+    } else if (nvalid) {  // the one partially filled word of the row
+        for (uint32_t e = 0; e < nvalid; ++e) {
+            const int32_t v = tile_value<ELEM>(tile, e);
+            const int32_t h = v >> 1;
+            const uint32_t bitv = 1u << e;
+            if (h == key) w[0] |= bitv;
+            if (NAL > 1 && h == key + 1) w[1] |= bitv;
+            if (NAL > 2 && h == key + 2) w[2] |= bitv;
+            if (NAL > 3 && h == key + 3) w[3] |= bitv;
+            if (FIRST) {
+                if (e & 1) acc.phase |= (uint32_t)(v ^ dpx);
+                if ((uint32_t)(h - 1) >= n_allele) {
+                    const uint32_t cl = classify_bad<ELEM>(v);
+                    acc.nmiss += cl & 1u; acc.neov += (cl >> 1) & 1u; acc.err |= cl >> 2;
+                }
+            }
+        }
+    }
+}
+
 template <int ELEM>
 __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -314,68 +384,17 @@ __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
             const uint32_t nvalid = (data && ngt > elem0) ? min(32u, ngt - elem0) : 0u;
             for (uint32_t alt0 = 1; alt0 < n_allele || alt0 == 1; alt0 += 4) {
                 const uint32_t nal = n_allele > alt0 ? min(4u, n_allele - alt0) : 0u;
-                const int32_t key = (int32_t)alt0 + 1;  // (v >> 1) of ALT alt0
-                uint32_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
-                if (nvalid == 32) {
-#pragma unroll
-                    for (uint32_t k = 0; k < NCH; ++k) {
-                        const uint32_t c = (k + rot) & (NCH - 1);
-                        const int4 q = *reinterpret_cast<const int4*>(tile + c * 16);
-                        int32_t v[EPC];
-                        if (ELEM == 4) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
-                        else {
-                            const uint32_t qq[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
-#pragma unroll
-                            for (uint32_t e = 0; e < EPC; ++e) v[e % EPC] = (int32_t)(int8_t)(qq[e >> 2] >> (8 * (e & 3)));
-                        }
-                        bool badc = false;
-#pragma unroll
-                        for (uint32_t e = 0; e < EPC; ++e) {
-                            const int32_t h = v[e] >> 1;
-                            const uint32_t bitv = 1u << (k * EPC + e);
-                            if (h == key) w0 |= bitv;
-                            if (nal > 1 && h == key + 1) w1 |= bitv;
-                            if (nal > 2 && h == key + 2) w2 |= bitv;
-                            if (nal > 3 && h == key + 3) w3 |= bitv;
-                            if (alt0 == 1) {
-                                badc |= (uint32_t)(h - 1) >= n_allele;
-                                if (e & 1) phase |= (uint32_t)(v[e] ^ dpx);
-                            }
-                        }
-                        if (alt0 == 1 && badc) {
-#pragma unroll
-                            for (uint32_t e = 0; e < EPC; ++e) {
-                                if ((uint32_t)((v[e] >> 1) - 1) >= n_allele) {
-                                    const uint32_t cl = classify_bad<ELEM>(v[e]);
-                                    nmiss += cl & 1u; neov += (cl >> 1) & 1u; err |= cl >> 2;
-                                }
-                            }
-                        }
-                    }
-                    // undo the chunk rotation: chunk k of w* is genotype chunk (k + rot)
-                    const uint32_t sh = rot * (EPC);
-                    w0 = __funnelshift_l(w0, w0, sh);
-                    if (nal > 1) w1 = __funnelshift_l(w1, w1, sh);
-                    if (nal > 2) w2 = __funnelshift_l(w2, w2, sh);
-                    if (nal > 3) w3 = __funnelshift_l(w3, w3, sh);
-                } else if (nvalid) {  // the one partially filled word of the row
-                    for (uint32_t e = 0; e < nvalid; ++e) {
-                        const int32_t v = tile_value<ELEM>(tile, e);
-                        const int32_t h = v >> 1;
-                        const uint32_t bitv = 1u << e;
-                        if (h == key) w0 |= bitv;
-                        if (nal > 1 && h == key + 1) w1 |= bitv;
-                        if (nal > 2 && h == key + 2) w2 |= bitv;
-                        if (nal > 3 && h == key + 3) w3 |= bitv;
-                        if (alt0 == 1) {
-                            if (e & 1) phase |= (uint32_t)(v ^ dpx);
-                            if ((uint32_t)(h - 1) >= n_allele) {
-                                const uint32_t cl = classify_bad<ELEM>(v);
-                                nmiss += cl & 1u; neov += (cl >> 1) & 1u; err |= cl >> 2;
-                            }
-                        }
-                    }
+                uint32_t w[4] = {0, 0, 0, 0};
+                ScanAcc acc = {nmiss, neov, phase, err};
+                if (alt0 == 1) {
+                    if (nal <= 1) scan_words<ELEM, 1, true>(tile, nvalid, rot, (int32_t)alt0 + 1, n_allele, dpx, w, acc);
+                    else if (nal == 2) scan_words<ELEM, 2, true>(tile, nvalid, rot, (int32_t)alt0 + 1, n_allele, dpx, w, acc);
+                    else scan_words<ELEM, 4, true>(tile, nvalid, rot, (int32_t)alt0 + 1, n_allele, dpx, w, acc);
+                } else {
+                    scan_words<ELEM, 4, false>(tile, nvalid, rot, (int32_t)alt0 + 1, n_allele, dpx, w, acc);
                 }
+                nmiss = acc.nmiss; neov = acc.neov; phase = acc.phase; err = acc.err;
+                const uint32_t w0 = w[0], w1 = nal > 1 ? w[1] : 0u, w2 = nal > 2 ? w[2] : 0u, w3 = nal > 3 ? w[3] : 0u;
                 if (wi < p.WS) {
                     uint32_t* row = p.bitrows + (size_t)(line0 + alt0 - 1) * p.WS + wi;
                     if (nal > 0) row[0] = w0;
