@@ -879,19 +879,21 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     bool any_hap_job = false;
     for (uint32_t j = 0; j < d.n_gt_jobs; ++j) any_hap_job |= job_hap[j] != 0;
     const uint32_t TWv2 = 2 * d.WS + 4;
-    uint32_t un_warps = 0, un_slices = 0;
+    uint32_t un_warps = 0, un_slices = 0, un_wpw = 32;
     size_t un_smem = 0;
     const bool use_v2 = d.n_gt_jobs && !any_hap_job && N <= 65534 && !getenv("XSI_PBWT_V1");
     if (use_v2) {
-        const uint32_t Wn = (N + 31) / 32, chunks = (Wn + 31) / 32;  // 32-word (1024-haplotype) chunks
-        uint32_t target = (2 * (uint32_t)ctx->sm_count + n_blocks - 1) / n_blocks;
-        un_warps = (chunks + target - 1) / target;
-        const uint32_t min_warps = std::min<uint32_t>(chunks, 4);
-        if (un_warps < min_warps) un_warps = min_warps;
-        if (const char* sw = getenv("XSI_UNPERM_WARPS")) { const int v = atoi(sw); if (v >= 1 && v <= 32) un_warps = std::min<uint32_t>(chunks, (uint32_t)v); }
-        if (un_warps > 32) un_warps = 32;
-        un_slices = (chunks + un_warps - 1) / un_warps;
-        un_smem = (size_t)un_warps * 2048 + (size_t)D2_STAGES * TWv2 * 4 + 2 * D2_STAGES * 8;
+        // words per warp: the largest of 32/16/8 that still puts ~24 warps on every SM
+        const uint32_t Wn = (N + 31) / 32;
+        const uint64_t want = (uint64_t)ctx->sm_count * 24;
+        un_wpw = 8;
+        for (uint32_t w : {32u, 16u}) if ((uint64_t)n_blocks * ((Wn + w - 1) / w) >= want) { un_wpw = w; break; }
+        if (const char* sw = getenv("XSI_UNPERM_WPW")) { const int v = atoi(sw); if (v == 8 || v == 16 || v == 32) un_wpw = (uint32_t)v; }
+        const uint32_t warps_total = (Wn + un_wpw - 1) / un_wpw;
+        un_warps = std::min<uint32_t>(16, warps_total);
+        if (const char* sw = getenv("XSI_UNPERM_WARPS")) { const int v = atoi(sw); if (v >= 1 && v <= 32) un_warps = std::min<uint32_t>(warps_total, (uint32_t)v); }
+        un_slices = (warps_total + un_warps - 1) / un_warps;
+        un_smem = (size_t)un_warps * un_wpw * 64 + (size_t)D2_STAGES * TWv2 * 4 + 2 * D2_STAGES * 8;
     }
     const bool v2_ok = use_v2 && un_smem <= ctx->smem_optin;
     dd.tabs = nullptr; dd.TW = TWv2; dd.n_gt_jobs = d.n_gt_jobs;
@@ -902,8 +904,12 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
 
     // ---- kernels ----
     if (nsp + nms + nev) {
-        { PROF("sparse_index"); sparse_index_kernel<<<(n_blocks * 3 + 63) / 64, 64, 0, ctx->stream>>>(dd); }
+        // latency-bound list walk: runs beside the WAH pipeline on the side stream, joined before the error read
+        CK(cudaEventRecord(ctx->ev_side, ctx->stream));
+        CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_side, 0));
+        sparse_index_kernel<<<(n_blocks * 3 + 63) / 64, 64, 0, ctx->stream2>>>(dd);
         CKL();
+        CK(cudaEventRecord(ctx->ev_side, ctx->stream2));
     }
     if (njobs) {
         { PROF("wah_tile_sum"); wah_tile_sum_kernel<<<ntiles, D0_THREADS, 0, ctx->stream>>>(dd); }
@@ -922,8 +928,17 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
         { PROF("wah_expand"); wah_expand_kernel<<<(njobs + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(dd, wpc, Gpad, Tpad); }
         CKL();
         if (v2_ok) {
-            CK(cudaFuncSetAttribute(pbwt_unpermute_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)un_smem));
-            { PROF("pbwt_unpermute"); pbwt_unpermute_v2_kernel<<<dim3(n_blocks, un_slices), un_warps * 32, un_smem, ctx->stream>>>(dd); }
+            const dim3 g(n_blocks, un_slices);
+            if (un_wpw == 32) {
+                CK(cudaFuncSetAttribute(pbwt_unpermute_v2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)un_smem));
+                PROF("pbwt_unpermute"); pbwt_unpermute_v2_kernel<32><<<g, un_warps * 32, un_smem, ctx->stream>>>(dd);
+            } else if (un_wpw == 16) {
+                CK(cudaFuncSetAttribute(pbwt_unpermute_v2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)un_smem));
+                PROF("pbwt_unpermute"); pbwt_unpermute_v2_kernel<16><<<g, un_warps * 32, un_smem, ctx->stream>>>(dd);
+            } else {
+                CK(cudaFuncSetAttribute(pbwt_unpermute_v2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)un_smem));
+                PROF("pbwt_unpermute"); pbwt_unpermute_v2_kernel<8><<<g, un_warps * 32, un_smem, ctx->stream>>>(dd);
+            }
             CKL();
         } else if (d.n_gt_jobs) {
             const uint32_t W = (N + 31) / 32;
@@ -951,6 +966,7 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
             }
         }
     }
+    if (nsp + nms + nev) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
     uint32_t herr = 0;
     CK(cudaMemcpyAsync(&herr, d.err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
