@@ -11,6 +11,8 @@
 //   E6 pack_wah         gather the per-line WAH words into the contiguous per-block matrix
 //   scan_u32            exclusive prefix sums for the output offsets
 #pragma once
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace xsi {
@@ -711,6 +713,160 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v2_kernel(EncDev p) {
         }
         __syncthreads();  // #2: a[] updated
     }
+}
+
+// =============================================================================================
+// E3 v3: PBWT permute on a thread-block CLUSTER (diploid lines, <= 65534 haplotypes).
+// State is the inverse permutation pos[i] (current position of haplotype i), sliced over the C
+// CTAs of a cluster (distributed shared memory); one cluster per PBWT block.  Per WAH line:
+//   1  every CTA scatters the carriers of its haplotype slice: ypart[pos[i]] = 1   (local atomics)
+//   -- every CTA arrives on every CTA's "bitmaps ready" mbarrier (one release per CTA, not a cluster barrier) --
+//   2  CTA c ORs word slice c of all C partial bitmaps (DSMEM loads), writes the permuted row slice
+//      to global (in place), turns it into table entries  T[chunk] = zeros-before-in-slice<<16 | 16 bits
+//      and stores them, with the slice's zero total, into EVERY CTA's table (DSMEM stores)
+//   -- same with the "table ready" mbarrier --
+//   3  pos[i] <- y[j] ? Z + j - zb(j) : zb(j),  j = pos[i],  zb(j) = base[slice(j)] + T lookup
+// With C CTAs the per-line critical path shrinks ~C-fold (phases 1 and 3), which is what matters
+// when a batch has fewer blocks than the GPU has SMs.  C = 1 runs the same code without DSMEM.
+// dynamic smem: pos[NW*WPW*32] u16 | ypart[C*WSL] u32 | T[2*C*WSL] u32 | zs[8] | base[8] | sc[36] | mbar[2]
+// =============================================================================================
+namespace cgx = cooperative_groups;
+
+struct PermV3Cfg { uint32_t C, WSL, SH, NW, WPW; };  // WSL = words per slice (power of 2), SH = log2(WSL*32)
+
+template <int C>
+__global__ void __launch_bounds__(1024, 1) pbwt_permute_v3_kernel(EncDev p, PermV3Cfg cfg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t N = 2 * p.n_samples, WS = p.WS;
+    const uint32_t WSL = cfg.WSL, WPW = cfg.WPW, NW = cfg.NW, SH = cfg.SH;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, nthr = blockDim.x;
+    const uint32_t WT = C * WSL;  // words of the padded row
+    uint16_t* pos = reinterpret_cast<uint16_t*>(smem_raw);
+    const uint32_t WTa = (WT + 3) & ~3u;  // keep the table 16-byte aligned
+    uint32_t* ypart = reinterpret_cast<uint32_t*>(smem_raw + (((size_t)NW * WPW * 64 + 15) & ~(size_t)15));
+    uint32_t* T = ypart + WTa;
+    uint32_t* zs = T + 2 * WTa;
+    uint32_t* base = zs + 8;
+    uint32_t* sc = base + 8;  // [0..31] warp totals of the slice scan, [32] Z
+    uint64_t* mb = reinterpret_cast<uint64_t*>(sc + 36);  // [0] partial bitmaps ready, [1] table slices ready (C arrivals each)
+    uint32_t crank = 0;
+    if (C > 1) crank = cgx::this_cluster().block_rank();
+    const uint32_t b = blockIdx.x / C;
+    const uint32_t l0 = p.blk_line0[b], nwah = p.blk_nwah[b];
+    const uint32_t* list = p.wah_list + l0;
+    const uint32_t sw0 = crank * WSL;            // first row word of this CTA's slice
+    const uint32_t ww0 = sw0 + warp * WPW;       // first row word of this warp
+    uint16_t* mypos = pos + warp * WPW * 32 + lane;
+    for (uint32_t q = 0; q < WPW; ++q) mypos[q * 32] = (uint16_t)((ww0 + q) * 32 + lane);
+    for (uint32_t i = tid; i < WT; i += nthr) ypart[i] = 0;
+    const uint32_t ypart_sa = smem_u32(ypart), T_sa = smem_u32(T), zs_sa = smem_u32(zs);  // shared-window addresses
+    const uint32_t mb_sa = smem_u32(mb);
+    if (C > 1 && tid == 0) { mbar_init(&mb[0], C); mbar_init(&mb[1], C); }
+    if (C > 1) cgx::this_cluster().sync(); else __syncthreads();
+    // row words of this warp for the coming line: lane l keeps words l, l+32 (WPW <= 64)
+    auto load_words = [&](uint32_t line, uint32_t& a0, uint32_t& a1) {
+        const uint32_t* row = p.bitrows + (size_t)line * WS;
+        const uint32_t w_a = ww0 + lane, w_b = ww0 + 32 + lane;
+        a0 = (lane < WPW && w_a < WS) ? row[w_a] : 0u;
+        a1 = (lane + 32 < WPW && w_b < WS) ? row[w_b] : 0u;
+    };
+    uint32_t cur0 = 0, cur1 = 0, nxt0 = 0, nxt1 = 0;
+    if (nwah) load_words(list[0] & 0x7FFFFFFFu, cur0, cur1);
+    const uint32_t pad_zeros = WT * 32 - N;  // phantom zero positions past N (all in the last slices)
+    for (uint32_t k = 0; k < nwah; ++k) {
+        const uint32_t line = list[k] & 0x7FFFFFFFu;
+        if (k + 1 < nwah) load_words(list[k + 1] & 0x7FFFFFFFu, nxt0, nxt1);
+        // ---- 1: scatter the carriers of this slice ----
+        for (uint32_t q = 0; q < WPW; ++q) {
+            const uint32_t wq = __shfl_sync(XSI_FULL, q < 32 ? cur0 : cur1, q & 31);
+            if (wq == 0) continue;  // warp-uniform: no carrier among these 32 haplotypes
+            if ((wq >> lane) & 1u) {
+                const uint32_t j = mypos[q * 32];
+                atomicOr(&ypart[j >> 5], 1u << (j & 31));
+            }
+        }
+        __syncthreads();  // this CTA's partial bitmap is complete
+        if (C > 1) {
+            if (tid < C) mbar_arrive_cluster(mapa_u32(mb_sa, tid));  // tell every CTA of the cluster
+            mbar_wait_cluster(&mb[0], k & 1u);                        // ... and wait until all of theirs are
+        }
+        // ---- 2: combine word slice `crank`, zero-prefix inside the slice, publish table entries ----
+        uint32_t run = 0;  // zeros of this thread's words so far (threads own consecutive words: tid*K ..)
+        const uint32_t K = (WSL + nthr - 1) / nthr;  // words per thread
+        uint32_t yw[2] = {0, 0};
+        for (uint32_t kk = 0; kk < K; ++kk) {
+            const uint32_t w = tid * K + kk;
+            uint32_t y = 0;
+            if (w < WSL) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) y |= (C > 1) ? ld_cluster_u32(mapa_u32(ypart_sa + 4 * (sw0 + w), c)) : ypart[sw0 + w];
+            }
+            yw[kk & 1] = y;
+            run += (w < WSL) ? 32u - __popc(y) : 0u;
+        }
+        uint32_t incl = run;
+#pragma unroll
+        for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, dd); if (lane >= (uint32_t)dd) incl += o; }
+        if (lane == 31) sc[warp] = incl;
+        __syncthreads();
+        {
+            const uint32_t wv = lane < (nthr >> 5) ? sc[lane] : 0u;
+            const uint32_t wbase = __reduce_add_sync(XSI_FULL, lane < warp ? wv : 0u);
+            const uint32_t total = __reduce_add_sync(XSI_FULL, wv);
+            uint32_t zp = wbase + incl - run;
+            for (uint32_t kk = 0; kk < K; ++kk) {
+                const uint32_t w = tid * K + kk;
+                if (w < WSL) {
+                    const uint32_t y = yw[kk & 1];
+                    const uint32_t e0 = (zp << 16) | (y & 0xFFFFu);
+                    const uint32_t zmid = zp + 16u - __popc(y & 0xFFFFu);
+                    const uint32_t e1 = (zmid << 16) | (y >> 16);
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        if (C > 1) st_cluster_v2(mapa_u32(T_sa + 8 * (sw0 + w), c), e0, e1);
+                        else *reinterpret_cast<uint2*>(T + 2 * (sw0 + w)) = make_uint2(e0, e1);
+                    }
+                    const uint32_t gw = sw0 + w;
+                    if (gw < WS) p.bitrows[(size_t)line * WS + gw] = y;  // permuted row, in place
+                    zp += 32u - __popc(y);
+                }
+            }
+            if (tid == 0) {
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    if (C > 1) st_cluster_u32(mapa_u32(zs_sa + 4 * crank, c), total);
+                    else zs[crank] = total;
+                }
+            }
+        }
+        __syncthreads();  // this CTA's table slice is stored everywhere
+        if (C > 1) {
+            if (tid < C) mbar_arrive_cluster(mapa_u32(mb_sa + 8, tid));
+            mbar_wait_cluster(&mb[1], k & 1u);  // every slice of the table has landed here; my ypart is no longer read
+        }
+        // ---- slice bases, clear the partial bitmap for the next line ----
+        if (tid == 0) {
+            uint32_t acc = 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c) { base[c] = acc; acc += zs[c]; }
+            sc[32] = acc - pad_zeros;  // Z: zeros among the N real positions
+        }
+        for (uint32_t i = tid; i < WT; i += nthr) ypart[i] = 0;
+        __syncthreads();
+        // ---- 3: pos[i] <- y[j] ? Z + j - zb(j) : zb(j) ----
+        const uint32_t Z = sc[32];
+#pragma unroll 4
+        for (uint32_t q = 0; q < WPW; ++q) {
+            const uint32_t j = mypos[q * 32];
+            const uint32_t e = T[j >> 4];
+            const uint32_t s = j & 15u;
+            uint32_t zb = (e >> 16) + __popc(~e & ((1u << s) - 1u));
+            if (C > 1) zb += base[j >> SH];
+            mypos[q * 32] = (uint16_t)(((e >> s) & 1u) ? Z + j - zb : zb);
+        }
+        cur0 = nxt0; cur1 = nxt1;
+    }
+    if (C > 1) cgx::this_cluster().sync();  // nobody exits while a peer may still touch its shared memory
 }
 
 // generic fallback for > 65536 haplotypes: a[] ping-pongs in global memory (L2 resident)

@@ -254,9 +254,77 @@ int launch_permute_v2(xsi_ctx* ctx, const EncDev& p, uint32_t NW, size_t smem) {
     return XSI_OK;
 }
 
+template <int C>
+int launch_permute_v3(xsi_ctx* ctx, const EncDev& p, const PermV3Cfg& cfg, size_t smem, bool probe_only, int* max_clusters) {
+    CK(cudaFuncSetAttribute(pbwt_permute_v3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(p.nb * C); lc.blockDim = dim3(cfg.NW * 32); lc.dynamicSmemBytes = smem; lc.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = C > 1 ? 1 : 0;
+    if (probe_only) {
+        *max_clusters = 1 << 30;
+        if (C > 1) CK(cudaOccupancyMaxActiveClusters(max_clusters, pbwt_permute_v3_kernel<C>, &lc));
+        return XSI_OK;
+    }
+    { PROF("pbwt_permute"); CK(cudaLaunchKernelEx(&lc, pbwt_permute_v3_kernel<C>, p, cfg)); }
+    CKL();
+    return XSI_OK;
+}
+
+PermV3Cfg permute_v3_cfg(uint32_t W, uint32_t C, size_t* smem) {
+    PermV3Cfg c;
+    c.C = C;
+    uint32_t per = (W + C - 1) / C, wsl = 1, sh = 5;
+    while (wsl < per) { wsl *= 2; ++sh; }
+    c.WSL = wsl; c.SH = sh;
+    c.NW = std::min<uint32_t>(32, wsl);
+    c.WPW = wsl / c.NW;
+    const size_t WTa = ((size_t)C * wsl + 3) & ~(size_t)3;
+    *smem = (((size_t)c.NW * c.WPW * 64 + 15) & ~(size_t)15) + WTa * 4 + 2 * WTa * 4 + (8 + 8 + 36) * 4 + 16;
+    return c;
+}
+
+int run_permute_v3(xsi_ctx* ctx, const EncDev& p, uint32_t W, bool* done) {
+    *done = false;
+    int forced = 0;
+    if (const char* s = getenv("XSI_PBWT_CLUSTER")) forced = atoi(s);
+    for (uint32_t C : {8u, 4u, 2u, 1u}) {
+        if (forced && (uint32_t)forced != C) continue;
+        if (!forced && C > 1 && (uint64_t)p.nb * C > (uint64_t)ctx->sm_count) continue;
+        size_t smem = 0;
+        const PermV3Cfg cfg = permute_v3_cfg(W, C, &smem);
+        if (smem > ctx->smem_optin || cfg.WPW > 64 || (uint64_t)C * cfg.WSL * 32 > 65536) continue;
+        int maxc = 0, rc;
+        switch (C) {
+            case 8: rc = launch_permute_v3<8>(ctx, p, cfg, smem, true, &maxc); break;
+            case 4: rc = launch_permute_v3<4>(ctx, p, cfg, smem, true, &maxc); break;
+            case 2: rc = launch_permute_v3<2>(ctx, p, cfg, smem, true, &maxc); break;
+            default: rc = launch_permute_v3<1>(ctx, p, cfg, smem, true, &maxc); break;
+        }
+        if (rc) return rc;
+        if (!forced && C > 1 && (uint32_t)maxc < p.nb) continue;  // the clusters would not all be resident at once
+        switch (C) {
+            case 8: rc = launch_permute_v3<8>(ctx, p, cfg, smem, false, &maxc); break;
+            case 4: rc = launch_permute_v3<4>(ctx, p, cfg, smem, false, &maxc); break;
+            case 2: rc = launch_permute_v3<2>(ctx, p, cfg, smem, false, &maxc); break;
+            default: rc = launch_permute_v3<1>(ctx, p, cfg, smem, false, &maxc); break;
+        }
+        *done = rc == XSI_OK;
+        return rc;
+    }
+    return XSI_OK;
+}
+
 int run_permute(xsi_ctx* ctx, const EncDev& p) {
     const uint32_t N = 2 * p.n_samples;
     const uint32_t W = (N + 31) / 32;
+    if (!ctx->enc.any_haploid && N <= 65534 && !getenv("XSI_PBWT_V1") && !getenv("XSI_PBWT_V2")) {
+        bool done = false;
+        const int rc = run_permute_v3(ctx, p, W, &done);
+        if (rc || done) return rc;
+    }
     if (!ctx->enc.any_haploid && N <= 65534 && !getenv("XSI_PBWT_V1")) {
         int wpw = 1;
         while ((W + wpw - 1) / wpw > 32) wpw *= 2;
