@@ -96,6 +96,39 @@ __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity
         : "memory");
 }
 
+// Asynchronous stores into another CTA's shared memory that complete transaction bytes on an mbarrier of
+// that CTA (both addresses from mapa_u32).  The receiver only waits on its own mbarrier: no release /
+// acquire fence at cluster scope (which ptxas turns into MEMBAR.ALL.GPU + CCTL.IVALL) is involved.
+__device__ __forceinline__ void st_async_b32(uint32_t cluster_addr, uint32_t v, uint32_t cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];" ::"r"(cluster_addr), "r"(v),
+                 "r"(cluster_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_v2(uint32_t cluster_addr, uint32_t a, uint32_t b, uint32_t cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v2.b32 [%0], {%1, %2}, [%3];" ::"r"(cluster_addr),
+                 "r"(a), "r"(b), "r"(cluster_mbar)
+                 : "memory");
+}
+__device__ __forceinline__ void st_async_v4(uint32_t cluster_addr, uint4 v, uint32_t cluster_mbar) {
+    asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.v4.b32 [%0], {%1, %2, %3, %4}, [%5];" ::"r"(
+                     cluster_addr),
+                 "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"(cluster_mbar)
+                 : "memory");
+}
+// predicated OR into a shared-memory word (32-bit shared-window address, no generic-address arithmetic, no branch)
+__device__ __forceinline__ void red_or_shared_if(uint32_t test, uint32_t saddr, uint32_t val) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %0, 0;\n"
+        "@p red.shared::cta.or.b32 [%1], %2;\n"
+        "}\n" ::"r"(test),
+        "r"(saddr), "r"(val)
+        : "memory");
+}
+// barrier among the first `nthreads` threads of the CTA (a multiple of 32), hardware barrier 1
+__device__ __forceinline__ void named_bar_sync1(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
+
 // ---- genotype value helpers (htslib/vcf.h:892-898) ------------------------------------------
 template <int ELEM>
 __device__ __forceinline__ int32_t load_gt(const void* base, uint64_t idx) {

@@ -869,6 +869,204 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v3_kernel(EncDev p, Perm
     if (C > 1) cgx::this_cluster().sync();  // nobody exits while a peer may still touch its shared memory
 }
 
+// =============================================================================================
+// E3 v4: PBWT permute on a thread-block cluster with a fence-free exchange (diploid lines,
+// <= 65534 haplotypes).  Same formulation as v3 (inverse permutation pos[i], sliced over the C
+// CTAs of a cluster) with three changes that remove its stalls (ncu r01: CCTL.IVALL + MEMBAR.ALL.GPU
+// of the cluster-scope release/acquire pairs were 30% of all samples, barrier stalls another 12%):
+//   * every cross-CTA transfer is a PUSH with st.async (..mbarrier::complete_tx::bytes): the sender
+//     stores into the receiver's shared memory and the hardware completes transaction bytes on the
+//     receiver's mbarrier; the receiver waits on its own mbarrier only.  No cluster-scope fence.
+//   * pos[] lives in REGISTERS: thread t owns KH consecutive haplotypes (two uint16 per register) and
+//     reads its KH bits of a natural bit-row with one coalesced load, prefetched four lines ahead.
+//   * the pos update of line k and the scatter of line k+1's carriers are one fused pass.
+// Per WAH line k and CTA c (slice = WSL row words = WSL*32 positions):
+//   0  (fused with step 3 of line k-1)  ypart[pos[i]] = 1 for the carriers i of this CTA's haplotypes
+//   -- __syncthreads --
+//   1  push ypart word slice d to CTA d (st.async.v4 -> ystage[c] of d, mbY of d), d != c; clear it
+//   -- wait own mbY: the C-1 foreign partial slices have landed --
+//   2  first WSL/WPT threads: y = OR of the C partial slices; permuted row slice -> global (in place);
+//      zero prefix inside the slice (warp scan + named barrier); T[chunk] = zeros-before-in-slice<<16 |
+//      16 inverted bits, stored locally and pushed to every other CTA (st.async.v2 -> T, mbT) with the slice total
+//   -- every thread arrives on own mbT; wait: whole table here, everybody done with step 2 --
+//   3  pos[i] <- x_k[i] ? Z + j - zb(j) : zb(j),  j = pos[i],  zb(j) = base[slice(j)] + T lookup;
+//      the slice bases sit in lanes 0..C-1 of every warp and are fetched with one SHFL.
+// dynamic smem (u32): ypart[WT] | ystage[C][WSL] | T[2*WT] | zs[8] | sc[32] | mbar[2] (u64),  WT = C*WSL
+// =============================================================================================
+struct PermV4Cfg { uint32_t WSL, SH; };  // WSL = words per slice (power of 2, >= 32), SH = log2(WSL*32)
+
+template <int C, int KH>
+__global__ void __launch_bounds__(1024, 1) pbwt_permute_v4_kernel(EncDev p, PermV4Cfg cfg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int XW = KH == 64 ? 2 : 1;   // 32-bit words holding this thread's KH bits of a bit-row
+    constexpr int WPT = KH == 64 ? 2 : 1;  // row words per thread in step 2 (NT = WSL*32/KH threads)
+    const uint32_t N = 2 * p.n_samples, WS = p.WS;
+    const uint32_t WSL = cfg.WSL, SH = cfg.SH;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, NT = blockDim.x;
+    const uint32_t WT = C * WSL;
+    uint32_t* ypart = reinterpret_cast<uint32_t*>(smem_raw);
+    uint32_t* ystage = ypart + WT;
+    uint32_t* T = ystage + WT;
+    uint32_t* zs = T + 2 * WT;
+    uint32_t* sc = zs + 8;
+    uint64_t* mb = reinterpret_cast<uint64_t*>(sc + 32);  // [0] mbY: partial slices landed, [1] mbT: table complete
+    uint32_t crank = 0;
+    if (C > 1) crank = cgx::this_cluster().block_rank();
+    const uint32_t b = blockIdx.x / C;
+    const uint32_t nwah = p.blk_nwah[b];
+    const uint32_t* list = p.wah_list + p.blk_line0[b];
+    const uint32_t sw0 = crank * WSL;         // first row word of this CTA's slice
+    const uint32_t hb = sw0 * 32 + tid * KH;  // first haplotype of this thread
+    const uint32_t NP = WSL / WPT;            // threads taking part in step 2
+    const uint32_t ypart_sa = smem_u32(ypart), ystage_sa = smem_u32(ystage), T_sa = smem_u32(T), zs_sa = smem_u32(zs), mb_sa = smem_u32(mb);
+
+    // pos of this thread's haplotypes (identity at block start, gt_block.hpp:179): one register each, or two
+    // uint16 per register (haplotypes hb+2q low, hb+2q+1 high) when KH > 16
+    constexpr bool PACK = KH > 16;
+    uint32_t pk[PACK ? KH / 2 : KH];
+#pragma unroll
+    for (int q = 0; q < (PACK ? KH / 2 : KH); ++q) pk[q] = PACK ? ((hb + 2 * q) | ((hb + 2 * q + 1) << 16)) : (hb + q);
+    for (uint32_t i = tid; i < WT; i += NT) ypart[i] = 0;
+    if (tid == 0) { mbar_init(&mb[0], 1); mbar_init(&mb[1], NT); }
+    if (C > 1) cgx::this_cluster().sync(); else __syncthreads();
+    if (nwah == 0) return;  // uniform over the cluster
+
+    // The row word(s) holding this thread's KH bits of a natural-order bit-row.  Loaded four lines ahead and kept
+    // raw: the bits are only extracted (extract_x) when the line becomes "next", so nothing waits on the load.
+    auto load_x = [&](uint32_t entry, uint32_t (&x)[XW]) {
+        const uint32_t* row = p.bitrows + (size_t)(entry & 0x7FFFFFFFu) * WS;
+        const uint32_t w = hb >> 5;
+        x[0] = w < WS ? row[w] : 0u;
+        if (KH == 64) x[XW - 1] = w + 1 < WS ? row[w + 1] : 0u;
+    };
+    auto extract_x = [&](uint32_t v) { return KH >= 32 ? v : ((v >> (hb & 31u)) & ((1u << (KH & 31)) - 1u)); };
+    uint32_t x0[XW], x1[XW], x2[XW], x3[XW];  // lines k, k+1 (extracted bits), k+2, k+3 (raw words)
+#pragma unroll
+    for (int i = 0; i < XW; ++i) x0[i] = x1[i] = x2[i] = x3[i] = 0;
+    load_x(list[0], x0);
+    if (nwah > 1) load_x(list[1], x1);
+    if (nwah > 2) load_x(list[2], x2);
+    if (nwah > 3) load_x(list[3], x3);
+#pragma unroll
+    for (int i = 0; i < XW; ++i) { x0[i] = extract_x(x0[i]); x1[i] = extract_x(x1[i]); }
+    uint32_t e0 = list[0], e1 = nwah > 1 ? list[1] : 0u, e2 = nwah > 2 ? list[2] : 0u, e3 = nwah > 3 ? list[3] : 0u,
+             e4 = nwah > 4 ? list[4] : 0u;  // list[k .. k+4]
+    // step 0 of the first line
+#pragma unroll
+    for (int q = 0; q < KH; ++q)
+        red_or_shared_if(x0[q >> 5] & (1u << (q & 31)), ypart_sa + (((hb + q) >> 3) & ~3u), 1u << ((hb + q) & 31u));
+    const uint32_t pad_zeros = WT * 32 - N;  // positions past N never hold a carrier; they are not real zeros
+
+    for (uint32_t k = 0; k < nwah; ++k) {
+        const uint32_t par = k & 1u;
+        uint32_t xf[XW];
+#pragma unroll
+        for (int i = 0; i < XW; ++i) xf[i] = 0;
+        if (k + 4 < nwah) load_x(e4, xf);
+        const uint32_t e5 = k + 5 < nwah ? list[k + 5] : 0u;
+        if (C > 1 && tid == 0) mbar_expect_tx(&mb[0], (C - 1) * WSL * 4);
+        __syncthreads();  // ypart of this CTA is complete
+        // ---- 1: push the foreign word slices, clear them ----
+        if (C > 1) {
+            for (uint32_t ch = tid; ch < WT / 4; ch += NT) {
+                const uint32_t w4 = ch * 4, dest = w4 >> (SH - 5);
+                if (dest != crank) {
+                    uint4* src = reinterpret_cast<uint4*>(ypart) + ch;
+                    const uint4 v = *src;
+                    *src = make_uint4(0, 0, 0, 0);
+                    st_async_v4(mapa_u32(ystage_sa + 4 * (crank * WSL + (w4 & (WSL - 1))), dest), v, mapa_u32(mb_sa, dest));
+                }
+            }
+        }
+        // ---- 2: combine my slice, publish its table entries ----
+        if (tid < NP) {
+            if (C > 1) mbar_wait(&mb[0], par);
+            uint32_t y[WPT], run = 0;
+#pragma unroll
+            for (int i = 0; i < WPT; ++i) {
+                const uint32_t w = tid * WPT + i;
+                uint32_t yy = ypart[sw0 + w];
+                ypart[sw0 + w] = 0;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (C > 1 && (uint32_t)c != crank) yy |= ystage[c * WSL + w];
+                y[i] = yy;
+                run += 32u - __popc(yy);
+            }
+            uint32_t incl = run;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, dd); if (lane >= (uint32_t)dd) incl += o; }
+            uint32_t wbase = 0, total = __shfl_sync(XSI_FULL, incl, 31);
+            if (NP > 32) {
+                if (lane == 31) sc[warp] = incl;
+                named_bar_sync1(NP);
+                const uint32_t wv = lane < (NP >> 5) ? sc[lane] : 0u;
+                wbase = __reduce_add_sync(XSI_FULL, lane < warp ? wv : 0u);
+                total = __reduce_add_sync(XSI_FULL, wv);
+            }
+            uint32_t zp = wbase + incl - run;
+            uint32_t* grow = p.bitrows + (size_t)(e0 & 0x7FFFFFFFu) * WS;
+#pragma unroll
+            for (int i = 0; i < WPT; ++i) {
+                const uint32_t w = tid * WPT + i, gw = sw0 + w, yy = y[i];
+                const uint32_t ny = ~yy;  // the table keeps the ZERO positions as set bits
+                const uint32_t e0 = (zp << 16) | (ny & 0xFFFFu);
+                const uint32_t zmid = zp + __popc(ny & 0xFFFFu);
+                const uint32_t e1 = (zmid << 16) | (ny >> 16);
+                *reinterpret_cast<uint2*>(T + 2 * gw) = make_uint2(e0, e1);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (C > 1 && (uint32_t)c != crank) st_async_v2(mapa_u32(T_sa + 8 * gw, c), e0, e1, mapa_u32(mb_sa + 8, c));
+                if (gw < WS) grow[gw] = yy;  // permuted row, in place
+                zp += 32u - __popc(yy);
+            }
+            if (tid == 0) {
+                zs[crank] = total;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+                    if (C > 1 && (uint32_t)c != crank) st_async_b32(mapa_u32(zs_sa + 4 * crank, c), total, mapa_u32(mb_sa + 8, c));
+            }
+        }
+        if (C > 1 && tid == 0) mbar_expect_tx(&mb[1], (C - 1) * (WSL * 8 + 4));  // counts as thread 0's arrival
+        else mbar_arrive(&mb[1]);
+        mbar_wait(&mb[1], par);
+        // ---- 3 (+ step 0 of line k+1) ----
+        uint32_t basev = 0, Z = 0;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { const uint32_t v = zs[c]; if (lane > (uint32_t)c) basev += v; Z += v; }
+        Z -= pad_zeros;
+#pragma unroll
+        for (int q = 0; q < KH; ++q) {
+            const uint32_t j = PACK ? ((q & 1) ? (pk[q >> 1] >> 16) : (pk[q >> 1] & 0xFFFFu)) : pk[q];
+            const uint32_t e = T[j >> 4];
+            uint32_t zb = (e >> 16) + __popc(e & ~(0xFFFFFFFFu << (j & 15u)));
+            if (C > 1) zb += __shfl_sync(XSI_FULL, basev, j >> SH);
+            const uint32_t np = (x0[q >> 5] & (1u << (q & 31))) ? Z + j - zb : zb;
+            if (!PACK) pk[q] = np;
+            else if (q & 1) pk[q >> 1] = (pk[q >> 1] & 0xFFFFu) | (np << 16);
+            else pk[q >> 1] = (pk[q >> 1] & 0xFFFF0000u) | np;
+        }
+        // step 0 of line k+1: carriers are the minority (mean allele frequency of a WAH line ~8%), so this is a
+        // separate, branchy pass that leaves the update loop above branch-free
+#pragma unroll
+        for (int i = 0; i < XW; ++i) {
+            if (x1[i] == 0) continue;
+#pragma unroll
+            for (int qq = 0; qq < (KH < 32 ? KH : 32); ++qq) {
+                const int q = i * 32 + qq;
+                if (x1[i] & (1u << qq)) {
+                    const uint32_t np = PACK ? ((q & 1) ? (pk[q >> 1] >> 16) : (pk[q >> 1] & 0xFFFFu)) : pk[q];
+                    atomicOr(&ypart[np >> 5], 1u << (np & 31u));
+                }
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < XW; ++i) { x0[i] = x1[i]; x1[i] = extract_x(x2[i]); x2[i] = x3[i]; x3[i] = xf[i]; }
+        e0 = e1; e1 = e2; e2 = e3; e3 = e4; e4 = e5;
+    }
+    if (C > 1) cgx::this_cluster().sync();  // nobody exits while a peer may still push into its shared memory
+}
+
 // generic fallback for > 65536 haplotypes: a[] ping-pongs in global memory (L2 resident)
 __global__ void __launch_bounds__(1024, 1) pbwt_permute_gmem_kernel(EncDev p, uint32_t* a_pool) {
     __shared__ uint32_t zc[64];

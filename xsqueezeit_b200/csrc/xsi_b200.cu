@@ -317,9 +317,87 @@ int run_permute_v3(xsi_ctx* ctx, const EncDev& p, uint32_t W, bool* done) {
     return XSI_OK;
 }
 
+template <int C, int KH>
+int launch_permute_v4(xsi_ctx* ctx, const EncDev& p, const PermV4Cfg& cfg, uint32_t NT, size_t smem, bool probe_only, int* max_clusters) {
+    CK(cudaFuncSetAttribute(pbwt_permute_v4_kernel<C, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(p.nb * C); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = smem; lc.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = C > 1 ? 1 : 0;
+    if (probe_only) {
+        *max_clusters = 1 << 30;
+        if (C > 1) CK(cudaOccupancyMaxActiveClusters(max_clusters, pbwt_permute_v4_kernel<C, KH>, &lc));
+        return XSI_OK;
+    }
+    { PROF("pbwt_permute"); CK(cudaLaunchKernelEx(&lc, pbwt_permute_v4_kernel<C, KH>, p, cfg)); }
+    CKL();
+    return XSI_OK;
+}
+
+template <int C>
+int launch_permute_v4_kh(xsi_ctx* ctx, const EncDev& p, const PermV4Cfg& cfg, uint32_t KH, uint32_t NT, size_t smem, bool probe_only, int* maxc) {
+    switch (KH) {
+        case 8: return launch_permute_v4<C, 8>(ctx, p, cfg, NT, smem, probe_only, maxc);
+        case 16: return launch_permute_v4<C, 16>(ctx, p, cfg, NT, smem, probe_only, maxc);
+        case 32: return launch_permute_v4<C, 32>(ctx, p, cfg, NT, smem, probe_only, maxc);
+        default: return launch_permute_v4<C, 64>(ctx, p, cfg, NT, smem, probe_only, maxc);
+    }
+}
+
+int launch_permute_v4_c(xsi_ctx* ctx, const EncDev& p, uint32_t C, const PermV4Cfg& cfg, uint32_t KH, uint32_t NT, size_t smem, bool probe_only, int* maxc) {
+    switch (C) {
+        case 8: return launch_permute_v4_kh<8>(ctx, p, cfg, KH, NT, smem, probe_only, maxc);
+        case 4: return launch_permute_v4_kh<4>(ctx, p, cfg, KH, NT, smem, probe_only, maxc);
+        case 2: return launch_permute_v4_kh<2>(ctx, p, cfg, KH, NT, smem, probe_only, maxc);
+        default: return launch_permute_v4_kh<1>(ctx, p, cfg, KH, NT, smem, probe_only, maxc);
+    }
+}
+
+// Picks the cluster size C (the largest whose clusters are all co-resident, so that a batch with fewer
+// blocks than SMs still fills the GPU) and the haplotypes per thread KH; XSI_PBWT_CLUSTER / XSI_PBWT_KH override.
+int run_permute_v4(xsi_ctx* ctx, const EncDev& p, uint32_t W, bool* done) {
+    *done = false;
+    int forced = 0, forced_kh = 0;
+    if (const char* s = getenv("XSI_PBWT_CLUSTER")) forced = atoi(s);
+    if (const char* s = getenv("XSI_PBWT_KH")) forced_kh = atoi(s);
+    for (uint32_t C : {8u, 4u, 2u, 1u}) {
+        if (forced && (uint32_t)forced != C) continue;
+        PermV4Cfg cfg;
+        uint32_t per = (W + C - 1) / C, wsl = 32, sh = 10;
+        while (wsl < per) { wsl *= 2; ++sh; }
+        cfg.WSL = wsl; cfg.SH = sh;
+        const uint32_t HS = wsl * 32;
+        if ((uint64_t)C * HS > 65536) continue;
+        if (!forced && C > 1 && wsl * (C / 2) >= W) continue;  // half the cluster would already cover the row
+        uint32_t KH = std::max<uint32_t>(8, HS / 1024);
+        if (HS / KH > 512 && C == 8 && KH < 64) KH *= 2;  // 512-thread CTAs: two per SM
+        if (forced_kh == 8 || forced_kh == 16 || forced_kh == 32 || forced_kh == 64) KH = (uint32_t)forced_kh;
+        const uint32_t NT = HS / KH;
+        if (NT > 1024 || NT < 32 || NT < wsl / (KH == 64 ? 2 : 1)) continue;
+        const size_t WT = (size_t)C * wsl;
+        const size_t smem = (4 * WT + 8 + 32) * 4 + 16;
+        if (smem > ctx->smem_optin) continue;
+        int maxc = 0;
+        int rc = launch_permute_v4_c(ctx, p, C, cfg, KH, NT, smem, true, &maxc);
+        if (rc) return rc;
+        if (!forced && C > 1 && (uint32_t)maxc < p.nb) continue;  // the clusters would not all be resident at once
+        rc = launch_permute_v4_c(ctx, p, C, cfg, KH, NT, smem, false, &maxc);
+        *done = rc == XSI_OK;
+        return rc;
+    }
+    return XSI_OK;
+}
+
 int run_permute(xsi_ctx* ctx, const EncDev& p) {
     const uint32_t N = 2 * p.n_samples;
     const uint32_t W = (N + 31) / 32;
+    if (!ctx->enc.any_haploid && N <= 65534 && !getenv("XSI_PBWT_V1") && !getenv("XSI_PBWT_V2") && !getenv("XSI_PBWT_V3")) {
+        bool done = false;
+        const int rc = run_permute_v4(ctx, p, W, &done);
+        if (rc || done) return rc;
+    }
     if (!ctx->enc.any_haploid && N <= 65534 && !getenv("XSI_PBWT_V1") && !getenv("XSI_PBWT_V2")) {
         bool done = false;
         const int rc = run_permute_v3(ctx, p, W, &done);
