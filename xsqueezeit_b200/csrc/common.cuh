@@ -126,6 +126,11 @@ __device__ __forceinline__ void red_or_shared_if(uint32_t test, uint32_t saddr, 
         "r"(saddr), "r"(val)
         : "memory");
 }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t saddr) {  // plain shared load from a 32-bit shared-window address
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(saddr));
+    return v;
+}
 // barrier among the first `nthreads` threads of the CTA (a multiple of 32), hardware barrier 1
 __device__ __forceinline__ void named_bar_sync1(uint32_t nthreads) { asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory"); }
 

@@ -55,6 +55,7 @@ struct DecDev {
     uint32_t* tabs;             // [n_gt_jobs][TW] or NULL: per 16 positions (zeros before << 16 | y bits), then at
                                 // [2*WS] the line's total zeros; TW = 2*WS + 4; for D2 v2
     uint32_t TW, n_gt_jobs;
+    uint32_t tab_inv;           // 0xFFFF: table entries keep the zero positions as set bits (D2 v3), 0: the y bits (D2 v2)
     uint32_t n_samples;         // header.num_samples
     uint32_t aet;               // 2 or 4
     const uint8_t* dline_flags; // [Lt]
@@ -249,7 +250,7 @@ __global__ void wah_expand_kernel(DecDev d, uint32_t warps_per_cta, uint32_t Gpa
             const uint32_t zp = zcarry + incl - nz;
             if (2 * m + 1 < d.TW) {
                 *reinterpret_cast<uint2*>(tab + 2 * m) =
-                    make_uint2((zp << 16) | (o & 0xFFFFu), ((zp + 16u - __popc(o & 0xFFFFu)) << 16) | (o >> 16));
+                    make_uint2((zp << 16) | ((o & 0xFFFFu) ^ d.tab_inv), ((zp + 16u - __popc(o & 0xFFFFu)) << 16) | ((o >> 16) ^ d.tab_inv));
             }
             zcarry += __shfl_sync(XSI_FULL, incl, 31);
         }
@@ -476,6 +477,89 @@ __global__ void __launch_bounds__(1024) pbwt_unpermute_v2_kernel(DecDev d) {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
         if (lane < WPW && word0 + lane < WS) d.rows[(size_t)job * WS + word0 + lane] = xkeep;  // natural-order row, in place
+    }
+}
+
+// =============================================================================================
+// D2 v3: same inverse-permutation formulation as v2, with the state in REGISTERS.  Thread t owns KH
+// consecutive haplotypes: their positions never touch shared memory (v2: one LDS + one STS per
+// haplotype and line), and the KH decoded bits of a line are assembled inside the thread (v2: one
+// ballot per 32 haplotypes), so the only shared-memory traffic left is the random table lookup
+// itself.  A dedicated producer warp keeps the TMA table ring full; consumer warps only wait on
+// `full` and arrive on `empty`.  The KH lookups of a thread are independent (ILP hides the LDS latency).
+// grid = (PBWT block, haplotype slice of NC*KH), block = NC consumer threads + 32 producer threads
+// dynamic smem: ring[D][TW] u32 | full[D], empty[D] u64
+// =============================================================================================
+constexpr int D3_STAGES = 4;
+template <int KH>  // haplotypes per thread: 8, 16 or 32 (one uint8 / uint16 / uint32 store per thread and line)
+__global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t N = 2 * d.n_samples, TW = d.TW, WS = d.WS;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t NC = blockDim.x - 32;  // consumer threads
+    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw);
+    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)D3_STAGES * TW);
+    uint64_t* empty = full + D3_STAGES;
+    const DecBlock blk = d.blocks[blockIdx.x];
+    const uint32_t nwah = blk.n_wah;
+    const uint32_t tab_bytes = TW * 4;
+    if (tid == 0) {
+        for (int s = 0; s < D3_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NC >> 5); }
+        fence_proxy_async();
+    }
+    __syncthreads();
+    if (nwah == 0 || blockIdx.y * NC * KH >= N) return;
+    const uint32_t* tabs = d.tabs + (size_t)blk.wah0 * TW;
+    if (tid >= NC) {  // ---- producer warp ----
+        if (lane == 0) {
+            for (uint32_t k = 0; k < nwah; ++k) {
+                const uint32_t st = k % D3_STAGES, use = k / D3_STAGES;
+                if (use > 0) mbar_wait(&empty[st], (use - 1) & 1u);
+                mbar_expect_tx(&full[st], tab_bytes);
+                bulk_g2s(ring + (size_t)st * TW, tabs + (size_t)k * TW, tab_bytes, &full[st]);
+            }
+        }
+        return;
+    }
+    // ---- consumers ----
+    // Table entries for v3 hold the ZERO positions as set bits (DecDev::tab_inv): with w = e << (31 - s), s = j & 15,
+    // the sign of w says "position j holds a zero" and popc(w & 0x7FFFFFFF) counts the zeros in [16c, j).
+    const uint32_t hb = (blockIdx.y * NC + tid) * KH;  // first haplotype of this thread
+    const uint32_t nvalid = hb >= N ? 0u : (N - hb >= (uint32_t)KH ? (uint32_t)KH : N - hb);
+    uint32_t pk[KH];
+    // identity at block start (gt_block.hpp:179).  Haplotypes past N start at 0 and wander inside [0, N] (their
+    // lookups stay inside the table); their bits are masked off before the store.
+#pragma unroll
+    for (int q = 0; q < KH; ++q) pk[q] = (uint32_t)q < nvalid ? hb + q : 0u;
+    const uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+    const bool store = hb < WS * 32;
+    const uint32_t ring_sa = smem_u32(ring);
+    for (uint32_t k = 0; k < nwah; ++k) {
+        const uint32_t st = k % D3_STAGES, use = k / D3_STAGES;
+        mbar_wait(&full[st], use & 1u);
+        const uint32_t stw = st * TW;  // word offset of this stage in the ring
+        uint32_t e[KH];
+#pragma unroll
+        for (int q = 0; q < KH; ++q) e[q] = lds_u32(ring_sa + (((pk[q] >> 4) + stw) << 2));
+        const uint32_t Z = lds_u32(ring_sa + ((2 * WS + stw) << 2));
+        uint32_t xinv = 0;
+#pragma unroll
+        for (int q = KH - 1; q >= 0; --q) {
+            const uint32_t j = pk[q];
+            const uint32_t w = __funnelshift_l(0u, e[q], ~j | 16u);  // e << (31 - (j & 15)): the shift wraps mod 32
+            const uint32_t zb = (e[q] >> 16) + __popc(w & 0x7FFFFFFFu);
+            pk[q] = ((int32_t)w < 0) ? zb : Z + j - zb;
+            xinv = __funnelshift_l(w, xinv, 1);  // (xinv << 1) | sign(w)
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
+        if (store) {  // natural-order row, in place
+            const uint32_t x = ~xinv & vmask;
+            const size_t row = (size_t)(blk.wah0 + k) * WS;
+            if (KH == 32) d.rows[row + (hb >> 5)] = x;
+            else if (KH == 16) reinterpret_cast<uint16_t*>(d.rows + row)[hb >> 4] = (uint16_t)x;
+            else reinterpret_cast<uint8_t*>(d.rows + row)[hb >> 3] = (uint8_t)x;
+        }
     }
 }
 

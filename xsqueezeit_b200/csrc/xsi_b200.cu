@@ -371,6 +371,8 @@ int run_permute_v4(xsi_ctx* ctx, const EncDev& p, uint32_t W, bool* done) {
         const uint32_t HS = wsl * 32;
         if ((uint64_t)C * HS > 65536) continue;
         if (!forced && C > 1 && wsl * (C / 2) >= W) continue;  // half the cluster would already cover the row
+        // one CTA per SM: two 512-thread CTAs of a C=8 cluster sharing an SM lose to C=4 (20.6 vs 17.3 ms at 32 HRC blocks)
+        if (!forced && C > 1 && (uint64_t)p.nb * C > (uint64_t)ctx->sm_count) continue;
         uint32_t KH = std::max<uint32_t>(8, HS / 1024);
         if (HS / KH > 512 && C == 8 && KH < 64) KH *= 2;  // 512-thread CTAs: two per SM
         if (forced_kh == 8 || forced_kh == 16 || forced_kh == 32 || forced_kh == 64) KH = (uint32_t)forced_kh;
@@ -1041,8 +1043,22 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
         un_slices = (warps_total + un_warps - 1) / un_warps;
         un_smem = (size_t)un_warps * un_wpw * 64 + (size_t)D2_STAGES * TWv2 * 4 + 2 * D2_STAGES * 8;
     }
-    const bool v2_ok = use_v2 && un_smem <= ctx->smem_optin;
-    dd.tabs = nullptr; dd.TW = TWv2; dd.n_gt_jobs = d.n_gt_jobs;
+    // D2 v3 (positions in registers) is the default; XSI_UNPERM_V2=1 keeps the shared-memory version
+    uint32_t v3_kh = 0, v3_nc = 0, v3_slices = 0;
+    const size_t v3_smem = (size_t)D3_STAGES * TWv2 * 4 + 2 * D3_STAGES * 8;
+    if (use_v2 && !getenv("XSI_UNPERM_V2") && v3_smem <= ctx->smem_optin) {
+        // haplotypes per thread: the largest of 32/16/8 that still gives every SM ~768 consumer threads
+        const uint64_t want = (uint64_t)ctx->sm_count * 768;
+        v3_kh = 8;
+        for (uint32_t kh : {32u, 16u}) if ((uint64_t)n_blocks * ((N + kh - 1) / kh) >= want) { v3_kh = kh; break; }
+        if (const char* sw = getenv("XSI_UNPERM_KH")) { const int v = atoi(sw); if (v == 8 || v == 16 || v == 32) v3_kh = (uint32_t)v; }
+        const uint32_t thr_total = ((N + v3_kh - 1) / v3_kh + 31) / 32 * 32;
+        v3_nc = std::min<uint32_t>(512, thr_total);
+        if (const char* sw = getenv("XSI_UNPERM_NC")) { const int v = atoi(sw); if (v >= 32 && v <= 512 && v % 32 == 0) v3_nc = std::min<uint32_t>(thr_total, (uint32_t)v); }
+        v3_slices = (thr_total + v3_nc - 1) / v3_nc;
+    }
+    const bool v2_ok = use_v2 && (v3_kh || un_smem <= ctx->smem_optin);
+    dd.tabs = nullptr; dd.TW = TWv2; dd.n_gt_jobs = d.n_gt_jobs; dd.tab_inv = v3_kh ? 0xFFFFu : 0u;
     if (v2_ok) {
         CK(d.tabs.ensure((size_t)d.n_gt_jobs * TWv2 * 4));
         dd.tabs = d.tabs.as<uint32_t>();
@@ -1073,7 +1089,20 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
         CK(cudaFuncSetAttribute(wah_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         { PROF("wah_expand"); wah_expand_kernel<<<(njobs + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(dd, wpc, Gpad, Tpad); }
         CKL();
-        if (v2_ok) {
+        if (v3_kh) {
+            const dim3 g(n_blocks, v3_slices);
+            if (v3_kh == 32) {
+                CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem));
+                PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<32><<<g, v3_nc + 32, v3_smem, ctx->stream>>>(dd);
+            } else if (v3_kh == 16) {
+                CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem));
+                PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<16><<<g, v3_nc + 32, v3_smem, ctx->stream>>>(dd);
+            } else {
+                CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem));
+                PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<8><<<g, v3_nc + 32, v3_smem, ctx->stream>>>(dd);
+            }
+            CKL();
+        } else if (v2_ok) {
             const dim3 g(n_blocks, un_slices);
             if (un_wpw == 32) {
                 CK(cudaFuncSetAttribute(pbwt_unpermute_v2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)un_smem));
