@@ -259,18 +259,19 @@ def run_reference(args, steps, warmup, label_impl=True):
 # ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
-def algorithmic_bytes(kernel, G, L_wah, L, WS, payload):
+def algorithmic_bytes(kernel, G, L_wah, L, WS, payload, elem=4):
     """Bytes a kernel must move per step (DESIGN.md 'Kernels'): G genotypes, L binary lines of WS words."""
     row = WS * 4
     return {
-        "scan_rows": 4 * G + L * row,                 # int32 rows in, one bit-row per binary line out
+        "scan_rows": elem * G + L * row,                 # int32 rows in, one bit-row per binary line out
         "pbwt_permute": 2 * L_wah * row,              # bit-row in, permuted bit-row out (a[] stays in smem)
         "wah_encode_rows": L_wah * row + payload,
         "pack_wah": 2 * payload,
         "sparse_emit": (L - L_wah) * row,
         "wah_expand": payload + L_wah * row,
         "pbwt_unpermute": 2 * L_wah * row,
-        "compose_records": 4 * G + L * row,           # bit-rows / index lists in, int32 rows out
+        "compose_simple": elem * G + L * row,
+        "compose_records": elem * G + L * row,           # bit-rows / index lists in, int32 rows out
     }.get(kernel)
 
 
@@ -284,6 +285,8 @@ def main():
     ap.add_argument("--blocks", type=int, default=32, help="PBWT blocks per GPU per step (resident leg)")
     ap.add_argument("--e2e-blocks", type=int, default=8, help="PBWT blocks per GPU per step (host-buffer leg)")
     ap.add_argument("--block-len", type=int, default=BLOCK_LEN)
+    ap.add_argument("--elem", type=int, default=4, choices=[1, 4],
+                    help="bytes per genotype of the resident rows: 4 = int32 (the metric's boundary type), 1 = raw BCF int8")
     ap.add_argument("--ref-records", type=int, default=1024)
     ap.add_argument("--ref-workers", type=int, default=0)
     ap.add_argument("--ref-worker", type=int, default=-1, help=argparse.SUPPRESS)
@@ -351,9 +354,11 @@ def main():
     B = args.blocks
     R = B * BL
     G = R * H
-    gt = torch.empty((R, H), dtype=torch.int32, device=dev)
+    EL = args.elem
+    rdt = torch.int32 if EL == 4 else torch.int8
+    gt = torch.empty((R, H), dtype=rdt, device=dev)
     HrcSynth(S, 1002 + 131 * rank, dev).fill(gt)
-    dec = torch.empty((R, H), dtype=torch.int32, device=dev)
+    dec = torch.empty((R, H), dtype=rdt, device=dev)
     nal = np.full(R, 2, np.uint32)
     pos = xb.bm_positions(nal, BL)
     blk = (pos >> np.uint64(15)).astype(np.uint32)
@@ -367,9 +372,9 @@ def main():
 
     host_ms = {"encode_launch": 0.0, "encode_collect": 0.0, "decode_load_blocks": 0.0, "decode_records": 0.0}
 
-    def encode_step(gt_ptr, on_device, n_rec):
+    def encode_step(gt_ptr, on_device, n_rec, elem=4):
         t0 = time.perf_counter()
-        ctx.encode_launch(gt_ptr, nal[:n_rec], S, BL, thr, 1, gt_on_device=on_device)
+        ctx.encode_launch(gt_ptr, nal[:n_rec], S, BL, thr, 1, gt_on_device=on_device, gt_elem_bytes=elem)
         t1 = time.perf_counter()
         n = ctypes.c_uint32()
         bp = ctypes.POINTER(ctypes.c_void_p)()
@@ -384,19 +389,20 @@ def main():
             _ = torch.cumsum(gathered, 0)
         return blocks
 
-    def decode_step(blocks, out_ptr, on_device, n_rec):
+    def decode_step(blocks, out_ptr, on_device, n_rec, elem=4):
         t0 = time.perf_counter()
         ctx.decode_load_blocks(blocks, S, 2)
         t1 = time.perf_counter()
-        ctx._check(L.xsi_decode_records(ctx.h, n_rec, blk[:n_rec].ctypes.data, off[:n_rec].ctypes.data,
-                                        nal[:n_rec].ctypes.data, out_ptr, H, 1 if on_device else 0, None, None, 0))
+        fn = L.xsi_decode_records if elem == 4 else L.xsi_decode_records_i8
+        ctx._check(fn(ctx.h, n_rec, blk[:n_rec].ctypes.data, off[:n_rec].ctypes.data,
+                      nal[:n_rec].ctypes.data, out_ptr, H, 1 if on_device else 0, None, None, 0))
         ctx.sync()
         host_ms["decode_load_blocks"] += (t1 - t0) * 1e3
         host_ms["decode_records"] += (time.perf_counter() - t1) * 1e3
 
-    def run_leg(n_rec, gt_ptr, out_ptr, on_device, nsteps, nwarm, sampler=None):
+    def run_leg(n_rec, gt_ptr, out_ptr, on_device, nsteps, nwarm, sampler=None, elem=4):
         for _ in range(nwarm):
-            decode_step(encode_step(gt_ptr, on_device, n_rec), out_ptr, on_device, n_rec)
+            decode_step(encode_step(gt_ptr, on_device, n_rec, elem), out_ptr, on_device, n_rec, elem)
         ctx.profile_read()
         for k in host_ms:
             host_ms[k] = 0.0
@@ -409,9 +415,9 @@ def main():
         for _ in range(nsteps):
             a, b, c = ev(), ev(), ev()
             a.record(stream)
-            blocks = encode_step(gt_ptr, on_device, n_rec)
+            blocks = encode_step(gt_ptr, on_device, n_rec, elem)
             b.record(stream)
-            decode_step(blocks, out_ptr, on_device, n_rec)
+            decode_step(blocks, out_ptr, on_device, n_rec, elem)
             c.record(stream)
             e0.append(a); e1.append(b); e2.append(c)
             payload = sum(s for _, s in blocks)
@@ -433,7 +439,7 @@ def main():
         return float(t.item())
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    res = run_leg(R, gt.data_ptr(), dec.data_ptr(), True, steps, warmup, sampler)
+    res = run_leg(R, gt.data_ptr(), dec.data_ptr(), True, steps, warmup, sampler, elem=EL)
     verified = bool(torch.equal(gt, dec))
     t_all, t_enc, t_dec = maxr(res["t_all"]), maxr(res["t_enc"]), maxr(res["t_dec"])
     value = 2.0 * G * world * steps / t_all / 1e9
@@ -455,7 +461,7 @@ def main():
         L_lines, L_wah = res["lines"]
         for k, (n, ms) in prof.items():
             kernels[k] = {"launches": n, "ms_per_step": ms / steps, "share": ms / total_ms if total_ms else None}
-        ab = algorithmic_bytes(top, G, L_wah, L_lines, WS, res["payload"])
+        ab = algorithmic_bytes(top, G, L_wah, L_lines, WS, res["payload"], EL)
         if ab:
             n, ms = prof[top]
             ach = ab * steps / (ms / 1e3) / 1e9
@@ -464,28 +470,38 @@ def main():
                     "algorithmic_bytes_per_step": ab, "launches_per_step": n / steps, "ms_per_launch": ms / n}
 
     # ---- e2e: pinned host buffers through the same calls ----
+    # `e2e` keeps the reference's own boundary types (int32 rows: bcf_get_genotypes in, fill_genotype_array out);
+    # `e2e_bcf_int8` moves the records' raw BCF FORMAT/GT bytes instead (gt_elem_bytes = 1 in, xsi_decode_records_i8
+    # out: SURVEY 8(f).1), a quarter of the PCIe traffic for the same genotypes.
     e2e = None
+    e2e_i8 = None
     if not args.no_e2e and not args.profile_only:
         import psutil
         Be = max(1, min(args.e2e_blocks, B))
         while Be > 1 and 2 * Be * BL * H * 4 > 0.5 * psutil.virtual_memory().available / max(1, world):
             Be //= 2
         Re = Be * BL
-        h_in = torch.empty((Re, H), dtype=torch.int32, pin_memory=True)
-        h_out = torch.empty((Re, H), dtype=torch.int32, pin_memory=True)
-        h_in.copy_(gt[:Re])
-        torch.cuda.synchronize(dev)
-        r2 = run_leg(Re, h_in.data_ptr(), h_out.data_ptr(), False, max(1, min(steps, 3)), 1)
-        ok2 = bool(torch.equal(h_in, h_out))
-        verified = verified and ok2
         ns = max(1, min(steps, 3))
-        t2 = maxr(r2["t_all"])
-        e2e = {"value": 2.0 * Re * H * world * ns / t2 / 1e9, "unit": "Ggt/s",
-               "h2d_bytes_per_step": Re * H * 4 + r2["payload"], "d2h_bytes_per_step": Re * H * 4 + r2["payload"],
-               "compress_ggts": Re * H * world * ns / maxr(r2["t_enc"]) / 1e9,
-               "decompress_ggts": Re * H * world * ns / maxr(r2["t_dec"]) / 1e9,
-               "blocks_per_step": Be, "ms_per_step": t2 / ns * 1e3, "host_buffers": "pinned int32 rows in and out"}
-        del h_in, h_out
+
+        def host_leg(dtype, elem, label):
+            nonlocal verified
+            h_in = torch.empty((Re, H), dtype=dtype, pin_memory=True)
+            h_out = torch.empty((Re, H), dtype=dtype, pin_memory=True)
+            for r0 in range(0, Re, BL):
+                h_in[r0:r0 + BL].copy_(gt[r0:r0 + BL].to(dtype))
+            torch.cuda.synchronize(dev)
+            r2 = run_leg(Re, h_in.data_ptr(), h_out.data_ptr(), False, ns, 1, elem=elem)
+            ok2 = bool(torch.equal(h_in, h_out))
+            verified = verified and ok2
+            t2 = maxr(r2["t_all"])
+            return {"value": 2.0 * Re * H * world * ns / t2 / 1e9, "unit": "Ggt/s",
+                    "h2d_bytes_per_step": Re * H * elem + r2["payload"], "d2h_bytes_per_step": Re * H * elem + r2["payload"],
+                    "compress_ggts": Re * H * world * ns / maxr(r2["t_enc"]) / 1e9,
+                    "decompress_ggts": Re * H * world * ns / maxr(r2["t_dec"]) / 1e9,
+                    "blocks_per_step": Be, "ms_per_step": t2 / ns * 1e3, "host_buffers": label, "verified": ok2}
+
+        e2e = host_leg(torch.int32, 4, "pinned int32 rows in and out (bcf_get_genotypes / fill_genotype_array types)")
+        e2e_i8 = host_leg(torch.int8, 1, "pinned int8 rows in and out (raw BCF FORMAT/GT payload)")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and not args.profile_only:
@@ -497,12 +513,12 @@ def main():
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "Ggt/s", "n_gpus": world, "steps": steps, "warmup": warmup,
                 "ms_per_step": t_all / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "int32", "data": "synthetic",
+                "dtype": "int32" if EL == 4 else "int8", "data": "synthetic",
                 "config": {"workload": workload, "blocks_per_gpu_per_step": B, "records_per_gpu_per_step": R,
-                           "genotypes_per_gpu_per_step": G, "input": "int32 rows resident in HBM (%.1f GB, > L2; no flush needed)" % (G * 4 / 1e9),
+                           "genotypes_per_gpu_per_step": G, "input": "%s rows resident in HBM (%.1f GB, > L2; no flush needed)" % ("int32" if EL == 4 else "int8", G * EL / 1e9),
                            "xsi_payload_bytes_per_step": res["payload"], "binary_lines": res["lines"][0], "wah_lines": res["lines"][1], "parallelism": "blocks sharded over %d GPU(s)" % world},
                 "compress_ggts": G * world * steps / t_enc / 1e9, "decompress_ggts": G * world * steps / t_dec / 1e9,
-                "verified": verified, "roofline": roof, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "cpu_baseline": cpu, "e2e": e2e,
+                "verified": verified, "roofline": roof, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8,
                 "gpu_launches": res["launches"], "clocks": res["clocks"]}
         print(json.dumps(line))
     ctx.close()

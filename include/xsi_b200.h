@@ -110,6 +110,14 @@ int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const
 int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                        const uint32_t* n_alleles, int32_t* out, uint64_t out_stride, int32_t out_on_device,
                        uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride);
+/* Same, but row i is the record's raw BCF FORMAT/GT payload (int8: the bytes bcf_update_genotypes +
+ * bcf_write1 put into the record, htslib vcf.h:152-158; vector end = 0x81), so the extract side
+ * (gt_decompressor_new.hpp:275-320) can splice rows into BCF records without narrowing int32 on the
+ * CPU.  out_stride in int8 elements.  XSI_E_UNSUPPORTED when a record has more than 63 alleles
+ * (BCF itself switches to int16 there).                                                        */
+int xsi_decode_records_i8(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                          const uint32_t* n_alleles, int8_t* out, uint64_t out_stride, int32_t out_on_device,
+                          uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride);
 /* Blocks until everything queued on the context stream is done. */
 int xsi_sync(xsi_ctx* ctx);
 

@@ -67,7 +67,19 @@ def check_decode(ctx, path, image, n_allele, block_len, one_by_one=False):
             b, nb = rd.fill_genotype_array(int(n_allele[r]), int(pos[r]))
             assert filled[r] == nb and np.array_equal(out[r, :nb], b[:nb]), r
             assert np.array_equal(counts[r, :int(n_allele[r])], rd.allele_counts()), r
+        if int(np.max(n_allele)) <= 63:
+            # raw BCF int8 rows (xsi_decode_records_i8): the int32 values narrowed the way htslib stores them
+            out8, filled8, _ = acc.fill_genotype_arrays(n_allele, pos, elem_bytes=1)
+            assert np.array_equal(filled8, filled)
+            for r in range(len(n_allele)):
+                nb = int(filled[r])
+                assert np.array_equal(out8[r, :nb], narrow_i8(out[r, :nb])), r
     acc.close()
+
+
+def narrow_i8(row):
+    """int32 genotype values -> BCF int8 payload (vector end 0x81, htslib vcf.h bcf_int8_vector_end)."""
+    return np.where(row == synth.EOV, -127, row).astype(np.int8)
 
 
 def roundtrip(ctx, tmp_path, ds, block_len, maf, elem=4, one_by_one=False, blocks_per_batch=8):
@@ -223,6 +235,28 @@ def test_zstd_layer_roundtrip(ctx, tmp_path):
     assert acc.zstd
     acc.close()
     check_decode(ctx, p, img, ds["n_allele"], 100)
+
+
+def test_int8_rows_aligned_fast_path(ctx, tmp_path):
+    """int8 egress through the TMA-store kernel (rows a multiple of 16 bytes) incl. sparse and negated-sparse lines."""
+    ds = synth.make_dataset(400, 1024, seed=21)
+    roundtrip(ctx, tmp_path, ds, 128, 0.01)
+    ds = synth.make_dataset(300, 1000, seed=22, missing=0.002)  # diploid rows 2000 B: 16-byte multiple; odd ones are not
+    roundtrip(ctx, tmp_path, ds, 128, 0.01)
+
+
+def test_int8_rows_reject_wide_alleles(ctx, tmp_path):
+    import xsqueezeit_b200 as xb
+    ds = synth.make_dataset(20, 64, seed=23, max_alt=70, multi_frac=1.0)
+    if int(ds["n_allele"].max()) <= 63:
+        pytest.skip("generator produced no record with more than 63 alleles")
+    p = gpu_encode(ctx, tmp_path, ds, 128, 0.01)
+    acc = xb.Accessor(p, ctx)
+    pos = xb.bm_positions(ds["n_allele"], 128)
+    with pytest.raises(xb.XsiError) as e:
+        acc.fill_genotype_arrays(ds["n_allele"], pos, elem_bytes=1)
+    assert e.value.code == -5  # XSI_E_UNSUPPORTED
+    acc.close()
 
 
 def test_error_codes(ctx):

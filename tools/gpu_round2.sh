@@ -1,6 +1,6 @@
 # round-1 refresh after pbwt_permute_v4: tests, smoke, bench, reference arm, ncu launch list + full captures
 mkdir -p gpurun_out
-T=r01b
+T=${T:-r01c}
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/${T}_smi.txt
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1

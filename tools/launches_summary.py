@@ -16,7 +16,8 @@ def main():
         a = agg.setdefault(name, [0, 0.0, r[7], r[8]])
         a[0] += 1
         a[1] += float(r[14]) / 1e6
-    ours = {k: v for k, v in agg.items() if k.startswith("xsi::")}
+    pat = re.compile(r"^(xsi::)?(scan_rows|build_wah|pbwt_|wah_|scan_u32|sparse_|pack_wah|compose_)")
+    ours = {k: v for k, v in agg.items() if pat.match(k)}  # newer ncu prints the names without the namespace
     tot = sum(v[1] for v in ours.values())
     print("# xsi:: kernels: %d launches, %.3f ms (ncu-serialised, cold cache); other (torch generator / fills): %d launches, %.3f ms"
           % (sum(v[0] for v in ours.values()), tot, sum(v[0] for k, v in agg.items() if k not in ours),

@@ -82,6 +82,8 @@ def lib():
     L.xsi_decode_load_blocks.argtypes = [vp, u32, P(vp), P(u64), u64, i32]
     L.xsi_decode_records.restype = i32
     L.xsi_decode_records.argtypes = [vp, u64, vp, vp, vp, vp, u64, i32, vp, vp, u32]
+    L.xsi_decode_records_i8.restype = i32
+    L.xsi_decode_records_i8.argtypes = [vp, u64, vp, vp, vp, vp, u64, i32, vp, vp, u32]
     L.xsi_writer_open.restype = i32
     L.xsi_writer_open.argtypes = [ctypes.c_char_p, u32, ctypes.c_char_p, u32, u64, i32, i32, i32, P(vp)]
     L.xsi_writer_add_blocks.restype = i32
@@ -223,23 +225,24 @@ class Context:
         self._dec_hap = 2 * int(num_samples)
 
     def decode_records(self, block_index, line_offset, n_alleles, out=None, out_stride=None, out_on_device=False,
-                       want_counts=False):
+                       want_counts=False, elem_bytes=4):
+        """elem_bytes=4: int32 rows (bcf_get_genotypes values); 1: raw BCF int8 FORMAT/GT rows."""
         bi = np.ascontiguousarray(block_index, dtype=np.uint32)
         lo = np.ascontiguousarray(line_offset, dtype=np.uint32)
         na = np.ascontiguousarray(n_alleles, dtype=np.uint32)
         n = bi.size
         stride = int(out_stride or self._dec_hap)
         if out is None:
-            out = np.empty((n, stride), dtype=np.int32)
+            out = np.empty((n, stride), dtype=np.int32 if elem_bytes == 4 else np.int8)
         filled = np.zeros(n, dtype=np.uint32)
         counts = None
         cs = 0
         if want_counts:
             cs = int(na.max()) if n else 2
             counts = np.zeros((n, cs), dtype=np.uint64)
-        self._check(self._L.xsi_decode_records(self.h, n, bi.ctypes.data, lo.ctypes.data, na.ctypes.data, _ptr(out), stride,
-                                               1 if out_on_device else 0, filled.ctypes.data,
-                                               None if counts is None else counts.ctypes.data, cs))
+        fn = self._L.xsi_decode_records if elem_bytes == 4 else self._L.xsi_decode_records_i8
+        self._check(fn(self.h, n, bi.ctypes.data, lo.ctypes.data, na.ctypes.data, _ptr(out), stride,
+           1 if out_on_device else 0, filled.ctypes.data, None if counts is None else counts.ctypes.data, cs))
         return out, filled, counts
 
 
@@ -423,8 +426,9 @@ class Accessor:
     def get_allele_counts(self):
         return self._counts
 
-    def fill_genotype_arrays(self, n_alleles, positions, out=None, out_on_device=False, want_counts=False):
-        """Batch form: decodes every requested record; blocks are loaded in runs."""
+    def fill_genotype_arrays(self, n_alleles, positions, out=None, out_on_device=False, want_counts=False, elem_bytes=4):
+        """Batch form: decodes every requested record; blocks are loaded in runs.
+        elem_bytes=1 yields the records' raw BCF int8 FORMAT/GT rows instead of int32."""
         positions = np.asarray(positions, dtype=np.uint64)
         n_alleles = np.asarray(n_alleles, dtype=np.uint32)
         blk = ((positions & np.uint64(0xFFFFFFFF)) >> np.uint64(self.BM_BLOCK_BITS)).astype(np.int64)
@@ -432,7 +436,7 @@ class Accessor:
         stride = max(int(self.hap_samples), 2 * int(self.num_samples))
         n = positions.size
         if out is None:
-            out = np.empty((n, stride), dtype=np.int32)
+            out = np.empty((n, stride), dtype=np.int32 if elem_bytes == 4 else np.int8)
         filled = np.zeros(n, dtype=np.uint32)
         counts = np.zeros((n, int(n_alleles.max()) if n else 2), dtype=np.uint64) if want_counts else None
         i = 0
@@ -441,9 +445,10 @@ class Accessor:
             while j < n and blk[j] == blk[i]:
                 j += 1
             self._load(int(blk[i]), 1)
-            sub_out = out[i:j] if not out_on_device else int(out) + i * stride * 4
+            sub_out = out[i:j] if not out_on_device else int(out) + i * stride * elem_bytes
             o, f, c = self.ctx.decode_records(np.zeros(j - i, np.uint32), off[i:j], n_alleles[i:j], out=sub_out,
-                                              out_stride=stride, out_on_device=out_on_device, want_counts=want_counts)
+                                              out_stride=stride, out_on_device=out_on_device, want_counts=want_counts,
+                                              elem_bytes=elem_bytes)
             filled[i:j] = f
             if want_counts:
                 counts[i:j, :c.shape[1]] = c

@@ -684,7 +684,7 @@ struct ReqDev {
     const uint32_t* line;      // [n] first binary line within the block
     const uint32_t* nall;      // [n]
     uint32_t n;
-    int32_t* out; uint64_t out_stride;
+    void* out; uint64_t out_stride;  // int32 (bcf_get_genotypes) or int8 (raw BCF FORMAT/GT) rows, stride in elements
     uint32_t* filled;          // [n]
     uint32_t* counts; uint32_t counts_stride;  // [n][counts_stride]
     uint8_t* scratch;          // [grid][2][Npad]  allele code / phase-by-index flag (general path)
@@ -698,8 +698,26 @@ __device__ __forceinline__ uint32_t rd_entry(const uint8_t* m, uint64_t e, uint3
 }
 
 constexpr int D4_THREADS = 256;
+// Output element: int32 = what bcf_get_genotypes / fill_genotype_array hand out; int8 = the BCF record's own
+// FORMAT/GT payload (htslib vcf.h:152-158, what bcf_update_genotypes narrows to when every value fits):
+// same (allele+1)<<1|phased code, vector end = 0x81 (bcf_int8_vector_end).
+template <typename OT> __device__ __forceinline__ OT gt_out(int32_t v);
+template <> __device__ __forceinline__ int32_t gt_out<int32_t>(int32_t v) { return v; }
+template <> __device__ __forceinline__ int8_t gt_out<int8_t>(int32_t v) { return v == XSI_I32_VECTOR_END ? (int8_t)0x81 : (int8_t)v; }
+template <typename OT> __device__ __forceinline__ void store4(OT* p, int32_t a, int32_t b, int32_t c, int32_t e);
+template <> __device__ __forceinline__ void store4<int32_t>(int32_t* p, int32_t a, int32_t b, int32_t c, int32_t e) { *reinterpret_cast<int4*>(p) = make_int4(a, b, c, e); }
+template <> __device__ __forceinline__ void store4<int8_t>(int8_t* p, int32_t a, int32_t b, int32_t c, int32_t e) {
+    *reinterpret_cast<uint32_t*>(p) = (uint32_t)(a & 0xFF) | ((uint32_t)(b & 0xFF) << 8) | ((uint32_t)(c & 0xFF) << 16) | ((uint32_t)(e & 0xFF) << 24);
+}
 constexpr uint8_t CODE_MISSING = 254, CODE_EOV = 255;
 
+// a record goes through compose_simple when it has one ALT line, no overlay, and its row is a whole number of 16-byte units
+template <typename OT>
+__device__ __forceinline__ bool compose_is_simple(uint32_t nall, uint8_t f0, uint32_t n) {
+    return nall == 2 && !(f0 & (DL_MISSING | DL_EOV | DL_PHASE)) && (n * (uint32_t)sizeof(OT)) % 16u == 0;
+}
+
+template <typename OT>
 __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, ReqDev q, int skip_simple) {
     const uint32_t tid = threadIdx.x;
     const uint32_t S = d.n_samples, NH = 2 * S;
@@ -711,11 +729,11 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
         const uint8_t f0 = d.dline_flags[gl0];
         const uint32_t n = (f0 & DL_HAPLOID) ? S : NH;
         const int32_t DP = (int32_t)(blk.default_phasing & 1u);
-        int32_t* out = q.out + (size_t)ri * q.out_stride;
+        OT* out = static_cast<OT*>(q.out) + (size_t)ri * q.out_stride;
         uint32_t* cnts = q.counts ? q.counts + (size_t)ri * q.counts_stride : nullptr;
         const uint8_t* spm = d.blob + blk.sparse_off;
         const bool weird = (f0 & (DL_MISSING | DL_EOV | DL_PHASE)) != 0;
-        if (skip_simple && nall == 2 && !weird) continue;  // written by compose_simple_kernel
+        if (skip_simple && compose_is_simple<OT>(nall, f0, n)) continue;  // written by compose_simple_kernel
         if (tid == 0 && q.filled) q.filled[ri] = n;
 
         if (nall == 2 && !weird) {
@@ -729,8 +747,8 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
                     int32_t v[4];
 #pragma unroll
                     for (int k = 0; k < 4; ++k) v[k] = (int32_t)((((bits >> k) & 1u) + 1u) << 1) | (hap ? 0 : ((int32_t)((i4 + k) & 1u) & DP));
-                    if (i4 + 3 < n && ((reinterpret_cast<uintptr_t>(out + i4) & 15) == 0)) *reinterpret_cast<int4*>(out + i4) = make_int4(v[0], v[1], v[2], v[3]);
-                    else for (int k = 0; k < 4; ++k) if (i4 + k < n) out[i4 + k] = v[k];
+                    if (i4 + 3 < n && ((reinterpret_cast<uintptr_t>(out + i4) & (4 * sizeof(OT) - 1)) == 0)) store4<OT>(out + i4, v[0], v[1], v[2], v[3]);
+                    else for (int k = 0; k < 4; ++k) if (i4 + k < n) out[i4 + k] = (OT)v[k];
                 }
                 if (cnts && tid == 0) { const uint32_t ones = d.job_ones[job]; cnts[1] = ones; cnts[0] = n - ones; }
             } else {
@@ -739,11 +757,11 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
                 const bool neg = (hdr & msb) != 0;
                 const uint32_t cnt = hdr & ~msb;
                 const int32_t dflt = neg ? 4 : 2, spv = neg ? 2 : 4;  // bcf_gt_unphased(1) = 4, (0) = 2
-                for (uint32_t i = tid; i < n; i += D4_THREADS) out[i] = dflt | ((int32_t)(i & 1u) & DP);
+                for (uint32_t i = tid; i < n; i += D4_THREADS) out[i] = (OT)(dflt | ((int32_t)(i & 1u) & DP));
                 __syncthreads();
                 for (uint32_t k = tid; k < cnt; k += D4_THREADS) {
                     const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet);
-                    if (i < q.out_stride) out[i] = spv | ((int32_t)(i & 1u) & DP);
+                    if (i < q.out_stride) out[i] = (OT)(spv | ((int32_t)(i & 1u) & DP));
                 }
                 if (cnts && tid == 0) { const uint32_t ones = neg ? n - cnt : cnt; cnts[1] = ones; cnts[0] = n - ones; }
             }
@@ -817,7 +835,7 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
                 v = (c == CODE_MISSING ? 0 : (int32_t)(((uint32_t)c + 1u) << 1)) | ((int32_t)(pf[i] & i & 1u) & DP);
                 if (prow && ((prow[i >> 5] >> (i & 31)) & 1u)) v ^= (int32_t)(i & 1u);
             }
-            out[i] = v;
+            out[i] = gt_out<OT>(v);
         }
         if (cnts && tid == 0) cnts[0] = n - (total_alt + n_missing + n_eov);
         __syncthreads();
@@ -841,24 +859,24 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 template <int N_PENDING>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
 
+template <typename OT>
 __global__ void __launch_bounds__(D4_THREADS, 2) compose_simple_kernel(DecDev d, ReqDev q) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];  // 2 tiles of D5_TILE int32
-    int32_t* tiles = reinterpret_cast<int32_t*>(smem_raw);
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // 2 tiles of D5_TILE elements
+    OT* tiles = reinterpret_cast<OT*>(smem_raw);
     const uint32_t tid = threadIdx.x;
     const uint32_t S = d.n_samples, NH = 2 * S;
     const uint32_t msb = d.aet == 2 ? 0x8000u : 0x80000000u;
     const uint32_t rot = tid & 7u;
     uint32_t buf = 0;
     for (uint32_t ri = blockIdx.x; ri < q.n; ri += gridDim.x) {
-        if (q.nall[ri] != 2) continue;
         const DecBlock blk = d.blocks[q.blk[ri]];
         const uint32_t gl0 = blk.line0 + q.line[ri];
         const uint8_t f0 = d.dline_flags[gl0];
-        if (f0 & (DL_MISSING | DL_EOV | DL_PHASE)) continue;
         const bool hap = (f0 & DL_HAPLOID) != 0;
         const uint32_t n = hap ? S : NH;
+        if (!compose_is_simple<OT>(q.nall[ri], f0, n)) continue;
         const int32_t DP = (int32_t)(blk.default_phasing & 1u);
-        int32_t* out = q.out + (size_t)ri * q.out_stride;
+        OT* out = static_cast<OT*>(q.out) + (size_t)ri * q.out_stride;
         const bool wah = (f0 & DL_WAH) != 0;
         const uint32_t ord = d.dline_ord[gl0];
         const uint32_t* row = d.rows + (size_t)ord * d.WS;
@@ -883,21 +901,35 @@ __global__ void __launch_bounds__(D4_THREADS, 2) compose_simple_kernel(DecDev d,
         for (uint32_t tt = 0; tt < ntiles; ++tt) {
             if (tid == 0) bulk_wait_read<1>();  // the store that last used this buffer has read it
             __syncthreads();
-            int32_t* tile = tiles + (size_t)buf * D5_TILE;
+            OT* tile = tiles + (size_t)buf * D5_TILE;
             const uint32_t elem0 = tt * D5_TILE;
             uint32_t w = 0;
             if (wah) { const uint32_t wi = tt * 256 + tid; w = wi < d.WS ? row[wi] : 0u; }
-            const uint32_t wr = __funnelshift_r(w, w, 4 * rot);  // chunk k of wr = chunk (k + rot) & 7 of w
             const int32_t ce = base_even, co = base_even | ph;
+            if (sizeof(OT) == 4) {
+                const uint32_t wr = __funnelshift_r(w, w, 4 * rot);  // chunk k of wr = chunk (k + rot) & 7 of w
 #pragma unroll
-            for (uint32_t k = 0; k < 8; ++k) {
-                const uint32_t c = (k + rot) & 7u;
-                int4 v;
-                v.x = ce + (int32_t)(((wr >> (4 * k)) & 1u) << 1);
-                v.y = co + (int32_t)(((wr >> (4 * k + 1)) & 1u) << 1);
-                v.z = ce + (int32_t)(((wr >> (4 * k + 2)) & 1u) << 1);
-                v.w = co + (int32_t)(((wr >> (4 * k + 3)) & 1u) << 1);
-                *reinterpret_cast<int4*>(tile + tid * 32 + c * 4) = v;
+                for (uint32_t k = 0; k < 8; ++k) {
+                    const uint32_t c = (k + rot) & 7u;
+                    int4 v;
+                    v.x = ce + (int32_t)(((wr >> (4 * k)) & 1u) << 1);
+                    v.y = co + (int32_t)(((wr >> (4 * k + 1)) & 1u) << 1);
+                    v.z = ce + (int32_t)(((wr >> (4 * k + 2)) & 1u) << 1);
+                    v.w = co + (int32_t)(((wr >> (4 * k + 3)) & 1u) << 1);
+                    *reinterpret_cast<int4*>(reinterpret_cast<int32_t*>(tile) + tid * 32 + c * 4) = v;
+                }
+            } else {
+                // 32 genotypes = 32 bytes per thread: nibble -> 4 bytes by one multiply (bit i lands in byte i), two
+                // 16-byte stores; the half order alternates every 4 threads so that a quarter-warp covers all banks
+                const uint32_t pat = (uint32_t)ce * 0x00010001u + (uint32_t)co * 0x01000100u;
+                uint32_t o[8];
+#pragma unroll
+                for (uint32_t k = 0; k < 8; ++k) o[k] = pat + ((((w >> (4 * k)) & 0xFu) * 0x00204081u & 0x01010101u) << 1);
+                const uint32_t flip = (tid >> 2) & 1u;
+                uint4* t4 = reinterpret_cast<uint4*>(reinterpret_cast<int8_t*>(tile) + tid * 32);
+                const uint4 lo = make_uint4(o[0], o[1], o[2], o[3]), hi = make_uint4(o[4], o[5], o[6], o[7]);
+                t4[flip] = flip ? hi : lo;
+                t4[flip ^ 1u] = flip ? lo : hi;
             }
             if (!wah && cnt) {
                 __syncthreads();
@@ -905,13 +937,13 @@ __global__ void __launch_bounds__(D4_THREADS, 2) compose_simple_kernel(DecDev d,
                 for (uint32_t k = tid; k < cnt; k += D4_THREADS) {
                     const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet);
                     const uint32_t li = i - elem0;
-                    if (li < (uint32_t)D5_TILE && i < n) tile[li] = spv | ((int32_t)(i & 1u) & DP);
+                    if (li < (uint32_t)D5_TILE && i < n) tile[li] = (OT)(spv | ((int32_t)(i & 1u) & DP));
                 }
             }
             fence_proxy_async();
             __syncthreads();
             if (tid == 0) {
-                const uint32_t bytes = min((uint32_t)D5_TILE, n - elem0) * 4u;
+                const uint32_t bytes = min((uint32_t)D5_TILE, n - elem0) * (uint32_t)sizeof(OT);
                 bulk_s2g(out + elem0, tile, bytes);
                 bulk_commit();
             }

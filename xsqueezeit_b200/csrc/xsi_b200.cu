@@ -1150,9 +1150,10 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     return XSI_OK;
 }
 
-extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
-                                  const uint32_t* n_alleles, int32_t* out, uint64_t out_stride, int32_t out_on_device,
-                                  uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
+template <typename OT>
+static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                               const uint32_t* n_alleles, OT* out, uint64_t out_stride, int32_t out_on_device,
+                               uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
     if (!ctx || !block_index || !line_offset || !n_alleles || !out) return XSI_E_ARG;
     auto& d = ctx->dec;
     if (!d.loaded) { ctx->err = "xsi_decode_records without loaded blocks"; return XSI_E_ARG; }
@@ -1164,13 +1165,15 @@ extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* bloc
     for (uint64_t i = 0; i < n; ++i) {
         if (block_index[i] >= d.nb) { ctx->err = "block index out of range"; return XSI_E_ARG; }
         if (n_alleles[i] < 2 || n_alleles[i] > 254) { ctx->err = "n_alleles out of range (2..254)"; return XSI_E_UNSUPPORTED; }
+        // BCF keeps FORMAT/GT as int8 only while (allele+1)<<1|1 <= 127 (htslib vcf.c bcf_update_format: wider types above)
+        if (sizeof(OT) == 1 && n_alleles[i] > 63) { ctx->err = "int8 genotype rows need n_alleles <= 63"; return XSI_E_UNSUPPORTED; }
         if ((uint64_t)line_offset[i] + n_alleles[i] - 1 > d.h_bin_lines[block_index[i]]) { ctx->err = "record runs past the end of its block"; return XSI_E_ARG; }
         max_all = std::max(max_all, n_alleles[i]);
     }
     const bool want_counts = allele_counts != nullptr;
     if (want_counts && counts_stride < max_all) { ctx->err = "counts_stride too small"; return XSI_E_ARG; }
     // chunk so that the staging buffers stay bounded
-    const uint64_t row_bytes = out_stride * 4;
+    const uint64_t row_bytes = out_stride * sizeof(OT);
     // host output is staged through a bounded device buffer; device output needs no chunking
     const uint64_t chunk = out_on_device ? std::min<uint64_t>(n, 1ull << 30)
                                          : std::max<uint64_t>(1, std::min<uint64_t>(n, (1ull << 30) / row_bytes));
@@ -1189,21 +1192,21 @@ extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* bloc
         q.filled = rq + 3 * cn;
         q.out_stride = out_stride;
         if (out_on_device) q.out = out + c0 * out_stride;
-        else { CK(d.out.ensure(cn * row_bytes)); q.out = d.out.as<int32_t>(); }
+        else { CK(d.out.ensure(cn * row_bytes)); q.out = d.out.p; }
         q.counts = nullptr; q.counts_stride = counts_stride;
         if (want_counts) { CK(d.counts.ensure(cn * counts_stride * 4)); q.counts = d.counts.as<uint32_t>(); }
         q.scratch = d.scratch.as<uint8_t>(); q.Npad = Npad;
         // rows that start and end on 16-byte boundaries take the TMA-store fast path for simple records
-        const bool fast = !getenv("XSI_COMPOSE_V1") && (reinterpret_cast<uintptr_t>(q.out) % 16 == 0) && (out_stride % 4 == 0) &&
-                          (d.n_samples % 4 == 0);
+        // (records whose own length is not, e.g. all-haploid rows of an odd sample count, stay with compose_records)
+        const bool fast = !getenv("XSI_COMPOSE_V1") && (reinterpret_cast<uintptr_t>(q.out) % 16 == 0) && (row_bytes % 16 == 0);
         if (fast) {
-            const size_t smem = (size_t)2 * D5_TILE * 4;
-            CK(cudaFuncSetAttribute(compose_simple_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const uint32_t g2 = (uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * 2);
-            { PROF("compose_simple"); compose_simple_kernel<<<g2, D4_THREADS, smem, ctx->stream>>>(d.dev, q); }
+            const size_t smem = (size_t)2 * D5_TILE * sizeof(OT);
+            CK(cudaFuncSetAttribute(compose_simple_kernel<OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const uint32_t g2 = (uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * (sizeof(OT) == 1 ? 4 : 2));
+            { PROF("compose_simple"); compose_simple_kernel<OT><<<g2, D4_THREADS, smem, ctx->stream>>>(d.dev, q); }
             CKL();
         }
-        { PROF("compose_records"); compose_records_kernel<<<grid, D4_THREADS, 0, ctx->stream>>>(d.dev, q, fast ? 1 : 0); }
+        { PROF("compose_records"); compose_records_kernel<OT><<<grid, D4_THREADS, 0, ctx->stream>>>(d.dev, q, fast ? 1 : 0); }
         CKL();
         if (!out_on_device) CK(cudaMemcpyAsync(out + c0 * out_stride, q.out, cn * row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (n_filled) CK(cudaMemcpyAsync(n_filled + c0, q.filled, cn * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1219,4 +1222,18 @@ extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* bloc
         }
     }
     return XSI_OK;
+}
+
+extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                                  const uint32_t* n_alleles, int32_t* out, uint64_t out_stride, int32_t out_on_device,
+                                  uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
+    return decode_records_impl<int32_t>(ctx, n, block_index, line_offset, n_alleles, out, out_stride, out_on_device, n_filled,
+                                        allele_counts, counts_stride);
+}
+
+extern "C" int xsi_decode_records_i8(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                                     const uint32_t* n_alleles, int8_t* out, uint64_t out_stride, int32_t out_on_device,
+                                     uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
+    return decode_records_impl<int8_t>(ctx, n, block_index, line_offset, n_alleles, out, out_stride, out_on_device, n_filled,
+                                       allele_counts, counts_stride);
 }
