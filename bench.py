@@ -440,7 +440,7 @@ def main():
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
     res = run_leg(R, gt.data_ptr(), dec.data_ptr(), True, steps, warmup, sampler, elem=EL)
-    verified = bool(torch.equal(gt, dec))
+    verified = all(bool(torch.equal(gt[r0:r0 + BL], dec[r0:r0 + BL])) for r0 in range(0, R, BL))  # block-wise: no batch-sized temporary
     t_all, t_enc, t_dec = maxr(res["t_all"]), maxr(res["t_enc"]), maxr(res["t_dec"])
     value = 2.0 * G * world * steps / t_all / 1e9
 

@@ -233,7 +233,8 @@ __global__ void __launch_bounds__(E1_THREADS) scan_rows_kernel(EncDev p) {
 // Needs 16-byte aligned rows (host checks; otherwise scan_rows_kernel runs).
 // =============================================================================================
 constexpr int S2_TILE = 8192;   // genotypes per tile = 256 threads x 32
-constexpr int S2_STAGES = 3;
+// ring depth: ~64-96 KB of bulk copies in flight per CTA whatever the element size (8 KB int8 tiles need a deeper ring)
+constexpr int s2_stages(int elem) { return elem == 4 ? 3 : 8; }
 
 template <int ELEM>
 __device__ __forceinline__ int32_t tile_value(const unsigned char* base, uint32_t i) {
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
     __shared__ uint32_t s_misc[4];
     __shared__ int32_t s_slot[3];
     constexpr uint32_t TILE_BYTES = S2_TILE * ELEM;
+    constexpr uint32_t S2_STAGES = s2_stages(ELEM);
     constexpr uint32_t TBYTES = 32 * ELEM;              // bytes of one thread's 32 genotypes
     constexpr uint32_t NCH = TBYTES / 16;               // 16-byte chunks per thread: 8 (int32) / 2 (int8)
     constexpr uint32_t EPC = 16 / ELEM;                 // genotypes per chunk: 4 / 16
@@ -337,7 +339,7 @@ __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
     const unsigned char* gbase = reinterpret_cast<const unsigned char*>(p.gt);
     const uint32_t rot = ELEM == 4 ? (tid & 7u) : ((tid >> 2) & 1u);  // chunk rotation of this thread
     if (tid == 0) {
-        for (int s = 0; s < S2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], E1_WARPS); }
+        for (uint32_t s = 0; s < S2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], E1_WARPS); }
         fence_proxy_async();
     }
     __syncthreads();
@@ -359,7 +361,7 @@ __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
             pr += gridDim.x; pt = 0;
         }
     };
-    if (tid == 0) for (int s = 0; s < S2_STAGES - 1; ++s) produce();
+    if (tid == 0) for (uint32_t s = 0; s + 1 < S2_STAGES; ++s) produce();
     uint32_t consumed = 0;
     const int32_t dpx = p.default_phasing & 1;
 

@@ -569,7 +569,8 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         if (rows_aligned16 && !getenv("XSI_SCAN_V1")) {
             // TMA-fed persistent scan: 2 CTAs per SM, each walks records blockIdx.x, +gridDim.x, ...
             const uint32_t grid = (uint32_t)std::min<uint64_t>(R, (uint64_t)ctx->sm_count * 2);
-            const size_t smem = (size_t)S2_STAGES * S2_TILE * d->gt_elem_bytes + 2 * S2_STAGES * 8;
+            const size_t stages = (size_t)s2_stages(d->gt_elem_bytes);
+            const size_t smem = stages * S2_TILE * d->gt_elem_bytes + 2 * stages * 8;
             PROF("scan_rows");
             if (d->gt_elem_bytes == 4) {
                 CK(cudaFuncSetAttribute(scan_rows_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -872,10 +873,16 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     std::vector<uint64_t> blob_off(n_blocks);
     uint64_t blob_size = 0, Lt = 0;
     for (uint32_t b = 0; b < n_blocks; ++b) {
-        int rc = parse_block(ctx, gt_blocks[b], sizes[b], pbs[b]);
-        if (rc) return rc;
         blob_off[b] = blob_size;
         blob_size += (sizes[b] + 15) / 16 * 16;
+    }
+    // the payload upload runs while the host parses the dictionaries and flag vectors
+    CK(d.blob.ensure(blob_size + 64));
+    for (uint32_t b = 0; b < n_blocks; ++b)
+        CK(cudaMemcpyAsync(d.blob.as<uint8_t>() + blob_off[b], gt_blocks[b], sizes[b], cudaMemcpyHostToDevice, ctx->stream));
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        int rc = parse_block(ctx, gt_blocks[b], sizes[b], pbs[b]);
+        if (rc) return rc;
         Lt += pbs[b].bin_lines;
     }
     d.Lt = Lt;
@@ -970,9 +977,6 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     for (uint32_t b = 0; b < n_blocks; ++b) d.h_bin_lines[b] = pbs[b].bin_lines;
 
     // ---- upload ----
-    CK(d.blob.ensure(blob_size + 64));
-    for (uint32_t b = 0; b < n_blocks; ++b)
-        CK(cudaMemcpyAsync(d.blob.as<uint8_t>() + blob_off[b], gt_blocks[b], sizes[b], cudaMemcpyHostToDevice, ctx->stream));
     const uint32_t NJp = njobs ? njobs : 1, ntiles = (uint32_t)tile_seg.size(), nseg = (uint32_t)segs.size();
     // meta: blocks | segs
     const size_t m_blk = 0, m_seg = m_blk + sizeof(DecBlock) * n_blocks, m_end = m_seg + sizeof(DecSeg) * (nseg ? nseg : 1);
