@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(E1_THREADS) scan_rows_kernel(EncDev p) {
 // =============================================================================================
 constexpr int S2_TILE = 8192;   // genotypes per tile = 256 threads x 32
 // ring depth: ~64-96 KB of bulk copies in flight per CTA whatever the element size (8 KB int8 tiles need a deeper ring)
-constexpr int s2_stages(int elem) { return elem == 4 ? 3 : 8; }
+__host__ __device__ constexpr int s2_stages(int elem) { return elem == 4 ? 3 : 8; }
 
 template <int ELEM>
 __device__ __forceinline__ int32_t tile_value(const unsigned char* base, uint32_t i) {
