@@ -334,6 +334,7 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
     ctx = xb.Context(local_rank)

@@ -118,6 +118,13 @@ int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, co
 int xsi_decode_records_i8(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                           const uint32_t* n_alleles, int8_t* out, uint64_t out_stride, int32_t out_on_device,
                           uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride);
+/* Counts only, no row is materialised: replaces AccessorInternals::fill_allele_counts
+ * (accessor_internals.hpp:404, accessor_internals_new.hpp:407-440,747-752; the AC/AN recompute of af_stats).
+ * Row i of allele_counts (host) receives n_alleles[i] counts.  As in the reference, count[0] is
+ * CURRENT_N_HAPS - sum(ALT counts): missing and end-of-vector entries are NOT subtracted here
+ * (fill_genotype_array / xsi_decode_records does subtract them).                               */
+int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                             const uint32_t* n_alleles, uint64_t* allele_counts, uint32_t counts_stride);
 /* Blocks until everything queued on the context stream is done. */
 int xsi_sync(xsi_ctx* ctx);
 

@@ -104,7 +104,18 @@ uint64_t xsi_ref_fill_genotype_array(void* h, int32_t* gt_arr, uint64_t gt_arr_s
     }
 }
 
-// allele counts as left by the last fill_genotype_array (accessor.hpp:56)
+// Accessor::fill_allele_counts (accessor.hpp:52-54): counts without materialising the row
+int xsi_ref_fill_allele_counts(void* h, uint64_t n_alleles, uint64_t position) {
+    try {
+        static_cast<Accessor*>(h)->fill_allele_counts(n_alleles, position);
+        return 0;
+    } catch (const char* e) {
+        fprintf(stderr, "xsi_ref_fill_allele_counts: reference threw: %s\n", e);
+        return -1;
+    }
+}
+
+// allele counts as left by the last fill_genotype_array / fill_allele_counts (accessor.hpp:56)
 uint64_t xsi_ref_allele_counts(void* h, uint64_t* out, uint64_t cap) {
     const std::vector<size_t>& ac = static_cast<Accessor*>(h)->get_allele_counts();
     for (size_t i = 0; i < ac.size() && i < cap; ++i) out[i] = ac[i];

@@ -812,6 +812,35 @@ int64_t xo_fill_genotype_array(xo_reader* r, int32_t* gt_arr, uint64_t gt_arr_si
     cursor_seek(r, offset);
     return fill_advance(r, gt_arr, gt_arr_size, n_alleles);
 }
+/* accessor_internals_new.hpp:407-440 fill_allele_counts_advance behind :747-752 fill_allele_counts: counts only.
+ * As in the reference, allele_counts[0] = CURRENT_N_HAPS - total_alt (missing / end-of-vector entries are NOT
+ * subtracted here, unlike fill_genotype_array) and the missing / phase cursors are not advanced. */
+int64_t xo_fill_allele_counts(xo_reader* r, uint64_t n_alleles, uint64_t position) {
+    uint64_t block_id = (position & 0xFFFFFFFFull) >> 15;
+    uint64_t offset = position & 0x7FFF;
+    if (r->cur_block != (int64_t)block_id) { int rc = open_block(r, block_id); if (rc) { r->cur_block = -1; return rc; } }
+    cursor_seek(r, offset);
+    cursor_t* c = &r->c;
+    const uint16_t* end = (const uint16_t*)(r->file + r->len);
+    if (n_alleles < 1 || n_alleles > 255) return -1;
+    const uint64_t N = cur_n(r);
+    uint64_t total_alt = 0;
+    r->n_counts = n_alleles;
+    memset(r->allele_counts, 0, sizeof(r->allele_counts));
+    for (uint64_t alt = 1; alt < n_alleles; ++alt) {
+        if (c->is_wah[c->pos]) {
+            c->wah_p = (const uint8_t*)wah_extract((const uint16_t*)c->wah_p, end, r->y, N, r->N_HAPS + 15, &r->ones);
+        } else {
+            uint32_t n; const uint8_t* p = sparse_header(r, c->sparse_p, &n);
+            c->sparse_p = p + (size_t)n * r->aet;
+        }
+        update_a(r);
+        c->pos++;
+        r->allele_counts[alt] = r->ones; total_alt += r->ones;
+    }
+    r->allele_counts[0] = N - total_alt;
+    return (int64_t)n_alleles;
+}
 uint64_t xo_allele_counts(const xo_reader* r, uint64_t* out, uint64_t cap) {
     for (uint64_t i = 0; i < r->n_counts && i < cap; ++i) out[i] = r->allele_counts[i];
     return r->n_counts;

@@ -35,6 +35,8 @@ uint64_t   xo_num_blocks(const xo_reader* r);
 /* returns number of filled entries, <0 on error */
 int64_t xo_fill_genotype_array(xo_reader* r, int32_t* gt_arr, uint64_t gt_arr_size, uint64_t n_alleles,
                                uint64_t position);
+/* counts only (Accessor::fill_allele_counts); read them with xo_allele_counts. returns n_alleles, <0 on error */
+int64_t xo_fill_allele_counts(xo_reader* r, uint64_t n_alleles, uint64_t position);
 uint64_t xo_allele_counts(const xo_reader* r, uint64_t* out, uint64_t cap);
 
 #ifdef __cplusplus

@@ -52,6 +52,8 @@ def lib():
         L.xo_num_blocks.argtypes = [vp]
         L.xo_fill_genotype_array.restype = ctypes.c_int64
         L.xo_fill_genotype_array.argtypes = [vp, vp, u64, u64, u64]
+        L.xo_fill_allele_counts.restype = ctypes.c_int64
+        L.xo_fill_allele_counts.argtypes = [vp, u64, u64]
         L.xo_allele_counts.restype = u64
         L.xo_allele_counts.argtypes = [vp, vp, u64]
         _lib = L
@@ -137,6 +139,13 @@ class Reader:
         if n < 0:
             raise RuntimeError("oracle fill_genotype_array rc=%d" % n)
         return out, int(n)
+
+    def fill_allele_counts(self, n_alleles, position):
+        """Accessor::fill_allele_counts: counts only (allele_counts[0] ignores missing / end-of-vector entries)."""
+        n = lib().xo_fill_allele_counts(self.h, n_alleles, position)
+        if n < 0:
+            raise RuntimeError("oracle fill_allele_counts rc=%d" % n)
+        return self.allele_counts()
 
     def allele_counts(self):
         buf = np.zeros(256, dtype=np.uint64)

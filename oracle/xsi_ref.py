@@ -36,6 +36,8 @@ def lib():
         L.xsi_ref_fill_genotype_array.restype = ctypes.c_uint64
         L.xsi_ref_fill_genotype_array.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64,
                                                   ctypes.c_uint64, ctypes.c_uint64]
+        L.xsi_ref_fill_allele_counts.restype = ctypes.c_int
+        L.xsi_ref_fill_allele_counts.argtypes = [ctypes.c_void_p, ctypes.c_uint64, ctypes.c_uint64]
         L.xsi_ref_allele_counts.restype = ctypes.c_uint64
         L.xsi_ref_allele_counts.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint64]
         L.xsi_ref_accessor_close.restype = None
@@ -77,6 +79,11 @@ class RefAccessor:
         if n == 2**64 - 1:
             raise RuntimeError("reference fill_genotype_array threw")
         return out, int(n)
+
+    def fill_allele_counts(self, n_alleles, position):
+        if lib().xsi_ref_fill_allele_counts(self.h, n_alleles, position) != 0:
+            raise RuntimeError("reference fill_allele_counts threw")
+        return self.allele_counts()
 
     def allele_counts(self):
         buf = np.zeros(256, dtype=np.uint64)

@@ -67,6 +67,12 @@ def check_decode(ctx, path, image, n_allele, block_len, one_by_one=False):
             b, nb = rd.fill_genotype_array(int(n_allele[r]), int(pos[r]))
             assert filled[r] == nb and np.array_equal(out[r, :nb], b[:nb]), r
             assert np.array_equal(counts[r, :int(n_allele[r])], rd.allele_counts()), r
+        # counts only (xsi_decode_allele_counts == Accessor::fill_allele_counts), oracle in file order on a fresh cursor
+        ac = acc.fill_allele_counts_batch(n_allele, pos)
+        rd2 = xo.Reader(image)
+        for r in range(len(n_allele)):
+            assert np.array_equal(ac[r, :int(n_allele[r])], rd2.fill_allele_counts(int(n_allele[r]), int(pos[r]))), r
+        rd2.close()
         if int(np.max(n_allele)) <= 63:
             # raw BCF int8 rows (xsi_decode_records_i8): the int32 values narrowed the way htslib stores them
             out8, filled8, _ = acc.fill_genotype_arrays(n_allele, pos, elem_bytes=1)

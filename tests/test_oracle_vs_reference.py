@@ -35,6 +35,13 @@ def both(ds, block_len, maf, zstd=False):
             assert na == nb and np.array_equal(a[:na], b[:nb]), r
             assert np.array_equal(acc.allele_counts(), rd.allele_counts()), r
         acc.close()
+        # counts only (Accessor::fill_allele_counts), fresh cursors on both sides, records in file order
+        acc = xsi_ref.RefAccessor(p)
+        rd = xo.Reader(img)
+        for r in range(len(nal)):
+            assert np.array_equal(acc.fill_allele_counts(int(nal[r]), int(pos[r])),
+                                  rd.fill_allele_counts(int(nal[r]), int(pos[r]))), r
+        acc.close()
     return img
 
 

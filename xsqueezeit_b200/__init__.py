@@ -84,6 +84,8 @@ def lib():
     L.xsi_decode_records.argtypes = [vp, u64, vp, vp, vp, vp, u64, i32, vp, vp, u32]
     L.xsi_decode_records_i8.restype = i32
     L.xsi_decode_records_i8.argtypes = [vp, u64, vp, vp, vp, vp, u64, i32, vp, vp, u32]
+    L.xsi_decode_allele_counts.restype = i32
+    L.xsi_decode_allele_counts.argtypes = [vp, u64, vp, vp, vp, vp, u32]
     L.xsi_writer_open.restype = i32
     L.xsi_writer_open.argtypes = [ctypes.c_char_p, u32, ctypes.c_char_p, u32, u64, i32, i32, i32, P(vp)]
     L.xsi_writer_add_blocks.restype = i32
@@ -244,6 +246,19 @@ class Context:
         self._check(fn(self.h, n, bi.ctypes.data, lo.ctypes.data, na.ctypes.data, _ptr(out), stride,
            1 if out_on_device else 0, filled.ctypes.data, None if counts is None else counts.ctypes.data, cs))
         return out, filled, counts
+
+
+    def decode_allele_counts(self, block_index, line_offset, n_alleles):
+        """Counts only (AccessorInternals::fill_allele_counts); returns uint64 [n, max(n_alleles)]."""
+        bi = np.ascontiguousarray(block_index, dtype=np.uint32)
+        lo = np.ascontiguousarray(line_offset, dtype=np.uint32)
+        na = np.ascontiguousarray(n_alleles, dtype=np.uint32)
+        n = bi.size
+        cs = int(na.max()) if n else 2
+        counts = np.zeros((n, cs), dtype=np.uint64)
+        self._check(self._L.xsi_decode_allele_counts(self.h, n, bi.ctypes.data, lo.ctypes.data, na.ctypes.data,
+                                                     counts.ctypes.data, cs))
+        return counts
 
 
 # ---- file-level parameters (host logic, not the hot path) --------------------------------------
@@ -425,6 +440,31 @@ class Accessor:
 
     def get_allele_counts(self):
         return self._counts
+
+    def fill_allele_counts(self, n_alleles, position):
+        """AccessorInternals::fill_allele_counts: counts without the genotype row; read with get_allele_counts()."""
+        b, off = self.split_bm(position)
+        self._load(b, 1)
+        self._counts = self.ctx.decode_allele_counts([b - self._loaded[0]], [off], [n_alleles])[0, :n_alleles].copy()
+
+    def fill_allele_counts_batch(self, n_alleles, positions):
+        """Batch form of fill_allele_counts: uint64 [n, max(n_alleles)]."""
+        positions = np.asarray(positions, dtype=np.uint64)
+        n_alleles = np.asarray(n_alleles, dtype=np.uint32)
+        blk = ((positions & np.uint64(0xFFFFFFFF)) >> np.uint64(self.BM_BLOCK_BITS)).astype(np.int64)
+        off = (positions & np.uint64((1 << self.BM_BLOCK_BITS) - 1)).astype(np.uint32)
+        n = positions.size
+        counts = np.zeros((n, int(n_alleles.max()) if n else 2), dtype=np.uint64)
+        i = 0
+        while i < n:
+            j = i
+            while j < n and blk[j] == blk[i]:
+                j += 1
+            self._load(int(blk[i]), 1)
+            c = self.ctx.decode_allele_counts(np.zeros(j - i, np.uint32), off[i:j], n_alleles[i:j])
+            counts[i:j, :c.shape[1]] = c
+            i = j
+        return counts
 
     def fill_genotype_arrays(self, n_alleles, positions, out=None, out_on_device=False, want_counts=False, elem_bytes=4):
         """Batch form: decodes every requested record; blocks are loaded in runs.

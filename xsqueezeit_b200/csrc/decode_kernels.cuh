@@ -843,6 +843,40 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
 }
 
 // =============================================================================================
+// D5: allele counts only (fill_allele_counts_advance, accessor_internals_new.hpp:407-440): per ALT line the
+// carriers counted when the line was expanded (WAH) or its list header (sparse, negated: N - count);
+// allele_counts[0] = CURRENT_N_HAPS - sum, WITHOUT the missing / end-of-vector correction of fill_genotype_array.
+// =============================================================================================
+__global__ void __launch_bounds__(128) allele_counts_kernel(DecDev d, ReqDev q) {
+    const uint32_t ri = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ri >= q.n) return;
+    const DecBlock blk = d.blocks[q.blk[ri]];
+    const uint32_t nall = q.nall[ri];
+    const uint32_t gl0 = blk.line0 + q.line[ri];
+    const uint32_t S = d.n_samples, NH = 2 * S;
+    const uint32_t msb = d.aet == 2 ? 0x8000u : 0x80000000u;
+    const uint32_t n = (d.dline_flags[gl0] & DL_HAPLOID) ? S : NH;
+    const uint8_t* spm = d.blob + blk.sparse_off;
+    uint32_t* cnts = q.counts + (size_t)ri * q.counts_stride;
+    uint32_t total = 0;
+    for (uint32_t alt = 1; alt < nall; ++alt) {
+        const uint32_t gl = gl0 + alt - 1;
+        const uint8_t fl = d.dline_flags[gl];
+        uint32_t ones;
+        if (fl & DL_WAH) ones = d.job_ones[d.dline_ord[gl]];
+        else {
+            const uint32_t hdr = rd_entry(spm, d.sp_off[d.dline_ord[gl]], d.aet);
+            const uint32_t cnt = hdr & ~msb;
+            ones = (hdr & msb) ? ((fl & DL_HAPLOID) ? S : NH) - cnt : cnt;
+        }
+        cnts[alt] = ones;
+        total += ones;
+    }
+    cnts[0] = n - total;
+    if (q.filled) q.filled[ri] = n;
+}
+
+// =============================================================================================
 // D4 fast path: records with one ALT line and no missing / end-of-vector / phase overlay (the bulk
 // of any file).  Persistent CTAs build 8192-genotype int32 tiles in shared memory -- a thread
 // expands its own 32-bit word of the bit-row (WAH lines) or writes the default pattern that the

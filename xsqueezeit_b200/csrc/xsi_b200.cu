@@ -1235,6 +1235,42 @@ extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* bloc
                                         allele_counts, counts_stride);
 }
 
+extern "C" int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                                        const uint32_t* n_alleles, uint64_t* allele_counts, uint32_t counts_stride) {
+    if (!ctx || !block_index || !line_offset || !n_alleles || !allele_counts) return XSI_E_ARG;
+    auto& d = ctx->dec;
+    if (!d.loaded) { ctx->err = "xsi_decode_allele_counts without loaded blocks"; return XSI_E_ARG; }
+    if (n == 0) return XSI_OK;
+    if (n >= (1ull << 31)) { ctx->err = "too many records in one call"; return XSI_E_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    uint32_t max_all = 2;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (block_index[i] >= d.nb) { ctx->err = "block index out of range"; return XSI_E_ARG; }
+        if (n_alleles[i] < 2 || n_alleles[i] > 254) { ctx->err = "n_alleles out of range (2..254)"; return XSI_E_UNSUPPORTED; }
+        if ((uint64_t)line_offset[i] + n_alleles[i] - 1 > d.h_bin_lines[block_index[i]]) { ctx->err = "record runs past the end of its block"; return XSI_E_ARG; }
+        max_all = std::max(max_all, n_alleles[i]);
+    }
+    if (counts_stride < max_all) { ctx->err = "counts_stride too small"; return XSI_E_ARG; }
+    CK(d.req.ensure(n * 4 * 4));
+    uint32_t* rq = d.req.as<uint32_t>();
+    CK(cudaMemcpyAsync(rq, block_index, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(rq + n, line_offset, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(rq + 2 * n, n_alleles, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ReqDev q = {};
+    q.blk = rq; q.line = rq + n; q.nall = rq + 2 * n; q.n = (uint32_t)n;
+    CK(d.counts.ensure(n * counts_stride * 4));
+    q.counts = d.counts.as<uint32_t>(); q.counts_stride = counts_stride;
+    { PROF("allele_counts"); allele_counts_kernel<<<(uint32_t)((n + 127) / 128), 128, 0, ctx->stream>>>(d.dev, q); }
+    CKL();
+    CK(d.h_stage.ensure(n * counts_stride * 4));
+    CK(cudaMemcpyAsync(d.h_stage.p, q.counts, n * counts_stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const uint32_t* hc = d.h_stage.as<uint32_t>();
+    for (uint64_t i = 0; i < n; ++i)
+        for (uint32_t k = 0; k < n_alleles[i]; ++k) allele_counts[i * counts_stride + k] = hc[i * counts_stride + k];
+    return XSI_OK;
+}
+
 extern "C" int xsi_decode_records_i8(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                                      const uint32_t* n_alleles, int8_t* out, uint64_t out_stride, int32_t out_on_device,
                                      uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
