@@ -1,11 +1,14 @@
-# r01f: multi-context (full-duplex PCIe) host-buffer leg
+# r01f: tests + smoke + default bench (multi-context full-duplex host-buffer leg)
 mkdir -p gpurun_out
 T=${T:-r01f}
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log
+tail -5 gpurun_out/${T}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" >> gpurun_out/${T}_pytest.log 2>&1; echo "smoke rc=$?"
 timeout 900 python bench.py --steps 5 --warmup 3 > gpurun_out/${T}_bench_b32.json 2> gpurun_out/${T}_bench_b32.err; echo "bench rc=$?"
 tail -5 gpurun_out/${T}_bench_b32.err
-python - <<'P'
+python - <<P
 import json
-d=json.loads(open('gpurun_out/r01f_bench_b32.json').read().strip().splitlines()[-1])
+d=json.loads(open('gpurun_out/${T}_bench_b32.json').read().strip().splitlines()[-1])
 print('value',d['value'],'verified',d['verified'])
 for k in ('e2e','e2e_bcf_int8'):
     print(k, json.dumps(d[k]))
