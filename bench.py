@@ -505,9 +505,10 @@ def main():
         # xsi_ctx (stream + pools) taking whole blocks round-robin, so that one block's upload overlaps another's
         # download and the kernels of a third: PCIe runs full duplex.  All work of all steps is inside the timed
         # region (CUDA events on worker 0's stream around start/join of the threads).
-        def host_leg_mt(dtype, elem, label, serial):
+        def host_leg_mt(dtype, elem, label, serial, narrow=True):
             nonlocal verified
             import threading
+            os.environ["XSI_HOST_NARROW"] = "1" if narrow else "0"  # read by the library at every call
             W = max(1, min(args.e2e_workers, Be))
             h_in = torch.empty((Re, H), dtype=dtype, pin_memory=True)
             h_out = torch.empty((Re, H), dtype=dtype, pin_memory=True)
@@ -556,6 +557,7 @@ def main():
             run(1)  # warm-up: pools of every context sized
             s0 = torch.cuda.ExternalStream(ctxs[0].stream, device=dev)
             launches0 = sum(c.kernel_launches for c in ctxs)
+            tr0 = [c.transport_stats for c in ctxs]
             barrier()
             a, z = ev(), ev()
             a.record(s0)
@@ -566,11 +568,21 @@ def main():
             ok2 = bool(torch.equal(h_in, h_out)) and ok_serial
             verified = verified and ok2
             pl = sum(payload)
+            # bytes that crossed the bus: rows the library moved in the int8 transport encoding count 1 byte per genotype
+            tr1 = [c.transport_stats for c in ctxs]
+            nar_h2d = sum(b_[0] - a_[0] for a_, b_ in zip(tr0, tr1)) // ns
+            nar_d2h = sum(b_[1] - a_[1] for a_, b_ in zip(tr0, tr1)) // ns
+            bus_h2d = Re * H * elem + pl - (nar_h2d * 3 if elem == 4 else 0)
+            bus_d2h = Re * H * elem + pl - (nar_d2h * 3 if elem == 4 else 0)
             out = {"value": 2.0 * Re * H * world * ns / t2 / 1e9, "unit": "Ggt/s",
-                   "h2d_bytes_per_step": Re * H * elem + pl, "d2h_bytes_per_step": Re * H * elem + pl,
+                   "h2d_bytes_per_step": bus_h2d, "d2h_bytes_per_step": bus_d2h,
+                   "host_buffer_bytes_per_step_each_way": Re * H * elem,
                    "blocks_per_step": Be, "ms_per_step": t2 / ns * 1e3, "steps": ns, "host_buffers": label,
                    "host_threads": W, "contexts": W, "gpu_launches": sum(c.kernel_launches for c in ctxs) - launches0,
-                   "pcie_gbs_each_way": (Re * H * elem + pl) * ns / t2 / 1e9, "verified": ok2}
+                   "pcie_gbs_each_way": (bus_h2d + bus_d2h) / 2 * ns / t2 / 1e9, "verified": ok2}
+            if elem == 4:
+                out["transport"] = ("int32 rows cross PCIe in their BCF int8 encoding, converted on %d host threads beside the DMA (csrc/host_narrow.cpp)"
+                                    % L.xsi_host_threads()) if nar_h2d else "int32 over PCIe (XSI_HOST_NARROW=0)"
             if r2 is not None:
                 ts_ = maxr(r2["t_all"])
                 out["serial"] = {"value": 2.0 * Re * H * world * ns / ts_ / 1e9,
@@ -586,6 +598,8 @@ def main():
         del dec
         torch.cuda.empty_cache()
         e2e = host_leg_mt(torch.int32, 4, "pinned int32 rows in and out (bcf_get_genotypes / fill_genotype_array types)", True)
+        e2e["int32_over_pcie"] = host_leg_mt(torch.int32, 4, "pinned int32 rows in and out, moved as int32 (XSI_HOST_NARROW=0)", False, narrow=False)
+        os.environ["XSI_HOST_NARROW"] = "1"
         e2e_i8 = host_leg_mt(torch.int8, 1, "pinned int8 rows in and out (raw BCF FORMAT/GT payload)", True)
 
     cpu = None

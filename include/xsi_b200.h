@@ -129,6 +129,24 @@ int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t* block_ind
 int xsi_sync(xsi_ctx* ctx);
 
 /* ------------------------------------------------------------------------------------------
+ * Host rows over PCIe.  bcf_get_genotypes widens the record's int8 FORMAT/GT payload to int32
+ * (htslib/vcf.c:4728-4795) and fill_genotype_array returns int32 (accessor_internals.hpp:399-413).
+ * With HOST int32 buffers, xsi_encode_launch / xsi_decode_records move the rows across the bus in
+ * their BCF int8 encoding and convert on the host (worker pool, beside the DMA) whenever every
+ * value has one (at most 63 alleles); otherwise int32 moves as is.  Transport only: results are
+ * identical either way.  Environment: XSI_HOST_NARROW=0 disables it, XSI_HOST_THREADS sets the
+ * pool size.  The two conversions are exported for tests and for callers that stage rows themselves.
+ * ------------------------------------------------------------------------------------------ */
+/* returns 1 when every value was representable, 0 otherwise (dst then holds garbage) */
+int  xsi_host_narrow_i32_i8(const int32_t* src, int8_t* dst, uint64_t n);
+/* row r: dst[r*dst_stride + j] = int32 form of src[r*src_stride + j] for j < len[r] */
+void xsi_host_widen_i8_i32(const int8_t* src, uint64_t src_stride, int32_t* dst, uint64_t dst_stride,
+                           const uint32_t* len, uint64_t n_rows);
+uint32_t xsi_host_threads(void);
+/* bytes this context has moved host->device / device->host in the int8 transport encoding */
+void xsi_transport_stats(const xsi_ctx* ctx, uint64_t* narrowed_h2d_bytes, uint64_t* narrowed_d2h_bytes);
+
+/* ------------------------------------------------------------------------------------------
  * Host container layer (no GPU work by itself): the .xsi file, byte-compatible with
  * XsiFactoryExt (include/xsi_factory.hpp:435-639) and readable like Accessor (include/accessor.hpp).
  * ------------------------------------------------------------------------------------------ */

@@ -265,6 +265,27 @@ def test_int8_rows_reject_wide_alleles(ctx, tmp_path):
     acc.close()
 
 
+def test_host_rows_int8_transport_and_int32_fallbacks(ctx, tmp_path, monkeypatch):
+    """Host int32 rows cross PCIe as int8 (csrc/host_narrow.cpp) when every value fits, as int32 otherwise or when
+    XSI_HOST_NARROW=0; the .xsi bytes and the decoded rows are the same on all three routes."""
+    ds = synth.make_dataset(500, 520, seed=31, max_alt=3, multi_frac=0.1, missing=0.01, unphased=0.02, haploid_samples=0.3)
+    ds["gt"][7] = synth.I32_MISSING
+    h0, d0 = ctx.transport_stats
+    roundtrip(ctx, tmp_path, ds, 128, 0.01)
+    h1, d1 = ctx.transport_stats
+    assert h1 - h0 == ds["gt"].size and d1 > d0
+    monkeypatch.setenv("XSI_HOST_NARROW", "0")
+    roundtrip(ctx, tmp_path, ds, 128, 0.01)
+    assert ctx.transport_stats == (h1, d1)
+    monkeypatch.delenv("XSI_HOST_NARROW")
+    # alleles above 62 have no int8 encoding: the upload and the download fall back to int32 on their own
+    wide = synth.make_dataset(40, 64, seed=23, max_alt=70, multi_frac=1.0)
+    if int(wide["n_allele"].max()) <= 64 or int((wide["gt"] > 127).sum()) == 0:
+        pytest.skip("generator produced no genotype value above 127")
+    roundtrip(ctx, tmp_path, wide, 16, 0.01)
+    assert ctx.transport_stats[0] == h1
+
+
 def test_error_codes(ctx):
     import xsqueezeit_b200 as xb
     gt = synth.encode_gt(np.zeros((4, 20), np.int8)).reshape(-1).copy()

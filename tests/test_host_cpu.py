@@ -110,3 +110,43 @@ def test_reader_rejects_garbage(xb, tmp_path):
     r = ctypes.c_void_p()
     assert xb.lib().xsi_reader_open(str(p).encode(), ctypes.byref(r)) == -6
     assert xb.lib().xsi_reader_open(b"/nonexistent/file.xsi", ctypes.byref(r)) == -8
+
+
+def test_host_int8_transport_conversions(xb):
+    """int32 <-> BCF int8 transport encoding (csrc/host_narrow.cpp) against numpy, every ISA level it dispatches to."""
+    L = xb.lib()
+    rng = np.random.default_rng(7)
+    n = 3 * (1 << 18) + 77  # several pool tasks + a ragged tail
+    src = rng.integers(0, 128, n).astype(np.int32)
+    src[rng.integers(0, n, 1000)] = np.int32(-2**31)        # bcf_int32_missing
+    src[rng.integers(0, n, 1000)] = np.int32(-2**31 + 1)    # bcf_int32_vector_end
+    want = np.where(src < 0, 0x80 | (src & 1), src).astype(np.uint8)
+    for m in (0, 1, 15, 16, 63, 64, 65, 4097, n):
+        dst = np.zeros(m + 8, np.uint8)
+        dst[m:] = 0xEE
+        assert L.xsi_host_narrow_i32_i8(src.ctypes.data, dst.ctypes.data, m) == 1
+        assert np.array_equal(dst[:m], want[:m]) and (dst[m:] == 0xEE).all()
+    # values without an int8 encoding are reported, wherever they sit
+    for bad in (128, 255, 256, 1 << 20, -1, -2**31 + 2, -2**31 + 0x80, 2**31 - 1):
+        for at in (0, 17, n - 1, n // 2):
+            s2 = src.copy()
+            s2[at] = np.int32(bad)
+            dst = np.zeros(n, np.uint8)
+            assert L.xsi_host_narrow_i32_i8(s2.ctypes.data, dst.ctypes.data, n) == 0, (bad, at)
+    # widen: ragged rows, untouched tails, unaligned destinations
+    rows, s8, s32 = 37, 4099, 4111
+    b = rng.integers(0, 128, (rows, s8)).astype(np.uint8)
+    b[rng.random((rows, s8)) < 0.01] = 0x80
+    b[rng.random((rows, s8)) < 0.01] = 0x81
+    ln = rng.integers(0, s8 + 1, rows).astype(np.uint32)
+    ln[0], ln[1] = 0, s8
+    out = np.full((rows, s32), 0x5A5A5A5A, np.int32)
+    L.xsi_host_widen_i8_i32(b.ctypes.data, s8, out.ctypes.data, s32, ln.ctypes.data, rows)
+    wide = np.where(b >= 0x80, np.int64(-2**31) + (b & 1), b).astype(np.int32)
+    for r in range(rows):
+        assert np.array_equal(out[r, :ln[r]], wide[r, :ln[r]]) and (out[r, ln[r]:] == 0x5A5A5A5A).all()
+    # one long row (split over several tasks) and the round trip
+    big = np.zeros(n, np.int32)
+    L.xsi_host_widen_i8_i32(want.ctypes.data, n, big.ctypes.data, n, np.array([n], np.uint32).ctypes.data, 1)
+    assert np.array_equal(big, src)
+    assert L.xsi_host_threads() >= 1

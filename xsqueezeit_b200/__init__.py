@@ -86,6 +86,14 @@ def lib():
     L.xsi_decode_records_i8.argtypes = [vp, u64, vp, vp, vp, vp, u64, i32, vp, vp, u32]
     L.xsi_decode_allele_counts.restype = i32
     L.xsi_decode_allele_counts.argtypes = [vp, u64, vp, vp, vp, vp, u32]
+    L.xsi_host_narrow_i32_i8.restype = i32
+    L.xsi_host_narrow_i32_i8.argtypes = [vp, vp, u64]
+    L.xsi_host_widen_i8_i32.restype = None
+    L.xsi_host_widen_i8_i32.argtypes = [vp, u64, vp, u64, vp, u64]
+    L.xsi_host_threads.restype = u32
+    L.xsi_host_threads.argtypes = []
+    L.xsi_transport_stats.restype = None
+    L.xsi_transport_stats.argtypes = [vp, P(u64), P(u64)]
     L.xsi_writer_open.restype = i32
     L.xsi_writer_open.argtypes = [ctypes.c_char_p, u32, ctypes.c_char_p, u32, u64, i32, i32, i32, P(vp)]
     L.xsi_writer_add_blocks.restype = i32
@@ -149,6 +157,13 @@ class Context:
     @property
     def kernel_launches(self):
         return int(self._L.xsi_kernel_launches(self.h))
+
+    @property
+    def transport_stats(self):
+        """(bytes moved host->device, device->host) in the int8 transport encoding of host int32 rows."""
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        self._L.xsi_transport_stats(self.h, ctypes.byref(a), ctypes.byref(b))
+        return int(a.value), int(b.value)
 
     def sync(self):
         self._check(self._L.xsi_sync(self.h))

@@ -8,8 +8,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 SO = os.path.join(HERE, "libxsi_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-SOURCES = ["xsi_b200.cu", "xsi_container.cpp"]
-DEPS = SOURCES + ["common.cuh", "encode_kernels.cuh", "decode_kernels.cuh", "host_util.hpp",
+SOURCES = ["xsi_b200.cu", "xsi_container.cpp", "host_narrow.cpp"]
+DEPS = SOURCES + ["common.cuh", "encode_kernels.cuh", "decode_kernels.cuh", "host_util.hpp", "host_narrow.hpp",
                   os.path.join("..", "..", "include", "xsi_b200.h")]
 
 
@@ -27,7 +27,7 @@ def build(force=False, verbose=False):
         raise RuntimeError("nvcc not found at %s and %s is missing or stale" % (NVCC, SO))
     cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
            "-Xcompiler", "-fPIC,-O2", "-shared", "-diag-suppress", "550", "-o", SO] + \
-          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl"]
+          [os.path.join(CSRC, s) for s in SOURCES] + ["-ldl", "-lpthread"]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd, cwd=CSRC)

@@ -12,6 +12,7 @@
 #include "../../include/xsi_b200.h"
 #include "decode_kernels.cuh"
 #include "encode_kernels.cuh"
+#include "host_narrow.hpp"
 #include "host_util.hpp"
 
 using namespace xsi;
@@ -68,6 +69,14 @@ struct xsi_ctx {
     struct Span { const char* name; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::string profile_text;
+
+    // pinned ring for host int32 rows that cross PCIe as int8 (host_narrow.cpp): slots of RING_BYTES
+    static constexpr int RING_SLOTS = 3;
+    static constexpr size_t RING_BYTES = 16u << 20;
+    PinBuf ring;
+    cudaEvent_t ring_ev[RING_SLOTS] = {nullptr, nullptr, nullptr};
+    bool ring_busy[RING_SLOTS] = {false, false, false};
+    uint64_t narrowed_h2d = 0, narrowed_d2h = 0;  // bytes that crossed the bus narrowed (statistics)
 
     // ---------------- encode ----------------
     struct {
@@ -175,6 +184,8 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
                       &d.a_pool, &d.x_pool, &d.req, &d.out, &d.scratch, &d.counts, &d.seg_total, &d.tabs})
         b->release();
     d.h_stage.release();
+    ctx->ring.release();
+    for (cudaEvent_t ev : ctx->ring_ev) if (ev) cudaEventDestroy(ev);
     cudaEventDestroy(ctx->ev_side);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream2);
@@ -220,6 +231,63 @@ extern "C" int xsi_sync(xsi_ctx* ctx) {
     CK(cudaStreamSynchronize(ctx->stream));
     return XSI_OK;
 }
+
+extern "C" int xsi_host_narrow_i32_i8(const int32_t* src, int8_t* dst, uint64_t n) {
+    return (src && dst) ? (narrow_i32_to_i8(src, dst, n) ? 1 : 0) : 0;
+}
+extern "C" void xsi_host_widen_i8_i32(const int8_t* src, uint64_t src_stride, int32_t* dst, uint64_t dst_stride,
+                                      const uint32_t* len, uint64_t n_rows) {
+    if (src && dst && len) widen_rows_i8_to_i32(src, src_stride, dst, dst_stride, len, n_rows);
+}
+extern "C" uint32_t xsi_host_threads(void) { return host_threads(); }
+extern "C" void xsi_transport_stats(const xsi_ctx* ctx, uint64_t* h2d, uint64_t* d2h) {
+    if (h2d) *h2d = ctx ? ctx->narrowed_h2d : 0;
+    if (d2h) *d2h = ctx ? ctx->narrowed_d2h : 0;
+}
+
+// =================================================================================================
+// Host rows over PCIe as int8 (transport only, see host_narrow.cpp).  XSI_HOST_NARROW=0 moves int32.
+// =================================================================================================
+namespace {
+
+bool host_narrow_on() {
+    const char* s = getenv("XSI_HOST_NARROW");
+    return !(s && s[0] == '0');
+}
+
+int ring_prepare(xsi_ctx* ctx) {
+    CK(ctx->ring.ensure(xsi_ctx::RING_SLOTS * xsi_ctx::RING_BYTES));
+    for (int i = 0; i < xsi_ctx::RING_SLOTS; ++i)
+        if (!ctx->ring_ev[i]) CK(cudaEventCreateWithFlags(&ctx->ring_ev[i], cudaEventDisableTiming));
+    return XSI_OK;
+}
+int ring_wait(xsi_ctx* ctx, int slot) {
+    if (ctx->ring_busy[slot]) { CK(cudaEventSynchronize(ctx->ring_ev[slot])); ctx->ring_busy[slot] = false; }
+    return XSI_OK;
+}
+
+// Uploads n host int32 genotypes as int8 into dst (device): narrowing of chunk c+1 on the worker pool runs
+// beside the DMA of chunk c.  Returns 1 when done, 0 when a value has no int8 encoding (nothing usable was
+// uploaded; the caller moves int32 instead), < 0 on error.
+int upload_narrowed(xsi_ctx* ctx, const int32_t* src, size_t n, int8_t* dst) {
+    int rc = ring_prepare(ctx);
+    if (rc) return rc;
+    const size_t CH = xsi_ctx::RING_BYTES;
+    int slot = 0;
+    for (size_t a = 0; a < n; a += CH, slot = (slot + 1) % xsi_ctx::RING_SLOTS) {
+        const size_t m = std::min(CH, n - a);
+        if ((rc = ring_wait(ctx, slot))) return rc;
+        int8_t* stage = ctx->ring.as<int8_t>() + (size_t)slot * CH;
+        if (!narrow_i32_to_i8(src + a, stage, m)) return 0;
+        CK(cudaMemcpyAsync(dst + a, stage, m, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
+        ctx->ring_busy[slot] = true;
+    }
+    ctx->narrowed_h2d += n;
+    return 1;
+}
+
+}  // namespace
 
 // =================================================================================================
 // ENCODE
@@ -468,7 +536,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
     e.h_ngt.resize(R); e.h_line0.resize(R); e.h_goff.resize(R);
     e.h_blk_line0.assign(e.nb + 1, 0); e.h_blk_rec0.assign(e.nb + 1, 0);
     uint64_t goff = 0, L = 0;
-    bool rows_aligned16 = true;  // every row starts and ends on a 16-byte boundary -> TMA-fed scan
+    bool al4 = true, al1 = true;  // every row starts and ends on a 16-byte boundary (int32 / int8 elements) -> TMA-fed scan
     e.max_ploidy = 0;
     e.any_haploid = false;
     for (uint64_t r = 0; r < R; ++r) {
@@ -481,7 +549,8 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         if (r % d->block_len == 0) { e.h_blk_line0[r / d->block_len] = (uint32_t)L; e.h_blk_rec0[r / d->block_len] = (uint32_t)r; }
         e.h_ngt[r] = S * pl;
         e.h_goff[r] = goff;
-        if ((goff * (uint64_t)d->gt_elem_bytes) % 16 || ((uint64_t)S * pl * d->gt_elem_bytes) % 16) rows_aligned16 = false;
+        if ((goff * 4) % 16 || ((uint64_t)S * pl * 4) % 16) al4 = false;
+        if (goff % 16 || ((uint64_t)S * pl) % 16) al1 = false;
         e.h_line0[r] = (uint32_t)L;
         goff += (uint64_t)S * pl;
         L += e.h_nallele[r] - 1;
@@ -499,13 +568,25 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
     const uint64_t Lp = L ? L : 1;
 
     // ---- device buffers ----
-    const size_t gt_bytes = goff * (size_t)d->gt_elem_bytes;
+    int elem = d->gt_elem_bytes;  // element size of the rows on the DEVICE
     const void* dgt = d->gt;
     if (!d->gt_on_device) {
-        CK(e.gt.ensure(gt_bytes));
-        CK(cudaMemcpyAsync(e.gt.p, d->gt, gt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        bool moved = false;
+        if (elem == 4 && host_narrow_on()) {
+            // int32 rows from bcf_get_genotypes cross the bus in their BCF int8 encoding (host_narrow.cpp)
+            CK(e.gt.ensure(goff));
+            const int rc = upload_narrowed(ctx, static_cast<const int32_t*>(d->gt), goff, e.gt.as<int8_t>());
+            if (rc < 0) return rc;
+            if (rc == 1) { moved = true; elem = 1; }
+        }
+        if (!moved) {
+            const size_t gt_bytes = goff * (size_t)elem;
+            CK(e.gt.ensure(gt_bytes));
+            CK(cudaMemcpyAsync(e.gt.p, d->gt, gt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+        }
         dgt = e.gt.p;
     }
+    bool rows_aligned16 = elem == 4 ? al4 : al1;
     if (reinterpret_cast<uintptr_t>(dgt) % 16) rows_aligned16 = false;
     // tables: goff[R] u64 | ngt[R] | nallele[R] | line0[R] | line_rec[L] | blk_line0[nb+1]
     const size_t t_goff = 0, t_ngt = t_goff + R * 8, t_nal = t_ngt + R * 4, t_l0 = t_nal + R * 4, t_lr = t_l0 + R * 4,
@@ -569,10 +650,10 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         if (rows_aligned16 && !getenv("XSI_SCAN_V1")) {
             // TMA-fed persistent scan: 2 CTAs per SM, each walks records blockIdx.x, +gridDim.x, ...
             const uint32_t grid = (uint32_t)std::min<uint64_t>(R, (uint64_t)ctx->sm_count * 2);
-            const size_t stages = (size_t)s2_stages(d->gt_elem_bytes);
-            const size_t smem = stages * S2_TILE * d->gt_elem_bytes + 2 * stages * 8;
+            const size_t stages = (size_t)s2_stages(elem);
+            const size_t smem = stages * S2_TILE * elem + 2 * stages * 8;
             PROF("scan_rows");
-            if (d->gt_elem_bytes == 4) {
+            if (elem == 4) {
                 CK(cudaFuncSetAttribute(scan_rows_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 scan_rows_v2_kernel<4><<<grid, E1_THREADS, smem, ctx->stream>>>(p);
             } else {
@@ -581,7 +662,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
             }
         } else {
             PROF("scan_rows");
-            if (d->gt_elem_bytes == 4) scan_rows_kernel<4><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
+            if (elem == 4) scan_rows_kernel<4><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
             else scan_rows_kernel<1><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
         }
         CKL();
@@ -1176,14 +1257,10 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
     }
     const bool want_counts = allele_counts != nullptr;
     if (want_counts && counts_stride < max_all) { ctx->err = "counts_stride too small"; return XSI_E_ARG; }
-    // chunk so that the staging buffers stay bounded
-    const uint64_t row_bytes = out_stride * sizeof(OT);
-    // host output is staged through a bounded device buffer; device output needs no chunking
-    const uint64_t chunk = out_on_device ? std::min<uint64_t>(n, 1ull << 30)
-                                         : std::max<uint64_t>(1, std::min<uint64_t>(n, (1ull << 30) / row_bytes));
     const uint32_t Npad = (N + 63) / 64 * 64;
-    for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
-        const uint64_t cn = std::min(chunk, n - c0);
+    // uploads the requests of records [c0, c0+cn) and composes their rows (element type DT) at dev_out, stride in elements
+    auto compose_chunk = [&](auto* dev_out, uint64_t stride, uint64_t c0, uint64_t cn, ReqDev& q) -> int {
+        using DT = std::remove_pointer_t<decltype(dev_out)>;
         CK(d.req.ensure(cn * 4 * 4));
         uint32_t* rq = d.req.as<uint32_t>();
         CK(cudaMemcpyAsync(rq, block_index + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1191,36 +1268,97 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
         CK(cudaMemcpyAsync(rq + 2 * cn, n_alleles + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
         const uint32_t grid = (uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * 8);
         CK(d.scratch.ensure((size_t)grid * 2 * Npad));
-        ReqDev q;
         q.blk = rq; q.line = rq + cn; q.nall = rq + 2 * cn; q.n = (uint32_t)cn;
         q.filled = rq + 3 * cn;
-        q.out_stride = out_stride;
-        if (out_on_device) q.out = out + c0 * out_stride;
-        else { CK(d.out.ensure(cn * row_bytes)); q.out = d.out.p; }
+        q.out_stride = stride;
+        q.out = dev_out;
         q.counts = nullptr; q.counts_stride = counts_stride;
         if (want_counts) { CK(d.counts.ensure(cn * counts_stride * 4)); q.counts = d.counts.as<uint32_t>(); }
         q.scratch = d.scratch.as<uint8_t>(); q.Npad = Npad;
         // rows that start and end on 16-byte boundaries take the TMA-store fast path for simple records
         // (records whose own length is not, e.g. all-haploid rows of an odd sample count, stay with compose_records)
-        const bool fast = !getenv("XSI_COMPOSE_V1") && (reinterpret_cast<uintptr_t>(q.out) % 16 == 0) && (row_bytes % 16 == 0);
+        const bool fast = !getenv("XSI_COMPOSE_V1") && (reinterpret_cast<uintptr_t>(q.out) % 16 == 0) && ((stride * sizeof(DT)) % 16 == 0);
         if (fast) {
-            const size_t smem = (size_t)2 * D5_TILE * sizeof(OT);
-            CK(cudaFuncSetAttribute(compose_simple_kernel<OT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const uint32_t g2 = (uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * (sizeof(OT) == 1 ? 4 : 2));
-            { PROF("compose_simple"); compose_simple_kernel<OT><<<g2, D4_THREADS, smem, ctx->stream>>>(d.dev, q); }
+            const size_t smem = (size_t)2 * D5_TILE * sizeof(DT);
+            CK(cudaFuncSetAttribute(compose_simple_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            const uint32_t g2 = (uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * (sizeof(DT) == 1 ? 4 : 2));
+            { PROF("compose_simple"); compose_simple_kernel<DT><<<g2, D4_THREADS, smem, ctx->stream>>>(d.dev, q); }
             CKL();
         }
-        { PROF("compose_records"); compose_records_kernel<OT><<<grid, D4_THREADS, 0, ctx->stream>>>(d.dev, q, fast ? 1 : 0); }
+        { PROF("compose_records"); compose_records_kernel<DT><<<grid, D4_THREADS, 0, ctx->stream>>>(d.dev, q, fast ? 1 : 0); }
         CKL();
+        return XSI_OK;
+    };
+    // counts of chunk [c0, c0+cn) to the caller (synchronises the stream)
+    auto fetch_counts = [&](const ReqDev& q, uint64_t c0, uint64_t cn) -> int {
+        CK(d.h_stage.ensure(cn * counts_stride * 4));
+        CK(cudaMemcpyAsync(d.h_stage.p, q.counts, cn * counts_stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        const uint32_t* hc = d.h_stage.as<uint32_t>();
+        for (uint64_t i = 0; i < cn; ++i)
+            for (uint32_t k = 0; k < n_alleles[c0 + i]; ++k) allele_counts[(c0 + i) * counts_stride + k] = hc[i * counts_stride + k];
+        return XSI_OK;
+    };
+
+    // ---- host int32 rows: composed and moved as BCF int8, widened on the host beside the DMA (host_narrow.cpp) ----
+    const uint64_t stride8 = ((uint64_t)N + 15) / 16 * 16;
+    if (sizeof(OT) == 4 && !out_on_device && max_all <= 63 && stride8 <= xsi_ctx::RING_BYTES && host_narrow_on()) {
+        int rc = ring_prepare(ctx);
+        if (rc) return rc;
+        const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (1ull << 30) / stride8));
+        const uint64_t rps = xsi_ctx::RING_BYTES / stride8;  // rows per ring slot
+        std::vector<uint32_t> filled;
+        for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
+            const uint64_t cn = std::min(chunk, n - c0);
+            CK(d.out.ensure(cn * stride8));
+            ReqDev q;
+            if ((rc = compose_chunk(d.out.as<int8_t>(), stride8, c0, cn, q))) return rc;
+            filled.resize(cn);
+            CK(cudaMemcpyAsync(filled.data(), q.filled, cn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+            if (want_counts) { if ((rc = fetch_counts(q, c0, cn))) return rc; }
+            else CK(cudaStreamSynchronize(ctx->stream));
+            if (n_filled) memcpy(n_filled + c0, filled.data(), cn * 4);
+            const uint64_t nsub = (cn + rps - 1) / rps;
+            for (uint64_t k = 0; k <= nsub; ++k) {
+                if (k < nsub) {
+                    const int slot = (int)(k % xsi_ctx::RING_SLOTS);
+                    const uint64_t r0 = k * rps, rn = std::min(rps, cn - r0);
+                    if ((rc = ring_wait(ctx, slot))) return rc;
+                    CK(cudaMemcpyAsync(ctx->ring.as<int8_t>() + (size_t)slot * xsi_ctx::RING_BYTES, d.out.as<int8_t>() + r0 * stride8,
+                                       rn * stride8, cudaMemcpyDeviceToHost, ctx->stream));
+                    CK(cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
+                    ctx->ring_busy[slot] = true;
+                }
+                if (k >= 1) {
+                    const int slot = (int)((k - 1) % xsi_ctx::RING_SLOTS);
+                    const uint64_t r0 = (k - 1) * rps, rn = std::min(rps, cn - r0);
+                    if ((rc = ring_wait(ctx, slot))) return rc;
+                    widen_rows_i8_to_i32(ctx->ring.as<int8_t>() + (size_t)slot * xsi_ctx::RING_BYTES, stride8,
+                                         reinterpret_cast<int32_t*>(out) + (c0 + r0) * out_stride, out_stride, filled.data() + r0, rn);
+                }
+            }
+            ctx->narrowed_d2h += cn * stride8;
+        }
+        return XSI_OK;
+    }
+
+    // chunk so that the staging buffers stay bounded
+    const uint64_t row_bytes = out_stride * sizeof(OT);
+    // host output is staged through a bounded device buffer; device output needs no chunking
+    const uint64_t chunk = out_on_device ? std::min<uint64_t>(n, 1ull << 30)
+                                         : std::max<uint64_t>(1, std::min<uint64_t>(n, (1ull << 30) / row_bytes));
+    for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
+        const uint64_t cn = std::min(chunk, n - c0);
+        ReqDev q;
+        OT* dev_out;
+        if (out_on_device) dev_out = out + c0 * out_stride;
+        else { CK(d.out.ensure(cn * row_bytes)); dev_out = d.out.as<OT>(); }
+        int rc = compose_chunk(dev_out, out_stride, c0, cn, q);
+        if (rc) return rc;
         if (!out_on_device) CK(cudaMemcpyAsync(out + c0 * out_stride, q.out, cn * row_bytes, cudaMemcpyDeviceToHost, ctx->stream));
         if (n_filled) CK(cudaMemcpyAsync(n_filled + c0, q.filled, cn * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if (want_counts) {
-            CK(d.h_stage.ensure(cn * counts_stride * 4));
-            CK(cudaMemcpyAsync(d.h_stage.p, q.counts, cn * counts_stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
-            CK(cudaStreamSynchronize(ctx->stream));
-            const uint32_t* hc = d.h_stage.as<uint32_t>();
-            for (uint64_t i = 0; i < cn; ++i)
-                for (uint32_t k = 0; k < n_alleles[c0 + i]; ++k) allele_counts[(c0 + i) * counts_stride + k] = hc[i * counts_stride + k];
+            if ((rc = fetch_counts(q, c0, cn))) return rc;
         } else if (!out_on_device || n_filled || c0 + chunk < n) {
             CK(cudaStreamSynchronize(ctx->stream));
         }
