@@ -344,6 +344,7 @@ def main():
     stream = torch.cuda.ExternalStream(ctx.stream, device=dev)
     S, H, BL = args.samples, 2 * args.samples, args.block_len
     thr = xb.mac_threshold(S, 2, MAF)
+    AET = 2 if S <= 65535 else 4  # header.aet_bytes: uint16 indices up to 65,535 samples (xsi_factory.hpp:425)
     if args.profile_only:
         steps, warmup = 1, 1
 
@@ -393,7 +394,7 @@ def main():
 
     def decode_step(blocks, out_ptr, on_device, n_rec, elem=4):
         t0 = time.perf_counter()
-        ctx.decode_load_blocks(blocks, S, 2)
+        ctx.decode_load_blocks(blocks, S, AET)
         t1 = time.perf_counter()
         fn = L.xsi_decode_records if elem == 4 else L.xsi_decode_records_i8
         ctx._check(fn(ctx.h, n_rec, blk[:n_rec].ctypes.data, off[:n_rec].ctypes.data,
@@ -538,7 +539,7 @@ def main():
                             c._check(L.xsi_encode_collect(c.h, ctypes.byref(n), ctypes.byref(bp), ctypes.byref(sz)))
                             blocks = [(bp[i], sz[i]) for i in range(n.value)]
                             payload[w] += sum(x[1] for x in blocks)
-                            c.decode_load_blocks(blocks, S, 2)
+                            c.decode_load_blocks(blocks, S, AET)
                             c._check(fn(c.h, BL, blk[:BL].ctypes.data, off[:BL].ctypes.data, nal[:BL].ctypes.data,
                                         h_out.data_ptr() + r0 * row_bytes, H, 0, None, None, 0))
                             c.sync()

@@ -232,6 +232,17 @@ def test_uint32_index_path(ctx, tmp_path):
     roundtrip(ctx, tmp_path, ds, 5, 0.001)
 
 
+def test_biobank_width(ctx, tmp_path, monkeypatch):
+    # S5 shape: 500,000 samples = 1,000,000 haplotypes (uint32 indices, WAH lines longer than 65,535 words)
+    # encode: grid-wide cooperative PBWT kernel (6 blocks = groups of 4 + 2 at 32 haplotypes per thread, and one
+    # block at a time at 8); decode: the wide inverse-permutation kernel with L2-resident tables
+    ds = synth.make_dataset(48, 500000, seed=17, n_founders=16, fmin=0.0005)
+    roundtrip(ctx, tmp_path, ds, 8, 0.001)
+    monkeypatch.setenv("XSI_PBWT_KH", "8")
+    monkeypatch.setenv("XSI_UNPERM_KH", "32")
+    roundtrip(ctx, tmp_path, ds, 20, 0.001)
+
+
 def test_zstd_layer_roundtrip(ctx, tmp_path):
     import xsqueezeit_b200 as xb
     ds = synth.make_dataset(400, 150, seed=16, missing=0.01)

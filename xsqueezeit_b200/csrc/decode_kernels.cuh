@@ -56,6 +56,7 @@ struct DecDev {
                                 // [2*WS] the line's total zeros; TW = 2*WS + 4; for D2 v2
     uint32_t TW, n_gt_jobs;
     uint32_t tab_inv;           // 0xFFFF: table entries keep the zero positions as set bits (D2 v3), 0: the y bits (D2 v2)
+    uint32_t tab_wide;          // 1: one entry per 32 positions, {zeros before (u32), zero positions as set bits} (D2 wide, > 65534 haplotypes)
     uint32_t n_samples;         // header.num_samples
     uint32_t aet;               // 2 or 4
     const uint8_t* dline_flags; // [Lt]
@@ -249,8 +250,9 @@ __global__ void wah_expand_kernel(DecDev d, uint32_t warps_per_cta, uint32_t Gpa
             for (int q = 1; q < 32; q <<= 1) { const uint32_t t = __shfl_up_sync(XSI_FULL, incl, q); if (lane >= (uint32_t)q) incl += t; }
             const uint32_t zp = zcarry + incl - nz;
             if (2 * m + 1 < d.TW) {
-                *reinterpret_cast<uint2*>(tab + 2 * m) =
-                    make_uint2((zp << 16) | ((o & 0xFFFFu) ^ d.tab_inv), ((zp + 16u - __popc(o & 0xFFFFu)) << 16) | ((o >> 16) ^ d.tab_inv));
+                *reinterpret_cast<uint2*>(tab + 2 * m) = d.tab_wide
+                    ? make_uint2(zp, ~o)
+                    : make_uint2((zp << 16) | ((o & 0xFFFFu) ^ d.tab_inv), ((zp + 16u - __popc(o & 0xFFFFu)) << 16) | ((o >> 16) ^ d.tab_inv));
             }
             zcarry += __shfl_sync(XSI_FULL, incl, 31);
         }
@@ -563,7 +565,53 @@ __global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d) {
     }
 }
 
-// generic fallback for > 65536 haplotypes: a[] and x[] in global memory
+// =============================================================================================
+// D2 wide: the v3 formulation for MORE than 65,534 haplotypes (biobank scale, uint32 indices).  A line's
+// table (one {zeros before, zero-position bits} pair per 32 positions, N/4 bytes: 250 KB at a million
+// haplotypes) no longer fits shared memory, and no ring could hold several of them; it stays in
+// global memory, where the tables of the lines in flight are L2-resident (126 MB), and every lookup is
+// one 8-byte read-only load.  State = KH positions per thread in registers, haplotypes independent
+// given the tables, so there is no barrier of any kind and the whole GPU works on one PBWT block:
+// grid = (PBWT block, haplotype slice of blockDim.x*KH).
+// =============================================================================================
+template <int KH>  // haplotypes per thread: 8, 16 or 32
+__global__ void __launch_bounds__(256) pbwt_unpermute_wide_kernel(DecDev d) {
+    const uint32_t N = 2 * d.n_samples, TW = d.TW, WS = d.WS;
+    const DecBlock blk = d.blocks[blockIdx.x];
+    const uint32_t nwah = blk.n_wah;
+    const uint32_t hb = (blockIdx.y * blockDim.x + threadIdx.x) * KH;  // first haplotype of this thread
+    if (nwah == 0 || hb >= WS * 32) return;
+    const uint32_t nvalid = hb >= N ? 0u : (N - hb >= (uint32_t)KH ? (uint32_t)KH : N - hb);
+    uint32_t pk[KH];
+    // identity at block start (gt_block.hpp:179); slots past N wander inside [0, N] and are masked off at the store
+#pragma unroll
+    for (int q = 0; q < KH; ++q) pk[q] = (uint32_t)q < nvalid ? hb + q : 0u;
+    const uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+    const uint32_t* tab = d.tabs + (size_t)blk.wah0 * TW;
+    uint32_t* row = d.rows + (size_t)blk.wah0 * WS;
+    for (uint32_t k = 0; k < nwah; ++k, tab += TW, row += WS) {
+        const uint2* T = reinterpret_cast<const uint2*>(tab);
+        uint2 e[KH];
+#pragma unroll
+        for (int q = 0; q < KH; ++q) e[q] = __ldg(T + (pk[q] >> 5));
+        const uint32_t Z = __ldg(tab + 2 * WS);
+        uint32_t xinv = 0;
+#pragma unroll
+        for (int q = KH - 1; q >= 0; --q) {
+            const uint32_t j = pk[q];
+            const uint32_t w = __funnelshift_l(0u, e[q].y, ~j);  // e.y << (31 - (j & 31)): sign = "position j holds a zero"
+            const uint32_t zb = e[q].x + __popc(w & 0x7FFFFFFFu);
+            pk[q] = ((int32_t)w < 0) ? zb : Z + j - zb;
+            xinv = __funnelshift_l(w, xinv, 1);
+        }
+        const uint32_t x = ~xinv & vmask;  // natural-order row, in place
+        if (KH == 32) row[hb >> 5] = x;
+        else if (KH == 16) reinterpret_cast<uint16_t*>(row)[hb >> 4] = (uint16_t)x;
+        else reinterpret_cast<uint8_t*>(row)[hb >> 3] = (uint8_t)x;
+    }
+}
+
+// generic fallback (all-haploid lines above 65,534 haplotypes): a[] and x[] in global memory
 __global__ void __launch_bounds__(1024, 1) pbwt_unpermute_gmem_kernel(DecDev d, const uint8_t* __restrict__ job_hap,
                                                                       uint32_t* a_pool, uint8_t* x_pool) {
     __shared__ uint32_t zc[64];

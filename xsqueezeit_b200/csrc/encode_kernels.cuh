@@ -1069,6 +1069,164 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v4_kernel(EncDev p, Perm
     if (C > 1) cgx::this_cluster().sync();  // nobody exits while a peer may still push into its shared memory
 }
 
+// =============================================================================================
+// E3 grid: PBWT permute for MORE than 65,534 haplotypes (biobank scale, uint32 indices).  A million
+// positions do not fit one SM (nor a 16-CTA cluster: 4 MB of positions + 125 KB bitmaps), so the WHOLE
+// GPU works on a few PBWT blocks at once, one WAH line of each per step, as a cooperative launch:
+//   state   pos[i] (inverse permutation) in REGISTERS, KH haplotypes per thread, TPB threads per PBWT block
+//   A  (fused with C of the previous line) carriers scatter into the line's bitmap Y in global memory (L2 atomics)
+//   -- grid barrier --
+//   B  one warp per 8192-position chunk: takes the chunk's Y words (and clears them for the line after
+//      next), writes them as the permuted row (in place), publishes the chunk's carrier count in a tagged
+//      flag word, sums the flags of the chunks before it, and writes the chunk's table
+//      {zeros before, zero-position bits} per 32 positions (global, L2-resident: N/4 bytes per block)
+//   -- grid barrier --
+//   C  pos[i] <- x[i] ? Z + j - zb(j) : zb(j),  j = pos[i],  one 8-byte L2 load per haplotype
+// Two grid barriers and one flag exchange per line, shared by all blocks of the group.
+// =============================================================================================
+struct PermGridCfg {
+    uint32_t b0, nbg;   // PBWT blocks [b0, b0+nbg) of the batch
+    uint32_t TPB;       // threads per PBWT block (multiple of 32); thread t owns haplotypes [t*KH, t*KH+KH)
+    uint32_t WSP;       // row words padded to a multiple of 256 (chunks of 8192 positions)
+    uint32_t* Y;        // [nbg][2][WSP], zero on entry (and on exit)
+    uint32_t* T;        // [nbg][2*WSP+4]: per row word {zeros before, ~y}; [2*WSP] = Z
+    uint32_t* flags;    // [nbg][WSP/256], zero on entry: (line+1) << 14 | carriers in the chunk
+    uint32_t* bar;      // grid barrier counter, zero on entry
+};
+
+__device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.volatile.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+template <int KH>  // 8, 16 or 32
+__global__ void __launch_bounds__(1024, 1) pbwt_permute_grid_kernel(EncDev p, PermGridCfg c) {
+    const uint32_t N = 2 * p.n_samples, WS = p.WS, WSP = c.WSP, NCH = WSP >> 8;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u;
+    const uint32_t gtid = blockIdx.x * 1024u + tid, gwarp = gtid >> 5;
+    // ---- role 1: owner of KH haplotypes of block bi ----
+    const uint32_t bi = gtid / c.TPB, hb = (gtid % c.TPB) * KH;
+    const bool owner = bi < c.nbg && hb < N;
+    const uint32_t nwah = owner ? p.blk_nwah[c.b0 + bi] : 0u;
+    const uint32_t* list = p.wah_list + p.blk_line0[c.b0 + (bi < c.nbg ? bi : 0)];
+    uint32_t* Yo = c.Y + (size_t)bi * 2 * WSP;
+    const uint32_t* To = c.T + (size_t)bi * (2 * WSP + 4);
+    uint32_t pk[KH];
+    const uint32_t nvalid = !owner ? 0u : (N - hb >= (uint32_t)KH ? (uint32_t)KH : N - hb);
+    // identity at block start (gt_block.hpp:179); slots past N sit at position 0 and never carry
+#pragma unroll
+    for (int q = 0; q < KH; ++q) pk[q] = (uint32_t)q < nvalid ? hb + q : 0u;
+    const uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+    // the KH bits of this thread in a natural-order bit-row (rows of later lines are untouched until their step B)
+    auto load_x = [&](uint32_t k) -> uint32_t {
+        if (k >= nwah) return 0u;
+        const uint32_t v = __ldcg(p.bitrows + (size_t)(list[k] & 0x7FFFFFFFu) * WS + (hb >> 5));
+        return (KH >= 32 ? v : (v >> (hb & 31u))) & vmask;
+    };
+    // ---- role 2: warp gwarp owns chunk cc of block cb ----
+    const uint32_t cb = gwarp / NCH, cc = gwarp % NCH;
+    const bool chunker = cb < c.nbg;
+    const uint32_t cnwah = chunker ? p.blk_nwah[c.b0 + cb] : 0u;
+    const uint32_t* clist = p.wah_list + p.blk_line0[c.b0 + (chunker ? cb : 0)];
+    uint32_t max_nwah = 0;
+    for (uint32_t i = 0; i < c.nbg; ++i) max_nwah = max(max_nwah, p.blk_nwah[c.b0 + i]);
+
+    uint32_t bar_target = 0;
+    auto grid_sync = [&]() {
+        bar_target += gridDim.x;
+        __syncthreads();
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(c.bar, 1u);
+            while (ld_volatile_u32(c.bar) < bar_target) {}
+            __threadfence();
+        }
+        __syncthreads();
+    };
+
+    uint32_t x0 = load_x(0), x1 = load_x(1), x2 = load_x(2);
+    // step A of the first line (positions are the identity)
+#pragma unroll
+    for (int q = 0; q < KH; ++q)
+        if (x0 & (1u << q)) atomicOr(Yo + (pk[q] >> 5), 1u << (pk[q] & 31u));
+
+    for (uint32_t k = 0; k < max_nwah; ++k) {
+        const uint32_t par = k & 1u;
+        grid_sync();  // every carrier of line k has landed
+        // ---- B ----
+        if (chunker && k < cnwah) {
+            uint32_t* Yc = c.Y + ((size_t)cb * 2 + par) * WSP + cc * 256 + lane * 8;
+            uint32_t y[8];
+            {
+                const uint4 a = __ldcg(reinterpret_cast<const uint4*>(Yc)), b = __ldcg(reinterpret_cast<const uint4*>(Yc) + 1);
+                y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
+                __stcg(reinterpret_cast<uint4*>(Yc), make_uint4(0, 0, 0, 0));
+                __stcg(reinterpret_cast<uint4*>(Yc) + 1, make_uint4(0, 0, 0, 0));
+            }
+            uint32_t nz = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) nz += 32u - __popc(y[i]);
+            uint32_t incl = nz;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, dd); if (lane >= (uint32_t)dd) incl += o; }
+            const uint32_t chunk_zeros = __shfl_sync(XSI_FULL, incl, 31);
+            uint32_t* fl = c.flags + (size_t)cb * NCH;
+            if (lane == 0) {
+                asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(fl + cc), "r"(((k + 1) << 14) | (8192u - chunk_zeros)) : "memory");
+            }
+            // permuted row, in place
+            const uint32_t w0 = cc * 256 + lane * 8;
+            uint32_t* grow = p.bitrows + (size_t)(clist[k] & 0x7FFFFFFFu) * WS;
+            if (w0 < WS) *reinterpret_cast<uint4*>(grow + w0) = make_uint4(y[0], y[1], y[2], y[3]);
+            if (w0 + 4 < WS) *reinterpret_cast<uint4*>(grow + w0 + 4) = make_uint4(y[4], y[5], y[6], y[7]);
+            // zeros before this chunk: the flags of the chunks before it
+            uint32_t before = 0;
+            for (uint32_t i = lane; i < cc; i += 32) {
+                uint32_t f;
+                do { f = ld_volatile_u32(fl + i); } while ((f >> 14) != k + 1);
+                before += 8192u - (f & 0x3FFFu);
+            }
+            before = __reduce_add_sync(XSI_FULL, before);
+            uint32_t zp = before + incl - nz;
+            uint32_t* Tc = c.T + (size_t)cb * (2 * WSP + 4) + 2 * (size_t)w0;
+#pragma unroll
+            for (int i = 0; i < 8; i += 2) {
+                const uint32_t z1 = zp + 32u - __popc(y[i]);
+                __stcg(reinterpret_cast<uint4*>(Tc + 2 * i), make_uint4(zp, ~y[i], z1, ~y[i + 1]));
+                zp = z1 + 32u - __popc(y[i + 1]);
+            }
+            // Z: zeros among the N real positions (the padding past N never holds a carrier)
+            if (cc == NCH - 1 && lane == 31) __stcg(c.T + (size_t)cb * (2 * WSP + 4) + 2 * WSP, zp - (WSP * 32 - N));
+        }
+        grid_sync();  // every table of line k is complete
+        // ---- C (+ A of line k+1) ----
+        if (k < nwah) {
+            const uint32_t Z = __ldcg(To + 2 * WSP);
+            const uint2* T2 = reinterpret_cast<const uint2*>(To);
+#pragma unroll
+            for (int q0 = 0; q0 < KH; q0 += 8) {
+                uint2 e[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) e[q] = __ldcg(T2 + (pk[q0 + q] >> 5));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint32_t j = pk[q0 + q];
+                    const uint32_t zb = e[q].x + __popc(e[q].y & ~(0xFFFFFFFFu << (j & 31u)));
+                    pk[q0 + q] = (x0 & (1u << (q0 + q))) ? Z + j - zb : zb;
+                }
+            }
+            if (x1) {
+                uint32_t* Yn = Yo + (par ^ 1u) * WSP;
+#pragma unroll
+                for (int q = 0; q < KH; ++q)
+                    if (x1 & (1u << q)) atomicOr(Yn + (pk[q] >> 5), 1u << (pk[q] & 31u));
+            }
+            x0 = x1; x1 = x2; x2 = load_x(k + 3);
+        }
+    }
+}
+
 // generic fallback for > 65536 haplotypes: a[] ping-pongs in global memory (L2 resident)
 __global__ void __launch_bounds__(1024, 1) pbwt_permute_gmem_kernel(EncDev p, uint32_t* a_pool) {
     __shared__ uint32_t zc[64];

@@ -460,9 +460,78 @@ int run_permute_v4(xsi_ctx* ctx, const EncDev& p, uint32_t W, bool* done) {
     return XSI_OK;
 }
 
+template <int KH>
+int launch_permute_grid(xsi_ctx* ctx, const EncDev& p, const PermGridCfg& cfg, bool probe_only, int* per_sm) {
+    if (probe_only) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, pbwt_permute_grid_kernel<KH>, 1024, 0));
+        return XSI_OK;
+    }
+    void* args[] = {const_cast<EncDev*>(&p), const_cast<PermGridCfg*>(&cfg)};
+    { PROF("pbwt_permute"); CK(cudaLaunchCooperativeKernel((const void*)pbwt_permute_grid_kernel<KH>, dim3(ctx->sm_count), dim3(1024), args, 0, ctx->stream)); }
+    CKL();
+    return XSI_OK;
+}
+int launch_permute_grid_kh(xsi_ctx* ctx, uint32_t KH, const EncDev& p, const PermGridCfg& cfg, bool probe_only, int* per_sm) {
+    switch (KH) {
+        case 8: return launch_permute_grid<8>(ctx, p, cfg, probe_only, per_sm);
+        case 16: return launch_permute_grid<16>(ctx, p, cfg, probe_only, per_sm);
+        default: return launch_permute_grid<32>(ctx, p, cfg, probe_only, per_sm);
+    }
+}
+
+// > 65,534 haplotypes: the whole GPU advances a group of PBWT blocks line by line (cooperative launch).
+// Groups are as many blocks as the positions-in-registers budget allows (sm_count*1024 threads x KH <= 32).
+int run_permute_grid(xsi_ctx* ctx, const EncDev& p, bool* done) {
+    *done = false;
+    auto& e = ctx->enc;
+    const uint32_t N = 2 * p.n_samples;
+    const uint64_t GT = (uint64_t)ctx->sm_count * 1024;
+    const uint32_t WSP = (p.WS + 255) & ~255u, NCH = WSP / 256;
+    auto tpb_of = [&](uint32_t kh) { return (uint32_t)((((uint64_t)N + kh - 1) / kh + 31) / 32 * 32); };
+    if (GT / tpb_of(32) == 0) return XSI_OK;  // more than ~4.8 M haplotypes: generic kernel
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
+    if (!coop) return XSI_OK;
+    const uint32_t max_group = (uint32_t)std::min<uint64_t>(GT / tpb_of(32), (GT / 32) / NCH);
+    const size_t per_block = (size_t)2 * WSP + (2 * WSP + 4) + NCH;
+    CK(e.a_pool.ensure(((size_t)max_group * per_block + 4) * 4));
+    for (uint32_t b0 = 0; b0 < p.nb;) {
+        const uint32_t rem = p.nb - b0;
+        uint32_t KH = 32;
+        if (const char* s = getenv("XSI_PBWT_KH")) { const int v = atoi(s); if (v == 8 || v == 16 || v == 32) KH = (uint32_t)v; }
+        else for (uint32_t kh : {8u, 16u}) if (GT / tpb_of(kh) >= rem) { KH = kh; break; }
+        PermGridCfg cfg;
+        cfg.TPB = tpb_of(KH);
+        cfg.b0 = b0;
+        cfg.nbg = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(rem, GT / cfg.TPB), (GT / 32) / NCH);
+        if (cfg.nbg == 0) return XSI_OK;
+        cfg.WSP = WSP;
+        uint32_t* base = e.a_pool.as<uint32_t>();
+        cfg.Y = base;
+        cfg.T = cfg.Y + (size_t)cfg.nbg * 2 * WSP;
+        cfg.flags = cfg.T + (size_t)cfg.nbg * (2 * WSP + 4);
+        cfg.bar = cfg.flags + (size_t)cfg.nbg * NCH;
+        int per_sm = 0;
+        int rc = launch_permute_grid_kh(ctx, KH, p, cfg, true, &per_sm);
+        if (rc) return rc;
+        if (per_sm < 1) return XSI_OK;
+        CK(cudaMemsetAsync(base, 0, ((size_t)cfg.nbg * per_block + 4) * 4, ctx->stream));
+        rc = launch_permute_grid_kh(ctx, KH, p, cfg, false, &per_sm);
+        if (rc) return rc;
+        b0 += cfg.nbg;
+    }
+    *done = true;
+    return XSI_OK;
+}
+
 int run_permute(xsi_ctx* ctx, const EncDev& p) {
     const uint32_t N = 2 * p.n_samples;
     const uint32_t W = (N + 31) / 32;
+    if (!ctx->enc.any_haploid && N > 65534 && !getenv("XSI_PBWT_V1")) {
+        bool done = false;
+        const int rc = run_permute_grid(ctx, p, &done);
+        if (rc || done) return rc;
+    }
     if (!ctx->enc.any_haploid && N <= 65534 && !getenv("XSI_PBWT_V1") && !getenv("XSI_PBWT_V2") && !getenv("XSI_PBWT_V3")) {
         bool done = false;
         const int rc = run_permute_v4(ctx, p, W, &done);
@@ -1143,8 +1212,19 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
         v3_slices = (thr_total + v3_nc - 1) / v3_nc;
     }
     const bool v2_ok = use_v2 && (v3_kh || un_smem <= ctx->smem_optin);
-    dd.tabs = nullptr; dd.TW = TWv2; dd.n_gt_jobs = d.n_gt_jobs; dd.tab_inv = v3_kh ? 0xFFFFu : 0u;
-    if (v2_ok) {
+    // D2 wide: more than 65,534 haplotypes (tables stay in global memory / L2)
+    const bool use_wide = d.n_gt_jobs && !any_hap_job && N > 65534 && !getenv("XSI_PBWT_V1");
+    uint32_t wide_kh = 0, wide_slices = 0;
+    if (use_wide) {
+        // haplotypes per thread: the largest of 32/16/8 that still gives every SM ~1024 threads
+        const uint64_t want = (uint64_t)ctx->sm_count * 1024;
+        wide_kh = 8;
+        for (uint32_t kh : {32u, 16u}) if ((uint64_t)n_blocks * ((N + kh - 1) / kh) >= want) { wide_kh = kh; break; }
+        if (const char* sw = getenv("XSI_UNPERM_KH")) { const int v = atoi(sw); if (v == 8 || v == 16 || v == 32) wide_kh = (uint32_t)v; }
+        wide_slices = (uint32_t)(((uint64_t)d.WS * 32 + 256ull * wide_kh - 1) / (256ull * wide_kh));
+    }
+    dd.tabs = nullptr; dd.TW = TWv2; dd.n_gt_jobs = d.n_gt_jobs; dd.tab_inv = v3_kh ? 0xFFFFu : 0u; dd.tab_wide = use_wide ? 1u : 0u;
+    if (v2_ok || use_wide) {
         CK(d.tabs.ensure((size_t)d.n_gt_jobs * TWv2 * 4));
         dd.tabs = d.tabs.as<uint32_t>();
     }
@@ -1186,6 +1266,13 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
                 CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem));
                 PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<8><<<g, v3_nc + 32, v3_smem, ctx->stream>>>(dd);
             }
+            CKL();
+        } else if (use_wide) {
+            const dim3 g(n_blocks, wide_slices);
+            PROF("pbwt_unpermute");
+            if (wide_kh == 32) pbwt_unpermute_wide_kernel<32><<<g, 256, 0, ctx->stream>>>(dd);
+            else if (wide_kh == 16) pbwt_unpermute_wide_kernel<16><<<g, 256, 0, ctx->stream>>>(dd);
+            else pbwt_unpermute_wide_kernel<8><<<g, 256, 0, ctx->stream>>>(dd);
             CKL();
         } else if (v2_ok) {
             const dim3 g(n_blocks, un_slices);
