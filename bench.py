@@ -21,6 +21,7 @@ scaling); the only exchange is the all-gather of per-block byte counts that buil
 block offset table (reference xsi_factory.hpp:533,554,575).
 """
 import argparse
+import zlib
 import ctypes
 import json
 import os
@@ -291,6 +292,8 @@ def main():
     ap.add_argument("--ref-records", type=int, default=1024)
     ap.add_argument("--ref-workers", type=int, default=0)
     ap.add_argument("--ref-worker", type=int, default=-1, help=argparse.SUPPRESS)
+    ap.add_argument("--resident-contexts", type=int, default=0,
+                    help="also time the resident leg from this many host threads (one xsi_ctx each, blocks split between them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="one resident step, no e2e / cpu legs (for ncu)")
@@ -403,6 +406,8 @@ def main():
         host_ms["decode_load_blocks"] += (t1 - t0) * 1e3
         host_ms["decode_records"] += (time.perf_counter() - t1) * 1e3
 
+    crcs = []
+
     def run_leg(n_rec, gt_ptr, out_ptr, on_device, nsteps, nwarm, sampler=None, elem=4):
         for _ in range(nwarm):
             decode_step(encode_step(gt_ptr, on_device, n_rec, elem), out_ptr, on_device, n_rec, elem)
@@ -427,6 +432,7 @@ def main():
             lines = ctx.encode_line_counts()
         barrier()
         clocks = sampler.stop() if sampler else None
+        crcs[:] = [zlib.crc32(ctypes.string_at(p_, s_)) for p_, s_ in blocks]  # outside the timed region
         t_enc = sum(a.elapsed_time(b) for a, b in zip(e0, e1)) / 1e3
         t_dec = sum(b.elapsed_time(c) for b, c in zip(e1, e2)) / 1e3
         t_all = e0[0].elapsed_time(e2[-1]) / 1e3
@@ -448,7 +454,8 @@ def main():
     value = 2.0 * G * world * steps / t_all / 1e9
 
     # ---- roofline of the dominant kernel (per-kernel CUDA-event times of the timed region) ----
-    prof = res["prof"]
+    host_phases = {k: {"calls": n, "ms_per_step": ms / steps} for k, (n, ms) in res["prof"].items() if k.startswith("host:")}
+    prof = {k: v for k, v in res["prof"].items() if not k.startswith("host:")}
     WS = ((H + 31) // 32 + 3) // 4 * 4
     roof = None
     roof_all = []
@@ -486,6 +493,75 @@ def main():
         roof = roof_of(top)
         # every kernel with more than 5% of the step, so that the HBM-bound ones are judged next to the dominant one
         roof_all = [r for r in (roof_of(k) for k in sorted(prof, key=lambda k: -prof[k][1]) if prof[k][1] > 0.05 * total_ms) if r]
+
+    # ---- resident leg from several contexts: the same batch, blocks split over W host threads with one xsi_ctx
+    #      (stream + pools) each, so that one context's PBWT chain (SM-bound, 4 SMs per block) runs beside another's
+    #      HBM-bound scan / compose kernels ----
+    resident_mt = None
+    if args.resident_contexts > 1 and not args.profile_only:
+        W = min(args.resident_contexts, B)
+        ctxs = [xb.Context(local_rank) for _ in range(W)]
+        row_bytes = H * EL
+        fn = L.xsi_decode_records if EL == 4 else L.xsi_decode_records_i8
+        errs = []
+        dec.zero_()
+        torch.cuda.synchronize(dev)
+        crc_single = list(crcs)
+        crc_mt = [None] * B
+        last_blocks = [None] * B
+
+        def work(w, nrounds):
+            c = ctxs[w]
+            b0, b1 = w * B // W, (w + 1) * B // W
+            r0, nr = b0 * BL, (b1 - b0) * BL
+            try:
+                for _ in range(nrounds):
+                    c.encode_launch(gt.data_ptr() + r0 * row_bytes, nal[:nr], S, BL, thr, 1, gt_on_device=True, gt_elem_bytes=EL)
+                    n = ctypes.c_uint32()
+                    bp = ctypes.POINTER(ctypes.c_void_p)()
+                    sz = ctypes.POINTER(ctypes.c_uint64)()
+                    c._check(L.xsi_encode_collect(c.h, ctypes.byref(n), ctypes.byref(bp), ctypes.byref(sz)))
+                    for i in range(n.value):
+                        last_blocks[b0 + i] = (bp[i], sz[i])  # hashed after the timed region (valid until the next launch)
+                    c.decode_load_blocks([(bp[i], sz[i]) for i in range(n.value)], S, AET)
+                    c._check(fn(c.h, nr, blk[:nr].ctypes.data, off[:nr].ctypes.data, nal[:nr].ctypes.data,
+                                dec.data_ptr() + r0 * row_bytes, H, 1, None, None, 0))
+                    c.sync()
+            except Exception as ex:
+                errs.append(repr(ex))
+
+
+        def run_mt(nrounds):
+            ts = [threading.Thread(target=work, args=(w, nrounds)) for w in range(W)]
+            for t in ts:
+                t.start()
+            for t in ts:
+                t.join()
+            if errs:
+                raise SystemExit("bench.py: resident worker failed: " + errs[0])
+
+        run_mt(max(1, warmup))
+        s0 = torch.cuda.ExternalStream(ctxs[0].stream, device=dev)
+        l0 = sum(c.kernel_launches for c in ctxs)
+        barrier()
+        a, z = ev(), ev()
+        a.record(s0)
+        run_mt(steps)
+        z.record(s0)
+        barrier()
+        tm = maxr(a.elapsed_time(z) / 1e3)
+        okm = all(bool(torch.equal(gt[r0:r0 + BL], dec[r0:r0 + BL])) for r0 in range(0, R, BL))
+        verified = verified and okm
+        crc_mt = [zlib.crc32(ctypes.string_at(p_, s_)) for p_, s_ in last_blocks]
+        enc_same = crc_mt == crc_single
+        bad_blocks = [r0 // BL for r0 in range(0, R, BL) if not bool(torch.equal(gt[r0:r0 + BL], dec[r0:r0 + BL]))]
+        verified = verified and enc_same
+        resident_mt = {"value": 2.0 * G * world * steps / tm / 1e9, "unit": "Ggt/s", "contexts": W, "host_threads": W,
+                       "encoded_blocks_equal_single_context": enc_same, "blocks_decoded_wrong": bad_blocks,
+                       "blocks_encoded_differently": [i for i in range(B) if crc_mt[i] != crc_single[i]],
+                       "ms_per_step": tm / steps * 1e3, "gpu_launches": sum(c.kernel_launches for c in ctxs) - l0, "verified": okm}
+        for c in ctxs:
+            c.close()
 
     # ---- e2e: pinned host buffers through the same calls ----
     # `e2e` keeps the reference's own boundary types (int32 rows: bcf_get_genotypes in, fill_genotype_array out);
@@ -618,7 +694,7 @@ def main():
                            "genotypes_per_gpu_per_step": G, "input": "%s rows resident in HBM (%.1f GB, > L2; no flush needed)" % ("int32" if EL == 4 else "int8", G * EL / 1e9),
                            "xsi_payload_bytes_per_step": res["payload"], "binary_lines": res["lines"][0], "wah_lines": res["lines"][1], "parallelism": "blocks sharded over %d GPU(s)" % world},
                 "compress_ggts": G * world * steps / t_enc / 1e9, "decompress_ggts": G * world * steps / t_dec / 1e9,
-                "verified": verified, "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8,
+                "verified": verified, "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8,
                 "gpu_launches": res["launches"], "clocks": res["clocks"]}
         print(json.dumps(line))
     ctx.close()

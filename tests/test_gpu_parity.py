@@ -310,3 +310,44 @@ def test_error_codes(ctx):
     with pytest.raises(xb.XsiError) as e:
         ctx.encode_launch(np.zeros(2 * 40000, np.int32), [2], 40000, 8192, 0, 1)
     assert e.value.code == -5
+
+
+def test_concurrent_contexts(tmp_path, monkeypatch):
+    """Four host threads, one xsi_ctx each, encode and decode HRC-width blocks at the same time (one context per thread
+    is the C ABI's threading model).  XSI_UNPERM_NC=128 multiplies the CTAs of the inverse-PBWT kernel, which is what
+    exposed a stage of its table ring being refilled while reads of it were still queued."""
+    import threading
+    import xsqueezeit_b200 as xb
+    monkeypatch.setenv("XSI_UNPERM_NC", "128")
+    ds = synth.make_dataset(192, 32488, seed=33, n_founders=128, fmin=0.0005)
+    img = oracle_image(ds, 64, 0.001)
+    rd = xo.Reader(img)
+    pos = xo.bm_positions(ds["n_allele"], 64)
+    want = [rd.fill_genotype_array(2, int(pos[r]))[0].copy() for r in range(192)]
+    errs = []
+
+    def work(w):
+        try:
+            c = xb.Context(0)
+            for it in range(3):
+                p = str(tmp_path / ("t%d_%d.xsi" % (w, it)))
+                xb.Compressor(c, maf=0.001, reset_sort_block_length=64).compress_to_file(p, ds["gt"], ds["ngt"], ds["n_allele"], ds["n_samples"])
+                if open(p, "rb").read() != img:
+                    errs.append("thread %d: .xsi bytes differ" % w)
+                acc = xb.Accessor(p, c)
+                out, filled, _ = acc.fill_genotype_arrays(ds["n_allele"], pos)
+                for r in range(192):
+                    if filled[r] != want[r].size or not np.array_equal(out[r, :filled[r]], want[r]):
+                        errs.append("thread %d: row %d differs" % (w, r))
+                        break
+                acc.close()
+            c.close()
+        except Exception as ex:  # surfaced after join
+            errs.append(repr(ex))
+
+    ts = [threading.Thread(target=work, args=(w,)) for w in range(4)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not errs, errs[:3]

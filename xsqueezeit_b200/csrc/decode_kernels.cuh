@@ -249,7 +249,9 @@ __global__ void wah_expand_kernel(DecDev d, uint32_t warps_per_cta, uint32_t Gpa
 #pragma unroll
             for (int q = 1; q < 32; q <<= 1) { const uint32_t t = __shfl_up_sync(XSI_FULL, incl, q); if (lane >= (uint32_t)q) incl += t; }
             const uint32_t zp = zcarry + incl - nz;
-            if (2 * m + 1 < d.TW) {
+            // (lanes past the row must not store: their entry would land on the Z slot at [2*WS], which lane 0
+            // writes below -- two lanes, one address, no ordering between them)
+            if (m < d.WS) {
                 *reinterpret_cast<uint2*>(tab + 2 * m) = d.tab_wide
                     ? make_uint2(zp, ~o)
                     : make_uint2((zp << 16) | ((o & 0xFFFFu) ^ d.tab_inv), ((zp + 16u - __popc(o & 0xFFFFu)) << 16) | ((o >> 16) ^ d.tab_inv));
@@ -553,8 +555,6 @@ __global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d) {
             pk[q] = ((int32_t)w < 0) ? zb : Z + j - zb;
             xinv = __funnelshift_l(w, xinv, 1);  // (xinv << 1) | sign(w)
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
         if (store) {  // natural-order row, in place
             const uint32_t x = ~xinv & vmask;
             const size_t row = (size_t)(blk.wah0 + k) * WS;
@@ -562,6 +562,14 @@ __global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d) {
             else if (KH == 16) reinterpret_cast<uint16_t*>(d.rows + row)[hb >> 4] = (uint16_t)x;
             else reinterpret_cast<uint8_t*>(d.rows + row)[hb >> 3] = (uint8_t)x;
         }
+        // Release the stage only when this warp's table reads have PERFORMED, not merely issued.  Without the fence
+        // ptxas schedules the arrive right after the LDS issue (their results are consumed later); with consumers
+        // that were starved on `full` all waking at once, the shared-memory pipe is backed up far enough for the
+        // producer's next TMA fill of the stage to overtake reads still queued (seen as wrong rows / wild positions
+        // when several contexts decode concurrently; XSI_UNPERM_NC=128 made it near-certain).
+        __threadfence_block();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
     }
 }
 

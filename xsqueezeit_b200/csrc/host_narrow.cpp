@@ -214,6 +214,8 @@ constexpr size_t SLICE = 1u << 18;  // elements per task
 
 unsigned host_threads() { return pool().size(); }
 
+void host_parallel_for(size_t n_tasks, const std::function<void(size_t)>& fn) { pool().run(n_tasks, fn); }
+
 bool narrow_i32_to_i8(const int32_t* src, int8_t* dst, size_t n) {
     const int lvl = isa_level();
     auto one = [lvl](const int32_t* s, int8_t* d, size_t m) {

@@ -2,11 +2,15 @@
 #pragma once
 #include <cstddef>
 #include <cstdint>
+#include <functional>
 
 namespace xsi {
 
 // worker threads the conversions run on (XSI_HOST_THREADS, default: the cores this process may use, <= 32)
 unsigned host_threads();
+
+// fn(0) .. fn(n_tasks-1) on the worker pool (the caller takes part); one job at a time per process
+void host_parallel_for(size_t n_tasks, const std::function<void(size_t)>& fn);
 
 // dst[i] = BCF int8 encoding of src[i].  Returns false when some value has no int8 encoding (allele index
 // above 62, or a negative value other than bcf_int32_missing / bcf_int32_vector_end); dst is then garbage.

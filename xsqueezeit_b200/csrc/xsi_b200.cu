@@ -2,6 +2,7 @@
 // host-side assembly of byte-exact GT blocks.  No CPU fallback lives here: every genotype
 // operation is a kernel from encode_kernels.cuh / decode_kernels.cuh.
 #include <algorithm>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,6 +70,7 @@ struct xsi_ctx {
     struct Span { const char* name; cudaEvent_t a, b; };
     std::vector<Span> spans;
     std::string profile_text;
+    std::map<std::string, std::pair<int, double>> host_spans;  // host-side phases (wall clock), reported as "host:<name>"
 
     // pinned ring for host int32 rows that cross PCIe as int8 (host_narrow.cpp): slots of RING_BYTES
     static constexpr int RING_SLOTS = 3;
@@ -111,7 +113,7 @@ struct xsi_ctx {
         std::vector<uint32_t> h_bin_lines;
         DevBuf blob, meta, rows, job_u32, job_hap, tile_u32, dline, lists, err, a_pool, x_pool, req, out, scratch, counts,
             seg_total, tabs;
-        PinBuf h_stage;
+        PinBuf h_stage, h_meta;
         DecDev dev;
     } dec;
 };
@@ -133,12 +135,29 @@ struct ProfScope {
     ~ProfScope() { if (on) { cudaEventRecord(b, c->stream); c->spans.push_back({name, a, b}); } }
 };
 #define PROF(name) ProfScope prof_scope__(ctx, name)
+// HOSTSPAN("host:parse");  wall-clock time of a host-side phase, to the end of the enclosing scope (profiling only)
+struct HostSpan {
+    xsi_ctx* c; const char* name; std::chrono::steady_clock::time_point t0;
+    HostSpan(xsi_ctx* ctx, const char* n) : c(ctx), name(n), t0(std::chrono::steady_clock::now()) {}
+    ~HostSpan() {
+        if (!c->profile) return;
+        auto& s = c->host_spans[name];
+        s.first++;
+        s.second += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
+};
+#define HOSTSPAN_CAT2(a, b) a##b
+#define HOSTSPAN_CAT(a, b) HOSTSPAN_CAT2(a, b)
+#define HOSTSPAN(name) HostSpan HOSTSPAN_CAT(host_span__, __LINE__)(ctx, name)
+// XSI_DEBUG_SYNC=1 waits for every kernel right after its launch, so that a device fault names its launch site
+static const bool g_debug_sync = getenv("XSI_DEBUG_SYNC") != nullptr;
 #define CKL()                                                                                      \
     do {                                                                                           \
         ctx->launches++;                                                                           \
         cudaError_t e__ = cudaGetLastError();                                                      \
+        if (e__ == cudaSuccess && g_debug_sync) e__ = cudaStreamSynchronize(ctx->stream);          \
         if (e__ != cudaSuccess) {                                                                  \
-            ctx->err = std::string("kernel launch: ") + cudaGetErrorString(e__);                   \
+            ctx->err = std::string("kernel launch (xsi_b200.cu:") + std::to_string(__LINE__) + "): " + cudaGetErrorString(e__); \
             return XSI_E_CUDA;                                                                     \
         }                                                                                          \
     } while (0)
@@ -184,6 +203,7 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
                       &d.a_pool, &d.x_pool, &d.req, &d.out, &d.scratch, &d.counts, &d.seg_total, &d.tabs})
         b->release();
     d.h_stage.release();
+    d.h_meta.release();
     ctx->ring.release();
     for (cudaEvent_t ev : ctx->ring_ev) if (ev) cudaEventDestroy(ev);
     cudaEventDestroy(ctx->ev_side);
@@ -223,6 +243,11 @@ extern "C" const char* xsi_profile_read(xsi_ctx* ctx) {
         snprintf(line, sizeof line, "%s %d %.6f\n", n.c_str(), agg[n].first, agg[n].second);
         ctx->profile_text += line;
     }
+    for (auto& kv : ctx->host_spans) {
+        snprintf(line, sizeof line, "%s %d %.6f\n", kv.first.c_str(), kv.second.first, kv.second.second);
+        ctx->profile_text += line;
+    }
+    ctx->host_spans.clear();
     return ctx->profile_text.c_str();
 }
 extern "C" int xsi_sync(xsi_ctx* ctx) {
@@ -601,41 +626,78 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
     e.aet = S <= 65535 ? 2 : 4;
     e.nb = (uint32_t)((R + d->block_len - 1) / d->block_len);
     // ---- host tables ----
-    e.h_nallele.assign(d->n_allele, d->n_allele + R);
-    e.h_ngt.resize(R); e.h_line0.resize(R); e.h_goff.resize(R);
+    std::chrono::steady_clock::time_point t_tables = std::chrono::steady_clock::now();
+    // two passes over chunks of records on the worker pool: per-chunk sums, serial prefix, fill
+    e.h_nallele.resize(R); e.h_ngt.resize(R); e.h_line0.resize(R); e.h_goff.resize(R);
     e.h_blk_line0.assign(e.nb + 1, 0); e.h_blk_rec0.assign(e.nb + 1, 0);
+    constexpr uint64_t TCH = 1u << 16;
+    const size_t nch = (size_t)((R + TCH - 1) / TCH);
+    struct ChunkSum { uint64_t g = 0, l = 0; int rc = XSI_OK; const char* err = nullptr; int max_pl = 0; bool hap = false, al4 = true, al1 = true; };
+    std::vector<ChunkSum> cs(nch);
+    host_parallel_for(nch, [&](size_t c) {
+        ChunkSum& k = cs[c];
+        const uint64_t r1 = std::min<uint64_t>(R, (c + 1) * TCH);
+        for (uint64_t r = c * TCH; r < r1; ++r) {
+            const uint32_t pl = d->ploidy ? d->ploidy[r] : 2;
+            const uint32_t na = d->n_allele[r];
+            if (pl > 2) { k.err = "Ploidy higher than 2 is not yet supported"; k.rc = XSI_E_PLOIDY; return; }
+            if (pl == 0) { k.err = "record with ploidy 0"; k.rc = XSI_E_ARG; return; }
+            if (na < 1 || na > (uint32_t)E1_MAXALLELE) { k.err = "n_allele out of range (1..256)"; k.rc = XSI_E_UNSUPPORTED; return; }
+            if ((int)pl > k.max_pl) k.max_pl = (int)pl;
+            if (pl == 1) k.hap = true;
+            k.g += (uint64_t)S * pl;
+            k.l += na - 1;
+        }
+    });
     uint64_t goff = 0, L = 0;
     bool al4 = true, al1 = true;  // every row starts and ends on a 16-byte boundary (int32 / int8 elements) -> TMA-fed scan
     e.max_ploidy = 0;
     e.any_haploid = false;
-    for (uint64_t r = 0; r < R; ++r) {
-        const uint32_t pl = d->ploidy ? d->ploidy[r] : 2;
-        if (pl > 2) { ctx->err = "Ploidy higher than 2 is not yet supported"; return XSI_E_PLOIDY; }
-        if (pl == 0) { ctx->err = "record with ploidy 0"; return XSI_E_ARG; }
-        if (e.h_nallele[r] < 1 || e.h_nallele[r] > (uint32_t)E1_MAXALLELE) { ctx->err = "n_allele out of range (1..256)"; return XSI_E_UNSUPPORTED; }
-        if ((int)pl > e.max_ploidy) e.max_ploidy = (int)pl;
-        if (pl == 1) e.any_haploid = true;
-        if (r % d->block_len == 0) { e.h_blk_line0[r / d->block_len] = (uint32_t)L; e.h_blk_rec0[r / d->block_len] = (uint32_t)r; }
-        e.h_ngt[r] = S * pl;
-        e.h_goff[r] = goff;
-        if ((goff * 4) % 16 || ((uint64_t)S * pl * 4) % 16) al4 = false;
-        if (goff % 16 || ((uint64_t)S * pl) % 16) al1 = false;
-        e.h_line0[r] = (uint32_t)L;
-        goff += (uint64_t)S * pl;
-        L += e.h_nallele[r] - 1;
+    for (size_t c = 0; c < nch; ++c) {
+        ChunkSum& k = cs[c];
+        if (k.rc) { ctx->err = k.err; return k.rc; }
+        const uint64_t g = k.g, l = k.l;
+        k.g = goff; k.l = L;  // now: the chunk's first element / line
+        goff += g; L += l;
         if (L >= (1ull << 31)) { ctx->err = "too many binary lines in batch"; return XSI_E_ARG; }
+        e.max_ploidy = std::max(e.max_ploidy, k.max_pl);
+        e.any_haploid |= k.hap;
     }
+    e.L = L;
+    e.h_line_rec.resize(L ? L : 1);
+    host_parallel_for(nch, [&](size_t c) {
+        ChunkSum& k = cs[c];
+        uint64_t g = k.g, l = k.l;
+        const uint64_t r1 = std::min<uint64_t>(R, (c + 1) * TCH);
+        for (uint64_t r = c * TCH; r < r1; ++r) {
+            const uint32_t pl = d->ploidy ? d->ploidy[r] : 2;
+            const uint32_t na = d->n_allele[r];
+            if (r % d->block_len == 0) { e.h_blk_line0[r / d->block_len] = (uint32_t)l; e.h_blk_rec0[r / d->block_len] = (uint32_t)r; }
+            e.h_nallele[r] = na;
+            e.h_ngt[r] = S * pl;
+            e.h_goff[r] = g;
+            if ((g * 4) % 16 || ((uint64_t)S * pl * 4) % 16) k.al4 = false;
+            if (g % 16 || ((uint64_t)S * pl) % 16) k.al1 = false;
+            e.h_line0[r] = (uint32_t)l;
+            for (uint32_t a = 1; a < na; ++a) e.h_line_rec[l + a - 1] = (uint32_t)r;
+            g += (uint64_t)S * pl;
+            l += na - 1;
+        }
+    });
+    for (size_t c = 0; c < nch; ++c) { al4 &= cs[c].al4; al1 &= cs[c].al1; }
     e.h_blk_line0[e.nb] = (uint32_t)L; e.h_blk_rec0[e.nb] = (uint32_t)R;
     for (uint32_t b = 0; b < e.nb; ++b)
         if (e.h_blk_line0[b + 1] - e.h_blk_line0[b] >= 32768) { ctx->err = "block with >= 32768 binary lines (BM offset is 15 bits)"; return XSI_E_UNSUPPORTED; }
-    e.L = L;
-    e.h_line_rec.resize(L ? L : 1);
-    for (uint64_t r = 0; r < R; ++r) for (uint32_t a = 1; a < e.h_nallele[r]; ++a) e.h_line_rec[e.h_line0[r] + a - 1] = (uint32_t)r;
     const uint32_t N2 = 2 * S;
     e.WS = ((N2 + 31) / 32 + 3) / 4 * 4;
     e.SLOTW = ((N2 + 14) / 15 + 2 + 7) / 8 * 8;
     const uint64_t Lp = L ? L : 1;
 
+    if (ctx->profile) {
+        auto& sp = ctx->host_spans["host:encode_tables"];
+        sp.first++;
+        sp.second += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_tables).count();
+    }
     // ---- device buffers ----
     int elem = d->gt_elem_bytes;  // element size of the rows on the DEVICE
     const void* dgt = d->gt;
@@ -812,22 +874,21 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
             const uint64_t* off_ph = reinterpret_cast<const uint64_t*>(ho + o_ph);
             const uint8_t* lflags = e.h_flags.as<uint8_t>();
             const uint8_t* rflags = lflags + Lp;
-            struct Copy { uint64_t dst; const void* src; uint64_t bytes; };
-            std::vector<Copy> copies;
-            std::vector<std::vector<uint8_t>> heads(e.nb);   // dictionary + first bool vector of each block
-            struct Tail { uint64_t at; std::vector<uint8_t> bytes; };
-            std::vector<Tail> tails;                          // later bool vectors (missing / eov / phase / haploid)
-            e.block_at.assign(e.nb, 0);
-            e.block_sizes.assign(e.nb, 0);
-            e.n_wah_lines = 0;
-            uint64_t arena_size = 0;
-            for (uint32_t b = 0; b < e.nb; ++b) {
+            HOSTSPAN("host:encode_layout");
+            struct Copy { uint64_t dst; const void* src; uint64_t bytes; };  // dst relative to the block start
+            struct Tail { uint64_t at; std::vector<uint8_t> bytes; };       // later bool vectors (missing / eov / phase / haploid)
+            struct Layout { std::vector<uint8_t> head; std::vector<Tail> tails; std::vector<Copy> copies; uint64_t size = 0; uint64_t n_wah = 0; };
+            std::vector<Layout> lay(e.nb);
+            // one task per block on the worker pool; the arena offsets are a prefix sum afterwards
+            host_parallel_for(e.nb, [&](size_t bb) {
+                const uint32_t b = (uint32_t)bb;
+                Layout& ly = lay[b];
                 const uint32_t r0 = e.h_blk_rec0[b], r1 = e.h_blk_rec0[b + 1], l0 = e.h_blk_line0[b], l1 = e.h_blk_line0[b + 1];
                 const uint32_t nrec = r1 - r0, nlines = l1 - l0;
                 bool any_missing = false, any_eov = false, any_phase = false, any_hap = false;
                 uint32_t max_pl = 1;  // gt_block.hpp:168
                 std::vector<uint8_t> v_wah(nlines), v_miss(nlines, 0), v_eov(nlines, 0), v_phase(nlines, 0), v_hap(nrec, 0);
-                for (uint32_t l = l0; l < l1; ++l) { v_wah[l - l0] = (lflags[l] & LF_WAH) ? 1 : 0; e.n_wah_lines += v_wah[l - l0]; }
+                for (uint32_t l = l0; l < l1; ++l) { v_wah[l - l0] = (lflags[l] & LF_WAH) ? 1 : 0; ly.n_wah += v_wah[l - l0]; }
                 for (uint32_t r = r0; r < r1; ++r) {
                     const uint8_t f = rflags[r];
                     const uint32_t pl = e.h_ngt[r] / e.n_samples;
@@ -856,9 +917,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
                 if (any_hap) ins(KEY_LINE_HAPLOID, VAL_UNDEFINED);
                 const std::vector<uint32_t> order = ord.order();
 
-                const uint64_t base = arena_size;
-                e.block_at[b] = base;
-                std::vector<uint8_t>& head = heads[b];
+                std::vector<uint8_t>& head = ly.head;
                 put_u32(head, 0xFFFFFFFFu);
                 put_u32(head, (uint32_t)order.size());
                 const size_t dict_at = head.size();
@@ -870,15 +929,15 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
                 auto section = [&](uint32_t key, const void* dev, uint64_t first, uint64_t last, uint32_t unit) {
                     val[key] = (uint32_t)pos;
                     const uint64_t bytes = (last - first) * unit;
-                    if (bytes) copies.push_back({base + pos, (const uint8_t*)dev + first * unit, bytes});
+                    if (bytes) ly.copies.push_back({pos, (const uint8_t*)dev + first * unit, bytes});
                     pos += bytes;
                 };
                 auto boolvec = [&](uint32_t key, const std::vector<uint8_t>& v) {
                     val[key] = (uint32_t)pos;
-                    Tail t; t.at = base + pos;
+                    Tail t; t.at = pos;
                     wah16_encode_bools(v, t.bytes);
                     pos += t.bytes.size();
-                    tails.push_back(std::move(t));
+                    ly.tails.push_back(std::move(t));
                 };
                 section(KEY_MATRIX_WAH, e.out_wah.p, off_wh[l0], off_wh[l1], 2);
                 section(KEY_MATRIX_SPARSE, e.out_sparse.p, off_sp[l0], off_sp[l1], e.aet);
@@ -891,18 +950,28 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
                     const uint32_t v = val[order[i]];
                     memcpy(head.data() + dict_at + 8 * i + 4, &v, 4);
                 }
-                e.block_sizes[b] = pos;
-                arena_size = (base + pos + 15) / 16 * 16;
+                ly.size = pos;
+            });
+            e.block_at.assign(e.nb, 0);
+            e.block_sizes.assign(e.nb, 0);
+            e.n_wah_lines = 0;
+            uint64_t arena_size = 0;
+            for (uint32_t b = 0; b < e.nb; ++b) {
+                e.block_at[b] = arena_size;
+                e.block_sizes[b] = lay[b].size;
+                e.n_wah_lines += lay[b].n_wah;
+                arena_size = (arena_size + lay[b].size + 15) / 16 * 16;
             }
             CK(e.arena.ensure(arena_size + 16));
             uint8_t* ar = e.arena.as<uint8_t>();
             e.block_ptrs.assign(e.nb, nullptr);
             for (uint32_t b = 0; b < e.nb; ++b) {
-                e.block_ptrs[b] = ar + e.block_at[b];
-                memcpy(ar + e.block_at[b], heads[b].data(), heads[b].size());
+                uint8_t* at = ar + e.block_at[b];
+                e.block_ptrs[b] = at;
+                memcpy(at, lay[b].head.data(), lay[b].head.size());
+                for (const Tail& t : lay[b].tails) memcpy(at + t.at, t.bytes.data(), t.bytes.size());
+                for (const Copy& c : lay[b].copies) CK(cudaMemcpyAsync(at + c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->stream));
             }
-            for (const Tail& t : tails) memcpy(ar + t.at, t.bytes.data(), t.bytes.size());
-            for (const Copy& c : copies) CK(cudaMemcpyAsync(ar + c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->stream));
         }
         e.launched = true;
         return XSI_OK;
@@ -959,16 +1028,16 @@ uint64_t section_end(const ParsedBlock& pb, uint32_t off, uint64_t size) {
     return end;
 }
 
-int parse_block(xsi_ctx* ctx, const uint8_t* p, uint64_t size, ParsedBlock& pb) {
-    if (size < 8 || rd_u32(p) != 0xFFFFFFFFu) { ctx->err = "GT block: missing dictionary marker"; return XSI_E_FORMAT; }
+int parse_block(std::string& err, const uint8_t* p, uint64_t size, ParsedBlock& pb) {
+    if (size < 8 || rd_u32(p) != 0xFFFFFFFFu) { err = "GT block: missing dictionary marker"; return XSI_E_FORMAT; }
     const uint32_t n = rd_u32(p + 4);
-    if (8 + (uint64_t)n * 8 > size) { ctx->err = "GT block: truncated dictionary"; return XSI_E_FORMAT; }
+    if (8 + (uint64_t)n * 8 > size) { err = "GT block: truncated dictionary"; return XSI_E_FORMAT; }
     for (uint32_t i = 0; i < n; ++i) pb.dict[rd_u32(p + 8 + 8 * (size_t)i)] = rd_u32(p + 12 + 8 * (size_t)i);
     auto need = [&](uint32_t k, uint32_t& v) { auto it = pb.dict.find(k); if (it == pb.dict.end()) return false; v = it->second; return true; };
     uint32_t dp = 0, ws = 0;
-    if (!need(KEY_BCF_LINES, pb.bcf_lines) || !need(KEY_BINARY_LINES, pb.bin_lines) || !need(KEY_DEFAULT_PHASING, dp)) { ctx->err = "GT block: required key missing"; return XSI_E_FORMAT; }
+    if (!need(KEY_BCF_LINES, pb.bcf_lines) || !need(KEY_BINARY_LINES, pb.bin_lines) || !need(KEY_DEFAULT_PHASING, dp)) { err = "GT block: required key missing"; return XSI_E_FORMAT; }
     pb.default_phasing = dp == 1 ? 1 : 0;  // accessor_internals_new.hpp:77-81
-    if (!need(KEY_WEIRDNESS_STRATEGY, ws) || ws != WS_SPARSE) { ctx->err = "GT block: only the sparse missing/EOV strategy is supported (file written with --wah-encode-missing?)"; return XSI_E_UNSUPPORTED; }
+    if (!need(KEY_WEIRDNESS_STRATEGY, ws) || ws != WS_SPARSE) { err = "GT block: only the sparse missing/EOV strategy is supported (file written with --wah-encode-missing?)"; return XSI_E_UNSUPPORTED; }
     auto vec = [&](uint32_t key, std::vector<uint8_t>& v, bool& present) {
         present = false;
         auto it = pb.dict.find(key);
@@ -978,10 +1047,10 @@ int parse_block(xsi_ctx* ctx, const uint8_t* p, uint64_t size, ParsedBlock& pb) 
     };
     bool pw = false, ps = false, ph = false;
     vec(KEY_LINE_SELECT, pb.is_wah, pw);
-    if (!pw) { ctx->err = "GT block: no LINE_SELECT vector"; return XSI_E_FORMAT; }
+    if (!pw) { err = "GT block: no LINE_SELECT vector"; return XSI_E_FORMAT; }
     std::vector<uint8_t> sort;
     vec(KEY_LINE_SORT, sort, ps);
-    if (ps && sort != pb.is_wah) { ctx->err = "GT block: LINE_SORT differs from LINE_SELECT (not produced by the v5 writer)"; return XSI_E_UNSUPPORTED; }
+    if (ps && sort != pb.is_wah) { err = "GT block: LINE_SORT differs from LINE_SELECT (not produced by the v5 writer)"; return XSI_E_UNSUPPORTED; }
     vec(KEY_LINE_MISSING, pb.has_missing, pb.p_missing);
     vec(KEY_LINE_END_OF_VECTORS, pb.has_eov, pb.p_eov);
     vec(KEY_LINE_NON_UNIFORM_PHASING, pb.has_phase, pb.p_phase);
@@ -1016,12 +1085,8 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     d.WS = ((N + 31) / 32 + 3) / 4 * 4;
 
     std::vector<ParsedBlock> pbs(n_blocks);
-    std::vector<DecBlock> blocks(n_blocks);
-    std::vector<DecSeg> segs;
-    std::vector<uint32_t> job_gcum, job_nbits, job_seg, tile_seg, tile_word0;
-    std::vector<uint8_t> job_hap;
     std::vector<uint64_t> blob_off(n_blocks);
-    uint64_t blob_size = 0, Lt = 0;
+    uint64_t blob_size = 0;
     for (uint32_t b = 0; b < n_blocks; ++b) {
         blob_off[b] = blob_size;
         blob_size += (sizes[b] + 15) / 16 * 16;
@@ -1030,138 +1095,171 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     CK(d.blob.ensure(blob_size + 64));
     for (uint32_t b = 0; b < n_blocks; ++b)
         CK(cudaMemcpyAsync(d.blob.as<uint8_t>() + blob_off[b], gt_blocks[b], sizes[b], cudaMemcpyHostToDevice, ctx->stream));
-    for (uint32_t b = 0; b < n_blocks; ++b) {
-        int rc = parse_block(ctx, gt_blocks[b], sizes[b], pbs[b]);
-        if (rc) return rc;
-        Lt += pbs[b].bin_lines;
-    }
-    d.Lt = Lt;
-    std::vector<uint8_t> dl_flags(Lt ? Lt : 1, 0);
-    std::vector<uint32_t> dl_ord(Lt ? Lt : 1, 0), dl_mord(Lt ? Lt : 1, 0), dl_eord(Lt ? Lt : 1, 0), dl_pord(Lt ? Lt : 1, 0);
-    // pass 1: GT WAH jobs of every block (contiguous per block), lists ordinals
-    uint32_t njobs = 0, nsp = 0, nms = 0, nev = 0;
-    uint64_t line_base = 0;
-    struct PhaseTmp { uint32_t b; uint32_t gl; uint32_t nbits; };
-    std::vector<PhaseTmp> phase_lines;
-    auto add_tiles = [&](uint32_t seg_index, uint32_t n_words) {
-        for (uint32_t w = 0; w < n_words; w += D0_TILE) { tile_seg.push_back(seg_index); tile_word0.push_back(w); }
+
+    // ---- pass A (worker pool, one task per block): parse, count what the block contributes ----
+    struct BlkPlan {
+        int rc = XSI_OK; std::string err;
+        uint32_t n_wah = 0, n_sp = 0, n_ms = 0, n_ev = 0, n_ph = 0;
+        uint32_t wah_words = 0, ph_words = 0;  // u16 words of the WAH / phase matrix
+        uint32_t wah_val = 0, ph_val = 0;
+        bool any_hap = false;
+        // prefix sums (filled serially)
+        uint64_t line0 = 0;
+        uint32_t wah0 = 0, sp0 = 0, ms0 = 0, ev0 = 0, ph0 = 0, seg_w = 0, seg_p = 0, tile_w = 0, tile_p = 0;
     };
-    for (uint32_t b = 0; b < n_blocks; ++b) {
-        const ParsedBlock& pb = pbs[b];
-        DecBlock& bk = blocks[b];
-        memset(&bk, 0, sizeof(bk));
-        bk.blob_off = blob_off[b];
-        bk.line0 = (uint32_t)line_base; bk.n_lines = pb.bin_lines;
-        bk.default_phasing = pb.default_phasing;
-        auto moff = [&](uint32_t key) -> uint64_t {
-            auto it = pb.dict.find(key);
-            if (it == pb.dict.end() || it->second == VAL_UNDEFINED || it->second >= sizes[b]) return ~0ull;
-            return blob_off[b] + it->second;
-        };
-        bk.sparse_off = moff(KEY_MATRIX_SPARSE); bk.miss_off = moff(KEY_MATRIX_MISSING_SPARSE); bk.eov_off = moff(KEY_MATRIX_END_OF_VECTORS_SPARSE);
-        bk.wah0 = njobs; bk.sp0 = nsp; bk.ms0 = nms; bk.ev0 = nev;
-        uint32_t gc = 0;
-        const uint32_t seg_index = (uint32_t)segs.size();
-        for (uint32_t l = 0; l < pb.bin_lines; ++l) {
-            const uint64_t gl = line_base + l;
-            uint8_t f = 0;
-            const bool hap = pb.haploid[l] != 0;
-            if (hap) f |= DL_HAPLOID;
-            if (pb.is_wah[l]) {
-                f |= DL_WAH;
-                dl_ord[gl] = njobs++;
-                const uint32_t nbits = hap ? S : N;
-                job_gcum.push_back(gc); job_nbits.push_back(nbits); job_seg.push_back(seg_index); job_hap.push_back(hap ? 1 : 0);
-                gc += (nbits + 14) / 15;
-            } else {
-                dl_ord[gl] = nsp++;
+    std::vector<BlkPlan> plan(n_blocks);
+    {
+        HOSTSPAN("host:decode_parse");
+        host_parallel_for(n_blocks, [&](size_t b) {
+            BlkPlan& pl = plan[b];
+            ParsedBlock& pb = pbs[b];
+            pl.rc = parse_block(pl.err, gt_blocks[b], sizes[b], pb);
+            if (pl.rc) return;
+            for (uint32_t l = 0; l < pb.bin_lines; ++l) {
+                if (pb.is_wah[l]) { pl.n_wah++; if (pb.haploid[l]) pl.any_hap = true; } else pl.n_sp++;
+                pl.n_ms += pb.has_missing[l] != 0; pl.n_ev += pb.has_eov[l] != 0; pl.n_ph += pb.has_phase[l] != 0;
             }
-            if (pb.has_missing[l]) { f |= DL_MISSING; dl_mord[gl] = nms++; }
-            if (pb.has_eov[l]) { f |= DL_EOV; dl_eord[gl] = nev++; }
-            if (pb.has_phase[l]) { f |= DL_PHASE; phase_lines.push_back({b, (uint32_t)gl, hap ? S : N}); }
-            dl_flags[gl] = f;
-        }
-        bk.n_wah = njobs - bk.wah0; bk.n_sp = nsp - bk.sp0; bk.n_ms = nms - bk.ms0; bk.n_ev = nev - bk.ev0;
-        if (bk.n_wah) {
-            auto it = pb.dict.find(KEY_MATRIX_WAH);
-            if (it == pb.dict.end() || it->second == VAL_UNDEFINED || it->second >= sizes[b]) { ctx->err = "GT block: WAH lines without a WAH matrix"; return XSI_E_FORMAT; }
-            DecSeg sg;
-            sg.byte_off = blob_off[b] + it->second;
-            sg.n_words = (uint32_t)((section_end(pb, it->second, sizes[b]) - it->second) / 2);
-            sg.job0 = bk.wah0; sg.njobs = bk.n_wah; sg.tile0 = (uint32_t)tile_seg.size();
-            add_tiles(seg_index, sg.n_words);
-            segs.push_back(sg);
-        }
-        if ((bk.n_sp && bk.sparse_off == ~0ull) || (bk.n_ms && bk.miss_off == ~0ull) || (bk.n_ev && bk.eov_off == ~0ull)) { ctx->err = "GT block: index lists without their matrix"; return XSI_E_FORMAT; }
-        line_base += pb.bin_lines;
+            auto matrix = [&](uint32_t key, uint32_t& val, uint32_t& words, const char* what) {
+                auto it = pb.dict.find(key);
+                if (it == pb.dict.end() || it->second == VAL_UNDEFINED || it->second >= sizes[b]) { pl.err = what; pl.rc = XSI_E_FORMAT; return; }
+                val = it->second;
+                words = (uint32_t)((section_end(pb, it->second, sizes[b]) - it->second) / 2);
+            };
+            if (pl.n_wah) matrix(KEY_MATRIX_WAH, pl.wah_val, pl.wah_words, "GT block: WAH lines without a WAH matrix");
+            if (pl.n_ph && !pl.rc) matrix(KEY_MATRIX_NON_UNIFORM_PHASING, pl.ph_val, pl.ph_words, "GT block: phase lines without their matrix");
+        });
+    }
+    for (uint32_t b = 0; b < n_blocks; ++b)
+        if (plan[b].rc) { ctx->err = plan[b].err; return plan[b].rc; }
+    // ---- serial prefix over blocks: GT WAH jobs of every block first (contiguous per block), then the phase
+    //      lines as extra expand-only jobs, one segment per block that has any ----
+    uint64_t Lt = 0;
+    uint32_t njobs = 0, nsp = 0, nms = 0, nev = 0, nseg = 0, ntiles = 0;
+    bool any_hap_job = false;
+    auto tiles_of = [](uint32_t words) { return (words + D0_TILE - 1) / D0_TILE; };
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        BlkPlan& pl = plan[b];
+        pl.line0 = Lt; Lt += pbs[b].bin_lines;
+        pl.wah0 = njobs; njobs += pl.n_wah;
+        pl.sp0 = nsp; nsp += pl.n_sp;
+        pl.ms0 = nms; nms += pl.n_ms;
+        pl.ev0 = nev; nev += pl.n_ev;
+        if (pl.n_wah) { pl.seg_w = nseg++; pl.tile_w = ntiles; ntiles += tiles_of(pl.wah_words); }
+        any_hap_job |= pl.any_hap;
     }
     d.n_gt_jobs = njobs;
-    // pass 2: phase lines are extra expand-only jobs after all GT jobs, one segment per block
-    {
-        size_t i = 0;
-        while (i < phase_lines.size()) {
-            const uint32_t b = phase_lines[i].b;
-            const ParsedBlock& pb = pbs[b];
-            auto it = pb.dict.find(KEY_MATRIX_NON_UNIFORM_PHASING);
-            if (it == pb.dict.end() || it->second == VAL_UNDEFINED || it->second >= sizes[b]) { ctx->err = "GT block: phase lines without their matrix"; return XSI_E_FORMAT; }
-            DecSeg sg;
-            const uint32_t seg_index = (uint32_t)segs.size();
-            sg.byte_off = blob_off[b] + it->second;
-            sg.n_words = (uint32_t)((section_end(pb, it->second, sizes[b]) - it->second) / 2);
-            sg.job0 = njobs; sg.tile0 = (uint32_t)tile_seg.size();
-            uint32_t gc = 0;
-            while (i < phase_lines.size() && phase_lines[i].b == b) {
-                dl_pord[phase_lines[i].gl] = njobs++;
-                job_gcum.push_back(gc); job_nbits.push_back(phase_lines[i].nbits); job_seg.push_back(seg_index); job_hap.push_back(0);
-                gc += (phase_lines[i].nbits + 14) / 15;
-                ++i;
-            }
-            sg.njobs = njobs - sg.job0;
-            add_tiles(seg_index, sg.n_words);
-            segs.push_back(sg);
-        }
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        BlkPlan& pl = plan[b];
+        if (!pl.n_ph) continue;
+        pl.ph0 = njobs; njobs += pl.n_ph;
+        pl.seg_p = nseg++; pl.tile_p = ntiles; ntiles += tiles_of(pl.ph_words);
     }
+    d.Lt = Lt;
     d.NJ = njobs;
-    d.h_blocks = blocks;
+    // ---- one pinned staging area for everything the kernels index ----
+    const uint32_t NJp = njobs ? njobs : 1, ntp = ntiles ? ntiles : 1;
+    const uint64_t Ltp = Lt ? Lt : 1;
+    size_t at = 0;
+    auto take = [&](size_t bytes) { const size_t o = at; at = (at + bytes + 15) / 16 * 16; return o; };
+    const size_t s_blk = take(sizeof(DecBlock) * n_blocks), s_seg = take(sizeof(DecSeg) * (nseg ? nseg : 1));
+    const size_t s_job = take((size_t)NJp * 3 * 4), s_hap = take(NJp), s_tile = take((size_t)ntp * 2 * 4), s_dl = take(Ltp * 17);
+    CK(d.h_meta.ensure(at));
+    uint8_t* hm = d.h_meta.as<uint8_t>();
+    DecBlock* blocks = reinterpret_cast<DecBlock*>(hm + s_blk);
+    DecSeg* segs = reinterpret_cast<DecSeg*>(hm + s_seg);
+    uint32_t* job_gcum = reinterpret_cast<uint32_t*>(hm + s_job), *job_nbits = job_gcum + NJp, *job_seg = job_nbits + NJp;
+    uint8_t* job_hap = hm + s_hap;
+    uint32_t* tile_seg = reinterpret_cast<uint32_t*>(hm + s_tile), *tile_word0 = tile_seg + ntp;
+    uint32_t* dl_ord = reinterpret_cast<uint32_t*>(hm + s_dl), *dl_mord = dl_ord + Ltp, *dl_eord = dl_mord + Ltp, *dl_pord = dl_eord + Ltp;
+    uint8_t* dl_flags = reinterpret_cast<uint8_t*>(dl_pord + Ltp);
+    // ---- pass B (worker pool): every block fills its own slices ----
+    {
+        HOSTSPAN("host:decode_tables");
+        host_parallel_for(n_blocks, [&](size_t b) {
+            const BlkPlan& pl = plan[b];
+            const ParsedBlock& pb = pbs[b];
+            DecBlock& bk = blocks[b];
+            memset(&bk, 0, sizeof(bk));
+            bk.blob_off = blob_off[b];
+            bk.line0 = (uint32_t)pl.line0; bk.n_lines = pb.bin_lines;
+            bk.default_phasing = pb.default_phasing;
+            auto moff = [&](uint32_t key) -> uint64_t {
+                auto it = pb.dict.find(key);
+                if (it == pb.dict.end() || it->second == VAL_UNDEFINED || it->second >= sizes[b]) return ~0ull;
+                return blob_off[b] + it->second;
+            };
+            bk.sparse_off = moff(KEY_MATRIX_SPARSE); bk.miss_off = moff(KEY_MATRIX_MISSING_SPARSE); bk.eov_off = moff(KEY_MATRIX_END_OF_VECTORS_SPARSE);
+            bk.wah0 = pl.wah0; bk.sp0 = pl.sp0; bk.ms0 = pl.ms0; bk.ev0 = pl.ev0;
+            bk.n_wah = pl.n_wah; bk.n_sp = pl.n_sp; bk.n_ms = pl.n_ms; bk.n_ev = pl.n_ev;
+            uint32_t jw = pl.wah0, jp = pl.ph0, sp = pl.sp0, ms = pl.ms0, ev = pl.ev0, gc = 0, gcp = 0;
+            for (uint32_t l = 0; l < pb.bin_lines; ++l) {
+                const uint64_t gl = pl.line0 + l;
+                uint8_t f = 0;
+                const bool hap = pb.haploid[l] != 0;
+                const uint32_t nbits = hap ? S : N;
+                if (hap) f |= DL_HAPLOID;
+                if (pb.is_wah[l]) {
+                    f |= DL_WAH;
+                    dl_ord[gl] = jw;
+                    job_gcum[jw] = gc; job_nbits[jw] = nbits; job_seg[jw] = pl.seg_w; job_hap[jw] = hap ? 1 : 0;
+                    gc += (nbits + 14) / 15;
+                    ++jw;
+                } else {
+                    dl_ord[gl] = sp++;
+                }
+                dl_mord[gl] = 0; dl_eord[gl] = 0; dl_pord[gl] = 0;
+                if (pb.has_missing[l]) { f |= DL_MISSING; dl_mord[gl] = ms++; }
+                if (pb.has_eov[l]) { f |= DL_EOV; dl_eord[gl] = ev++; }
+                if (pb.has_phase[l]) {
+                    f |= DL_PHASE;
+                    dl_pord[gl] = jp;
+                    job_gcum[jp] = gcp; job_nbits[jp] = nbits; job_seg[jp] = pl.seg_p; job_hap[jp] = 0;
+                    gcp += (nbits + 14) / 15;
+                    ++jp;
+                }
+                dl_flags[gl] = f;
+            }
+            auto segment = [&](uint32_t si, uint32_t val, uint32_t words, uint32_t job0, uint32_t nj, uint32_t tile0) {
+                DecSeg& sg = segs[si];
+                sg.byte_off = blob_off[b] + val; sg.n_words = words; sg.job0 = job0; sg.njobs = nj; sg.tile0 = tile0;
+                for (uint32_t w = 0, t = tile0; w < words; w += D0_TILE, ++t) { tile_seg[t] = si; tile_word0[t] = w; }
+            };
+            if (pl.n_wah) segment(pl.seg_w, pl.wah_val, pl.wah_words, pl.wah0, pl.n_wah, pl.tile_w);
+            if (pl.n_ph) segment(pl.seg_p, pl.ph_val, pl.ph_words, pl.ph0, pl.n_ph, pl.tile_p);
+        });
+    }
+    for (uint32_t b = 0; b < n_blocks; ++b) {
+        const DecBlock& bk = blocks[b];
+        if ((bk.n_sp && bk.sparse_off == ~0ull) || (bk.n_ms && bk.miss_off == ~0ull) || (bk.n_ev && bk.eov_off == ~0ull)) { ctx->err = "GT block: index lists without their matrix"; return XSI_E_FORMAT; }
+    }
+    d.h_blocks.assign(blocks, blocks + n_blocks);
     d.h_bin_lines.resize(n_blocks);
     for (uint32_t b = 0; b < n_blocks; ++b) d.h_bin_lines[b] = pbs[b].bin_lines;
 
-    // ---- upload ----
-    const uint32_t NJp = njobs ? njobs : 1, ntiles = (uint32_t)tile_seg.size(), nseg = (uint32_t)segs.size();
+    // ---- upload (from the pinned staging area: asynchronous) ----
     // meta: blocks | segs
     const size_t m_blk = 0, m_seg = m_blk + sizeof(DecBlock) * n_blocks, m_end = m_seg + sizeof(DecSeg) * (nseg ? nseg : 1);
     CK(d.meta.ensure(m_end));
-    CK(cudaMemcpyAsync(d.meta.as<uint8_t>() + m_blk, blocks.data(), sizeof(DecBlock) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
-    if (nseg) CK(cudaMemcpyAsync(d.meta.as<uint8_t>() + m_seg, segs.data(), sizeof(DecSeg) * nseg, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(d.meta.as<uint8_t>() + m_blk, blocks, sizeof(DecBlock) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
+    if (nseg) CK(cudaMemcpyAsync(d.meta.as<uint8_t>() + m_seg, segs, sizeof(DecSeg) * nseg, cudaMemcpyHostToDevice, ctx->stream));
     // job arrays: gcum | nbits | seg | word0 | ones
     CK(d.job_u32.ensure((size_t)NJp * 5 * 4));
     uint32_t* ju = d.job_u32.as<uint32_t>();
     if (njobs) {
-        CK(cudaMemcpyAsync(ju, job_gcum.data(), njobs * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ju + NJp, job_nbits.data(), njobs * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(ju + 2 * NJp, job_seg.data(), njobs * 4, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ju, job_gcum, (size_t)NJp * 3 * 4, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaMemsetAsync(ju + 3 * NJp, 0xFF, (size_t)njobs * 4, ctx->stream));
     }
     CK(d.job_hap.ensure(NJp));
-    if (njobs) CK(cudaMemcpyAsync(d.job_hap.p, job_hap.data(), njobs, cudaMemcpyHostToDevice, ctx->stream));
-    const uint32_t ntp = ntiles ? ntiles : 1;
+    if (njobs) CK(cudaMemcpyAsync(d.job_hap.p, job_hap, njobs, cudaMemcpyHostToDevice, ctx->stream));
     CK(d.tile_u32.ensure((size_t)ntp * 3 * 4));
     uint32_t* tu = d.tile_u32.as<uint32_t>();
-    if (ntiles) {
-        CK(cudaMemcpyAsync(tu, tile_seg.data(), ntiles * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(tu + ntp, tile_word0.data(), ntiles * 4, cudaMemcpyHostToDevice, ctx->stream));
-    }
-    const uint64_t Ltp = Lt ? Lt : 1;
+    if (ntiles) CK(cudaMemcpyAsync(tu, tile_seg, (size_t)ntp * 2 * 4, cudaMemcpyHostToDevice, ctx->stream));
     CK(d.dline.ensure(Ltp * 17));
     uint8_t* dlb = d.dline.as<uint8_t>();
-    CK(cudaMemcpyAsync(dlb, dl_ord.data(), Ltp * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(dlb + Ltp * 4, dl_mord.data(), Ltp * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(dlb + Ltp * 8, dl_eord.data(), Ltp * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(dlb + Ltp * 12, dl_pord.data(), Ltp * 4, cudaMemcpyHostToDevice, ctx->stream));
-    CK(cudaMemcpyAsync(dlb + Ltp * 16, dl_flags.data(), Ltp, cudaMemcpyHostToDevice, ctx->stream));
+    if (Lt) CK(cudaMemcpyAsync(dlb, dl_ord, Ltp * 17, cudaMemcpyHostToDevice, ctx->stream));
     CK(d.lists.ensure(((size_t)nsp + nms + nev + 3) * 8));
-    CK(d.err.ensure(16));
-    CK(cudaMemsetAsync(d.err.p, 0, 16, ctx->stream));
+    CK(d.err.ensure(64));
+    CK(cudaMemsetAsync(d.err.p, 0, 64, ctx->stream));
     CK(d.rows.ensure((size_t)NJp * d.WS * 4));
     CK(d.seg_total.ensure((size_t)(nseg ? nseg : 1) * 4));
 
@@ -1178,8 +1276,6 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     dd.sp_off = d.lists.as<uint64_t>(); dd.ms_off = dd.sp_off + nsp + 1; dd.ev_off = dd.ms_off + nms + 1;
     dd.err = d.err.as<uint32_t>();
     // D2 v2 (barrier-free, sliced over haplotypes) needs the per-line tables; all-haploid lines use v1
-    bool any_hap_job = false;
-    for (uint32_t j = 0; j < d.n_gt_jobs; ++j) any_hap_job |= job_hap[j] != 0;
     const uint32_t TWv2 = 2 * d.WS + 4;
     uint32_t un_warps = 0, un_slices = 0, un_wpw = 32;
     size_t un_smem = 0;
@@ -1230,7 +1326,13 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     }
 
     // ---- kernels ----
-    if (nsp + nms + nev) {
+    if (getenv("XSI_DEBUG_UPLOAD_SYNC")) CK(cudaStreamSynchronize(ctx->stream));
+    const bool side = !getenv("XSI_NO_SIDE_STREAM");
+    if ((nsp + nms + nev) && !side) {
+        sparse_index_kernel<<<(n_blocks * 3 + 63) / 64, 64, 0, ctx->stream>>>(dd);
+        CKL();
+    }
+    if ((nsp + nms + nev) && side) {
         // latency-bound list walk: runs beside the WAH pipeline on the side stream, joined before the error read
         CK(cudaEventRecord(ctx->ev_side, ctx->stream));
         CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_side, 0));
@@ -1313,7 +1415,7 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
             }
         }
     }
-    if (nsp + nms + nev) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
+    if ((nsp + nms + nev) && side) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_side, 0));
     uint32_t herr = 0;
     CK(cudaMemcpyAsync(&herr, d.err.p, 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
