@@ -240,6 +240,7 @@ def test_biobank_width(ctx, tmp_path, monkeypatch):
     roundtrip(ctx, tmp_path, ds, 8, 0.001)
     monkeypatch.setenv("XSI_PBWT_KH", "8")
     monkeypatch.setenv("XSI_UNPERM_KH", "32")
+    monkeypatch.setenv("XSI_UNPERM_WINDOW", "3")  # several launches per block: positions travel through pos_state
     roundtrip(ctx, tmp_path, ds, 20, 0.001)
 
 

@@ -579,25 +579,38 @@ __global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d) {
 // haplotypes) no longer fits shared memory, and no ring could hold several of them; it stays in
 // global memory, where the tables of the lines in flight are L2-resident (126 MB), and every lookup is
 // one 8-byte read-only load.  State = KH positions per thread in registers, haplotypes independent
-// given the tables, so there is no barrier of any kind and the whole GPU works on one PBWT block:
-// grid = (PBWT block, haplotype slice of blockDim.x*KH).
+// given the tables, so there is no barrier inside the kernel and the whole GPU works on one PBWT block:
+// grid = (PBWT block, haplotype slice of blockDim.x*KH), one launch per window of lines.
 // =============================================================================================
 template <int KH>  // haplotypes per thread: 8, 16 or 32
-__global__ void __launch_bounds__(256) pbwt_unpermute_wide_kernel(DecDev d) {
+__global__ void __launch_bounds__(256) pbwt_unpermute_wide_kernel(DecDev d, uint32_t k0, uint32_t k1, uint32_t* __restrict__ pos_state) {
     const uint32_t N = 2 * d.n_samples, TW = d.TW, WS = d.WS;
     const DecBlock blk = d.blocks[blockIdx.x];
     const uint32_t nwah = blk.n_wah;
-    const uint32_t hb = (blockIdx.y * blockDim.x + threadIdx.x) * KH;  // first haplotype of this thread
-    if (nwah == 0 || hb >= WS * 32) return;
+    const uint32_t t = blockIdx.y * blockDim.x + threadIdx.x;
+    const uint32_t hb = t * KH;  // first haplotype of this thread
+    if (k0 >= nwah || hb >= WS * 32) return;
     const uint32_t nvalid = hb >= N ? 0u : (N - hb >= (uint32_t)KH ? (uint32_t)KH : N - hb);
+    // Lines [k0, k1) of the block per launch: the launch boundary keeps every thread of the GPU within k1-k0 lines
+    // of each other, i.e. the tables in flight inside L2 (free-running threads drift apart by hundreds of lines and
+    // every lookup becomes a DRAM access: 486 GB of DRAM reads for 1.8 GB of tables, ncu r01o).  Positions travel
+    // between launches through pos_state, laid out [block][q][thread] (coalesced).
+    const uint32_t TT = gridDim.y * blockDim.x;
+    uint32_t* ps = pos_state + ((size_t)blockIdx.x * KH) * TT + t;
     uint32_t pk[KH];
-    // identity at block start (gt_block.hpp:179); slots past N wander inside [0, N] and are masked off at the store
+    if (k0 == 0) {
+        // identity at block start (gt_block.hpp:179); slots past N wander inside [0, N] and are masked off at the store
 #pragma unroll
-    for (int q = 0; q < KH; ++q) pk[q] = (uint32_t)q < nvalid ? hb + q : 0u;
+        for (int q = 0; q < KH; ++q) pk[q] = (uint32_t)q < nvalid ? hb + q : 0u;
+    } else {
+#pragma unroll
+        for (int q = 0; q < KH; ++q) pk[q] = ps[(size_t)q * TT];
+    }
     const uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
-    const uint32_t* tab = d.tabs + (size_t)blk.wah0 * TW;
-    uint32_t* row = d.rows + (size_t)blk.wah0 * WS;
-    for (uint32_t k = 0; k < nwah; ++k, tab += TW, row += WS) {
+    const uint32_t kend = min(k1, nwah);
+    const uint32_t* tab = d.tabs + (size_t)(blk.wah0 + k0) * TW;
+    uint32_t* row = d.rows + (size_t)(blk.wah0 + k0) * WS;
+    for (uint32_t k = k0; k < kend; ++k, tab += TW, row += WS) {
         const uint2* T = reinterpret_cast<const uint2*>(tab);
         uint2 e[KH];
 #pragma unroll
@@ -616,6 +629,10 @@ __global__ void __launch_bounds__(256) pbwt_unpermute_wide_kernel(DecDev d) {
         if (KH == 32) row[hb >> 5] = x;
         else if (KH == 16) reinterpret_cast<uint16_t*>(row)[hb >> 4] = (uint16_t)x;
         else reinterpret_cast<uint8_t*>(row)[hb >> 3] = (uint8_t)x;
+    }
+    if (kend < nwah) {
+#pragma unroll
+        for (int q = 0; q < KH; ++q) ps[(size_t)q * TT] = pk[q];
     }
 }
 

@@ -1371,11 +1371,22 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
             CKL();
         } else if (use_wide) {
             const dim3 g(n_blocks, wide_slices);
+            uint32_t max_nwah = 0;
+            for (uint32_t b = 0; b < n_blocks; ++b) max_nwah = std::max(max_nwah, plan[b].n_wah);
+            // lines per launch: the tables of a window (all blocks) stay inside ~half of L2
+            uint64_t win = (48ull << 20) / ((uint64_t)n_blocks * TWv2 * 4);
+            win = std::max<uint64_t>(8, std::min<uint64_t>(512, win));
+            if (const char* sw = getenv("XSI_UNPERM_WINDOW")) { const int v = atoi(sw); if (v >= 1) win = (uint64_t)v; }
+            CK(d.x_pool.ensure((size_t)n_blocks * wide_kh * wide_slices * 256 * 4));
+            uint32_t* ps = d.x_pool.as<uint32_t>();
             PROF("pbwt_unpermute");
-            if (wide_kh == 32) pbwt_unpermute_wide_kernel<32><<<g, 256, 0, ctx->stream>>>(dd);
-            else if (wide_kh == 16) pbwt_unpermute_wide_kernel<16><<<g, 256, 0, ctx->stream>>>(dd);
-            else pbwt_unpermute_wide_kernel<8><<<g, 256, 0, ctx->stream>>>(dd);
-            CKL();
+            for (uint32_t k0 = 0; k0 < max_nwah; k0 += (uint32_t)win) {
+                const uint32_t k1 = (uint32_t)std::min<uint64_t>(max_nwah, k0 + win);
+                if (wide_kh == 32) pbwt_unpermute_wide_kernel<32><<<g, 256, 0, ctx->stream>>>(dd, k0, k1, ps);
+                else if (wide_kh == 16) pbwt_unpermute_wide_kernel<16><<<g, 256, 0, ctx->stream>>>(dd, k0, k1, ps);
+                else pbwt_unpermute_wide_kernel<8><<<g, 256, 0, ctx->stream>>>(dd, k0, k1, ps);
+                CKL();
+            }
         } else if (v2_ok) {
             const dim3 g(n_blocks, un_slices);
             if (un_wpw == 32) {
