@@ -292,7 +292,7 @@ def main():
     ap.add_argument("--ref-records", type=int, default=1024)
     ap.add_argument("--ref-workers", type=int, default=0)
     ap.add_argument("--ref-worker", type=int, default=-1, help=argparse.SUPPRESS)
-    ap.add_argument("--resident-contexts", type=int, default=0,
+    ap.add_argument("--resident-contexts", type=int, default=3,
                     help="also time the resident leg from this many host threads (one xsi_ctx each, blocks split between them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
@@ -341,6 +341,9 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    if world > 1 and "XSI_HOST_THREADS" not in os.environ:
+        # the ranks of one box share its cores: size each rank's conversion pool accordingly (read once by the library)
+        os.environ["XSI_HOST_THREADS"] = str(max(2, len(os.sched_getaffinity(0)) // int(os.environ.get("LOCAL_WORLD_SIZE", world))))
     ctx = xb.Context(local_rank)
     ctx.profile(True)
     L = ctx._L
@@ -687,15 +690,22 @@ def main():
                    "compress_ggts": r["compress"], "decompress_ggts": r["decompress"], "verified": r["ok"]}
 
     if rank == 0:
-        line = {"metric": METRIC, "value": value, "unit": "Ggt/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-                "ms_per_step": t_all / steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        # `value`: the better of the two resident legs (same batch, same calls, both verified); the per-kernel numbers
+        # (`kernels`, `roofline`) always come from the one-context leg, where kernels do not overlap
+        use_mt = resident_mt is not None and resident_mt["verified"] and resident_mt["value"] > value
+        line = {"metric": METRIC, "value": resident_mt["value"] if use_mt else value, "unit": "Ggt/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": resident_mt["ms_per_step"] if use_mt else t_all / steps * 1e3,
+                "value_one_context": value, "ms_per_step_one_context": t_all / steps * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32" if EL == 4 else "int8", "data": "synthetic",
                 "config": {"workload": workload, "blocks_per_gpu_per_step": B, "records_per_gpu_per_step": R,
                            "genotypes_per_gpu_per_step": G, "input": "%s rows resident in HBM (%.1f GB, > L2; no flush needed)" % ("int32" if EL == 4 else "int8", G * EL / 1e9),
-                           "xsi_payload_bytes_per_step": res["payload"], "binary_lines": res["lines"][0], "wah_lines": res["lines"][1], "parallelism": "blocks sharded over %d GPU(s)" % world},
+                           "xsi_payload_bytes_per_step": res["payload"], "binary_lines": res["lines"][0], "wah_lines": res["lines"][1], "parallelism": "blocks sharded over %d GPU(s)" % world,
+                           "host_threads_per_gpu": resident_mt["contexts"] if use_mt else 1,
+                           "contexts_per_gpu": resident_mt["contexts"] if use_mt else 1},
                 "compress_ggts": G * world * steps / t_enc / 1e9, "decompress_ggts": G * world * steps / t_dec / 1e9,
                 "verified": verified, "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8,
-                "gpu_launches": res["launches"], "clocks": res["clocks"]}
+                "gpu_launches": resident_mt["gpu_launches"] if use_mt else res["launches"], "clocks": res["clocks"]}
         print(json.dumps(line))
     ctx.close()
     if dist is not None:

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-T=${T:-r01p}
+T=${T:-r01q}
 timeout 600 python -m pytest tests -m gpu -x -q -k "biobank or uint32" 2>&1 | tail -15
 timeout 900 python bench.py --samples 500000 --blocks 2 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${T}_bench_biobank.json 2> gpurun_out/${T}_bench_biobank.err; echo "biobank rc=$?"
 tail -n 3 gpurun_out/${T}_bench_biobank.err
@@ -12,8 +12,3 @@ for n in ("biobank",):
     except Exception as e:
         print(n, "failed", e)
 P
-for w in 32 64 256; do
-XSI_UNPERM_WINDOW=$w timeout 600 python bench.py --samples 500000 --blocks 2 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline 2>/dev/null | python -c "
-import json,sys
-d=json.loads(sys.stdin.read().strip().splitlines()[-1]); print('window $w: unpermute %.2f ms dec %.1f verified %s' % (d['kernels']['pbwt_unpermute']['ms_per_step'], d['decompress_ggts'], d['verified']))"
-done

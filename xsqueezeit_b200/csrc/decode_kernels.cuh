@@ -265,6 +265,128 @@ __global__ void wah_expand_kernel(DecDev d, uint32_t warps_per_cta, uint32_t Gpa
 }
 
 // =============================================================================================
+// D1 wide: one WAH line per CTA for long lines (> 65,534 haplotypes).  The warp-per-line kernel above needs
+// 2 bytes of shared memory per 15-bit group (133 KB at a million haplotypes: one warp per SM, 27 ms for 7,045
+// lines).  Here the NSEG warps of a CTA each own a segment of the OUTPUT (a multiple of 15 row words = 32 whole
+// groups, so word and group boundaries coincide): every warp walks the line's WAH words from the start (a few
+// thousand: the stream is compressed, the output is not), keeps the literals and the clipped one-runs that fall
+// into its segment, and expands only that.  Zero prefixes for the table are segment-relative first and get
+// their base after one block barrier.
+// dynamic smem per warp: g15[SEGG + 8] (u16) | tog[SEGT] (u32)
+// =============================================================================================
+constexpr int D1W_WARPS = 16;
+__global__ void __launch_bounds__(D1W_WARPS * 32) wah_expand_wide_kernel(DecDev d, uint32_t SEGW, uint32_t SEGT) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ uint32_t s_zeros[D1W_WARPS], s_ones[D1W_WARPS];
+    const uint32_t wi = threadIdx.x >> 5, lane = lane_id();
+    const uint32_t job = blockIdx.x;
+    const uint32_t SEGG = SEGW * 32 / 15;  // groups per segment (SEGW is a multiple of 15)
+    const size_t per_warp = ((size_t)(SEGG + 8) * 2 + 3) / 4 * 4 + (size_t)SEGT * 4;
+    uint16_t* g15 = reinterpret_cast<uint16_t*>(smem_raw + (size_t)wi * per_warp);
+    uint32_t* tog = reinterpret_cast<uint32_t*>(reinterpret_cast<unsigned char*>(g15) + ((size_t)(SEGG + 8) * 2 + 3) / 4 * 4);
+    const DecSeg sg = d.segs[d.job_seg[job]];
+    const uint16_t* w = reinterpret_cast<const uint16_t*>(d.blob + sg.byte_off);
+    const uint32_t nbits = d.job_nbits[job];
+    const uint32_t G = (nbits + 14) / 15;
+    const uint32_t ws = d.job_word0[job];
+    const uint32_t we = (job + 1 < sg.job0 + sg.njobs) ? d.job_word0[job + 1] : sg.n_words;
+    uint32_t* out = d.rows + (size_t)job * d.WS;
+    const bool bad = ws == 0xFFFFFFFFu || we == 0xFFFFFFFFu || we < ws;  // uniform over the CTA
+    if (bad) {
+        if (threadIdx.x == 0) atomicOr(d.err, DERR_WAH_STREAM);
+        for (uint32_t m = threadIdx.x; m < d.WS; m += blockDim.x) out[m] = 0;
+        return;
+    }
+    const uint32_t g_lo = wi * SEGG, g_hi = min(G, g_lo + SEGG);  // groups of this warp (empty when g_lo >= G)
+    for (uint32_t i = lane; i < SEGG + 8; i += 32) g15[i] = 0;
+    for (uint32_t i = lane; i < SEGT; i += 32) tog[i] = 0;
+    __syncwarp();
+    // ---- 1: walk the words; keep what falls into [g_lo, g_hi) ----
+    uint32_t gbase = 0;
+    if (g_lo < G) {
+        for (uint32_t b = ws; b < we; b += 32) {
+            const uint32_t i = b + lane;
+            const uint32_t word = i < we ? w[i] : 0u;
+            const uint32_t ng = i < we ? wah_word_groups(word) : 0u;
+            uint32_t incl = ng;
+#pragma unroll
+            for (int q = 1; q < 32; q <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, q); if (lane >= (uint32_t)q) incl += o; }
+            const uint32_t gs = gbase + incl - ng;
+            if (i < we && gs < G) {  // words past G groups belong to the next line / the alignment bytes
+                if (!(word & 0x8000u)) { if (gs >= g_lo && gs < g_hi) g15[gs - g_lo] = (uint16_t)word; }
+                else if ((word & 0x4000u) && ng) {  // run of all-one groups, clipped to the segment: toggle marks
+                    const uint32_t s0 = max(gs, g_lo), e0 = min(gs + ng, g_hi);
+                    if (s0 < e0) {
+                        atomicXor(&tog[(s0 - g_lo) >> 5], 1u << ((s0 - g_lo) & 31));
+                        atomicXor(&tog[(e0 - g_lo) >> 5], 1u << ((e0 - g_lo) & 31));
+                    }
+                }
+            }
+            const uint32_t endg = (i < we && gs < G) ? gs + ng : 0u;
+            gbase = max(gbase, __reduce_max_sync(XSI_FULL, endg));
+            if (gbase >= g_hi) break;
+        }
+        // the warp of the last segment has seen the whole line: it must end exactly at G groups
+        if (g_hi == G && gbase != G && lane == 0) atomicOr(d.err, DERR_WAH_STREAM);
+    }
+    __syncwarp();
+    // ---- 2: prefix-xor over the toggle bits -> bit g set iff group g_lo+g lies inside a ones-run ----
+    uint32_t carry = 0;
+    for (uint32_t b = 0; b < SEGT; b += 32) {
+        const uint32_t i = b + lane;
+        uint32_t tw = i < SEGT ? tog[i] : 0u;
+        tw ^= tw << 1; tw ^= tw << 2; tw ^= tw << 4; tw ^= tw << 8; tw ^= tw << 16;
+        const uint32_t pm = __ballot_sync(XSI_FULL, tw >> 31);
+        const uint32_t cin = (__popc(pm & lanemask_lt()) & 1u) ^ carry;
+        if (cin) tw = ~tw;
+        if (i < SEGT) tog[i] = tw;
+        carry ^= (__popc(pm) & 1u);
+    }
+    __syncwarp();
+    // ---- 3a: the row words of the segment, zero prefixes relative to the segment ----
+    const uint32_t nwords = (nbits + 31) >> 5;
+    const uint32_t m_lo = wi * SEGW, m_hi = min(d.WS, m_lo + SEGW);
+    uint32_t* tab = (d.tabs && job < d.n_gt_jobs) ? d.tabs + (size_t)job * d.TW : nullptr;
+    uint32_t ones = 0, zcarry = 0;
+    for (uint32_t m0 = m_lo; m0 < m_hi; m0 += 32) {
+        const uint32_t m = m0 + lane;
+        uint32_t o = 0;
+        if (m < m_hi && m < nwords) {
+            const uint32_t b0 = m * 32, g0 = b0 / 15, sh = b0 - g0 * 15;
+            uint64_t acc = 0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const uint32_t g = g0 + q;
+                uint32_t val = 0;
+                if (g < g_hi) { const uint32_t gr = g - g_lo; val = ((tog[gr >> 5] >> (gr & 31)) & 1u) ? 0x7FFFu : g15[gr]; }
+                acc |= (uint64_t)val << (15 * q);
+            }
+            o = (uint32_t)(acc >> sh);
+            if (m == nwords - 1 && (nbits & 31)) o &= (1u << (nbits & 31)) - 1u;
+        }
+        if (m < m_hi) out[m] = o;
+        ones += __popc(o);
+        const uint32_t nz = m < m_hi ? 32u - __popc(o) : 0u;
+        uint32_t incl = nz;
+#pragma unroll
+        for (int q = 1; q < 32; q <<= 1) { const uint32_t t = __shfl_up_sync(XSI_FULL, incl, q); if (lane >= (uint32_t)q) incl += t; }
+        if (tab && m < m_hi) *reinterpret_cast<uint2*>(tab + 2 * m) = make_uint2(zcarry + incl - nz, ~o);  // wide entries only
+        zcarry += __shfl_sync(XSI_FULL, incl, 31);
+    }
+    ones = __reduce_add_sync(XSI_FULL, ones);
+    if (lane == 0) { s_zeros[wi] = zcarry; s_ones[wi] = ones; }
+    __syncthreads();
+    // ---- 3b: segment bases ----
+    uint32_t base = 0, total_ones = 0;
+    for (uint32_t q = 0; q < (uint32_t)D1W_WARPS; ++q) { if (q < wi) base += s_zeros[q]; total_ones += s_ones[q]; }
+    if (tab && base) for (uint32_t m = m_lo + lane; m < m_hi; m += 32) tab[2 * m] += base;
+    if (threadIdx.x == 0) {
+        if (tab) tab[2 * d.WS] = nbits - total_ones;  // Z, total zeros of the line
+        d.job_ones[job] = total_ones;
+    }
+}
+
+// =============================================================================================
 // D2: undo the PBWT order, a[] in shared memory as uint16 (2*num_samples <= 65536)
 // =============================================================================================
 // dynamic smem: a[N] u16 | ybuf[2][WS] | xb[N+32] u8 | zc[64] | mbar[2]

@@ -1347,6 +1347,16 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
         CKL();
         { PROF("wah_find_lines"); wah_find_lines_kernel<<<ntiles, D0_THREADS, 0, ctx->stream>>>(dd); }
         CKL();
+        if (use_wide) {
+            // long lines: one CTA per line, every warp expands one segment of the row (a multiple of 15 words)
+            const uint32_t SEGW = ((d.WS + D1W_WARPS - 1) / D1W_WARPS + 14) / 15 * 15, SEGG = SEGW * 32 / 15, SEGT = (SEGG + 1 + 31) / 32 + 1;
+            const size_t per_warp_w = ((size_t)(SEGG + 8) * 2 + 3) / 4 * 4 + (size_t)SEGT * 4;
+            const size_t smem_w = per_warp_w * D1W_WARPS;
+            if (smem_w > ctx->smem_optin) { ctx->err = "haplotype count too large for the WAH expand kernel"; return XSI_E_UNSUPPORTED; }
+            CK(cudaFuncSetAttribute(wah_expand_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_w));
+            { PROF("wah_expand"); wah_expand_wide_kernel<<<njobs, D1W_WARPS * 32, smem_w, ctx->stream>>>(dd, SEGW, SEGT); }
+            CKL();
+        } else {
         const uint32_t G = (N + 14) / 15;
         const uint32_t Gpad = (G + 4 + 7) / 8 * 8, Tpad = (G + 1 + 31) / 32 + 1;
         const size_t per_warp = (size_t)Gpad * 2 + (size_t)Tpad * 4;
@@ -1356,6 +1366,7 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
         CK(cudaFuncSetAttribute(wah_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         { PROF("wah_expand"); wah_expand_kernel<<<(njobs + wpc - 1) / wpc, wpc * 32, smem, ctx->stream>>>(dd, wpc, Gpad, Tpad); }
         CKL();
+        }
         if (v3_kh) {
             const dim3 g(n_blocks, v3_slices);
             if (v3_kh == 32) {
