@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-T=${T:-r01q}
+T=${T:-r01s}
 timeout 600 python -m pytest tests -m gpu -x -q -k "biobank or uint32" 2>&1 | tail -15
 timeout 900 python bench.py --samples 500000 --blocks 2 --steps 2 --warmup 1 --no-e2e --no-cpu-baseline > gpurun_out/${T}_bench_biobank.json 2> gpurun_out/${T}_bench_biobank.err; echo "biobank rc=$?"
 tail -n 3 gpurun_out/${T}_bench_biobank.err

@@ -1072,25 +1072,30 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v4_kernel(EncDev p, Perm
 // =============================================================================================
 // E3 grid: PBWT permute for MORE than 65,534 haplotypes (biobank scale, uint32 indices).  A million
 // positions do not fit one SM (nor a 16-CTA cluster: 4 MB of positions + 125 KB bitmaps), so the WHOLE
-// GPU works on a few PBWT blocks at once, one WAH line of each per step, as a cooperative launch:
+// GPU works on a few PBWT blocks at once, one WAH line of each per step, as a cooperative launch with
+// ONE grid barrier per line:
 //   state   pos[i] (inverse permutation) in REGISTERS, KH haplotypes per thread, TPB threads per PBWT block
-//   A  (fused with C of the previous line) carriers scatter into the line's bitmap Y in global memory (L2 atomics)
+//   A  (fused with C of the previous line) every carrier sets its bit in the line's bitmap Y and adds one to
+//      the carrier count of its 128-position group, both in global memory (L2 atomics)
 //   -- grid barrier --
-//   B  one warp per 8192-position chunk: takes the chunk's Y words (and clears them for the line after
-//      next), writes them as the permuted row (in place), publishes the chunk's carrier count in a tagged
-//      flag word, sums the flags of the chunks before it, and writes the chunk's table
-//      {zeros before, zero-position bits} per 32 positions (global, L2-resident: N/4 bytes per block)
-//   -- grid barrier --
-//   C  pos[i] <- x[i] ? Z + j - zb(j) : zb(j),  j = pos[i],  one 8-byte L2 load per haplotype
-// Two grid barriers and one flag exchange per line, shared by all blocks of the group.
+//   B  every CTA takes the group counts of ITS block (N/128 words, 31 KB at a million haplotypes) into
+//      shared memory and scans them: zeros before every group, and Z
+//   C  pos[i] <- x[i] ? Z + j - zb(j) : zb(j),  j = pos[i],  zb(j) = scan[j >> 7] + zeros of the group's
+//      four bitmap words before j: one 16-byte L2 load per haplotype
+// Y and the counts are triple buffered: in the step that reads line k and scatters line k+1, the buffer of line
+// k-1 is copied out as that line's permuted row (in place, bitrows) and cleared for line k+2.
+// Cost per line and group of blocks (two blocks of a million haplotypes, r01r): 21.7 us, of which the random
+// 16-byte L2 loads of C are about 7 (the same L2 sector rate that bounds the wide decode kernel) and the rest is
+// the barrier, the scan and the atomics: fixed per step, so it amortises over the blocks of a group (4 at KH = 32).
+// (The first version exchanged chunk totals through flag words and built a table in a second phase with a second
+// grid barrier: same time per line, more moving parts.)
 // =============================================================================================
 struct PermGridCfg {
     uint32_t b0, nbg;   // PBWT blocks [b0, b0+nbg) of the batch
-    uint32_t TPB;       // threads per PBWT block (multiple of 32); thread t owns haplotypes [t*KH, t*KH+KH)
-    uint32_t WSP;       // row words padded to a multiple of 256 (chunks of 8192 positions)
-    uint32_t* Y;        // [nbg][2][WSP], zero on entry (and on exit)
-    uint32_t* T;        // [nbg][2*WSP+4]: per row word {zeros before, ~y}; [2*WSP] = Z
-    uint32_t* flags;    // [nbg][WSP/256], zero on entry: (line+1) << 14 | carriers in the chunk
+    uint32_t TPB;       // threads per PBWT block (a multiple of 1024: CTAs never straddle blocks)
+    uint32_t WSP;       // row words padded to a multiple of 32 (groups of 4 words, 8 groups per scan thread)
+    uint32_t* Y;        // [nbg][3][WSP], zero on entry
+    uint32_t* CNT;      // [nbg][3][WSP/4] carriers per 128-position group, zero on entry
     uint32_t* bar;      // grid barrier counter, zero on entry
 };
 
@@ -1102,128 +1107,143 @@ __device__ __forceinline__ uint32_t ld_volatile_u32(const uint32_t* p) {
 
 template <int KH>  // 8, 16 or 32
 __global__ void __launch_bounds__(1024, 1) pbwt_permute_grid_kernel(EncDev p, PermGridCfg c) {
-    const uint32_t N = 2 * p.n_samples, WS = p.WS, WSP = c.WSP, NCH = WSP >> 8;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u;
-    const uint32_t gtid = blockIdx.x * 1024u + tid, gwarp = gtid >> 5;
-    // ---- role 1: owner of KH haplotypes of block bi ----
-    const uint32_t bi = gtid / c.TPB, hb = (gtid % c.TPB) * KH;
-    const bool owner = bi < c.nbg && hb < N;
-    const uint32_t nwah = owner ? p.blk_nwah[c.b0 + bi] : 0u;
-    const uint32_t* list = p.wah_list + p.blk_line0[c.b0 + (bi < c.nbg ? bi : 0)];
-    uint32_t* Yo = c.Y + (size_t)bi * 2 * WSP;
-    const uint32_t* To = c.T + (size_t)bi * (2 * WSP + 4);
-    uint32_t pk[KH];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t* zpre = reinterpret_cast<uint32_t*>(smem_raw);  // [NG] zeros before every group of this CTA's block
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_Z;
+    const uint32_t N = 2 * p.n_samples, WS = p.WS, WSP = c.WSP, NG = WSP >> 2;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t ctas_per_block = c.TPB >> 10;
+    const uint32_t bi = blockIdx.x / ctas_per_block;                 // PBWT block of this CTA (uniform)
+    const uint32_t cib = blockIdx.x - bi * ctas_per_block;           // CTA index inside the block
+    const bool active = bi < c.nbg;
+    const uint32_t hb = (cib * 1024u + tid) * KH;
+    const bool owner = active && hb < N;
+    const uint32_t bnwah = active ? p.blk_nwah[c.b0 + bi] : 0u;      // lines of this CTA's block
+    const uint32_t nwah = owner ? bnwah : 0u;
+    const uint32_t* list = p.wah_list + p.blk_line0[c.b0 + (active ? bi : 0)];
+    uint32_t* Yb = c.Y + (size_t)(active ? bi : 0) * 3 * WSP;
+    uint32_t* Cb = c.CNT + (size_t)(active ? bi : 0) * 3 * NG;
+    uint32_t max_nwah = 0;
+    for (uint32_t i = 0; i < c.nbg; ++i) max_nwah = max(max_nwah, p.blk_nwah[c.b0 + i]);
     const uint32_t nvalid = !owner ? 0u : (N - hb >= (uint32_t)KH ? (uint32_t)KH : N - hb);
+    uint32_t pk[KH];
     // identity at block start (gt_block.hpp:179); slots past N sit at position 0 and never carry
 #pragma unroll
     for (int q = 0; q < KH; ++q) pk[q] = (uint32_t)q < nvalid ? hb + q : 0u;
     const uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
-    // the KH bits of this thread in a natural-order bit-row (rows of later lines are untouched until their step B)
+    // the KH bits of this thread in a natural-order bit-row (rows of later lines are untouched until their copy-out)
     auto load_x = [&](uint32_t k) -> uint32_t {
         if (k >= nwah) return 0u;
         const uint32_t v = __ldcg(p.bitrows + (size_t)(list[k] & 0x7FFFFFFFu) * WS + (hb >> 5));
         return (KH >= 32 ? v : (v >> (hb & 31u))) & vmask;
     };
-    // ---- role 2: warp gwarp owns chunk cc of block cb ----
-    const uint32_t cb = gwarp / NCH, cc = gwarp % NCH;
-    const bool chunker = cb < c.nbg;
-    const uint32_t cnwah = chunker ? p.blk_nwah[c.b0 + cb] : 0u;
-    const uint32_t* clist = p.wah_list + p.blk_line0[c.b0 + (chunker ? cb : 0)];
-    uint32_t max_nwah = 0;
-    for (uint32_t i = 0; i < c.nbg; ++i) max_nwah = max(max_nwah, p.blk_nwah[c.b0 + i]);
-
+    auto scatter = [&](uint32_t x, uint32_t buf) {
+        if (!x) return;
+        uint32_t* Yn = Yb + (size_t)buf * WSP;
+        uint32_t* Cn = Cb + (size_t)buf * NG;
+#pragma unroll
+        for (int q = 0; q < KH; ++q)
+            if (x & (1u << q)) { atomicOr(Yn + (pk[q] >> 5), 1u << (pk[q] & 31u)); atomicAdd(Cn + (pk[q] >> 7), 1u); }
+    };
     uint32_t bar_target = 0;
-    auto grid_sync = [&]() {
+    auto grid_arrive = [&]() {
         bar_target += gridDim.x;
         __syncthreads();
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(c.bar, 1u);
-            while (ld_volatile_u32(c.bar) < bar_target) {}
-            __threadfence();
-        }
+        if (tid == 0) { __threadfence(); atomicAdd(c.bar, 1u); }
+    };
+    auto grid_wait = [&]() {
+        if (tid == 0) { while (ld_volatile_u32(c.bar) < bar_target) {} __threadfence(); }
         __syncthreads();
     };
 
     uint32_t x0 = load_x(0), x1 = load_x(1), x2 = load_x(2);
-    // step A of the first line (positions are the identity)
-#pragma unroll
-    for (int q = 0; q < KH; ++q)
-        if (x0 & (1u << q)) atomicOr(Yo + (pk[q] >> 5), 1u << (pk[q] & 31u));
+    scatter(x0, 0);  // A of the first line (positions are the identity)
 
     for (uint32_t k = 0; k < max_nwah; ++k) {
-        const uint32_t par = k & 1u;
-        grid_sync();  // every carrier of line k has landed
-        // ---- B ----
-        if (chunker && k < cnwah) {
-            uint32_t* Yc = c.Y + ((size_t)cb * 2 + par) * WSP + cc * 256 + lane * 8;
-            uint32_t y[8];
-            {
-                const uint4 a = __ldcg(reinterpret_cast<const uint4*>(Yc)), b = __ldcg(reinterpret_cast<const uint4*>(Yc) + 1);
-                y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
-                __stcg(reinterpret_cast<uint4*>(Yc), make_uint4(0, 0, 0, 0));
-                __stcg(reinterpret_cast<uint4*>(Yc) + 1, make_uint4(0, 0, 0, 0));
+        const uint32_t cur = k % 3u, nxt = (k + 1) % 3u, old = (k + 2) % 3u;  // old = buffer of line k-1
+        grid_arrive();
+        grid_wait();  // every carrier of line k has landed; everybody is done with line k-1
+        // ---- housekeeping of line k-1's buffer (nobody reads it any more): permuted row out (in place), clear ----
+        if (active && k >= 1 && k - 1 < bnwah) {
+            uint32_t* Yo = Yb + (size_t)old * WSP;
+            uint32_t* Co = Cb + (size_t)old * NG;
+            uint32_t* grow = p.bitrows + (size_t)(list[k - 1] & 0x7FFFFFFFu) * WS;
+            for (uint32_t w4 = cib * 1024u + tid; w4 < (WSP >> 2); w4 += ctas_per_block * 1024u) {
+                const uint4 y = __ldcg(reinterpret_cast<const uint4*>(Yo) + w4);
+                if (4 * w4 < WS) *reinterpret_cast<uint4*>(grow + 4 * w4) = y;
+                __stcg(reinterpret_cast<uint4*>(Yo) + w4, make_uint4(0, 0, 0, 0));
+                __stcg(Co + w4, 0u);  // one group = four words
             }
-            uint32_t nz = 0;
-#pragma unroll
-            for (int i = 0; i < 8; ++i) nz += 32u - __popc(y[i]);
-            uint32_t incl = nz;
-#pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, dd); if (lane >= (uint32_t)dd) incl += o; }
-            const uint32_t chunk_zeros = __shfl_sync(XSI_FULL, incl, 31);
-            uint32_t* fl = c.flags + (size_t)cb * NCH;
-            if (lane == 0) {
-                asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(fl + cc), "r"(((k + 1) << 14) | (8192u - chunk_zeros)) : "memory");
-            }
-            // permuted row, in place
-            const uint32_t w0 = cc * 256 + lane * 8;
-            uint32_t* grow = p.bitrows + (size_t)(clist[k] & 0x7FFFFFFFu) * WS;
-            if (w0 < WS) *reinterpret_cast<uint4*>(grow + w0) = make_uint4(y[0], y[1], y[2], y[3]);
-            if (w0 + 4 < WS) *reinterpret_cast<uint4*>(grow + w0 + 4) = make_uint4(y[4], y[5], y[6], y[7]);
-            // zeros before this chunk: the flags of the chunks before it
-            uint32_t before = 0;
-            for (uint32_t i = lane; i < cc; i += 32) {
-                uint32_t f;
-                do { f = ld_volatile_u32(fl + i); } while ((f >> 14) != k + 1);
-                before += 8192u - (f & 0x3FFFu);
-            }
-            before = __reduce_add_sync(XSI_FULL, before);
-            uint32_t zp = before + incl - nz;
-            uint32_t* Tc = c.T + (size_t)cb * (2 * WSP + 4) + 2 * (size_t)w0;
-#pragma unroll
-            for (int i = 0; i < 8; i += 2) {
-                const uint32_t z1 = zp + 32u - __popc(y[i]);
-                __stcg(reinterpret_cast<uint4*>(Tc + 2 * i), make_uint4(zp, ~y[i], z1, ~y[i + 1]));
-                zp = z1 + 32u - __popc(y[i + 1]);
-            }
-            // Z: zeros among the N real positions (the padding past N never holds a carrier)
-            if (cc == NCH - 1 && lane == 31) __stcg(c.T + (size_t)cb * (2 * WSP + 4) + 2 * WSP, zp - (WSP * 32 - N));
         }
-        grid_sync();  // every table of line k is complete
-        // ---- C (+ A of line k+1) ----
-        if (k < nwah) {
-            const uint32_t Z = __ldcg(To + 2 * WSP);
-            const uint2* T2 = reinterpret_cast<const uint2*>(To);
+        if (active && k < bnwah) {
+            // ---- B: zeros before every 128-position group of this block (block-wide exclusive scan) ----
+            const uint32_t* Cc = Cb + (size_t)cur * NG;
+            uint32_t carry = 0;
+            for (uint32_t g0 = 0; g0 < NG; g0 += 8192u) {  // 8 groups per thread and pass
+                const uint32_t g = g0 + tid * 8u;
+                uint4 cn = make_uint4(0, 0, 0, 0), cm = make_uint4(0, 0, 0, 0);
+                if (g < NG) { cn = __ldcg(reinterpret_cast<const uint4*>(Cc + g)); cm = __ldcg(reinterpret_cast<const uint4*>(Cc + g) + 1); }
+                const uint32_t z0 = 128u - cn.x, z1 = 128u - cn.y, z2 = 128u - cn.z, z3 = 128u - cn.w;
+                const uint32_t z4 = 128u - cm.x, z5 = 128u - cm.y, z6 = 128u - cm.z, z7 = 128u - cm.w;
+                const uint32_t tot = g < NG ? z0 + z1 + z2 + z3 + z4 + z5 + z6 + z7 : 0u;
+                uint32_t incl = tot;
 #pragma unroll
-            for (int q0 = 0; q0 < KH; q0 += 8) {
-                uint2 e[8];
-#pragma unroll
-                for (int q = 0; q < 8; ++q) e[q] = __ldcg(T2 + (pk[q0 + q] >> 5));
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const uint32_t j = pk[q0 + q];
-                    const uint32_t zb = e[q].x + __popc(e[q].y & ~(0xFFFFFFFFu << (j & 31u)));
-                    pk[q0 + q] = (x0 & (1u << (q0 + q))) ? Z + j - zb : zb;
+                for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, dd); if (lane >= (uint32_t)dd) incl += o; }
+                if (lane == 31) s_warp[warp] = incl;
+                __syncthreads();
+                const uint32_t wv = s_warp[lane];
+                const uint32_t wbase = __reduce_add_sync(XSI_FULL, lane < warp ? wv : 0u);
+                const uint32_t wtot = __reduce_add_sync(XSI_FULL, wv);
+                const uint32_t ex = carry + wbase + incl - tot;
+                if (g < NG) {
+                    const uint32_t h = ex + z0 + z1 + z2 + z3;
+                    *reinterpret_cast<uint4*>(zpre + g) = make_uint4(ex, ex + z0, ex + z0 + z1, ex + z0 + z1 + z2);
+                    *reinterpret_cast<uint4*>(zpre + g + 4) = make_uint4(h, h + z4, h + z4 + z5, h + z4 + z5 + z6);
                 }
+                carry += wtot;
+                __syncthreads();
             }
-            if (x1) {
-                uint32_t* Yn = Yo + (par ^ 1u) * WSP;
+            if (tid == 0) s_Z = carry - (WSP * 32u - N);  // the padding past N never holds a carrier
+            __syncthreads();
+            // ---- C (+ A of line k+1) ----
+            if (k < nwah) {
+                const uint32_t Z = s_Z;
+                const uint4* Y4 = reinterpret_cast<const uint4*>(Yb + (size_t)cur * WSP);
 #pragma unroll
-                for (int q = 0; q < KH; ++q)
-                    if (x1 & (1u << q)) atomicOr(Yn + (pk[q] >> 5), 1u << (pk[q] & 31u));
+                for (int q0 = 0; q0 < KH; q0 += 4) {
+                    uint4 y[4];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) y[q] = __ldcg(Y4 + (pk[q0 + q] >> 7));
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        const uint32_t j = pk[q0 + q];
+                        const uint32_t wsel = (j >> 5) & 3u;
+                        // zeros of the group before j: whole words below wsel, then the low bits of word wsel
+                        const uint32_t n0 = ~y[q].x, n1 = ~y[q].y, n2 = ~y[q].z, n3 = ~y[q].w;
+                        uint32_t zb = zpre[j >> 7];
+                        zb += wsel > 0 ? __popc(n0) : 0u;
+                        zb += wsel > 1 ? __popc(n1) : 0u;
+                        zb += wsel > 2 ? __popc(n2) : 0u;
+                        const uint32_t wj = wsel == 0 ? n0 : wsel == 1 ? n1 : wsel == 2 ? n2 : n3;
+                        zb += __popc(wj & ~(0xFFFFFFFFu << (j & 31u)));
+                        pk[q0 + q] = (x0 & (1u << (q0 + q))) ? Z + j - zb : zb;
+                    }
+                }
+                scatter(x1, nxt);
+                x0 = x1; x1 = x2; x2 = load_x(k + 3);
             }
-            x0 = x1; x1 = x2; x2 = load_x(k + 3);
         }
+    }
+    // the block(s) with the most lines still hold their last permuted row (the others were served inside the loop)
+    grid_arrive();
+    grid_wait();
+    if (active && bnwah >= 1 && bnwah == max_nwah) {
+        const uint32_t old = (bnwah - 1) % 3u;
+        const uint32_t* Yo = Yb + (size_t)old * WSP;
+        uint32_t* grow = p.bitrows + (size_t)(list[bnwah - 1] & 0x7FFFFFFFu) * WS;
+        for (uint32_t w4 = cib * 1024u + tid; 4 * w4 < WS; w4 += ctas_per_block * 1024u)
+            *reinterpret_cast<uint4*>(grow + 4 * w4) = __ldcg(reinterpret_cast<const uint4*>(Yo) + w4);
     }
 }
 

@@ -486,62 +486,64 @@ int run_permute_v4(xsi_ctx* ctx, const EncDev& p, uint32_t W, bool* done) {
 }
 
 template <int KH>
-int launch_permute_grid(xsi_ctx* ctx, const EncDev& p, const PermGridCfg& cfg, bool probe_only, int* per_sm) {
+int launch_permute_grid(xsi_ctx* ctx, const EncDev& p, const PermGridCfg& cfg, size_t smem, bool probe_only, int* per_sm) {
+    CK(cudaFuncSetAttribute(pbwt_permute_grid_kernel<KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     if (probe_only) {
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, pbwt_permute_grid_kernel<KH>, 1024, 0));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(per_sm, pbwt_permute_grid_kernel<KH>, 1024, smem));
         return XSI_OK;
     }
     void* args[] = {const_cast<EncDev*>(&p), const_cast<PermGridCfg*>(&cfg)};
-    { PROF("pbwt_permute"); CK(cudaLaunchCooperativeKernel((const void*)pbwt_permute_grid_kernel<KH>, dim3(ctx->sm_count), dim3(1024), args, 0, ctx->stream)); }
+    { PROF("pbwt_permute"); CK(cudaLaunchCooperativeKernel((const void*)pbwt_permute_grid_kernel<KH>, dim3(ctx->sm_count), dim3(1024), args, smem, ctx->stream)); }
     CKL();
     return XSI_OK;
 }
-int launch_permute_grid_kh(xsi_ctx* ctx, uint32_t KH, const EncDev& p, const PermGridCfg& cfg, bool probe_only, int* per_sm) {
+int launch_permute_grid_kh(xsi_ctx* ctx, uint32_t KH, const EncDev& p, const PermGridCfg& cfg, size_t smem, bool probe_only, int* per_sm) {
     switch (KH) {
-        case 8: return launch_permute_grid<8>(ctx, p, cfg, probe_only, per_sm);
-        case 16: return launch_permute_grid<16>(ctx, p, cfg, probe_only, per_sm);
-        default: return launch_permute_grid<32>(ctx, p, cfg, probe_only, per_sm);
+        case 8: return launch_permute_grid<8>(ctx, p, cfg, smem, probe_only, per_sm);
+        case 16: return launch_permute_grid<16>(ctx, p, cfg, smem, probe_only, per_sm);
+        default: return launch_permute_grid<32>(ctx, p, cfg, smem, probe_only, per_sm);
     }
 }
 
 // > 65,534 haplotypes: the whole GPU advances a group of PBWT blocks line by line (cooperative launch).
-// Groups are as many blocks as the positions-in-registers budget allows (sm_count*1024 threads x KH <= 32).
+// Groups are as many blocks as the positions-in-registers budget allows (sm_count CTAs of 1024 threads, KH <= 32).
 int run_permute_grid(xsi_ctx* ctx, const EncDev& p, bool* done) {
     *done = false;
     auto& e = ctx->enc;
     const uint32_t N = 2 * p.n_samples;
-    const uint64_t GT = (uint64_t)ctx->sm_count * 1024;
-    const uint32_t WSP = (p.WS + 255) & ~255u, NCH = WSP / 256;
-    auto tpb_of = [&](uint32_t kh) { return (uint32_t)((((uint64_t)N + kh - 1) / kh + 31) / 32 * 32); };
-    if (GT / tpb_of(32) == 0) return XSI_OK;  // more than ~4.8 M haplotypes: generic kernel
+    const uint32_t ctas = (uint32_t)ctx->sm_count;
+    const uint32_t WSP = (p.WS + 31) & ~31u, NG = WSP / 4;  // NG a multiple of 8
+    const size_t smem = (size_t)NG * 4;
+    if (smem > ctx->smem_optin) return XSI_OK;  // more than ~7 M haplotypes: generic kernel
+    auto cpb_of = [&](uint32_t kh) { return (uint32_t)((((uint64_t)N + kh - 1) / kh + 1023) / 1024); };  // CTAs per PBWT block
+    if (cpb_of(32) > ctas) return XSI_OK;      // more than ~4.8 M haplotypes: generic kernel
     int coop = 0;
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device));
     if (!coop) return XSI_OK;
-    const uint32_t max_group = (uint32_t)std::min<uint64_t>(GT / tpb_of(32), (GT / 32) / NCH);
-    const size_t per_block = (size_t)2 * WSP + (2 * WSP + 4) + NCH;
+    const uint32_t max_group = ctas / cpb_of(32);
+    const size_t per_block = (size_t)3 * WSP + (size_t)3 * NG;
     CK(e.a_pool.ensure(((size_t)max_group * per_block + 4) * 4));
     for (uint32_t b0 = 0; b0 < p.nb;) {
         const uint32_t rem = p.nb - b0;
         uint32_t KH = 32;
         if (const char* s = getenv("XSI_PBWT_KH")) { const int v = atoi(s); if (v == 8 || v == 16 || v == 32) KH = (uint32_t)v; }
-        else for (uint32_t kh : {8u, 16u}) if (GT / tpb_of(kh) >= rem) { KH = kh; break; }
+        else for (uint32_t kh : {8u, 16u}) if (ctas / cpb_of(kh) >= rem) { KH = kh; break; }
         PermGridCfg cfg;
-        cfg.TPB = tpb_of(KH);
+        cfg.TPB = cpb_of(KH) * 1024u;
         cfg.b0 = b0;
-        cfg.nbg = (uint32_t)std::min<uint64_t>(std::min<uint64_t>(rem, GT / cfg.TPB), (GT / 32) / NCH);
+        cfg.nbg = std::min<uint32_t>(rem, ctas / cpb_of(KH));
         if (cfg.nbg == 0) return XSI_OK;
         cfg.WSP = WSP;
         uint32_t* base = e.a_pool.as<uint32_t>();
         cfg.Y = base;
-        cfg.T = cfg.Y + (size_t)cfg.nbg * 2 * WSP;
-        cfg.flags = cfg.T + (size_t)cfg.nbg * (2 * WSP + 4);
-        cfg.bar = cfg.flags + (size_t)cfg.nbg * NCH;
+        cfg.CNT = cfg.Y + (size_t)cfg.nbg * 3 * WSP;
+        cfg.bar = cfg.CNT + (size_t)cfg.nbg * 3 * NG;
         int per_sm = 0;
-        int rc = launch_permute_grid_kh(ctx, KH, p, cfg, true, &per_sm);
+        int rc = launch_permute_grid_kh(ctx, KH, p, cfg, smem, true, &per_sm);
         if (rc) return rc;
         if (per_sm < 1) return XSI_OK;
         CK(cudaMemsetAsync(base, 0, ((size_t)cfg.nbg * per_block + 4) * 4, ctx->stream));
-        rc = launch_permute_grid_kh(ctx, KH, p, cfg, false, &per_sm);
+        rc = launch_permute_grid_kh(ctx, KH, p, cfg, smem, false, &per_sm);
         if (rc) return rc;
         b0 += cfg.nbg;
     }
