@@ -134,8 +134,10 @@ int xsi_sync(xsi_ctx* ctx);
  * With HOST int32 buffers, xsi_encode_launch / xsi_decode_records move the rows across the bus in
  * their BCF int8 encoding and convert on the host (worker pool, beside the DMA) whenever every
  * value has one (at most 63 alleles); otherwise int32 moves as is.  Transport only: results are
- * identical either way.  Environment: XSI_HOST_NARROW=0 disables it, XSI_HOST_THREADS sets the
- * pool size.  The two conversions are exported for tests and for callers that stage rows themselves.
+ * identical either way.  PINNED host buffers get a second route beside it: whole chunks cross as int32
+ * by the DMA engine alone and are converted by a device kernel; each chunk takes whichever route is
+ * free.  Environment: XSI_HOST_NARROW=0 disables the int8 transport, XSI_HOST_DMA=0 the second route,
+ * XSI_HOST_THREADS sets the pool size.  The two conversions are exported for tests and for callers that stage rows themselves.
  * ------------------------------------------------------------------------------------------ */
 /* returns 1 when every value was representable, 0 otherwise (dst then holds garbage) */
 int  xsi_host_narrow_i32_i8(const int32_t* src, int8_t* dst, uint64_t n);

@@ -352,3 +352,37 @@ def test_concurrent_contexts(tmp_path, monkeypatch):
     for t in ts:
         t.join()
     assert not errs, errs[:3]
+
+
+def test_pinned_host_rows_two_routes(ctx, tmp_path):
+    """PINNED host int32 rows: chunks are split between the host conversion (worker pool + int8 DMA) and the plain int32
+    DMA + device conversion kernel, whichever route is free.  Same .xsi bytes, same rows."""
+    import torch
+    import xsqueezeit_b200 as xb
+    ds = synth.make_dataset(1100, 32488, seed=35, n_founders=128, fmin=0.0005)
+    n_el = ds["gt"].size
+    assert n_el >= 4 * (16 << 20)  # enough 16 Mi-genotype chunks for both routes
+    gt = torch.from_numpy(ds["gt"]).pin_memory()
+    img = oracle_image(ds, 8192, 0.001)
+    h0, d0 = ctx.transport_stats
+    p = str(tmp_path / "pinned.xsi")
+    xb.Compressor(ctx, maf=0.001, reset_sort_block_length=8192, blocks_per_batch=8).compress_to_file(
+        p, gt.numpy(), ds["ngt"], ds["n_allele"], ds["n_samples"])
+    assert open(p, "rb").read() == img
+    h1, d1 = ctx.transport_stats
+    assert 0 < h1 - h0 < n_el, "both upload routes should have carried chunks"
+    acc = xb.Accessor(p, ctx)
+    pos = xb.bm_positions(ds["n_allele"], 8192)
+    off = (pos & np.uint64(0x7FFF)).astype(np.uint32)
+    acc._load(0, 1)
+    out = torch.empty((1100, 64976), dtype=torch.int32).pin_memory()
+    out.fill_(-7)
+    o, filled, _ = ctx.decode_records(np.zeros(1100, np.uint32), off, ds["n_allele"], out=out.numpy(), out_stride=64976)
+    h2, d2 = ctx.transport_stats
+    assert 0 < d2 - d1 < n_el, "both download routes should have carried rows"
+    rd = xo.Reader(img)
+    res = out.numpy()
+    for r in range(1100):
+        b, nb = rd.fill_genotype_array(2, int(pos[r]))
+        assert filled[r] == nb and np.array_equal(res[r, :nb], b[:nb]), r
+    acc.close()

@@ -147,4 +147,46 @@ __device__ __forceinline__ int32_t load_gt(const void* base, uint64_t idx) {
 }
 __device__ __forceinline__ bool gt_is_missing(int32_t v) { return ((v >> 1) == 0) || v == XSI_I32_MISSING; }
 
+// ---- int32 <-> BCF int8 transport encoding on the device (the host side is csrc/host_narrow.cpp) ----------
+// n a multiple of 16 (the caller pads), both pointers 16-byte aligned; *bad |= 1 when a value has no int8 encoding
+__global__ void __launch_bounds__(256) narrow_i32_i8_kernel(const uint4* __restrict__ src, uint4* __restrict__ dst, uint64_t n16,
+                                                             uint32_t* bad) {
+    uint32_t lost = 0;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n16; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t o[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const uint4 v = __ldcs(src + 4 * i + k);
+            const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+            uint32_t w = 0;
+#pragma unroll
+            for (int b = 0; b < 4; ++b) {
+                w |= ((u[b] & 0x7Fu) | ((u[b] >> 24) & 0x80u)) << (8 * b);
+                lost |= (u[b] & 0x7FFFFF80u) | ((uint32_t)((int32_t)u[b] >> 31) & u[b] & 0x7Eu);
+            }
+            o[k] = w;
+        }
+        dst[i] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (lost) atomicOr(bad, 1u);
+}
+// rows of `len` int8 genotypes (stride8 apart) -> rows of int32 (len apart); len a multiple of 16, 16-byte aligned rows
+__global__ void __launch_bounds__(256) widen_rows_i8_i32_kernel(const int8_t* __restrict__ src, uint64_t stride8, int32_t* __restrict__ dst,
+                                                                 uint32_t len, uint32_t rows) {
+    const uint32_t per_row = len >> 4;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < (uint64_t)rows * per_row; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(i / per_row), c = (uint32_t)(i - (uint64_t)r * per_row);
+        const uint4 v = *reinterpret_cast<const uint4*>(src + r * stride8 + 16ull * c);
+        const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+        uint4* d4 = reinterpret_cast<uint4*>(dst + (uint64_t)r * len + 16ull * c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            uint32_t o[4];
+#pragma unroll
+            for (int b = 0; b < 4; ++b) { const uint32_t x = (u[k] >> (8 * b)) & 0xFFu; o[b] = (x & 0x7Fu) | ((x & 0x80u) << 24); }
+            __stcs(d4 + k, make_uint4(o[0], o[1], o[2], o[3]));
+        }
+    }
+}
+
 }  // namespace xsi

@@ -79,6 +79,15 @@ struct xsi_ctx {
     cudaEvent_t ring_ev[RING_SLOTS] = {nullptr, nullptr, nullptr};
     bool ring_busy[RING_SLOTS] = {false, false, false};
     uint64_t narrowed_h2d = 0, narrowed_d2h = 0;  // bytes that crossed the bus narrowed (statistics)
+    // second route for PINNED host int32 rows: plain DMA of int32 chunks (no host core involved), converted by a
+    // device kernel, running beside the host conversion of other chunks (whichever route is free takes the next chunk)
+    static constexpr int DMA_SLOTS = 4;                                 // staging slots of the DMA route
+    static constexpr size_t DMA_ELEMS = RING_BYTES / 4;                 // genotypes per slot: copies as large as the int8 ring's (16 MB)
+    DevBuf dma_stage, dma_flag;
+    cudaEvent_t dma_ev[DMA_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
+    bool dma_busy[DMA_SLOTS] = {false, false, false, false};
+    PinBuf dma_flag_host;
+    uint64_t dma_h2d = 0, dma_d2h = 0;  // int32 bytes moved by that route (statistics)
 
     // ---------------- encode ----------------
     struct {
@@ -205,7 +214,9 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
     d.h_stage.release();
     d.h_meta.release();
     ctx->ring.release();
+    ctx->dma_stage.release(); ctx->dma_flag.release(); ctx->dma_flag_host.release();
     for (cudaEvent_t ev : ctx->ring_ev) if (ev) cudaEventDestroy(ev);
+    for (cudaEvent_t ev : ctx->dma_ev) if (ev) cudaEventDestroy(ev);
     cudaEventDestroy(ctx->ev_side);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream2);
@@ -291,24 +302,90 @@ int ring_wait(xsi_ctx* ctx, int slot) {
     return XSI_OK;
 }
 
-// Uploads n host int32 genotypes as int8 into dst (device): narrowing of chunk c+1 on the worker pool runs
-// beside the DMA of chunk c.  Returns 1 when done, 0 when a value has no int8 encoding (nothing usable was
-// uploaded; the caller moves int32 instead), < 0 on error.
+bool host_ptr_is_pinned(const void* p) {
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+bool dma_route_on() {
+    const char* s = getenv("XSI_HOST_DMA");
+    return !(s && s[0] == '0');
+}
+int dma_prepare(xsi_ctx* ctx) {
+    CK(ctx->dma_stage.ensure((size_t)xsi_ctx::DMA_SLOTS * xsi_ctx::DMA_ELEMS * 4));
+    CK(ctx->dma_flag.ensure(16));
+    CK(ctx->dma_flag_host.ensure(16));
+    for (int i = 0; i < xsi_ctx::DMA_SLOTS; ++i)
+        if (!ctx->dma_ev[i]) CK(cudaEventCreateWithFlags(&ctx->dma_ev[i], cudaEventDisableTiming));
+    return XSI_OK;
+}
+// index of a free staging slot of the DMA route, or -1
+int dma_free_slot(xsi_ctx* ctx) {
+    for (int i = 0; i < xsi_ctx::DMA_SLOTS; ++i) {
+        if (ctx->dma_busy[i] && cudaEventQuery(ctx->dma_ev[i]) == cudaSuccess) ctx->dma_busy[i] = false;
+        if (!ctx->dma_busy[i]) return i;
+    }
+    cudaGetLastError();  // cudaErrorNotReady is not an error
+    return -1;
+}
+
+// Uploads n host int32 genotypes as int8 into dst (device).  Chunks of 16 Mi genotypes take one of two routes,
+// whichever is free: (a) narrowed by the worker pool into a pinned ring slot and copied as int8, (b) when the
+// source is pinned, copied as int32 by the DMA engine alone into a device staging slot and narrowed by a kernel
+// (side stream).  Returns 1 when done, 0 when a value has no int8 encoding (nothing usable was uploaded; the
+// caller moves int32 instead), < 0 on error.
 int upload_narrowed(xsi_ctx* ctx, const int32_t* src, size_t n, int8_t* dst) {
     int rc = ring_prepare(ctx);
     if (rc) return rc;
     const size_t CH = xsi_ctx::RING_BYTES;
+    const bool dma = dma_route_on() && n >= 4 * CH && host_ptr_is_pinned(src) && reinterpret_cast<uintptr_t>(src) % 16 == 0 &&
+                     reinterpret_cast<uintptr_t>(dst) % 16 == 0;
+    if (dma) {
+        if ((rc = dma_prepare(ctx))) return rc;
+        CK(cudaMemsetAsync(ctx->dma_flag.p, 0, 4, ctx->stream2));
+    }
     int slot = 0;
-    for (size_t a = 0; a < n; a += CH, slot = (slot + 1) % xsi_ctx::RING_SLOTS) {
+    bool used_dma = false;
+    size_t by_host = 0;
+    const size_t DE = xsi_ctx::DMA_ELEMS;
+    for (size_t a = 0; a < n;) {
+        // top up the DMA route first (it needs no host core): units as large in bytes as the ring's int8 copies, so
+        // that the two routes share the bus evenly and the host route never waits long for its next chunk
+        while (dma && n - a >= DE) {
+            const int ds = dma_free_slot(ctx);
+            if (ds < 0) break;
+            int32_t* st = ctx->dma_stage.as<int32_t>() + (size_t)ds * DE;
+            CK(cudaMemcpyAsync(st, src + a, DE * 4, cudaMemcpyHostToDevice, ctx->stream2));
+            narrow_i32_i8_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream2>>>(reinterpret_cast<const uint4*>(st), reinterpret_cast<uint4*>(dst + a),
+                                                                              DE / 16, ctx->dma_flag.as<uint32_t>());
+            CKL();
+            CK(cudaEventRecord(ctx->dma_ev[ds], ctx->stream2));
+            ctx->dma_busy[ds] = true;
+            ctx->dma_h2d += DE * 4;
+            used_dma = true;
+            a += DE;
+        }
+        if (a >= n) break;
         const size_t m = std::min(CH, n - a);
         if ((rc = ring_wait(ctx, slot))) return rc;
         int8_t* stage = ctx->ring.as<int8_t>() + (size_t)slot * CH;
-        if (!narrow_i32_to_i8(src + a, stage, m)) return 0;
+        if (!narrow_i32_to_i8(src + a, stage, m)) { if (used_dma) cudaStreamSynchronize(ctx->stream2); return 0; }
         CK(cudaMemcpyAsync(dst + a, stage, m, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
         ctx->ring_busy[slot] = true;
+        slot = (slot + 1) % xsi_ctx::RING_SLOTS;
+        by_host += m;
+        a += m;
     }
-    ctx->narrowed_h2d += n;
+    if (used_dma) {
+        // join the side stream: its chunks are part of the rows the kernels on the main stream will read
+        uint32_t* hf = ctx->dma_flag_host.as<uint32_t>();
+        CK(cudaMemcpyAsync(hf, ctx->dma_flag.p, 4, cudaMemcpyDeviceToHost, ctx->stream2));
+        CK(cudaStreamSynchronize(ctx->stream2));
+        for (int i = 0; i < xsi_ctx::DMA_SLOTS; ++i) ctx->dma_busy[i] = false;
+        if (*hf) return 0;
+    }
+    ctx->narrowed_h2d += by_host;
     return 1;
 }
 
@@ -1531,26 +1608,68 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
             if (want_counts) { if ((rc = fetch_counts(q, c0, cn))) return rc; }
             else CK(cudaStreamSynchronize(ctx->stream));
             if (n_filled) memcpy(n_filled + c0, filled.data(), cn * 4);
+            // Sub-chunks of `rps` rows take one of two routes, whichever is free: (a) copied as int8 into a pinned ring
+            // slot and widened by the worker pool, (b) when `out` is pinned and the rows are full diploid rows, widened
+            // by a device kernel into a staging slot and copied as int32 by the DMA engine alone (side stream).
             const uint64_t nsub = (cn + rps - 1) / rps;
-            for (uint64_t k = 0; k <= nsub; ++k) {
-                if (k < nsub) {
-                    const int slot = (int)(k % xsi_ctx::RING_SLOTS);
-                    const uint64_t r0 = k * rps, rn = std::min(rps, cn - r0);
-                    if ((rc = ring_wait(ctx, slot))) return rc;
-                    CK(cudaMemcpyAsync(ctx->ring.as<int8_t>() + (size_t)slot * xsi_ctx::RING_BYTES, d.out.as<int8_t>() + r0 * stride8,
-                                       rn * stride8, cudaMemcpyDeviceToHost, ctx->stream));
-                    CK(cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
-                    ctx->ring_busy[slot] = true;
-                }
-                if (k >= 1) {
-                    const int slot = (int)((k - 1) % xsi_ctx::RING_SLOTS);
-                    const uint64_t r0 = (k - 1) * rps, rn = std::min(rps, cn - r0);
-                    if ((rc = ring_wait(ctx, slot))) return rc;
-                    widen_rows_i8_to_i32(ctx->ring.as<int8_t>() + (size_t)slot * xsi_ctx::RING_BYTES, stride8,
-                                         reinterpret_cast<int32_t*>(out) + (c0 + r0) * out_stride, out_stride, filled.data() + r0, rn);
-                }
+            const uint64_t du = std::max<uint64_t>(1, xsi_ctx::DMA_ELEMS / N);  // rows per unit of the DMA route (16 MB of int32)
+            const bool dma = dma_route_on() && stride8 == N && nsub >= 4 && host_ptr_is_pinned(out) && reinterpret_cast<uintptr_t>(out) % 16 == 0 &&
+                             (out_stride * 4) % 16 == 0 && (uint64_t)N <= xsi_ctx::DMA_ELEMS;
+            if (dma) {
+                if ((rc = dma_prepare(ctx))) return rc;
+                CK(cudaEventRecord(ctx->ev_side, ctx->stream));          // rows composed (the stream was synchronised above,
+                CK(cudaStreamWaitEvent(ctx->stream2, ctx->ev_side, 0));  // this only keeps the dependency explicit)
             }
-            ctx->narrowed_d2h += cn * stride8;
+            bool used_dma = false;
+            int slot = 0, pend_slot = -1;
+            uint64_t pend_r0 = 0, pend_rn = 0, by_host = 0;
+            auto widen_pending = [&]() -> int {
+                if (pend_slot < 0) return XSI_OK;
+                int rr = ring_wait(ctx, pend_slot);
+                if (rr) return rr;
+                widen_rows_i8_to_i32(ctx->ring.as<int8_t>() + (size_t)pend_slot * xsi_ctx::RING_BYTES, stride8,
+                                     reinterpret_cast<int32_t*>(out) + (c0 + pend_r0) * out_stride, out_stride, filled.data() + pend_r0, pend_rn);
+                pend_slot = -1;
+                return XSI_OK;
+            };
+            for (uint64_t r0 = 0; r0 < cn;) {
+                // top up the DMA route first (no host core involved): units as large in bytes as the ring's int8 copies
+                while (dma && cn - r0 >= du) {
+                    bool full = true;
+                    for (uint64_t i = 0; i < du && full; ++i) full = filled[r0 + i] == N;
+                    const int ds = full ? dma_free_slot(ctx) : -1;
+                    if (ds < 0) break;
+                    int32_t* st = ctx->dma_stage.as<int32_t>() + (size_t)ds * xsi_ctx::DMA_ELEMS;
+                    widen_rows_i8_i32_kernel<<<ctx->sm_count * 2, 256, 0, ctx->stream2>>>(d.out.as<int8_t>() + r0 * stride8, stride8, st, N, (uint32_t)du);
+                    CKL();
+                    int32_t* dsth = reinterpret_cast<int32_t*>(out) + (c0 + r0) * out_stride;
+                    if (out_stride == N) CK(cudaMemcpyAsync(dsth, st, du * (size_t)N * 4, cudaMemcpyDeviceToHost, ctx->stream2));
+                    else CK(cudaMemcpy2DAsync(dsth, out_stride * 4, st, (size_t)N * 4, (size_t)N * 4, du, cudaMemcpyDeviceToHost, ctx->stream2));
+                    CK(cudaEventRecord(ctx->dma_ev[ds], ctx->stream2));
+                    ctx->dma_busy[ds] = true;
+                    ctx->dma_d2h += du * (uint64_t)N * 4;
+                    used_dma = true;
+                    r0 += du;
+                }
+                if (r0 >= cn) break;
+                const uint64_t rn = std::min(rps, cn - r0);
+                if ((rc = ring_wait(ctx, slot))) return rc;
+                CK(cudaMemcpyAsync(ctx->ring.as<int8_t>() + (size_t)slot * xsi_ctx::RING_BYTES, d.out.as<int8_t>() + r0 * stride8,
+                                   rn * stride8, cudaMemcpyDeviceToHost, ctx->stream));
+                CK(cudaEventRecord(ctx->ring_ev[slot], ctx->stream));
+                ctx->ring_busy[slot] = true;
+                if ((rc = widen_pending())) return rc;  // the previous sub-chunk of this route, while this one's copy runs
+                pend_slot = slot; pend_r0 = r0; pend_rn = rn;
+                slot = (slot + 1) % xsi_ctx::RING_SLOTS;
+                by_host += rn * stride8;
+                r0 += rn;
+            }
+            if ((rc = widen_pending())) return rc;
+            if (used_dma) {
+                CK(cudaStreamSynchronize(ctx->stream2));
+                for (int i = 0; i < xsi_ctx::DMA_SLOTS; ++i) ctx->dma_busy[i] = false;
+            }
+            ctx->narrowed_d2h += by_host;
         }
         return XSI_OK;
     }
