@@ -52,7 +52,11 @@ class HrcSynth:
     switches to a pseudo-random founder with probability `switch` per site; per-genotype flips;
     sites whose expected carrier count is below 2*MAC threshold are placed on copiers of one founder."""
 
-    def __init__(self, n_samples, seed, device, founders=256, switch=1e-3, flip=1e-4, maf=MAF):
+    def __init__(self, n_samples, seed, device, founders=256, switch=1e-3, flip=1e-4, maf=MAF, chrx=False):
+        # chrx: SURVEY 8(d) S4 -- every 2nd sample haploid (second entry = end of vector), 5% of the records with 2-3 ALT
+        # alleles, 0.5% missing alleles, 1% unphased genotypes
+        self.chrx = chrx
+        self.n_allele = []
         import torch
         self.t = torch
         self.S, self.H, self.K = n_samples, 2 * n_samples, founders
@@ -88,7 +92,23 @@ class HrcSynth:
             carriers = (founder == kstar) & (t.rand(rc, H, device=self.dev, generator=self.g) < p[:, None])
             allele = t.where(rare[:, None], carriers, allele)
         # htslib encoding: (allele+1)<<1 | phased, phase bit only on the 2nd allele of a sample ("0|1")
-        out.copy_(((allele.to(t.int32) + 1) << 1) | self.odd[None, :])
+        if not self.chrx:
+            self.n_allele.append(np.full(rc, 2, np.uint32))
+            out.copy_(((allele.to(t.int32) + 1) << 1) | self.odd[None, :])
+            return
+        a = allele.to(t.int32)
+        nalt = t.where(t.rand(rc, device=self.dev, generator=self.g) < 0.05,
+                       t.randint(2, 4, (rc,), device=self.dev, generator=self.g), t.ones(rc, dtype=t.int64, device=self.dev))
+        alt = (t.rand(rc, H, device=self.dev, generator=self.g) * nalt[:, None].to(t.float32)).to(t.int32).clamp_(max=2) + 1
+        alt = t.minimum(alt, nalt[:, None].to(t.int32))
+        a = t.where(a > 0, alt, a)                                             # carriers get one of the ALT alleles
+        phase = self.odd[None, :] & ~(t.rand(rc, H, device=self.dev, generator=self.g) < 0.01).to(t.int32)  # 1% unphased
+        val = ((a + 1) << 1) | phase
+        val = t.where(t.rand(rc, H, device=self.dev, generator=self.g) < 0.005, phase, val)                   # missing allele
+        male = ((self.hid >> 1) & 1).bool() & (self.hid & 1).bool()               # 2nd entry of every 2nd sample
+        val = t.where(male[None, :], t.full_like(val, -2147483647), val)          # bcf_int32_vector_end
+        self.n_allele.append((nalt + 1).to(t.int32).cpu().numpy().astype(np.uint32))
+        out.copy_(val)
 
     def fill(self, out, chunk=256):
         for r0 in range(0, out.shape[0], chunk):
@@ -294,6 +314,8 @@ def main():
     ap.add_argument("--ref-worker", type=int, default=-1, help=argparse.SUPPRESS)
     ap.add_argument("--resident-contexts", type=int, default=3,
                     help="also time the resident leg from this many host threads (one xsi_ctx each, blocks split between them)")
+    ap.add_argument("--shape", default="hrc", choices=["hrc", "chrx"],
+                    help="chrx: mixed ploidy, multi-allelic, missing and unphased genotypes (SURVEY 8(d) S4); resident one-context leg only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="one resident step, no e2e / cpu legs (for ncu)")
@@ -306,7 +328,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = args.steps, max(args.warmup, 0)
-    workload = "HRC-shaped synthetic: %d haplotypes, PBWT blocks of %d records, maf %.3g" % (2 * args.samples, args.block_len, MAF)
+    workload = "%s synthetic: %d haplotypes, PBWT blocks of %d records, maf %.3g" % (
+        "HRC-shaped" if args.shape == "hrc" else "chrX-shaped (mixed ploidy, multi-allelic, missing, unphased)", 2 * args.samples, args.block_len, MAF)
 
     # ---------------- reference arm ----------------
     if args.impl == "reference":
@@ -366,9 +389,12 @@ def main():
     EL = args.elem
     rdt = torch.int32 if EL == 4 else torch.int8
     gt = torch.empty((R, H), dtype=rdt, device=dev)
-    HrcSynth(S, 1002 + 131 * rank, dev).fill(gt)
+    synth_gen = HrcSynth(S, 1002 + 131 * rank, dev, chrx=args.shape == "chrx")
+    synth_gen.fill(gt)
     dec = torch.empty((R, H), dtype=rdt, device=dev)
-    nal = np.full(R, 2, np.uint32)
+    nal = np.concatenate(synth_gen.n_allele).astype(np.uint32)
+    if args.shape == "chrx":
+        args.resident_contexts, args.no_e2e, args.no_cpu_baseline = 0, True, True
     pos = xb.bm_positions(nal, BL)
     blk = (pos >> np.uint64(15)).astype(np.uint32)
     off = (pos & np.uint64(0x7FFF)).astype(np.uint32)

@@ -913,7 +913,8 @@ __device__ __forceinline__ bool compose_is_simple(uint32_t nall, uint8_t f0, uin
 }
 
 template <typename OT>
-__global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, ReqDev q, int skip_simple) {
+__global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, ReqDev q, int skip_simple, int scratch_in_smem) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];  // [2][Npad] when scratch_in_smem (rows up to 24 K genotypes)
     const uint32_t tid = threadIdx.x;
     const uint32_t S = d.n_samples, NH = 2 * S;
     const uint32_t msb = d.aet == 2 ? 0x8000u : 0x80000000u;
@@ -965,7 +966,9 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
         }
 
         // -------- general path (accessor_internals_new.hpp:207-384) --------
-        uint8_t* val = q.scratch + (size_t)blockIdx.x * 2 * q.Npad;
+        // allele code / phase-by-index flag per genotype: shared memory when the row fits (a chrX-shaped file sends every
+        // record through here: 36 us per record with the scratch in global memory), else the per-CTA global scratch
+        uint8_t* val = scratch_in_smem ? smem_raw : q.scratch + (size_t)blockIdx.x * 2 * q.Npad;
         uint8_t* pf = val + q.Npad;
         uint32_t total_alt = 0;
         for (uint32_t alt = 1; alt < nall; ++alt) {

@@ -90,12 +90,64 @@ __device__ __forceinline__ void emit_pred_row(const void* gt, uint64_t goff, uin
     }
 }
 
+// Same rows when the record starts and ends on 16-byte boundaries: every thread builds whole words from its own
+// 32 consecutive genotypes with 16-byte loads that are all in flight at once (the row is L2-hot).  The ballot
+// version above chains 32 dependent loads per 1024 genotypes: 8 us per row at 5,008 haplotypes, which is what a
+// chrX-shaped file pays three times per record (end-of-vector, missing, phase).
+template <int ELEM, int KIND>
+__device__ __forceinline__ void emit_pred_row_vec(const void* gt, uint64_t goff, uint32_t ngt, uint32_t WS, int32_t key,
+                                                  uint32_t* __restrict__ dst) {
+    auto pred_of = [&](int32_t v, uint32_t i) -> uint32_t {
+        if (KIND == 0) return (uint32_t)(((v >> 1) - 1) == key);
+        if (KIND == 1) return (uint32_t)gt_is_missing(v);
+        if (KIND == 2) return (uint32_t)(v == XSI_I32_VECTOR_END);
+        return (uint32_t)((i & 1u) && ((v & 1) != key));
+    };
+    for (uint32_t w = threadIdx.x; w < WS; w += E1_THREADS) {
+        const uint32_t i0 = w * 32;
+        uint32_t word = 0;
+        if (i0 < ngt) {
+            if (ELEM == 4) {
+                const int4* src = reinterpret_cast<const int4*>(reinterpret_cast<const int32_t*>(gt) + goff + i0);
+                int4 v[8];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) v[k] = (i0 + 4u * k < ngt) ? __ldg(src + k) : make_int4(0, 0, 0, 0);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    if (i0 + 4u * k < ngt) {  // a row that ends on a 16-byte boundary has whole quads only
+                        word |= pred_of(v[k].x, 4 * k) << (4 * k);
+                        word |= pred_of(v[k].y, 4 * k + 1) << (4 * k + 1);
+                        word |= pred_of(v[k].z, 4 * k + 2) << (4 * k + 2);
+                        word |= pred_of(v[k].w, 4 * k + 3) << (4 * k + 3);
+                    }
+                }
+            } else {
+                const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const signed char*>(gt) + goff + i0);
+#pragma unroll
+                for (int k = 0; k < 2; ++k) {
+                    if (i0 + 16u * k < ngt) {
+                        const uint4 q = __ldg(src + k);
+                        const uint32_t u[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                        for (int b = 0; b < 16; ++b) {
+                            const int32_t sb = (int32_t)(signed char)((u[b >> 2] >> (8 * (b & 3))) & 0xFFu);
+                            const int32_t v = sb == -128 ? XSI_I32_MISSING : (sb == -127 ? XSI_I32_VECTOR_END : sb);
+                            word |= pred_of(v, 16 * k + b) << (16 * k + b);
+                        }
+                    }
+                }
+            }
+        }
+        dst[w] = word;
+    }
+}
+
 // Per-record decisions and the rare extra rows, shared by both scan kernels.  Expects the block's
 // s_cnt[alt] / s_misc {nmiss, neov, phase bits, err} to be complete (barrier before the call).
 template <int ELEM>
 __device__ __forceinline__ void finish_record(const EncDev& p, uint32_t r, uint32_t ngt, uint32_t n_allele, uint32_t line0,
                                               uint64_t goff, uint32_t P, uint32_t* s_cnt, uint8_t* s_lflag,
-                                              uint32_t* s_misc, int32_t* s_slot) {
+                                              uint32_t* s_misc, int32_t* s_slot, bool aligned16 = false) {
     // ---- per-record decisions (gt_block.hpp:292-338) ----
     if (threadIdx.x == 0) {
         const uint32_t nmiss = s_misc[0], neov = s_misc[1];
@@ -140,9 +192,15 @@ __device__ __forceinline__ void finish_record(const EncDev& p, uint32_t r, uint3
     for (uint32_t a = 1; a < n_allele; ++a)
         if (s_lflag[a] & LF_NEGATED)  // negated sparse lists REF carriers (block.hpp:59-65 with sparse_allele 0)
             emit_pred_row<ELEM, 0>(p.gt, goff, ngt, p.WS, 0, p.bitrows + (size_t)(line0 + a - 1) * p.WS);
-    if (s_slot[0] >= 0) emit_pred_row<ELEM, 1>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[0] * p.WS);
-    if (s_slot[1] >= 0) emit_pred_row<ELEM, 2>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[1] * p.WS);
-    if (s_slot[2] >= 0) emit_pred_row<ELEM, 3>(p.gt, goff, ngt, p.WS, p.default_phasing, p.phrows + (size_t)s_slot[2] * p.WS);
+    if (aligned16) {
+        if (s_slot[0] >= 0) emit_pred_row_vec<ELEM, 1>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[0] * p.WS);
+        if (s_slot[1] >= 0) emit_pred_row_vec<ELEM, 2>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[1] * p.WS);
+        if (s_slot[2] >= 0) emit_pred_row_vec<ELEM, 3>(p.gt, goff, ngt, p.WS, p.default_phasing, p.phrows + (size_t)s_slot[2] * p.WS);
+    } else {
+        if (s_slot[0] >= 0) emit_pred_row<ELEM, 1>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[0] * p.WS);
+        if (s_slot[1] >= 0) emit_pred_row<ELEM, 2>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[1] * p.WS);
+        if (s_slot[2] >= 0) emit_pred_row<ELEM, 3>(p.gt, goff, ngt, p.WS, p.default_phasing, p.phrows + (size_t)s_slot[2] * p.WS);
+    }
 }
 
 template <int ELEM>
@@ -440,7 +498,7 @@ __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
             if (err) atomicOr(&s_misc[3], 1u);
         }
         __syncthreads();
-        finish_record<ELEM>(p, r, ngt, n_allele, line0, goff, P, s_cnt, s_lflag, s_misc, s_slot);
+        finish_record<ELEM>(p, r, ngt, n_allele, line0, goff, P, s_cnt, s_lflag, s_misc, s_slot, true);
         __syncthreads();
     }
 }

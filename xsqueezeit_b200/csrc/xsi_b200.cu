@@ -1575,7 +1575,8 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
             { PROF("compose_simple"); compose_simple_kernel<DT><<<g2, D4_THREADS, smem, ctx->stream>>>(d.dev, q); }
             CKL();
         }
-        { PROF("compose_records"); compose_records_kernel<DT><<<grid, D4_THREADS, 0, ctx->stream>>>(d.dev, q, fast ? 1 : 0); }
+        const size_t rec_smem = (size_t)2 * Npad <= (48u << 10) ? (size_t)2 * Npad : 0;
+        { PROF("compose_records"); compose_records_kernel<DT><<<grid, D4_THREADS, rec_smem, ctx->stream>>>(d.dev, q, fast ? 1 : 0, rec_smem ? 1 : 0); }
         CKL();
         return XSI_OK;
     };
