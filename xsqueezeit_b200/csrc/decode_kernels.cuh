@@ -1100,25 +1100,43 @@ __global__ void __launch_bounds__(D4_THREADS, 2) compose_simple_kernel(DecDev d,
     const uint32_t msb = d.aet == 2 ? 0x8000u : 0x80000000u;
     const uint32_t rot = tid & 7u;
     uint32_t buf = 0;
-    for (uint32_t ri = blockIdx.x; ri < q.n; ri += gridDim.x) {
+    // The descriptor of a record is a chain of dependent loads (request -> block -> line flags -> ordinal -> list
+    // header): 4-5 L2 round trips, as long as the whole 20 KB row of a 1KGP3-shaped record takes.  It is fetched one
+    // record ahead, so the chain of record i+1 resolves while the tiles of record i are built.
+    struct Desc { uint32_t f0, ord, DP, cnt, nall; uint64_t e0, sparse_off; bool neg; };
+    auto fetch = [&](uint32_t ri) -> Desc {
+        Desc x;
         const DecBlock blk = d.blocks[q.blk[ri]];
         const uint32_t gl0 = blk.line0 + q.line[ri];
-        const uint8_t f0 = d.dline_flags[gl0];
+        x.f0 = d.dline_flags[gl0];
+        x.ord = d.dline_ord[gl0];
+        x.DP = blk.default_phasing & 1u;
+        x.sparse_off = blk.sparse_off;
+        x.nall = q.nall[ri];
+        x.e0 = 0; x.cnt = 0; x.neg = false;
+        if (!(x.f0 & DL_WAH) && x.nall == 2 && !(x.f0 & (DL_MISSING | DL_EOV | DL_PHASE))) {
+            x.e0 = d.sp_off[x.ord];
+            const uint32_t hdr = rd_entry(d.blob + blk.sparse_off, x.e0, d.aet);
+            x.neg = (hdr & msb) != 0; x.cnt = hdr & ~msb;
+        }
+        return x;
+    };
+    Desc nx = {};
+    if (blockIdx.x < q.n) nx = fetch(blockIdx.x);
+    for (uint32_t ri = blockIdx.x; ri < q.n; ri += gridDim.x) {
+        const Desc cur = nx;
+        if (ri + gridDim.x < q.n) nx = fetch(ri + gridDim.x);
+        const uint8_t f0 = (uint8_t)cur.f0;
         const bool hap = (f0 & DL_HAPLOID) != 0;
         const uint32_t n = hap ? S : NH;
-        if (!compose_is_simple<OT>(q.nall[ri], f0, n)) continue;
-        const int32_t DP = (int32_t)(blk.default_phasing & 1u);
+        if (!compose_is_simple<OT>(cur.nall, f0, n)) continue;
+        const int32_t DP = (int32_t)cur.DP;
         OT* out = static_cast<OT*>(q.out) + (size_t)ri * q.out_stride;
         const bool wah = (f0 & DL_WAH) != 0;
-        const uint32_t ord = d.dline_ord[gl0];
+        const uint32_t ord = cur.ord;
         const uint32_t* row = d.rows + (size_t)ord * d.WS;
-        const uint8_t* spm = d.blob + blk.sparse_off;
-        uint64_t e0 = 0; uint32_t cnt = 0; bool neg = false;
-        if (!wah) {
-            e0 = d.sp_off[ord];
-            const uint32_t hdr = rd_entry(spm, e0, d.aet);
-            neg = (hdr & msb) != 0; cnt = hdr & ~msb;
-        }
+        const uint8_t* spm = d.blob + cur.sparse_off;
+        const uint64_t e0 = cur.e0; const uint32_t cnt = cur.cnt; const bool neg = cur.neg;
         if (tid == 0) {
             if (q.filled) q.filled[ri] = n;
             if (q.counts) {

@@ -423,12 +423,21 @@ __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
     uint32_t consumed = 0;
     const int32_t dpx = p.default_phasing & 1;
 
+    // record descriptors one record ahead: their L2 latency (four loads) is otherwise exposed once per record, which
+    // is most of the per-record cost for short rows (1KGP3 shape: 20 KB per record)
+    uint32_t nx_ngt = 0, nx_nall = 0, nx_line0 = 0;
+    uint64_t nx_goff = 0;
+    if (blockIdx.x < p.R) { nx_ngt = p.rec_ngt[blockIdx.x]; nx_nall = p.rec_nallele[blockIdx.x]; nx_line0 = p.rec_line0[blockIdx.x]; nx_goff = p.rec_goff[blockIdx.x]; }
     for (uint32_t r = blockIdx.x; r < p.R; r += gridDim.x) {
-        const uint32_t ngt = p.rec_ngt[r], n_allele = p.rec_nallele[r], line0 = p.rec_line0[r];
-        const uint64_t goff = p.rec_goff[r];
+        const uint32_t ngt = nx_ngt, n_allele = nx_nall, line0 = nx_line0;
+        const uint64_t goff = nx_goff;
+        if (r + gridDim.x < p.R) {
+            const uint32_t rn = r + gridDim.x;
+            nx_ngt = __ldg(p.rec_ngt + rn); nx_nall = __ldg(p.rec_nallele + rn); nx_line0 = __ldg(p.rec_line0 + rn); nx_goff = __ldg(p.rec_goff + rn);
+        }
         const uint32_t P = p.n_samples ? ngt / p.n_samples : 0;
         const uint32_t ndt = (ngt + S2_TILE - 1) / S2_TILE;
-        for (uint32_t i = tid; i < E1_MAXALLELE; i += E1_THREADS) { s_cnt[i] = 0; s_lflag[i] = 0; }
+        for (uint32_t i = tid; i <= n_allele && i < E1_MAXALLELE; i += E1_THREADS) { s_cnt[i] = 0; s_lflag[i] = 0; }
         if (tid < 4) s_misc[tid] = 0;
         __syncthreads();
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, nmiss = 0, neov = 0, phase = 0, err = 0;
