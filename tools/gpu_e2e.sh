@@ -1,7 +1,6 @@
 mkdir -p gpurun_out
 T=${T:-e2e}
-timeout 600 python -m pytest tests -m gpu -x -q -k "two_routes or transport" 2>&1 | tail -3
-for envs in "A=1" "XSI_HOST_DMA=0"; do
+for envs in "XSI_DMA_SLOTS=2" "XSI_DMA_SLOTS=4" "XSI_DMA_SLOTS=8"; do
 env $envs timeout 600 python bench.py --blocks 8 --steps 3 --warmup 2 --resident-contexts 0 --no-cpu-baseline > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "bench rc=$? ($envs)"
 python - <<P
 import json

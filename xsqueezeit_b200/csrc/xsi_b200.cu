@@ -81,11 +81,11 @@ struct xsi_ctx {
     uint64_t narrowed_h2d = 0, narrowed_d2h = 0;  // bytes that crossed the bus narrowed (statistics)
     // second route for PINNED host int32 rows: plain DMA of int32 chunks (no host core involved), converted by a
     // device kernel, running beside the host conversion of other chunks (whichever route is free takes the next chunk)
-    static constexpr int DMA_SLOTS = 4;                                 // staging slots of the DMA route
+    static constexpr int DMA_SLOTS = 8;                                 // staging slots of the DMA route (XSI_DMA_SLOTS uses fewer)
     static constexpr size_t DMA_ELEMS = RING_BYTES / 4;                 // genotypes per slot: copies as large as the int8 ring's (16 MB)
     DevBuf dma_stage, dma_flag;
-    cudaEvent_t dma_ev[DMA_SLOTS] = {nullptr, nullptr, nullptr, nullptr};
-    bool dma_busy[DMA_SLOTS] = {false, false, false, false};
+    cudaEvent_t dma_ev[DMA_SLOTS] = {};
+    bool dma_busy[DMA_SLOTS] = {};
     PinBuf dma_flag_host;
     uint64_t dma_h2d = 0, dma_d2h = 0;  // int32 bytes moved by that route (statistics)
 
@@ -321,7 +321,12 @@ int dma_prepare(xsi_ctx* ctx) {
 }
 // index of a free staging slot of the DMA route, or -1
 int dma_free_slot(xsi_ctx* ctx) {
-    for (int i = 0; i < xsi_ctx::DMA_SLOTS; ++i) {
+    static const int n_slots = [] {
+        int v = 4;
+        if (const char* s = getenv("XSI_DMA_SLOTS")) v = atoi(s);
+        return std::max(1, std::min(v, (int)xsi_ctx::DMA_SLOTS));
+    }();
+    for (int i = 0; i < n_slots; ++i) {
         if (ctx->dma_busy[i] && cudaEventQuery(ctx->dma_ev[i]) == cudaSuccess) ctx->dma_busy[i] = false;
         if (!ctx->dma_busy[i]) return i;
     }
