@@ -22,6 +22,9 @@ GlobalAppOptions global_app_options;  // the reference expects its user to defin
 
 extern "C" {
 
+// The reference's --wah-encode-missing switch (xsqueezeit.hpp:58; read by GtBlock's constructor, gt_block.hpp:174-176).
+void xsi_ref_set_wah_encode_missing(int on) { global_app_options.wah_encode_missing = on != 0; }
+
 // Returns 0 on success, <0 on a reference `throw`.
 // gt: concatenated rows, row r starts at rec_off[r] and holds ngt[r] int32 (htslib GT encoding).
 int xsi_ref_encode_file(const char* out_path, const int32_t* gt, const uint64_t* rec_off,

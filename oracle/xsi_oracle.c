@@ -241,6 +241,8 @@ enum { K_BCF_LINES = 0, K_BIN_LINES = 1, K_MAX_PLOIDY = 2, K_DEF_PHASING = 3, K_
 typedef struct {
     uint64_t n_samples, mac_thr;
     int default_phasing, aet; /* aet: bytes of A_T (xsi_factory.hpp:425) */
+    int wah_missing;          /* --wah-encode-missing: weirdness_strat = WS_WAH (gt_block.hpp:174-176) */
+    buf_t miss_wah, eov_wah;  /* WAH lines of the missing / end-of-vector predicates (gt_block.hpp:340-372) */
     uint32_t *a, *b;          /* PBWT order, 2*n_samples entries (gt_block.hpp:171,179) */
     uint32_t bcf_lines, bin_lines, max_ploidy;
     int missing_found, eov_found, phase_found, haploid_found;
@@ -260,6 +262,7 @@ static void gtblock_free(gtblock_t* g) {
     free(g->a); free(g->b);
     free(g->is_wah.p); free(g->has_missing.p); free(g->has_eov.p); free(g->has_phase.p); free(g->haploid.p); free(g->n_alt.p);
     free(g->wah.p); free(g->sparse.p); free(g->miss.p); free(g->eov.p); free(g->phase.p);
+    free(g->miss_wah.p); free(g->eov_wah.p);
 }
 static void put_index(buf_t* b, int aet, uint32_t v) { if (aet == 2) buf_u16(b, (uint16_t)v); else buf_u32(b, v); }
 
@@ -367,6 +370,26 @@ static int gtblock_encode_line(gtblock_t* g, const int32_t* gt, uint32_t ngt, ui
     }
     if (has_missing) sparse_line(&g->miss, g->aet, gt, ngt, 1, 0, 0); /* gt_block.hpp:330-333 */
     if (has_eov) sparse_line(&g->eov, g->aet, gt, ngt, 2, 0, 0);      /* gt_block.hpp:335-338 */
+    if (g->wah_missing) {
+        /* gt_block.hpp:340-372 with WS_WAH: a_weirdness stays the identity (it is only sorted under WS_PBWT_WAH, :377),
+         * and for an all-haploid line a1 = haploid_rearrangement_from_diploid(identity) is the identity over
+         * ngt = n_samples entries, so both predicates are WAH encoded in natural order over ngt bits. */
+        for (int kind = 1; kind <= 2; ++kind) {
+            if (!(kind == 1 ? has_missing : has_eov)) continue;
+            buf_t* dst = kind == 1 ? &g->miss_wah : &g->eov_wah;
+            wah_state st = {0, 0};
+            uint64_t groups = ((uint64_t)ngt + 14) / 15;
+            for (uint64_t gi = 0; gi < groups; ++gi) {
+                uint16_t w = 0;
+                for (unsigned j = 0; j < 15; ++j) {
+                    uint64_t k = gi * 15 + j;
+                    if (k < ngt && (kind == 1 ? gt_missing(gt[k]) : gt[k] == BCF_VECTOR_END_I32)) w |= (uint16_t)(1u << j);
+                }
+                wah_push_group(dst, &st, w);
+            }
+            wah_finish(dst, &st);
+        }
+    }
     if (has_phase) {                                                    /* gt_block.hpp:398-401, wah.hpp:441-501 */
         wah_state st = {0, 0};
         uint64_t groups = ((uint64_t)ngt + 14) / 15;
@@ -415,7 +438,8 @@ static void gtblock_write(const gtblock_t* g, buf_t* out) {
     uint32_t val[0x40];
     memset(val, 0xFF, sizeof(val));
     val[K_BCF_LINES] = g->bcf_lines; val[K_BIN_LINES] = g->bin_lines; val[K_MAX_PLOIDY] = g->max_ploidy;
-    val[K_DEF_PHASING] = (uint32_t)g->default_phasing; val[K_WEIRD_STRAT] = 2; /* WS_SPARSE, gt_block.hpp:417 */
+    val[K_DEF_PHASING] = (uint32_t)g->default_phasing;
+    val[K_WEIRD_STRAT] = g->wah_missing ? 1 : 2; /* WS_WAH (gt_block.hpp:174-176) / WS_SPARSE (:417) */
     buf_u32(out, 0xFFFFFFFFu);
     buf_u32(out, nk);
     const size_t dict_at = out->n;
@@ -429,14 +453,14 @@ static void gtblock_write(const gtblock_t* g, buf_t* out) {
     if (g->missing_found) {
         val[K_LINE_MISSING] = (uint32_t)(out->n - start);
         put_reindexed(out, g, &g->has_missing);
-        val[K_MAT_MISSING_SPARSE] = (uint32_t)(out->n - start);
-        buf_put(out, g->miss.p, g->miss.n);
+        if (g->wah_missing) { val[K_MAT_MISSING] = (uint32_t)(out->n - start); buf_put(out, g->miss_wah.p, g->miss_wah.n); } /* :574-576 */
+        else { val[K_MAT_MISSING_SPARSE] = (uint32_t)(out->n - start); buf_put(out, g->miss.p, g->miss.n); }
     }
     if (g->eov_found) {
         val[K_LINE_EOV] = (uint32_t)(out->n - start);
         put_reindexed(out, g, &g->has_eov);
-        val[K_MAT_EOV_SPARSE] = (uint32_t)(out->n - start);
-        buf_put(out, g->eov.p, g->eov.n);
+        if (g->wah_missing) { val[K_MAT_EOV] = (uint32_t)(out->n - start); buf_put(out, g->eov_wah.p, g->eov_wah.n); } /* :596-598 */
+        else { val[K_MAT_EOV_SPARSE] = (uint32_t)(out->n - start); buf_put(out, g->eov.p, g->eov.n); }
     }
     if (g->phase_found) {
         val[K_LINE_PHASE] = (uint32_t)(out->n - start);
@@ -479,6 +503,13 @@ static void put_header(uint8_t* h, uint8_t ploidy, uint8_t aet, int default_phas
 int xo_encode(const int32_t* gt, const uint64_t* rec_off, const int32_t* ngt, const int32_t* n_allele,
               uint64_t n_records, uint64_t n_samples, uint64_t block_len, uint64_t mac_threshold,
               int default_phased, const char* sample_names, uint8_t** out, uint64_t* out_len) {
+    return xo_encode_opt(gt, rec_off, ngt, n_allele, n_records, n_samples, block_len, mac_threshold, default_phased, sample_names,
+                         0, out, out_len);
+}
+/* wah_encode_missing: the reference's --wah-encode-missing (xsqueezeit.hpp:58, gt_block.hpp:174-176) */
+int xo_encode_opt(const int32_t* gt, const uint64_t* rec_off, const int32_t* ngt, const int32_t* n_allele,
+                  uint64_t n_records, uint64_t n_samples, uint64_t block_len, uint64_t mac_threshold,
+                  int default_phased, const char* sample_names, int wah_encode_missing, uint8_t** out, uint64_t* out_len) {
     if (n_samples > 32767 && n_samples <= 65535) return -10; /* reference mixes uint16 a[] with >65535 haplotypes: undefined */
     const int aet_block = n_samples <= 65535 ? 2 : 4;     /* xsi_factory.hpp:425 */
     const int aet_header = n_samples * 2 <= 65535 ? 2 : 4; /* gt_compressor_new.hpp:182 */
@@ -497,6 +528,7 @@ int xo_encode(const int32_t* gt, const uint64_t* rec_off, const int32_t* ngt, co
                 gtblock_free(&g);
             }
             gtblock_init(&g, n_samples, mac_threshold, default_phased, aet_block);
+            g.wah_missing = wah_encode_missing ? 1 : 0;
             have = 1;
         }
         uint64_t lp = n_samples ? (uint64_t)ngt[r] / n_samples : 0;
@@ -540,6 +572,7 @@ typedef struct {
     int default_phasing;
     uint8_t *is_wah, *is_sort, *has_missing, *has_eov, *has_phase, *haploid; /* one byte per binary line (+15) */
     int weird, phase;
+    int ws; /* KEY_WEIRDNESS_STRATEGY: 2 = WS_SPARSE, 1 = WS_WAH (missing / end-of-vector lines as natural-order WAH) */
     const uint8_t *wah0, *sparse0, *miss0, *eov0, *phase0;
     const uint8_t *wah_p, *sparse_p, *miss_p, *eov_p, *phase_p;
     uint64_t pos, weird_pos, phase_pos;
@@ -634,7 +667,8 @@ static int open_block(xo_reader* r, uint64_t block_id) {
     uint32_t dp = dict_get(blk, K_DEF_PHASING, &f); if (!f) return -1;
     c->default_phasing = (dp == 1) ? 1 : 0; /* accessor_internals_new.hpp:77-81 */
     uint32_t ws = dict_get(blk, K_WEIRD_STRAT, &f);
-    if (!f || ws != 2) return -2; /* only WS_SPARSE is restated (default encoder setting) */
+    if (!f || (ws != 2 && ws != 1)) return -2; /* WS_SPARSE (default) and WS_WAH (--wah-encode-missing); WS_PBWT_WAH is not reachable from the CLI */
+    c->ws = (int)ws;
     int p;
     c->is_wah = load_flags(r, blk, K_LINE_SELECT, c->bin_lines, &p); if (!p) return -1;
     c->is_sort = load_flags(r, blk, K_LINE_SORT, c->bin_lines, &p);
@@ -647,7 +681,8 @@ static int open_block(xo_reader* r, uint64_t block_id) {
     c->haploid = load_flags(r, blk, K_LINE_HAPLOID, c->bin_lines, &p);
     if (!p) c->haploid = (uint8_t*)calloc(c->bin_lines + 32, 1);
     c->wah0 = dict_ptr(blk, K_MAT_WAH); c->sparse0 = dict_ptr(blk, K_MAT_SPARSE);
-    c->miss0 = dict_ptr(blk, K_MAT_MISSING_SPARSE); c->eov0 = dict_ptr(blk, K_MAT_EOV_SPARSE);
+    if (ws == 2) { c->miss0 = dict_ptr(blk, K_MAT_MISSING_SPARSE); c->eov0 = dict_ptr(blk, K_MAT_EOV_SPARSE); }
+    else { c->miss0 = dict_ptr(blk, K_MAT_MISSING); c->eov0 = dict_ptr(blk, K_MAT_EOV); } /* accessor_internals_new.hpp:128-137 */
     c->phase0 = dict_ptr(blk, K_MAT_PHASE);
     c->a = (uint32_t*)malloc(sizeof(uint32_t) * (r->N_HAPS + 1));
     c->b = (uint32_t*)malloc(sizeof(uint32_t) * (r->N_HAPS + 1));
@@ -682,10 +717,18 @@ static void update_a(xo_reader* r) {
     }
     memcpy(c->a + u, c->b, v * sizeof(uint32_t));
 }
-/* accessor_internals_new.hpp:478-537 (WS_SPARSE branch) */
-static void weird_advance(xo_reader* r, uint64_t steps) {
+static const uint16_t* wah_skip(const uint16_t* w, const uint16_t* end, uint64_t n_bits);
+/* accessor_internals_new.hpp:478-537: WS_SPARSE branch, and the WS_WAH branch (:492-501, no PBWT on a_weird) */
+static void weird_advance(xo_reader* r, uint64_t steps, uint64_t N) {
     cursor_t* c = &r->c; uint32_t n;
     for (uint64_t i = 0; i < steps; ++i) {
+        if (c->ws == 1) {
+            const uint16_t* end = (const uint16_t*)(r->file + r->len);
+            if (c->has_missing && c->has_missing[c->weird_pos]) c->miss_p = (const uint8_t*)wah_skip((const uint16_t*)c->miss_p, end, N);
+            if (c->has_eov && c->has_eov[c->weird_pos]) c->eov_p = (const uint8_t*)wah_skip((const uint16_t*)c->eov_p, end, N);
+            c->weird_pos++;
+            continue;
+        }
         if (c->has_missing && c->has_missing[c->weird_pos]) { const uint8_t* p = c->miss_p; n = rd_idx(p, r->aet) & (r->aet == 2 ? 0x7FFFu : 0x7FFFFFFFu); c->miss_p = p + (size_t)r->aet * (1 + n); }
         if (c->has_eov && c->has_eov[c->weird_pos]) { const uint8_t* p = c->eov_p; n = rd_idx(p, r->aet) & (r->aet == 2 ? 0x7FFFu : 0x7FFFFFFFu); c->eov_p = p + (size_t)r->aet * (1 + n); }
         c->weird_pos++;
@@ -715,7 +758,7 @@ static void cursor_seek(xo_reader* r, uint64_t position) {
             c->sparse_p = p + (size_t)n * r->aet; /* a sparse line never sorts in v5 files; if flagged, y is stale as in the reference */
         }
         update_a(r);
-        if (c->weird) weird_advance(r, 1);
+        if (c->weird) weird_advance(r, 1, N);
         if (c->phase) phase_advance(r, 1, N);
         c->pos++;
     }
@@ -780,7 +823,22 @@ static int64_t fill_advance(xo_reader* r, int32_t* gt, uint64_t gt_size, uint64_
         update_a(r);
         c->pos++;
     }
-    if (c->weird) {
+    if (c->weird && c->ws == 1) {
+        /* accessor_internals_new.hpp:307-321, 330-341: extract the WAH line, a_weird is the identity under WS_WAH */
+        if (c->has_missing && c->has_missing[START]) {
+            uint64_t ones = 0;
+            wah_extract((const uint16_t*)c->miss_p, end, r->x, N, r->N_HAPS + 15, &ones);
+            n_missing = ones;
+            for (uint64_t i = 0; i < N; ++i) if (r->x[i]) gt[i] = 0 | (int32_t)((i & 1) & (uint32_t)DP);
+        }
+        if (c->has_eov && c->has_eov[START]) {
+            uint64_t ones = 0;
+            wah_extract((const uint16_t*)c->eov_p, end, r->x, N, r->N_HAPS + 15, &ones);
+            n_eovs = ones;
+            for (uint64_t i = 0; i < N; ++i) if (r->x[i]) gt[i] = BCF_VECTOR_END_I32;
+        }
+        weird_advance(r, n_alleles - 1, N);
+    } else if (c->weird) {
         if (c->has_missing && c->has_missing[START]) {
             uint32_t n = rd_idx(c->miss_p, r->aet) & (r->aet == 2 ? 0x7FFFu : 0x7FFFFFFFu);
             n_missing = n;
@@ -791,7 +849,7 @@ static int64_t fill_advance(xo_reader* r, int32_t* gt, uint64_t gt_size, uint64_
             n_eovs = n;
             for (uint32_t k = 0; k < n; ++k) { uint32_t i = rd_idx(c->eov_p + (size_t)(k + 1) * r->aet, r->aet); if (i < gt_size) gt[i] = BCF_VECTOR_END_I32; }
         }
-        weird_advance(r, n_alleles - 1);
+        weird_advance(r, n_alleles - 1, N);
     }
     if (c->phase) {
         if (c->has_phase && c->has_phase[START]) {

@@ -24,6 +24,10 @@ uint64_t xo_mac_threshold(uint64_t n_samples, uint64_t first_record_ploidy, doub
 int xo_encode(const int32_t* gt, const uint64_t* rec_off, const int32_t* ngt, const int32_t* n_allele,
               uint64_t n_records, uint64_t n_samples, uint64_t block_len, uint64_t mac_threshold,
               int default_phased, const char* sample_names, uint8_t** out, uint64_t* out_len);
+/* same with the reference's --wah-encode-missing (missing / end-of-vector lines as natural-order WAH, WS_WAH) */
+int xo_encode_opt(const int32_t* gt, const uint64_t* rec_off, const int32_t* ngt, const int32_t* n_allele,
+                  uint64_t n_records, uint64_t n_samples, uint64_t block_len, uint64_t mac_threshold,
+                  int default_phased, const char* sample_names, int wah_encode_missing, uint8_t** out, uint64_t* out_len);
 void xo_free(void* p);
 
 /* reader / cursor decoder (reference Accessor + DecompressPointerGTBlock) */

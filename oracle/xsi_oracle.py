@@ -40,6 +40,9 @@ def lib():
         L.xo_encode.restype = i32
         L.xo_encode.argtypes = [vp, vp, vp, vp, u64, u64, u64, u64, i32, ctypes.c_char_p,
                                 ctypes.POINTER(vp), ctypes.POINTER(u64)]
+        L.xo_encode_opt.restype = i32
+        L.xo_encode_opt.argtypes = [vp, vp, vp, vp, u64, u64, u64, u64, i32, ctypes.c_char_p, i32,
+                                    ctypes.POINTER(vp), ctypes.POINTER(u64)]
         L.xo_free.restype = None
         L.xo_free.argtypes = [vp]
         L.xo_open.restype = vp
@@ -101,7 +104,8 @@ def mac_threshold(n_samples, first_ploidy, maf):
     return int(lib().xo_mac_threshold(n_samples, first_ploidy, float(maf)))
 
 
-def encode(gt, rec_off, ngt, n_allele, n_samples, block_len, mac_thr, default_phased_, sample_names=None):
+def encode(gt, rec_off, ngt, n_allele, n_samples, block_len, mac_thr, default_phased_, sample_names=None,
+           wah_encode_missing=False):
     """Returns the .xsi image (bytes) the reference writer would produce."""
     gt = np.ascontiguousarray(gt, dtype=np.int32)
     rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
@@ -112,8 +116,9 @@ def encode(gt, rec_off, ngt, n_allele, n_samples, block_len, mac_thr, default_ph
         blob = b"".join(s.encode() + b"\0" for s in sample_names)
     out = ctypes.c_void_p()
     n = ctypes.c_uint64()
-    rc = lib().xo_encode(gt.ctypes.data, rec_off.ctypes.data, ngt.ctypes.data, n_allele.ctypes.data, ngt.size,
-                         n_samples, block_len, mac_thr, int(default_phased_), blob, ctypes.byref(out), ctypes.byref(n))
+    rc = lib().xo_encode_opt(gt.ctypes.data, rec_off.ctypes.data, ngt.ctypes.data, n_allele.ctypes.data, ngt.size,
+                             n_samples, block_len, mac_thr, int(default_phased_), blob, 1 if wah_encode_missing else 0,
+                             ctypes.byref(out), ctypes.byref(n))
     if rc != 0:
         raise RuntimeError("oracle encode failed rc=%d" % rc)
     data = ctypes.string_at(out.value, n.value)

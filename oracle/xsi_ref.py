@@ -29,6 +29,8 @@ def lib():
             ctypes.c_char_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
             ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_uint64,
             ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_char_p]
+        L.xsi_ref_set_wah_encode_missing.restype = None
+        L.xsi_ref_set_wah_encode_missing.argtypes = [ctypes.c_int]
         L.xsi_ref_accessor_open.restype = ctypes.c_void_p
         L.xsi_ref_accessor_open.argtypes = [ctypes.c_char_p]
         L.xsi_ref_hap_samples.restype = ctypes.c_uint64
@@ -47,7 +49,7 @@ def lib():
 
 
 def encode_file(path, gt, rec_off, ngt, n_allele, n_samples, block_len, mac_threshold,
-                default_phased, zstd=False, zstd_level=7, sample_names=None):
+                default_phased, zstd=False, zstd_level=7, sample_names=None, wah_encode_missing=False):
     """Run the reference writer on in-memory rows. gt: int32 flat, rec_off: uint64 row starts."""
     gt = np.ascontiguousarray(gt, dtype=np.int32)
     rec_off = np.ascontiguousarray(rec_off, dtype=np.uint64)
@@ -56,9 +58,13 @@ def encode_file(path, gt, rec_off, ngt, n_allele, n_samples, block_len, mac_thre
     blob = None
     if sample_names is not None:
         blob = b"".join(s.encode() + b"\0" for s in sample_names)
-    rc = lib().xsi_ref_encode_file(path.encode(), gt.ctypes.data, rec_off.ctypes.data, ngt.ctypes.data,
-                                   n_allele.ctypes.data, len(ngt), n_samples, block_len, mac_threshold,
-                                   int(default_phased), int(zstd), zstd_level, 1, blob)
+    lib().xsi_ref_set_wah_encode_missing(1 if wah_encode_missing else 0)
+    try:
+        rc = lib().xsi_ref_encode_file(path.encode(), gt.ctypes.data, rec_off.ctypes.data, ngt.ctypes.data,
+                                       n_allele.ctypes.data, len(ngt), n_samples, block_len, mac_threshold,
+                                       int(default_phased), int(zstd), zstd_level, 1, blob)
+    finally:
+        lib().xsi_ref_set_wah_encode_missing(0)
     if rc != 0:
         raise RuntimeError("reference encode failed rc=%d" % rc)
 

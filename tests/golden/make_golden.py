@@ -83,6 +83,13 @@ def main():
             open(os.path.join(HERE, name + ".xsi"), "wb").write(xsi)
             manifest[name] = {"xsi_sha256": sha(xsi), "xsi_size": len(xsi), "maf": maf, "block_len": 8192,
                               "ref_decode_equals_input": bool(dec.size == gt.size and np.array_equal(dec, gt))}
+            # the same fixture through --wah-encode-missing (WS_WAH): the .xsi is stored too (the GPU decode tests read it)
+            xw = run_cli(src, pre + "_wm.xsi", opts + ["--wah-encode-missing"])
+            rows_w = ref_decode_all(pre + "_wm.xsi", nal, ngt, 8192)
+            dec_w = np.concatenate(rows_w) if rows_w else np.zeros(0, np.int32)
+            open(os.path.join(HERE, name + "_wah_missing.xsi"), "wb").write(xw)
+            manifest[name]["wah_missing"] = {"xsi_sha256": sha(xw), "xsi_size": len(xw),
+                                             "ref_decode_equals_default": bool(np.array_equal(dec_w, dec))}
             print(name, manifest[name])
 
         # chr20_small: too big to store raw (438 MB of int32) -> reference .xsi + metadata + hashes

@@ -78,6 +78,27 @@ def test_small_fixture_bytes_and_decode(name):
     assert [n for _, n in rows] == list(d["ref_decoded_ngt"])
 
 
+@pytest.mark.parametrize("name", SMALL)
+def test_small_fixture_wah_encode_missing(name):
+    """--wah-encode-missing (WS_WAH): oracle bytes equal the reference CLI's, oracle decode of it equals the default decode."""
+    d = np.load(os.path.join(G, name + ".npz"))
+    ns, nal, ngt, gt = int(d["n_samples"]), d["n_allele"], d["ngt"], d["gt"]
+    names = [str(x) for x in d["names"]]
+    off = xo.row_offsets(ngt)
+    dp = xo.default_phased(gt, off, ngt, ns)
+    thr = xo.mac_threshold(ns, int(ngt[0]) // ns, float(d["maf"]))
+    img = xo.encode(gt, off, ngt, nal, ns, int(d["block_len"]), thr, dp, names, wah_encode_missing=True)
+    gold = open(os.path.join(G, name + "_wah_missing.xsi"), "rb").read()
+    assert hashlib.sha256(gold).hexdigest() == MAN[name]["wah_missing"]["xsi_sha256"]
+    assert img == gold
+    assert MAN[name]["wah_missing"]["ref_decode_equals_default"]
+    r = xo.Reader(gold)
+    pos = xo.bm_positions(nal, int(d["block_len"]))
+    rows = [r.fill_genotype_array(int(nal[i]), int(pos[i])) for i in range(len(nal))]
+    dec = np.concatenate([o[:n] for o, n in rows])
+    assert np.array_equal(dec, d["ref_decoded"])
+
+
 def test_chr20_small_decode_then_all_option_hashes():
     man = MAN["chr20_small"]
     d = np.load(os.path.join(G, "chr20_small_meta.npz"))

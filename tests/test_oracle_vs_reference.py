@@ -101,3 +101,36 @@ def test_mixed_ploidy_records_biallelic():
     ds = dict(gt=np.concatenate(rows).astype(np.int32), ngt=np.array(ngt, np.int32),
               n_allele=np.full(200, 2, np.int32), n_samples=ns)
     both(ds, block_len=64, maf=0.01)
+
+
+def both_wah_missing(ds, block_len, maf):
+    """--wah-encode-missing (WS_WAH): missing / end-of-vector lines as natural-order WAH instead of index lists."""
+    gt, ngt, nal, ns = ds["gt"], ds["ngt"], ds["n_allele"], ds["n_samples"]
+    off = xo.row_offsets(ngt)
+    dp = xo.default_phased(gt, off, ngt, ns)
+    thr = xo.mac_threshold(ns, int(ngt[0]) // ns, maf)
+    img = xo.encode(gt, off, ngt, nal, ns, block_len, thr, dp, wah_encode_missing=True)
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "r.xsi")
+        xsi_ref.encode_file(p, gt, off, ngt, nal, ns, block_len, thr, dp, wah_encode_missing=True)
+        assert img == open(p, "rb").read()
+        acc = xsi_ref.RefAccessor(p)
+        rd = xo.Reader(img)
+        pos = xo.bm_positions(nal, block_len)
+        for r in range(len(nal)):
+            a, na = acc.fill_genotype_array(int(nal[r]), int(pos[r]))
+            b, nb = rd.fill_genotype_array(int(nal[r]), int(pos[r]))
+            assert na == nb and np.array_equal(a[:na], b[:nb]), r
+            assert np.array_equal(acc.allele_counts(), rd.allele_counts()), r
+        acc.close()
+    return img
+
+
+def test_wah_encode_missing():
+    ds = synth.make_dataset(400, 257, seed=41, max_alt=3, multi_frac=0.2, missing=0.02, unphased=0.02, haploid_samples=0.4)
+    img = both_wah_missing(ds, 128, 0.02)
+    off = xo.row_offsets(ds["ngt"])
+    plain = xo.encode(ds["gt"], off, ds["ngt"], ds["n_allele"], ds["n_samples"], 128, xo.mac_threshold(ds["n_samples"], 2, 0.02),
+                      xo.default_phased(ds["gt"], off, ds["ngt"], ds["n_samples"]))
+    assert img != plain
+    both_wah_missing(synth.make_dataset(60, 66000, seed=42, n_founders=16, fmin=0.001, missing=0.001), 20, 0.001)
