@@ -386,3 +386,34 @@ def test_pinned_host_rows_two_routes(ctx, tmp_path):
         b, nb = rd.fill_genotype_array(2, int(pos[r]))
         assert filled[r] == nb and np.array_equal(res[r, :nb], b[:nb]), r
     acc.close()
+
+
+@pytest.mark.parametrize("name", SMALL)
+def test_decode_reference_wah_encode_missing_files(ctx, name):
+    """Files the reference CLI wrote with --wah-encode-missing (missing / end-of-vector lines as natural-order WAH,
+    KEY_WEIRDNESS_STRATEGY = WS_WAH) decode to the same rows as the default files."""
+    import xsqueezeit_b200 as xb
+    d = np.load(os.path.join(G, name + ".npz"))
+    nal = d["n_allele"]
+    acc = xb.Accessor(os.path.join(G, name + "_wah_missing.xsi"), ctx)
+    pos = xb.bm_positions(nal, int(d["block_len"]))
+    out, filled, counts = acc.fill_genotype_arrays(nal, pos, want_counts=True)
+    rd = xo.Reader(open(os.path.join(G, name + "_wah_missing.xsi"), "rb").read())
+    got = np.concatenate([out[r, :filled[r]] for r in range(len(nal))])
+    assert np.array_equal(got, d["ref_decoded"])
+    for r in range(len(nal)):
+        rd.fill_genotype_array(int(nal[r]), int(pos[r]))
+        assert np.array_equal(counts[r, :int(nal[r])], rd.allele_counts()), r
+    acc.close()
+
+
+def test_decode_wah_encode_missing_synthetic(ctx, tmp_path):
+    """WS_WAH images written by the oracle (pinned to the reference for this mode): wide multi-allelic mixed-ploidy rows."""
+    import xsqueezeit_b200 as xb
+    ds = synth.make_dataset(500, 520, seed=43, max_alt=3, multi_frac=0.1, missing=0.01, unphased=0.02, haploid_samples=0.3)
+    gt, ngt, nal, ns = ds["gt"], ds["ngt"], ds["n_allele"], ds["n_samples"]
+    off = xo.row_offsets(ngt)
+    img = xo.encode(gt, off, ngt, nal, ns, 128, xo.mac_threshold(ns, 2, 0.01), xo.default_phased(gt, off, ngt, ns), wah_encode_missing=True)
+    p = str(tmp_path / "wm.xsi")
+    open(p, "wb").write(img)
+    check_decode(ctx, p, img, nal, 128)

@@ -20,6 +20,7 @@ namespace xsi {
 #define DL_MISSING 4u
 #define DL_EOV 8u
 #define DL_PHASE 16u
+#define DL_WEIRD_WAH 32u  // missing / end-of-vector lines of this record are WAH rows (WS_WAH): mord / eord are job ordinals
 
 struct DecSeg {       // one WAH matrix (GT lines or phase lines) of one block
     uint64_t byte_off;  // in blob
@@ -1010,14 +1011,28 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
             __syncthreads();
         }
         uint32_t n_missing = 0, n_eov = 0;
-        if (f0 & DL_MISSING) {
+        if ((f0 & DL_MISSING) && (f0 & DL_WEIRD_WAH)) {
+            // --wah-encode-missing files (accessor_internals_new.hpp:307-321): the line was expanded like any WAH row,
+            // natural order (a_weird is the identity under WS_WAH)
+            const uint32_t job = d.dline_mord[gl0];
+            const uint32_t* mrow = d.rows + (size_t)job * d.WS;
+            n_missing = d.job_ones[job];
+            for (uint32_t i = tid; i < n; i += D4_THREADS) if ((mrow[i >> 5] >> (i & 31)) & 1u) { val[i] = CODE_MISSING; pf[i] = 1; }
+            __syncthreads();
+        } else if (f0 & DL_MISSING) {
             const uint8_t* mm = d.blob + blk.miss_off;
             const uint64_t e0 = d.ms_off[d.dline_mord[gl0]];
             n_missing = rd_entry(mm, e0, d.aet) & ~msb;
             for (uint32_t k = tid; k < n_missing; k += D4_THREADS) { const uint32_t i = rd_entry(mm, e0 + 1 + k, d.aet); if (i < q.Npad) { val[i] = CODE_MISSING; pf[i] = 1; } }
             __syncthreads();
         }
-        if (f0 & DL_EOV) {
+        if ((f0 & DL_EOV) && (f0 & DL_WEIRD_WAH)) {
+            const uint32_t job = d.dline_eord[gl0];
+            const uint32_t* erow = d.rows + (size_t)job * d.WS;
+            n_eov = d.job_ones[job];
+            for (uint32_t i = tid; i < n; i += D4_THREADS) if ((erow[i >> 5] >> (i & 31)) & 1u) val[i] = CODE_EOV;
+            __syncthreads();
+        } else if (f0 & DL_EOV) {
             const uint8_t* mm = d.blob + blk.eov_off;
             const uint64_t e0 = d.ev_off[d.dline_eord[gl0]];
             n_eov = rd_entry(mm, e0, d.aet) & ~msb;

@@ -23,6 +23,7 @@ enum GtKey : uint32_t {
 constexpr uint32_t VAL_UNDEFINED = 0xFFFFFFFFu;
 constexpr uint32_t KEY_GT_ENTRY = 256;  // outer block dictionary, interfaces.hpp:167
 constexpr uint32_t WS_SPARSE = 2;       // gt_block.hpp:69,417
+constexpr uint32_t WS_WAH = 1;          // gt_block.hpp:68,174-176 (--wah-encode-missing)
 
 // The reference serialises both per-block dictionaries by iterating a
 // std::unordered_map<uint32_t,uint32_t> (interfaces.hpp:37-54; gt_block.hpp:461-510), so the

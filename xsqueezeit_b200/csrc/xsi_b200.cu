@@ -1100,6 +1100,7 @@ namespace {
 struct ParsedBlock {
     std::map<uint32_t, uint32_t> dict;
     uint32_t bcf_lines = 0, bin_lines = 0, default_phasing = 0;
+    uint32_t ws = WS_SPARSE;  // KEY_WEIRDNESS_STRATEGY: WS_SPARSE, or WS_WAH for --wah-encode-missing files
     std::vector<uint8_t> is_wah, has_missing, has_eov, has_phase, haploid;
     bool p_missing = false, p_eov = false, p_phase = false;
 };
@@ -1121,7 +1122,10 @@ int parse_block(std::string& err, const uint8_t* p, uint64_t size, ParsedBlock& 
     uint32_t dp = 0, ws = 0;
     if (!need(KEY_BCF_LINES, pb.bcf_lines) || !need(KEY_BINARY_LINES, pb.bin_lines) || !need(KEY_DEFAULT_PHASING, dp)) { err = "GT block: required key missing"; return XSI_E_FORMAT; }
     pb.default_phasing = dp == 1 ? 1 : 0;  // accessor_internals_new.hpp:77-81
-    if (!need(KEY_WEIRDNESS_STRATEGY, ws) || ws != WS_SPARSE) { err = "GT block: only the sparse missing/EOV strategy is supported (file written with --wah-encode-missing?)"; return XSI_E_UNSUPPORTED; }
+    // WS_SPARSE is the writer's default, WS_WAH what --wah-encode-missing selects (gt_block.hpp:174-176); WS_PBWT_WAH (a
+    // second PBWT over the weirdness lines, the v4 default) cannot be produced by the v5 command line
+    if (!need(KEY_WEIRDNESS_STRATEGY, ws) || (ws != WS_SPARSE && ws != WS_WAH)) { err = "GT block: unsupported weirdness strategy (a version-4 PBWT+WAH file?)"; return XSI_E_UNSUPPORTED; }
+    pb.ws = ws;
     auto vec = [&](uint32_t key, std::vector<uint8_t>& v, bool& present) {
         present = false;
         auto it = pb.dict.find(key);
@@ -1184,8 +1188,11 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     struct BlkPlan {
         int rc = XSI_OK; std::string err;
         uint32_t n_wah = 0, n_sp = 0, n_ms = 0, n_ev = 0, n_ph = 0;
+        uint32_t n_msw = 0, n_evw = 0;         // missing / end-of-vector lines stored as WAH (WS_WAH blocks): expand-only jobs
         uint32_t wah_words = 0, ph_words = 0;  // u16 words of the WAH / phase matrix
         uint32_t wah_val = 0, ph_val = 0;
+        uint32_t msw_words = 0, evw_words = 0, msw_val = 0, evw_val = 0;
+        uint32_t msw0 = 0, evw0 = 0, seg_m = 0, seg_e = 0, tile_m = 0, tile_e = 0;
         bool any_hap = false;
         // prefix sums (filled serially)
         uint64_t line0 = 0;
@@ -1201,7 +1208,9 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
             if (pl.rc) return;
             for (uint32_t l = 0; l < pb.bin_lines; ++l) {
                 if (pb.is_wah[l]) { pl.n_wah++; if (pb.haploid[l]) pl.any_hap = true; } else pl.n_sp++;
-                pl.n_ms += pb.has_missing[l] != 0; pl.n_ev += pb.has_eov[l] != 0; pl.n_ph += pb.has_phase[l] != 0;
+                if (pb.ws == WS_WAH) { pl.n_msw += pb.has_missing[l] != 0; pl.n_evw += pb.has_eov[l] != 0; }
+                else { pl.n_ms += pb.has_missing[l] != 0; pl.n_ev += pb.has_eov[l] != 0; }
+                pl.n_ph += pb.has_phase[l] != 0;
             }
             auto matrix = [&](uint32_t key, uint32_t& val, uint32_t& words, const char* what) {
                 auto it = pb.dict.find(key);
@@ -1211,6 +1220,8 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
             };
             if (pl.n_wah) matrix(KEY_MATRIX_WAH, pl.wah_val, pl.wah_words, "GT block: WAH lines without a WAH matrix");
             if (pl.n_ph && !pl.rc) matrix(KEY_MATRIX_NON_UNIFORM_PHASING, pl.ph_val, pl.ph_words, "GT block: phase lines without their matrix");
+            if (pl.n_msw && !pl.rc) matrix(KEY_MATRIX_MISSING, pl.msw_val, pl.msw_words, "GT block: WAH missing lines without their matrix");
+            if (pl.n_evw && !pl.rc) matrix(KEY_MATRIX_END_OF_VECTORS, pl.evw_val, pl.evw_words, "GT block: WAH end-of-vector lines without their matrix");
         });
     }
     for (uint32_t b = 0; b < n_blocks; ++b)
@@ -1237,6 +1248,11 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
         if (!pl.n_ph) continue;
         pl.ph0 = njobs; njobs += pl.n_ph;
         pl.seg_p = nseg++; pl.tile_p = ntiles; ntiles += tiles_of(pl.ph_words);
+    }
+    for (uint32_t b = 0; b < n_blocks; ++b) {  // WS_WAH blocks: their missing / end-of-vector lines, one segment each
+        BlkPlan& pl = plan[b];
+        if (pl.n_msw) { pl.msw0 = njobs; njobs += pl.n_msw; pl.seg_m = nseg++; pl.tile_m = ntiles; ntiles += tiles_of(pl.msw_words); }
+        if (pl.n_evw) { pl.evw0 = njobs; njobs += pl.n_evw; pl.seg_e = nseg++; pl.tile_e = ntiles; ntiles += tiles_of(pl.evw_words); }
     }
     d.Lt = Lt;
     d.NJ = njobs;
@@ -1276,6 +1292,8 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
             bk.wah0 = pl.wah0; bk.sp0 = pl.sp0; bk.ms0 = pl.ms0; bk.ev0 = pl.ev0;
             bk.n_wah = pl.n_wah; bk.n_sp = pl.n_sp; bk.n_ms = pl.n_ms; bk.n_ev = pl.n_ev;
             uint32_t jw = pl.wah0, jp = pl.ph0, sp = pl.sp0, ms = pl.ms0, ev = pl.ev0, gc = 0, gcp = 0;
+            uint32_t jm = pl.msw0, je = pl.evw0, gcm = 0, gce = 0;
+            const bool weird_wah = pb.ws == WS_WAH;
             for (uint32_t l = 0; l < pb.bin_lines; ++l) {
                 const uint64_t gl = pl.line0 + l;
                 uint8_t f = 0;
@@ -1292,8 +1310,20 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
                     dl_ord[gl] = sp++;
                 }
                 dl_mord[gl] = 0; dl_eord[gl] = 0; dl_pord[gl] = 0;
-                if (pb.has_missing[l]) { f |= DL_MISSING; dl_mord[gl] = ms++; }
-                if (pb.has_eov[l]) { f |= DL_EOV; dl_eord[gl] = ev++; }
+                if (pb.has_missing[l] && weird_wah) {
+                    f |= DL_MISSING | DL_WEIRD_WAH;
+                    dl_mord[gl] = jm;
+                    job_gcum[jm] = gcm; job_nbits[jm] = nbits; job_seg[jm] = pl.seg_m; job_hap[jm] = 0;
+                    gcm += (nbits + 14) / 15;
+                    ++jm;
+                } else if (pb.has_missing[l]) { f |= DL_MISSING; dl_mord[gl] = ms++; }
+                if (pb.has_eov[l] && weird_wah) {
+                    f |= DL_EOV | DL_WEIRD_WAH;
+                    dl_eord[gl] = je;
+                    job_gcum[je] = gce; job_nbits[je] = nbits; job_seg[je] = pl.seg_e; job_hap[je] = 0;
+                    gce += (nbits + 14) / 15;
+                    ++je;
+                } else if (pb.has_eov[l]) { f |= DL_EOV; dl_eord[gl] = ev++; }
                 if (pb.has_phase[l]) {
                     f |= DL_PHASE;
                     dl_pord[gl] = jp;
@@ -1310,6 +1340,8 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
             };
             if (pl.n_wah) segment(pl.seg_w, pl.wah_val, pl.wah_words, pl.wah0, pl.n_wah, pl.tile_w);
             if (pl.n_ph) segment(pl.seg_p, pl.ph_val, pl.ph_words, pl.ph0, pl.n_ph, pl.tile_p);
+            if (pl.n_msw) segment(pl.seg_m, pl.msw_val, pl.msw_words, pl.msw0, pl.n_msw, pl.tile_m);
+            if (pl.n_evw) segment(pl.seg_e, pl.evw_val, pl.evw_words, pl.evw0, pl.n_evw, pl.tile_e);
         });
     }
     for (uint32_t b = 0; b < n_blocks; ++b) {
