@@ -65,7 +65,8 @@ typedef struct {
     int32_t  default_phasing;  /* seek_default_phased, xcf.cpp:811-836                                      */
     int32_t  gt_elem_bytes;    /* 4: int32 rows (bcf_get_genotypes); 1: raw BCF int8 rows                   */
     int32_t  gt_on_device;     /* 0: gt is host memory (copied H2D inside the call); 1: device pointer      */
-    int32_t  reserved;
+    int32_t  wah_encode_missing; /* --wah-encode-missing (xsqueezeit.hpp:58, gt_block.hpp:174-176): missing and
+                                  end-of-vector lines as natural-order WAH (WS_WAH) instead of index lists  */
     const void*     gt;        /* rows back to back: row r starts at element sum(ploidy[0..r))*n_samples    */
     const uint32_t* n_allele;  /* host, per record: bcf1_t::n_allele                                        */
     const uint8_t*  ploidy;    /* host, per record: ngt / n_samples (1 or 2); NULL = all 2                  */

@@ -417,3 +417,26 @@ def test_decode_wah_encode_missing_synthetic(ctx, tmp_path):
     p = str(tmp_path / "wm.xsi")
     open(p, "wb").write(img)
     check_decode(ctx, p, img, nal, 128)
+
+
+def test_encode_wah_encode_missing(ctx, tmp_path):
+    """--wah-encode-missing on the writer side (xsi_encode_desc.wah_encode_missing / Compressor(wah_encode_missing=True)):
+    byte-exact against the oracle, which is pinned to the reference CLI for this mode; fixtures and synthetic rows."""
+    import xsqueezeit_b200 as xb
+    for name in SMALL:
+        d = np.load(os.path.join(G, name + ".npz"))
+        ns, nal, ngt, gt = int(d["n_samples"]), d["n_allele"], d["ngt"], d["gt"]
+        names = [str(x) for x in d["names"]]
+        p = str(tmp_path / (name + "_wm.xsi"))
+        xb.Compressor(ctx, maf=float(d["maf"]), reset_sort_block_length=int(d["block_len"]), wah_encode_missing=True).compress_to_file(
+            p, gt, ngt, nal, ns, sample_names=names)
+        gold = open(os.path.join(G, name + "_wah_missing.xsi"), "rb").read()
+        assert open(p, "rb").read() == gold, name
+    ds = synth.make_dataset(500, 520, seed=44, max_alt=3, multi_frac=0.1, missing=0.01, unphased=0.02, haploid_samples=0.3)
+    gt, ngt, nal, ns = ds["gt"], ds["ngt"], ds["n_allele"], ds["n_samples"]
+    off = xo.row_offsets(ngt)
+    img = xo.encode(gt, off, ngt, nal, ns, 128, xo.mac_threshold(ns, 2, 0.01), xo.default_phased(gt, off, ngt, ns), wah_encode_missing=True)
+    p = str(tmp_path / "wm_synth.xsi")
+    xb.Compressor(ctx, maf=0.01, reset_sort_block_length=128, wah_encode_missing=True).compress_to_file(p, gt, ngt, nal, ns)
+    assert open(p, "rb").read() == img
+    check_decode(ctx, p, img, nal, 128)

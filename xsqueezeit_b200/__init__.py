@@ -33,7 +33,7 @@ class XsiError(RuntimeError):
 class _EncodeDesc(ctypes.Structure):
     _fields_ = [("n_records", ctypes.c_uint64), ("n_samples", ctypes.c_uint32), ("block_len", ctypes.c_uint32),
                 ("mac_threshold", ctypes.c_uint64), ("default_phasing", ctypes.c_int32),
-                ("gt_elem_bytes", ctypes.c_int32), ("gt_on_device", ctypes.c_int32), ("reserved", ctypes.c_int32),
+                ("gt_elem_bytes", ctypes.c_int32), ("gt_on_device", ctypes.c_int32), ("wah_encode_missing", ctypes.c_int32),
                 ("gt", ctypes.c_void_p), ("n_allele", ctypes.c_void_p), ("ploidy", ctypes.c_void_p)]
 
 
@@ -181,7 +181,7 @@ class Context:
 
     # ---- encode --------------------------------------------------------------------------
     def encode_launch(self, gt, n_allele, n_samples, block_len, mac_threshold, default_phasing, ploidy=None,
-                      gt_elem_bytes=4, gt_on_device=False):
+                      gt_elem_bytes=4, gt_on_device=False, wah_encode_missing=False):
         """gt: numpy array (host) or an integer device address when gt_on_device."""
         self._na = np.ascontiguousarray(n_allele, dtype=np.uint32)
         self._pl = None if ploidy is None else np.ascontiguousarray(ploidy, dtype=np.uint8)
@@ -194,6 +194,7 @@ class Context:
         d.default_phasing = int(default_phasing)
         d.gt_elem_bytes = int(gt_elem_bytes)
         d.gt_on_device = 1 if gt_on_device else 0
+        d.wah_encode_missing = 1 if wah_encode_missing else 0
         d.gt = _ptr(gt)
         d.n_allele = self._na.ctypes.data
         d.ploidy = None if self._pl is None else self._pl.ctypes.data
@@ -304,13 +305,14 @@ class Compressor:
     in-memory genotype rows instead of htslib records.  Defaults follow include/xsqueezeit.hpp:101-113."""
 
     def __init__(self, ctx=None, maf=0.001, reset_sort_block_length=8192, zstd_compression_on=False,
-                 zstd_compression_level=7, blocks_per_batch=8):
+                 zstd_compression_level=7, blocks_per_batch=8, wah_encode_missing=False):
         self.ctx = ctx or Context(0)
         self.MAF = maf
         self.RESET_SORT_BLOCK_LENGTH = reset_sort_block_length
         self.zstd_compression_on = zstd_compression_on
         self.zstd_compression_level = zstd_compression_level
         self.blocks_per_batch = blocks_per_batch
+        self.wah_encode_missing = wah_encode_missing  # --wah-encode-missing (xsqueezeit.hpp:58)
 
     def set_maf(self, maf):
         self.MAF = maf
@@ -362,7 +364,8 @@ class Compressor:
             for r0 in range(0, R, step):
                 r1 = min(R, r0 + step)
                 self.ctx.encode_launch(gt[off[r0]:off[r1]], n_allele[r0:r1], n_samples, bl, thr, default_phased,
-                                       ploidy=ploidy[r0:r1].astype(np.uint8), gt_elem_bytes=gt_elem_bytes)
+                                       ploidy=ploidy[r0:r1].astype(np.uint8), gt_elem_bytes=gt_elem_bytes,
+                                       wah_encode_missing=self.wah_encode_missing)
                 n = ctypes.c_uint32()
                 blocks = ctypes.POINTER(ctypes.c_void_p)()
                 sizes = ctypes.POINTER(ctypes.c_uint64)()

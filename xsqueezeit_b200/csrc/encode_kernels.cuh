@@ -48,6 +48,11 @@ struct EncDev {
     uint32_t* blk_nwah;       // [nb]
     uint16_t* wahslots;       // [L][SLOTW]
     uint16_t* phslots;        // [phase_cap][SLOTW]
+    // --wah-encode-missing (WS_WAH): WAH of the missing / end-of-vector rows (natural order)
+    uint32_t wah_missing;     // 0 / 1
+    uint16_t* auxslots;       // [aux_cap][SLOTW]
+    uint32_t* rec_missw_n;    // [R] WAH words of the record's missing line (0 if none)
+    uint32_t* rec_eovw_n;     // [R]
 };
 
 #define ERR_ALLELE 1u
@@ -1457,6 +1462,15 @@ __global__ void __launch_bounds__(E4_WARPS * 32) wah_encode_rows_kernel(EncDev p
         const uint32_t n = wah_encode_row_warp(p.phrows + (size_t)slot * p.WS, p.WS, p.rec_ngt[r],
                                                p.phslots + (size_t)slot * p.SLOTW);
         if (lane_id() == 0) p.rec_phase_n[r] = n;
+    } else if (p.wah_missing && job < p.L + 3 * p.R) {
+        // gt_block.hpp:340-372 under WS_WAH: a_weirdness is the identity, the predicate rows are encoded as they are
+        const uint32_t which = (job - p.L) / p.R - 1;  // 0: missing, 1: end of vector
+        const uint32_t r = (job - p.L) - (which + 1) * p.R;
+        const int32_t slot = p.rec_aux[r * 3 + which];
+        if (slot < 0) return;
+        const uint32_t n = wah_encode_row_warp(p.auxrows + (size_t)slot * p.WS, p.WS, p.rec_ngt[r],
+                                               p.auxslots + (size_t)slot * p.SLOTW);
+        if (lane_id() == 0) (which == 0 ? p.rec_missw_n : p.rec_eovw_n)[r] = n;
     }
 }
 
@@ -1511,6 +1525,9 @@ struct EmitDev {
     const uint64_t* rec_phase_off;    // [R+1]
     void* out_sparse; void* out_miss; void* out_eov;
     uint16_t* out_wah; uint16_t* out_phase;
+    const uint64_t* rec_missw_off;    // [R+1] (WS_WAH only)
+    const uint64_t* rec_eovw_off;     // [R+1]
+    uint16_t* out_missw; uint16_t* out_eovw;
 };
 
 template <typename AT>
@@ -1573,6 +1590,13 @@ __global__ void __launch_bounds__(E6_WARPS * 32) pack_wah_kernel(EncDev p, EmitD
         if (!n) return;
         src = p.phslots + (size_t)p.rec_aux[r * 3 + 2] * p.SLOTW;
         dst = e.out_phase + e.rec_phase_off[r];
+    } else if (p.wah_missing && job < p.L + 3 * p.R) {
+        const uint32_t which = (job - p.L) / p.R - 1;
+        const uint32_t r = (job - p.L) - (which + 1) * p.R;
+        n = (which == 0 ? p.rec_missw_n : p.rec_eovw_n)[r];
+        if (!n) return;
+        src = p.auxslots + (size_t)p.rec_aux[r * 3 + which] * p.SLOTW;
+        dst = which == 0 ? e.out_missw + e.rec_missw_off[r] : e.out_eovw + e.rec_eovw_off[r];
     } else return;
     for (uint32_t i = lane; i < n; i += 32) dst[i] = src[i];
 }

@@ -101,9 +101,11 @@ struct xsi_ctx {
         std::vector<uint64_t> h_goff;
         DevBuf gt, tables, bitrows, auxrows, phrows, counters, rec_aux, line_u32, line_flags, rec_u32, rec_flags,
             wah_list, blk_nwah, wahslots, phslots, offs, scanjobs, out_wah, out_sparse, out_miss, out_eov, out_phase,
+            auxslots, out_missw, out_eovw,
             a_pool;
         PinBuf h_small, h_offs, h_out, h_flags;
-        uint64_t tot_sparse = 0, tot_miss = 0, tot_eov = 0, tot_wah = 0, tot_phase = 0;
+        uint64_t tot_sparse = 0, tot_miss = 0, tot_eov = 0, tot_wah = 0, tot_phase = 0, tot_missw = 0, tot_eovw = 0;
+        bool wah_missing = false;  // --wah-encode-missing (WS_WAH)
         PinBuf arena;                       // finished GT blocks, back to back (16-byte aligned starts)
         std::vector<uint64_t> block_at;     // offset of every block in the arena
         std::vector<const uint8_t*> block_ptrs;
@@ -204,7 +206,8 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
     auto& e = ctx->enc;
     for (DevBuf* b : {&e.gt, &e.tables, &e.bitrows, &e.auxrows, &e.phrows, &e.counters, &e.rec_aux, &e.line_u32,
                       &e.line_flags, &e.rec_u32, &e.rec_flags, &e.wah_list, &e.blk_nwah, &e.wahslots, &e.phslots,
-                      &e.offs, &e.scanjobs, &e.out_wah, &e.out_sparse, &e.out_miss, &e.out_eov, &e.out_phase, &e.a_pool})
+                      &e.offs, &e.scanjobs, &e.out_wah, &e.out_sparse, &e.out_miss, &e.out_eov, &e.out_phase, &e.a_pool,
+                      &e.auxslots, &e.out_missw, &e.out_eovw})
         b->release();
     for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags, &e.arena}) b->release();
     auto& d = ctx->dec;
@@ -708,6 +711,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
     const uint32_t S = d->n_samples;
     e.R = R; e.n_samples = S; e.block_len = d->block_len; e.default_phasing = d->default_phasing ? 1 : 0;
     e.aet = S <= 65535 ? 2 : 4;
+    e.wah_missing = d->wah_encode_missing != 0;
     e.nb = (uint32_t)((R + d->block_len - 1) / d->block_len);
     // ---- host tables ----
     std::chrono::steady_clock::time_point t_tables = std::chrono::steady_clock::now();
@@ -824,13 +828,13 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
     CK(e.rec_aux.ensure(R * 3 * 4));
     CK(e.line_u32.ensure(Lp * 3 * 4));  // cnt | sparse_n | wah_n
     CK(e.line_flags.ensure(Lp));
-    CK(e.rec_u32.ensure(R * 3 * 4));    // miss_n | eov_n | phase_n
+    CK(e.rec_u32.ensure(R * 5 * 4));    // miss_n | eov_n | phase_n | missw_n | eovw_n (the last two: WS_WAH only)
     CK(e.rec_flags.ensure(R));
     CK(e.wah_list.ensure(Lp * 4));
     CK(e.blk_nwah.ensure(e.nb * 4));
     // offsets: line_sparse_off[L+1] | rec_miss_off[R+1] | rec_eov_off[R+1] | line_wah_off[L+1] | rec_phase_off[R+1]
     const size_t o_sp = 0, o_ms = o_sp + (L + 1) * 8, o_ev = o_ms + (R + 1) * 8, o_wh = o_ev + (R + 1) * 8,
-                 o_ph = o_wh + (L + 1) * 8, o_end = o_ph + (R + 1) * 8;
+                 o_ph = o_wh + (L + 1) * 8, o_mw = o_ph + (R + 1) * 8, o_ew = o_mw + (R + 1) * 8, o_end = o_ew + (R + 1) * 8;
     CK(e.offs.ensure(o_end));
     CK(e.scanjobs.ensure(8 * sizeof(ScanJob)));
     if (e.aux_cap == 0) e.aux_cap = (uint32_t)std::max<uint64_t>(256, R / 16);
@@ -840,6 +844,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         CK(e.auxrows.ensure((size_t)e.aux_cap * e.WS * 4));
         CK(e.phrows.ensure((size_t)e.phase_cap * e.WS * 4));
         CK(e.phslots.ensure((size_t)e.phase_cap * e.SLOTW * 2));
+        if (e.wah_missing) CK(e.auxslots.ensure((size_t)e.aux_cap * e.SLOTW * 2));
         EncDev p;
         uint8_t* tb = e.tables.as<uint8_t>();
         p.gt = dgt;
@@ -860,6 +865,10 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         p.rec_flags = e.rec_flags.as<uint8_t>();
         p.wah_list = e.wah_list.as<uint32_t>(); p.blk_nwah = e.blk_nwah.as<uint32_t>();
         p.wahslots = e.wahslots.as<uint16_t>(); p.phslots = e.phslots.as<uint16_t>();
+        p.wah_missing = e.wah_missing ? 1u : 0u;
+        p.auxslots = e.auxslots.as<uint16_t>();
+        p.rec_missw_n = p.rec_phase_n + R; p.rec_eovw_n = p.rec_missw_n + R;
+        if (e.wah_missing) CK(cudaMemsetAsync(p.rec_missw_n, 0, R * 2 * 4, ctx->stream));
 
         CK(cudaMemsetAsync(e.counters.p, 0, 16, ctx->stream));
         if (rows_aligned16 && !getenv("XSI_SCAN_V1")) {
@@ -888,18 +897,21 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
             if (rc) return rc;
         }
         {
-            const uint64_t jobs = L + R;
+            const uint64_t jobs = L + (e.wah_missing ? 3 : 1) * R;
             { PROF("wah_encode_rows"); wah_encode_rows_kernel<<<(uint32_t)((jobs + E4_WARPS - 1) / E4_WARPS), E4_WARPS * 32, 0, ctx->stream>>>(p); }
             CKL();
         }
         uint8_t* ob = e.offs.as<uint8_t>();
-        ScanJob jobs[5] = {{p.line_sparse_n, reinterpret_cast<uint64_t*>(ob + o_sp), (uint32_t)L, 0},
+        ScanJob jobs[7] = {{p.line_sparse_n, reinterpret_cast<uint64_t*>(ob + o_sp), (uint32_t)L, 0},
                            {p.rec_miss_n, reinterpret_cast<uint64_t*>(ob + o_ms), (uint32_t)R, 0},
                            {p.rec_eov_n, reinterpret_cast<uint64_t*>(ob + o_ev), (uint32_t)R, 0},
                            {p.line_wah_n, reinterpret_cast<uint64_t*>(ob + o_wh), (uint32_t)L, 0},
-                           {p.rec_phase_n, reinterpret_cast<uint64_t*>(ob + o_ph), (uint32_t)R, 0}};
+                           {p.rec_phase_n, reinterpret_cast<uint64_t*>(ob + o_ph), (uint32_t)R, 0},
+                           {p.rec_missw_n, reinterpret_cast<uint64_t*>(ob + o_mw), (uint32_t)R, 0},
+                           {p.rec_eovw_n, reinterpret_cast<uint64_t*>(ob + o_ew), (uint32_t)R, 0}};
+        const uint32_t n_scans = e.wah_missing ? 7 : 5;
         CK(cudaMemcpyAsync(e.scanjobs.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice, ctx->stream));
-        { PROF("scan_u32"); scan_u32_kernel<<<5, SCAN_THREADS, 0, ctx->stream>>>(e.scanjobs.as<ScanJob>()); }
+        { PROF("scan_u32"); scan_u32_kernel<<<n_scans, SCAN_THREADS, 0, ctx->stream>>>(e.scanjobs.as<ScanJob>()); }
         CKL();
         // totals + counters + flags back, then size the outputs and lay the blocks out
         CK(e.h_offs.ensure(o_end + 64));
@@ -922,11 +934,14 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         e.tot_eov = reinterpret_cast<const uint64_t*>(ho + o_ev)[R];
         e.tot_wah = reinterpret_cast<const uint64_t*>(ho + o_wh)[L];
         e.tot_phase = reinterpret_cast<const uint64_t*>(ho + o_ph)[R];
+        e.tot_missw = e.wah_missing ? reinterpret_cast<const uint64_t*>(ho + o_mw)[R] : 0;
+        e.tot_eovw = e.wah_missing ? reinterpret_cast<const uint64_t*>(ho + o_ew)[R] : 0;
         CK(e.out_sparse.ensure(e.tot_sparse * e.aet + 16));
         CK(e.out_miss.ensure(e.tot_miss * e.aet + 16));
         CK(e.out_eov.ensure(e.tot_eov * e.aet + 16));
         CK(e.out_wah.ensure(e.tot_wah * 2 + 16));
         CK(e.out_phase.ensure(e.tot_phase * 2 + 16));
+        if (e.wah_missing) { CK(e.out_missw.ensure(e.tot_missw * 2 + 16)); CK(e.out_eovw.ensure(e.tot_eovw * 2 + 16)); }
         EmitDev em;
         em.line_sparse_off = reinterpret_cast<const uint64_t*>(ob + o_sp);
         em.rec_miss_off = reinterpret_cast<const uint64_t*>(ob + o_ms);
@@ -935,6 +950,8 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         em.rec_phase_off = reinterpret_cast<const uint64_t*>(ob + o_ph);
         em.out_sparse = e.out_sparse.p; em.out_miss = e.out_miss.p; em.out_eov = e.out_eov.p;
         em.out_wah = e.out_wah.as<uint16_t>(); em.out_phase = e.out_phase.as<uint16_t>();
+        em.rec_missw_off = reinterpret_cast<const uint64_t*>(ob + o_mw); em.rec_eovw_off = reinterpret_cast<const uint64_t*>(ob + o_ew);
+        em.out_missw = e.out_missw.as<uint16_t>(); em.out_eovw = e.out_eovw.as<uint16_t>();
         {
             const uint64_t jobs5 = L + 2 * R;
             const uint32_t grid = (uint32_t)((jobs5 + E5_WARPS - 1) / E5_WARPS);
@@ -944,7 +961,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
                 else sparse_emit_kernel<uint32_t><<<grid, E5_WARPS * 32, 0, ctx->stream>>>(p, em);
             }
             CKL();
-            const uint64_t jobs6 = L + R;
+            const uint64_t jobs6 = L + (e.wah_missing ? 3 : 1) * R;
             { PROF("pack_wah"); pack_wah_kernel<<<(uint32_t)((jobs6 + E6_WARPS - 1) / E6_WARPS), E6_WARPS * 32, 0, ctx->stream>>>(p, em); }
             CKL();
         }
@@ -956,6 +973,8 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
             const uint64_t* off_ev = reinterpret_cast<const uint64_t*>(ho + o_ev);
             const uint64_t* off_wh = reinterpret_cast<const uint64_t*>(ho + o_wh);
             const uint64_t* off_ph = reinterpret_cast<const uint64_t*>(ho + o_ph);
+            const uint64_t* off_mw = reinterpret_cast<const uint64_t*>(ho + o_mw);
+            const uint64_t* off_ew = reinterpret_cast<const uint64_t*>(ho + o_ew);
             const uint8_t* lflags = e.h_flags.as<uint8_t>();
             const uint8_t* rflags = lflags + Lp;
             HOSTSPAN("host:encode_layout");
@@ -992,7 +1011,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
                 std::map<uint32_t, uint32_t> val;
                 auto ins = [&](uint32_t k, uint32_t v) { ord.insert(k); val[k] = v; };
                 ins(KEY_BCF_LINES, nrec); ins(KEY_BINARY_LINES, nlines); ins(KEY_MAX_LINE_PLOIDY, max_pl);
-                ins(KEY_DEFAULT_PHASING, (uint32_t)e.default_phasing); ins(KEY_WEIRDNESS_STRATEGY, WS_SPARSE);
+                ins(KEY_DEFAULT_PHASING, (uint32_t)e.default_phasing); ins(KEY_WEIRDNESS_STRATEGY, e.wah_missing ? WS_WAH : WS_SPARSE);
                 ins(KEY_LINE_SORT, VAL_UNDEFINED); ins(KEY_LINE_SELECT, VAL_UNDEFINED); ins(KEY_MATRIX_WAH, VAL_UNDEFINED);
                 ins(KEY_MATRIX_SPARSE, VAL_UNDEFINED);
                 if (any_missing) { ins(KEY_LINE_MISSING, VAL_UNDEFINED); ins(KEY_MATRIX_MISSING, VAL_UNDEFINED); ins(KEY_MATRIX_MISSING_SPARSE, VAL_UNDEFINED); }
@@ -1025,8 +1044,16 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
                 };
                 section(KEY_MATRIX_WAH, e.out_wah.p, off_wh[l0], off_wh[l1], 2);
                 section(KEY_MATRIX_SPARSE, e.out_sparse.p, off_sp[l0], off_sp[l1], e.aet);
-                if (any_missing) { boolvec(KEY_LINE_MISSING, v_miss); section(KEY_MATRIX_MISSING_SPARSE, e.out_miss.p, off_ms[r0], off_ms[r1], e.aet); }
-                if (any_eov) { boolvec(KEY_LINE_END_OF_VECTORS, v_eov); section(KEY_MATRIX_END_OF_VECTORS_SPARSE, e.out_eov.p, off_ev[r0], off_ev[r1], e.aet); }
+                if (any_missing) {
+                    boolvec(KEY_LINE_MISSING, v_miss);
+                    if (e.wah_missing) section(KEY_MATRIX_MISSING, e.out_missw.p, off_mw[r0], off_mw[r1], 2);  // gt_block.hpp:574-576
+                    else section(KEY_MATRIX_MISSING_SPARSE, e.out_miss.p, off_ms[r0], off_ms[r1], e.aet);
+                }
+                if (any_eov) {
+                    boolvec(KEY_LINE_END_OF_VECTORS, v_eov);
+                    if (e.wah_missing) section(KEY_MATRIX_END_OF_VECTORS, e.out_eovw.p, off_ew[r0], off_ew[r1], 2);  // :596-598
+                    else section(KEY_MATRIX_END_OF_VECTORS_SPARSE, e.out_eov.p, off_ev[r0], off_ev[r1], e.aet);
+                }
                 if (any_phase) { boolvec(KEY_LINE_NON_UNIFORM_PHASING, v_phase); section(KEY_MATRIX_NON_UNIFORM_PHASING, e.out_phase.p, off_ph[r0], off_ph[r1], 2); }
                 if (any_hap) boolvec(KEY_LINE_HAPLOID, v_hap);  // one bit per BCF line, gt_block.hpp:219-224,639-642
                 for (size_t i = 0; i < order.size(); ++i) {
