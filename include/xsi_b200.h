@@ -126,6 +126,15 @@ int xsi_decode_records_i8(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index,
  * (fill_genotype_array / xsi_decode_records does subtract them).                               */
 int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                              const uint32_t* n_alleles, uint64_t* allele_counts, uint32_t counts_stride);
+/* Sample subset: what the extractor's -s/-S does per record (fill_selected_genotypes,
+ * include/gt_decompressor_new.hpp:208-238, sample list from enable_select_samples :324-365).  Row i of `out`
+ * holds the entries of samples_to_use[0..n_sel) in that order (n_sel * ploidy values, ploidy 1 for an all-haploid
+ * record), n_filled[i] that length, and ac + i*ac_stride the selected carriers of ALT allele 1..n_alleles[i]-1
+ * (ac_s; ac may be NULL).  Host or device `out` as for xsi_decode_records; sample indices must be < num_samples. */
+int xsi_decode_records_subset(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                              const uint32_t* n_alleles, const uint32_t* samples_to_use, uint32_t n_sel,
+                              int32_t* out, uint64_t out_stride, int32_t out_on_device, uint32_t* n_filled,
+                              uint32_t* ac, uint32_t ac_stride);
 /* Blocks until everything queued on the context stream is done. */
 int xsi_sync(xsi_ctx* ctx);
 

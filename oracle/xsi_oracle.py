@@ -177,3 +177,18 @@ def bm_positions(n_allele, block_len):
         pos[r] = ((r // block_len) << 15) | off
         off += int(n_allele[r]) - 1
     return pos
+
+
+def select_samples(row, n, num_samples, samples_to_use, n_allele):
+    """fill_selected_genotypes (reference include/gt_decompressor_new.hpp:208-238): the selected samples' entries of a
+    decoded row of n values (ploidy n / num_samples, 1 or 2), in the order of samples_to_use, and ac_s[alt-1] = number of
+    selected entries whose allele is alt.  Returns (selected row, ac_s)."""
+    pl = n // num_samples
+    if pl not in (1, 2):
+        raise ValueError("PLOIDY ERROR")
+    sel = np.asarray(samples_to_use, dtype=np.int64)
+    idx = (sel[:, None] * pl + np.arange(pl)[None, :]).reshape(-1)
+    picked = np.asarray(row[:n])[idx]
+    allele = (picked >> 1) - 1
+    ac = np.array([int((allele == a).sum()) for a in range(1, n_allele)], dtype=np.uint32)
+    return picked, ac

@@ -440,3 +440,34 @@ def test_encode_wah_encode_missing(ctx, tmp_path):
     xb.Compressor(ctx, maf=0.01, reset_sort_block_length=128, wah_encode_missing=True).compress_to_file(p, gt, ngt, nal, ns)
     assert open(p, "rb").read() == img
     check_decode(ctx, p, img, nal, 128)
+
+
+def test_sample_subset(ctx, tmp_path):
+    """xsi_decode_records_subset against fill_selected_genotypes restated on oracle-decoded rows: arbitrary order, repeats,
+    mixed ploidy (end-of-vector), missing, multi-allelic; all-haploid records (ploidy 1 rows)."""
+    import xsqueezeit_b200 as xb
+    rng = np.random.default_rng(5)
+    al = (rng.random((150, 90)) < rng.uniform(0.0, 0.6, size=(150, 1))).astype(np.int8)
+    haploid = dict(gt=np.ascontiguousarray(synth.encode_gt(al, 0).reshape(-1)), ngt=np.full(150, 90, np.int32),
+                   n_allele=np.full(150, 2, np.int32), n_samples=90)
+    for ds, bl in ((synth.make_dataset(300, 257, seed=51, max_alt=4, multi_frac=0.3, missing=0.02, unphased=0.02, haploid_samples=0.4), 128),
+                   (synth.make_dataset(200, 1000, seed=52), 64), (haploid, 40)):
+        ns = ds["n_samples"]
+        p = gpu_encode(ctx, tmp_path, ds, bl, 0.01)
+        img = open(p, "rb").read()
+        acc = xb.Accessor(p, ctx)
+        rd = xo.Reader(img)
+        pos = xb.bm_positions(ds["n_allele"], bl)
+        sel = rng.permutation(ns)[: max(3, ns // 3)].astype(np.uint32)
+        sel[1] = sel[0]  # a repeated sample is allowed
+        nb = (len(pos) + bl - 1) // bl
+        acc._load(0, nb)
+        blk = (pos >> np.uint64(15)).astype(np.uint32)
+        off = (pos & np.uint64(0x7FFF)).astype(np.uint32)
+        out, filled, ac = ctx.decode_records_subset(blk, off, ds["n_allele"], sel)
+        for r in range(len(pos)):
+            row, n = rd.fill_genotype_array(int(ds["n_allele"][r]), int(pos[r]))
+            want, want_ac = xo.select_samples(row, n, ns, sel, int(ds["n_allele"][r]))
+            assert filled[r] == want.size and np.array_equal(out[r, :filled[r]], want), r
+            assert np.array_equal(ac[r, :int(ds["n_allele"][r]) - 1], want_ac), r
+        acc.close()

@@ -84,6 +84,8 @@ def lib():
     L.xsi_decode_records.argtypes = [vp, u64, vp, vp, vp, vp, u64, i32, vp, vp, u32]
     L.xsi_decode_records_i8.restype = i32
     L.xsi_decode_records_i8.argtypes = [vp, u64, vp, vp, vp, vp, u64, i32, vp, vp, u32]
+    L.xsi_decode_records_subset.restype = i32
+    L.xsi_decode_records_subset.argtypes = [vp, u64, vp, vp, vp, vp, u32, vp, u64, i32, vp, vp, u32]
     L.xsi_decode_allele_counts.restype = i32
     L.xsi_decode_allele_counts.argtypes = [vp, u64, vp, vp, vp, vp, u32]
     L.xsi_host_narrow_i32_i8.restype = i32
@@ -263,6 +265,24 @@ class Context:
            1 if out_on_device else 0, filled.ctypes.data, None if counts is None else counts.ctypes.data, cs))
         return out, filled, counts
 
+
+    def decode_records_subset(self, block_index, line_offset, n_alleles, samples_to_use, want_ac=True):
+        """Rows of the selected samples only, in the order given (the extractor's -s/-S, gt_decompressor_new.hpp:208-238),
+        their lengths, and the selected carriers per ALT allele (ac_s)."""
+        bi = np.ascontiguousarray(block_index, dtype=np.uint32)
+        lo = np.ascontiguousarray(line_offset, dtype=np.uint32)
+        na = np.ascontiguousarray(n_alleles, dtype=np.uint32)
+        sel = np.ascontiguousarray(samples_to_use, dtype=np.uint32)
+        n = bi.size
+        stride = 2 * sel.size
+        out = np.zeros((n, stride), dtype=np.int32)
+        filled = np.zeros(n, dtype=np.uint32)
+        acs = max(1, int(na.max()) - 1) if n else 1
+        ac = np.zeros((n, acs), dtype=np.uint32) if want_ac else None
+        self._check(self._L.xsi_decode_records_subset(self.h, n, bi.ctypes.data, lo.ctypes.data, na.ctypes.data, sel.ctypes.data,
+                                                      sel.size, out.ctypes.data, stride, 0, filled.ctypes.data,
+                                                      None if ac is None else ac.ctypes.data, acs))
+        return out, filled, ac
 
     def decode_allele_counts(self, block_index, line_offset, n_alleles):
         """Counts only (AccessorInternals::fill_allele_counts); returns uint64 [n, max(n_alleles)]."""

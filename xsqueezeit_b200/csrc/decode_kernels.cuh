@@ -1056,6 +1056,38 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
 }
 
 // =============================================================================================
+// D6: sample subset (-s/-S of the extractor: fill_selected_genotypes, gt_decompressor_new.hpp:208-238).  One CTA per
+// record: the selected samples' entries of the full row (ploidy 1 or 2 from the row length) are gathered into a
+// compact row, and the selected carriers of every ALT allele are counted (ac_s, the AC the extractor rewrites).
+// =============================================================================================
+__global__ void __launch_bounds__(256) select_samples_kernel(const int32_t* __restrict__ full, uint64_t full_stride,
+                                                              const uint32_t* __restrict__ filled, const uint32_t* __restrict__ nall,
+                                                              uint32_t num_samples, const uint32_t* __restrict__ sel, uint32_t n_sel,
+                                                              int32_t* __restrict__ out, uint64_t out_stride, uint32_t* __restrict__ out_filled,
+                                                              uint32_t* __restrict__ ac, uint32_t ac_stride, uint32_t n) {
+    __shared__ uint32_t s_ac[256];
+    for (uint32_t r = blockIdx.x; r < n; r += gridDim.x) {
+        const uint32_t pl = filled[r] / num_samples;  // CURRENT_LINE_PLOIDY
+        const uint32_t na = nall[r];
+        for (uint32_t a = threadIdx.x; a < 256; a += blockDim.x) s_ac[a] = 0;
+        __syncthreads();
+        const int32_t* src = full + (size_t)r * full_stride;
+        int32_t* dst = out + (size_t)r * out_stride;
+        for (uint32_t i = threadIdx.x; i < n_sel * pl; i += blockDim.x) {
+            const uint32_t s = i / pl, k = i - s * pl;
+            const int32_t v = src[(size_t)sel[s] * pl + k];
+            dst[i] = v;
+            const int32_t allele = (v >> 1) - 1;  // bcf_gt_allele; missing (-1) and end-of-vector never match an ALT
+            if (ac && allele >= 1 && (uint32_t)allele < na) atomicAdd(&s_ac[allele], 1u);
+        }
+        __syncthreads();
+        if (ac) for (uint32_t a = 1 + threadIdx.x; a < na; a += blockDim.x) ac[(size_t)r * ac_stride + a - 1] = s_ac[a];
+        if (threadIdx.x == 0 && out_filled) out_filled[r] = n_sel * pl;
+        __syncthreads();
+    }
+}
+
+// =============================================================================================
 // D5: allele counts only (fill_allele_counts_advance, accessor_internals_new.hpp:407-440): per ALT line the
 // carriers counted when the line was expanded (WAH) or its list header (sparse, negated: N - count);
 // allele_counts[0] = CURRENT_N_HAPS - sum, WITHOUT the missing / end-of-vector correction of fill_genotype_array.

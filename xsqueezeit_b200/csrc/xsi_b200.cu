@@ -1770,6 +1770,60 @@ extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* bloc
                                         allele_counts, counts_stride);
 }
 
+extern "C" int xsi_decode_records_subset(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                                         const uint32_t* n_alleles, const uint32_t* samples_to_use, uint32_t n_sel,
+                                         int32_t* out, uint64_t out_stride, int32_t out_on_device, uint32_t* n_filled,
+                                         uint32_t* ac, uint32_t ac_stride) {
+    if (!ctx || !block_index || !line_offset || !n_alleles || !samples_to_use || !out || n_sel == 0) return XSI_E_ARG;
+    auto& d = ctx->dec;
+    if (!d.loaded) { ctx->err = "xsi_decode_records_subset without loaded blocks"; return XSI_E_ARG; }
+    if (n == 0) return XSI_OK;
+    CK(cudaSetDevice(ctx->device));
+    const uint32_t N = 2 * d.n_samples;
+    if (out_stride < 2ull * n_sel) { ctx->err = "out_stride smaller than 2*n_sel"; return XSI_E_ARG; }
+    uint32_t max_all = 2;
+    for (uint64_t i = 0; i < n; ++i) max_all = std::max(max_all, n_alleles[i]);
+    if (ac && ac_stride + 1 < max_all) { ctx->err = "ac_stride too small"; return XSI_E_ARG; }
+    for (uint32_t i = 0; i < n_sel; ++i)
+        if (samples_to_use[i] >= d.n_samples) { ctx->err = "sample index out of range"; return XSI_E_ARG; }
+    // full rows of a chunk of records on the device (the ordinary decode), then the gather
+    const uint64_t full_stride = ((uint64_t)N + 3) / 4 * 4;
+    const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(n, (1ull << 30) / (full_stride * 4)));
+    DevBuf& full = d.a_pool;      // scratch pools that are idle between xsi_decode_load_blocks calls
+    DevBuf& aux = d.x_pool;
+    CK(full.ensure(chunk * full_stride * 4));
+    // aux: sel[n_sel] | filled_full[chunk] | nall[chunk] | filled_sub[chunk] | ac[chunk*ac_stride] | sub rows (host output only)
+    const size_t a_sel = 0, a_ff = a_sel + (size_t)n_sel * 4, a_na = a_ff + chunk * 4, a_fs = a_na + chunk * 4, a_ac = a_fs + chunk * 4,
+                 a_rows = (a_ac + (ac ? chunk * ac_stride * 4 : 0) + 15) / 16 * 16,
+                 a_end = a_rows + (out_on_device ? 0 : chunk * out_stride * 4);
+    CK(aux.ensure(a_end));
+    uint8_t* ab = aux.as<uint8_t>();
+    CK(cudaMemcpyAsync(ab + a_sel, samples_to_use, (size_t)n_sel * 4, cudaMemcpyHostToDevice, ctx->stream));
+    for (uint64_t c0 = 0; c0 < n; c0 += chunk) {
+        const uint64_t cn = std::min(chunk, n - c0);
+        int rc = xsi_decode_records(ctx, cn, block_index + c0, line_offset + c0, n_alleles + c0, full.as<int32_t>(), full_stride, 1,
+                                    nullptr, nullptr, 0);
+        if (rc) return rc;
+        // row lengths of the full rows (CURRENT_N_HAPS) were left in the request buffer by the compose kernels
+        const uint32_t* filled_full = d.req.as<uint32_t>() + 3 * cn;
+        CK(cudaMemcpyAsync(ab + a_na, n_alleles + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        int32_t* dst = out_on_device ? out + c0 * out_stride : reinterpret_cast<int32_t*>(ab + a_rows);
+        uint32_t* dac = ac ? reinterpret_cast<uint32_t*>(ab + a_ac) : nullptr;
+        if (dac) CK(cudaMemsetAsync(dac, 0, cn * ac_stride * 4, ctx->stream));
+        if (!out_on_device) CK(cudaMemsetAsync(dst, 0, cn * out_stride * 4, ctx->stream));
+        { PROF("select_samples");
+          select_samples_kernel<<<(uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(
+              full.as<int32_t>(), full_stride, filled_full, reinterpret_cast<const uint32_t*>(ab + a_na), d.n_samples,
+              reinterpret_cast<const uint32_t*>(ab + a_sel), n_sel, dst, out_stride, reinterpret_cast<uint32_t*>(ab + a_fs), dac, ac_stride, (uint32_t)cn); }
+        CKL();
+        if (!out_on_device) CK(cudaMemcpyAsync(out + c0 * out_stride, dst, cn * out_stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (n_filled) CK(cudaMemcpyAsync(n_filled + c0, ab + a_fs, cn * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if (ac) CK(cudaMemcpyAsync(ac + c0 * ac_stride, dac, cn * ac_stride * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+    }
+    return XSI_OK;
+}
+
 extern "C" int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                                         const uint32_t* n_alleles, uint64_t* allele_counts, uint32_t counts_stride) {
     if (!ctx || !block_index || !line_offset || !n_alleles || !allele_counts) return XSI_E_ARG;
