@@ -51,6 +51,11 @@ uint64_t xsi_kernel_launches(const xsi_ctx* ctx);
 int xsi_profile(xsi_ctx* ctx, int on);
 const char* xsi_profile_read(xsi_ctx* ctx);
 
+/* Page-locked host memory (cudaHostAlloc, portable) for bindings that stage rows for xsi_encode_launch or
+ * receive rows from xsi_decode_records*: pinned buffers cross PCIe by DMA without a bounce copy. */
+int  xsi_host_alloc(void** p, uint64_t bytes);
+void xsi_host_free(void* p);
+
 /* ------------------------------------------------------------------------------------------
  * ENCODE  -- replaces GtBlock<A_T,uint16_t>::encode_line + write_to_stream
  *            (include/gt_block.hpp:185-204,279-406), i.e. the IWritableBCFLineEncoder the
@@ -135,6 +140,9 @@ int xsi_decode_records_subset(xsi_ctx* ctx, uint64_t n, const uint32_t* block_in
                               const uint32_t* n_alleles, const uint32_t* samples_to_use, uint32_t n_sel,
                               int32_t* out, uint64_t out_stride, int32_t out_on_device, uint32_t* n_filled,
                               uint32_t* ac, uint32_t ac_stride);
+/* KEY_BCF_LINES / KEY_BINARY_LINES of loaded block `block_index` (gt_block.hpp:466-467): what a reader that
+ * decodes ahead of its caller needs to bound its window (bindings/accessor_internals_b200.hpp). */
+int xsi_decode_block_info(const xsi_ctx* ctx, uint32_t block_index, uint32_t* bcf_lines, uint32_t* binary_lines);
 /* Blocks until everything queued on the context stream is done. */
 int xsi_sync(xsi_ctx* ctx);
 

@@ -121,7 +121,7 @@ struct xsi_ctx {
         uint32_t nb = 0, n_samples = 0, aet = 2, WS = 0, NJ = 0, n_gt_jobs = 0;
         uint64_t Lt = 0;
         std::vector<DecBlock> h_blocks;
-        std::vector<uint32_t> h_bin_lines;
+        std::vector<uint32_t> h_bin_lines, h_bcf_lines;
         DevBuf blob, meta, rows, job_u32, job_hap, tile_u32, dline, lists, err, a_pool, x_pool, req, out, scratch, counts,
             seg_total, tabs;
         PinBuf h_stage, h_meta;
@@ -225,6 +225,17 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
     cudaStreamDestroy(ctx->stream2);
     delete ctx;
 }
+
+// pinned host buffers for bindings that stage rows themselves (bindings/gt_block_b200.hpp, accessor_internals_b200.hpp)
+extern "C" int xsi_host_alloc(void** p, uint64_t bytes) {
+    if (!p) return XSI_E_ARG;
+    *p = nullptr;
+    if (bytes == 0) return XSI_OK;
+    const cudaError_t e = cudaHostAlloc(p, bytes, cudaHostAllocPortable);
+    if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; return e == cudaErrorMemoryAllocation ? XSI_E_NOMEM : XSI_E_CUDA; }
+    return XSI_OK;
+}
+extern "C" void xsi_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" const char* xsi_last_error(const xsi_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" void* xsi_stream(xsi_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -1377,7 +1388,8 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     }
     d.h_blocks.assign(blocks, blocks + n_blocks);
     d.h_bin_lines.resize(n_blocks);
-    for (uint32_t b = 0; b < n_blocks; ++b) d.h_bin_lines[b] = pbs[b].bin_lines;
+    d.h_bcf_lines.resize(n_blocks);
+    for (uint32_t b = 0; b < n_blocks; ++b) { d.h_bin_lines[b] = pbs[b].bin_lines; d.h_bcf_lines[b] = pbs[b].bcf_lines; }
 
     // ---- upload (from the pinned staging area: asynchronous) ----
     // meta: blocks | segs
@@ -1586,6 +1598,13 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
     CK(cudaStreamSynchronize(ctx->stream));
     if (herr) { ctx->err = "malformed WAH / index stream in GT block (device check)"; return XSI_E_FORMAT; }
     d.loaded = true;
+    return XSI_OK;
+}
+
+extern "C" int xsi_decode_block_info(const xsi_ctx* ctx, uint32_t block_index, uint32_t* bcf_lines, uint32_t* binary_lines) {
+    if (!ctx || !ctx->dec.loaded || block_index >= ctx->dec.nb) return XSI_E_ARG;
+    if (bcf_lines) *bcf_lines = ctx->dec.h_bcf_lines[block_index];
+    if (binary_lines) *binary_lines = ctx->dec.h_bin_lines[block_index];
     return XSI_OK;
 }
 
