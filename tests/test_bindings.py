@@ -182,3 +182,20 @@ def test_reference_c_api_test_program(tmp_path):
     run([CLI, "-c", "-f", os.path.join(INP, "chr20_small.bcf"), "-o", out])
     p = run([os.path.join(OUT, "c_api_test_b200"), out + "_var.bcf"])
     assert b"is 2504" in p.stdout and b"21892 records" in p.stdout, p.stdout
+
+
+@pytest.mark.gpu
+@needs_bindings
+@pytest.mark.parametrize("name", ["chr20_small", "chr20_small_zstd_b1024", "micro_missing_non_uniform_phasing_ploidy", "micro_haploid",
+                                  "micro_mixed_ploidy", "test_region_target"])
+def test_bcf_ingest_tool(tmp_path, name):
+    """bindings/xsi_b200_bcf.cpp (threaded BGZF, raw int8 FORMAT/GT rows, several blocks per launch): the same file pair
+    as the reference CLI, byte for byte (zstd runs: same decoded records)"""
+    case = CLIMAN[name]
+    out = str(tmp_path / "i.xsi")
+    argv = [a for a in case["compress_argv"] if a != "-c"]
+    run([os.path.join(OUT, "xsi_b200_bcf"), "compress", os.path.join(INP, case["input"]), out, "--threads", "4", "--batch-blocks", "2"] + argv)
+    if "xsi_sha256" in case:
+        assert sha(open(out, "rb").read()) == case["xsi_sha256"]
+    line = run([CAPI, out + "_var.bcf"]).stdout.decode().split()
+    assert {"records": int(line[1]), "genotypes": int(line[3]), "checksum": line[7]} == case["capi_decode"]
