@@ -13,10 +13,20 @@
 //  * BGZF inflate runs on a thread pool (hts_set_threads);
 //  * K whole blocks go to the device per launch (their PBWT chains run side by side), and the encode of batch i runs
 //    on its own thread while the reader fills batch i+1.
-// What is kept from the reference's host side, called from its own objects (nothing copied): seek_default_phased and
-// seek_max_ploidy_from_first_entry (xcf.cpp:811-862), and the `_var.bcf` companion writer + CSI index
-// (replace_samples_by_pos_in_binary_matrix xcf.cpp:641-714, create_index_file xcf.cpp:39-57) on a second thread exactly as
-// xsqueezeit.cpp:119-128 runs it.
+//  * ONE pass over the input: the reference opens and parses it eight times (two checks, a sample count, the default-phase
+//    and ploidy pre-scans twice, the traversal, and the `_var.bcf` thread; each open parses a header with one dictionary
+//    entry per sample, 0.45 s at 32,488 samples).  Here the default phase (xcf.cpp:811-836), the first record's ploidy
+//    (xcf.cpp:838-862) and the `_var.bcf` companion (xcf.cpp:641-714: samples replaced by the pseudo-sample
+//    BIN_MATRIX_POS with FORMAT/BM = block<<15 | binary line offset) all come from the records the reader holds anyway;
+//    the companion is byte-identical to the reference's (tests/test_bindings.py).  --reference-var runs the reference's
+//    own function on a second thread instead (xsqueezeit.cpp:119-128).
+// The CSI index of the companion is built by the reference's create_index_file (xcf.cpp:39-57).
+//
+//   xsi_b200_bcf extract <in.xsi> <out.bcf> [-O b|u] [--threads T] [--window-bytes N] [--device D]
+// is the matching egress (`xsqueezeit -x`, gt_decompressor_new.hpp:109-206,275-320): records of the companion are read,
+// their rows decoded on the device as raw BCF int8 FORMAT/GT payload (xsi_decode_records_i8) in windows, and spliced into
+// the records as the typed vector bcf_update_genotypes would have built, so the CPU neither widens to int32 nor narrows
+// back (bcf_enc_vint); BGZF deflate of the output runs on the thread pool.  The output equals the reference's byte for byte.
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -28,6 +38,8 @@
 #include <string>
 #include <thread>
 #include <vector>
+
+#include <libgen.h>
 
 #include "xcf.hpp"  // reference host helpers (declarations only; objects come from oracle/_ref/obj)
 
@@ -55,7 +67,7 @@ struct Exchange {
     std::mutex m;
     std::condition_variable cv;
     Batch b[2];
-    int state[2] = {0, 0};  // 0 = free (reader owns), 1 = full (encoder owns)
+    int state[2] = {0, 2};  // 0 = free (reader owns), 1 = full (encoder owns), 2 = being allocated by the encoder thread
     std::string error;
 };
 
@@ -63,8 +75,10 @@ struct Options {
     std::string in, out;
     double maf = 0.001;
     size_t block_len = 8192;
-    bool zstd = false, wah_missing = false;
-    int zstd_level = 7, threads = 8, batch_blocks = 4, device = 0;
+    bool zstd = false, wah_missing = false, reference_var = false;
+    int zstd_level = 7, threads = 8, batch_blocks = 2, device = 0;
+    std::string output_type = "b";
+    size_t window_bytes = (size_t)64 << 20;
 };
 
 void widen_batch(Batch& b) {  // a record without an int8 GT payload arrived: the batch moves int32 from here on
@@ -81,39 +95,99 @@ void widen_batch(Batch& b) {  // a record without an int8 GT payload arrived: th
     b.elem_bytes = 4;
 }
 
+// the companion `_var.bcf`, written from the records of the one reader (what xcf.cpp:641-714 does in its own pass)
+struct VarWriter {
+    htsFile* fp = nullptr;
+    bcf_hdr_t* hdr = nullptr;
+    bcf1_t* v = nullptr;
+    size_t line = 0, block_len = 0;
+    int32_t offset = 0, block = 0;
+    bool open(const bcf_hdr_t* in_hdr, const std::string& path, const std::string& xsi_name, size_t bl, int threads) {
+        block_len = bl;
+        fp = hts_open(path.c_str(), "wz");  // bgzipped VCF text, xcf.cpp:647
+        if (!fp) return false;
+        if (threads > 1) hts_set_threads(fp, threads);
+        bcf_hdr_t* h0 = bcf_hdr_dup(in_hdr);
+        if (bcf_hdr_set_samples(h0, NULL, 0) < 0) return false;  // xcf.cpp:650
+        hdr = bcf_hdr_dup(h0);
+        bcf_hdr_destroy(h0);
+        bcf_hdr_add_sample(hdr, "BIN_MATRIX_POS");
+        bcf_hdr_append(hdr, "##FORMAT=<ID=BM,Number=1,Type=Integer,Description=\"Position in GT Binary Matrix\">");
+        std::string tmp(xsi_name);
+        bcf_hdr_append(hdr, std::string("##XSI=").append(std::string(basename((char*)tmp.c_str()))).c_str());
+        if (bcf_hdr_sync(hdr) < 0) fprintf(stderr, "bcf_hdr_sync() failed ... oh well\n");
+        v = bcf_init();
+        return bcf_hdr_write(fp, hdr) >= 0;
+    }
+    // rec: the full record as read; only its shared part (CHROM..INFO) is carried over
+    bool add(const bcf1_t* rec) {
+        bcf_clear(v);
+        v->rid = rec->rid; v->pos = rec->pos; v->rlen = rec->rlen; v->qual = rec->qual;
+        v->n_info = rec->n_info; v->n_allele = rec->n_allele; v->n_fmt = 0; v->n_sample = 0;
+        if (ks_resize(&v->shared, rec->shared.l ? rec->shared.l : 1) != 0) return false;
+        v->shared.l = rec->shared.l;
+        memcpy(v->shared.s, rec->shared.s, rec->shared.l);
+        v->indiv.l = 0;
+        bcf_unpack(v, BCF_UN_STR);
+        v->n_sample = 1;
+        if (line && (line % block_len) == 0) { block++; offset = 0; }
+        if (offset >> 15) throw "Variant BCF generation error, BM bits";  // xcf.cpp:691-694
+        int32_t bm = block << 15 | offset;
+        bcf_update_format_int32(hdr, v, "BM", &bm, 1);
+        if (bcf_write1(fp, hdr, v) < 0) return false;
+        if (rec->n_allele) offset += rec->n_allele - 1;
+        line++;
+        return true;
+    }
+    bool close() {
+        bool ok = true;
+        if (fp) ok = hts_close(fp) >= 0;
+        if (hdr) bcf_hdr_destroy(hdr);
+        if (v) bcf_destroy(v);
+        fp = nullptr; hdr = nullptr; v = nullptr;
+        return ok;
+    }
+};
+
 int compress(const Options& o) {
     const double t0 = now();
-    // file-level parameters exactly as GtCompressorStream::compress_to_file finds them (gt_compressor_new.hpp:84-109)
-    const int32_t default_phased = seek_default_phased(o.in);
-    const size_t first_ploidy = seek_max_ploidy_from_first_entry(o.in);
     bool fail = false;
-    std::thread variant_thread([&] {  // xsqueezeit.cpp:119-128
-        try {
-            replace_samples_by_pos_in_binary_matrix(o.in, o.out + "_var.bcf", o.out, true, o.block_len);
-        } catch (const char* e) {
-            fprintf(stderr, "%s\n", e);
-            fail = true;
-        }
-        create_index_file(o.out + "_var.bcf");
-    });
+    std::thread variant_thread;
+    if (o.reference_var)
+        variant_thread = std::thread([&] {  // xsqueezeit.cpp:119-128
+            try {
+                replace_samples_by_pos_in_binary_matrix(o.in, o.out + "_var.bcf", o.out, true, o.block_len);
+            } catch (const char* e) {
+                fprintf(stderr, "%s\n", e);
+                fail = true;
+            }
+            create_index_file(o.out + "_var.bcf");
+        });
+    auto join_var = [&] { if (variant_thread.joinable()) variant_thread.join(); };
 
     htsFile* fp = hts_open(o.in.c_str(), "r");
-    if (!fp) { fprintf(stderr, "Failed to open file %s\n", o.in.c_str()); variant_thread.join(); return 1; }
+    if (!fp) { fprintf(stderr, "Failed to open file %s\n", o.in.c_str()); join_var(); return 1; }
     if (o.threads > 1) hts_set_threads(fp, o.threads);
     bcf_hdr_t* hdr = bcf_hdr_read(fp);
-    if (!hdr) { fprintf(stderr, "Failed to read the header of %s\n", o.in.c_str()); variant_thread.join(); return 1; }
+    if (!hdr) { fprintf(stderr, "Failed to read the header of %s\n", o.in.c_str()); join_var(); return 1; }
     const size_t S = (size_t)bcf_hdr_nsamples(hdr);
+    if (S == 0) { fprintf(stderr, "The file %s has no samples\n", o.in.c_str()); join_var(); return 1; }  // xsqueezeit.cpp:111
     std::string names;
     for (size_t i = 0; i < S; ++i) { names += hdr->samples[i]; names.push_back('\0'); }
-    const uint64_t mac = (uint64_t)((double)(S * first_ploidy) * o.maf);  // gt_compressor_new.hpp:98-99
-
+    VarWriter var;
+    if (!o.reference_var && !var.open(hdr, o.out + "_var.bcf", o.out, o.block_len, std::max(1, o.threads / 4))) {
+        fprintf(stderr, "Failed to write header to file %s_var.bcf\n", o.out.c_str());
+        return 1;
+    }
+    // file-level parameters: found from the first records (below), needed when the first batch is handed over
+    int32_t default_phased = 1;
+    size_t first_ploidy = 0;
+    uint64_t mac = 0;
     xsi_writer* w = nullptr;
-    int rc = xsi_writer_open(o.out.c_str(), (uint32_t)S, names.data(), (uint32_t)o.block_len, mac, default_phased, o.zstd ? 1 : 0,
-                             o.zstd_level, &w);
-    if (rc != XSI_OK) { fprintf(stderr, "Failed to open file %s (rc %d)\n", o.out.c_str(), rc); variant_thread.join(); return 1; }
+    int rc = XSI_OK;
 
     Exchange ex;
-    int max_ploidy = (int)first_ploidy;
+    int max_ploidy = 0;
     uint64_t records = 0, genotypes = 0;
     double t_encode = 0;
     std::thread encoder([&] {
@@ -125,6 +199,17 @@ int compress(const Options& o) {
             ex.cv.notify_all();
             return;
         }
+        try {
+            ex.b[1].rows.reserve(o.block_len * (size_t)o.batch_blocks * S * 2);
+        } catch (const char*) {
+            std::lock_guard<std::mutex> l(ex.m);
+            ex.error = "pinned allocation failed";
+        }
+        {
+            std::lock_guard<std::mutex> l(ex.m);
+            ex.state[1] = 0;
+        }
+        ex.cv.notify_all();
         for (int k = 0;; k ^= 1) {
             {
                 std::unique_lock<std::mutex> l(ex.m);
@@ -180,6 +265,9 @@ int compress(const Options& o) {
     int k = 0;
     bool eof = false, err = false;
     const int gt_id = bcf_hdr_id2int(hdr, BCF_DT_ID, "GT");
+    size_t phase_counts[2] = {0, 0};
+    bool phase_known = false;
+    ex.b[0].rows.reserve(batch_records * S * 2);  // one allocation per batch buffer (int8, diploid); the encoder thread prepares the other
     while (!eof && !err) {
         {
             std::unique_lock<std::mutex> l(ex.m);
@@ -208,6 +296,13 @@ int compress(const Options& o) {
                 if (n != (int)ngt) { fprintf(stderr, "bcf_get_genotypes failed\n"); err = true; break; }
                 memcpy(b.rows.as<int32_t>() + b.n_elems, gt32, ngt * 4);
             }
+            if (records < 3 && !phase_known) {  // seek_default_phased, xcf.cpp:811-836: phase bit of every sample's 2nd allele
+                if (pl == 1) { default_phased = 0; phase_known = true; }
+                else for (size_t i = 0; i < S; ++i)
+                    phase_counts[(b.elem_bytes == 1 ? (int)b.rows.as<int8_t>()[b.n_elems + i * pl + 1] : b.rows.as<int32_t>()[b.n_elems + i * pl + 1]) & 1]++;
+            }
+            if (records == 0) first_ploidy = pl;  // seek_max_ploidy_from_first_entry, xcf.cpp:838-862
+            if (!o.reference_var && !var.add(rec)) { fprintf(stderr, "Failed to write the variant file\n"); err = true; break; }
             b.n_elems += ngt;
             b.n_allele.push_back((uint32_t)rec->n_allele);
             b.ploidy.push_back((uint8_t)pl);
@@ -216,6 +311,15 @@ int compress(const Options& o) {
             genotypes += ngt;
         }
         b.last = eof || err;
+        if (!w && !err) {  // first batch complete (at least 3 records unless the file is shorter): the file-level parameters are known
+            if (records == 0) { fprintf(stderr, "The file %s has no entries\n", o.in.c_str()); err = true; b.last = true; }  // xsqueezeit.cpp:114
+            if (!phase_known) default_phased = phase_counts[0] > phase_counts[1] ? 0 : 1;
+            mac = (uint64_t)((double)(S * first_ploidy) * o.maf);  // gt_compressor_new.hpp:98-99
+            max_ploidy = (int)first_ploidy;
+            rc = xsi_writer_open(o.out.c_str(), (uint32_t)S, names.data(), (uint32_t)o.block_len, mac, default_phased, o.zstd ? 1 : 0,
+                                 o.zstd_level, &w);
+            if (rc != XSI_OK) { fprintf(stderr, "Failed to open file %s (rc %d)\n", o.out.c_str(), rc); err = true; b.last = true; b.n_allele.clear(); }
+        }
         {
             std::lock_guard<std::mutex> l(ex.m);
             ex.state[k] = 1;
@@ -230,10 +334,16 @@ int compress(const Options& o) {
     bcf_hdr_destroy(hdr);
     hts_close(fp);
     if (!ex.error.empty()) { fprintf(stderr, "%s\n", ex.error.c_str()); err = true; }
-    rc = xsi_writer_close(w, max_ploidy);
-    if (rc != XSI_OK) { fprintf(stderr, "finalize failed (rc %d)\n", rc); err = true; }
+    if (w) {
+        rc = xsi_writer_close(w, max_ploidy);
+        if (rc != XSI_OK) { fprintf(stderr, "finalize failed (rc %d)\n", rc); err = true; }
+    }
     const double t_gt = now();
-    variant_thread.join();
+    if (!o.reference_var) {
+        if (!var.close()) { fprintf(stderr, "Failed to close the variant file\n"); err = true; }
+        if (!err) create_index_file(o.out + "_var.bcf");
+    }
+    join_var();
     const double t1 = now();
     if (fail || err) { fprintf(stderr, "Failure occurred, exiting...\n"); return 1; }
     printf("xsi_b200_bcf compress: records %llu genotypes %llu seconds %.6f gt_path_seconds %.6f encode_thread_seconds %.6f "
@@ -242,10 +352,148 @@ int compress(const Options& o) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// extract: `xsqueezeit -x` (gt_decompressor_new.hpp:109-206) with the rows spliced in as raw int8 FORMAT/GT payload
+// ------------------------------------------------------------------------------------------------------------------
+int extract(const Options& o) {
+    const double t0 = now();
+    xsi_reader* rd = nullptr;
+    int rc = xsi_reader_open(o.in.c_str(), &rd);
+    if (rc != XSI_OK) { fprintf(stderr, "Failed to open file %s (rc %d)\n", o.in.c_str(), rc); return 1; }
+    uint64_t S = 0, hap = 0, entries = 0, nvar = 0, rare = 0;
+    uint32_t ploidy = 0, aet = 0, nblocks = 0, block_len = 0;
+    int32_t zstd = 0, dph = 0;
+    xsi_reader_info(rd, &S, &hap, &ploidy, &aet, &nblocks, &block_len, &entries, &nvar, &zstd, &rare, &dph);
+    const std::string var_name = o.in + "_var.bcf";
+    htsFile* vin = hts_open(var_name.c_str(), "r");
+    if (!vin) { fprintf(stderr, "Failed to open file %s\n", var_name.c_str()); return 1; }
+    if (o.threads > 1) hts_set_threads(vin, 2);
+    bcf_hdr_t* hin = bcf_hdr_read(vin);
+    if (!hin) { fprintf(stderr, "Failed to read the header of %s\n", var_name.c_str()); return 1; }
+    // output header: create_output_file, gt_decompressor_new.hpp:471-530
+    bcf_hdr_t* hout = bcf_hdr_dup(hin);
+    bcf_hdr_remove(hout, BCF_HL_GEN, "XSI");
+    bcf_hdr_remove(hout, BCF_HL_FMT, "BM");
+    if (bcf_hdr_set_samples(hout, NULL, 0) < 0) { fprintf(stderr, "Failed to remove samples\n"); return 1; }
+    for (uint64_t i = 0; i < S; ++i) bcf_hdr_add_sample(hout, xsi_reader_sample_name(rd, i));
+    bcf_hdr_add_sample(hout, NULL);
+    if (bcf_hdr_sync(hout) < 0) fprintf(stderr, "bcf_hdr_sync() failed ...\n");
+    const char* flags = o.output_type == "u" ? "wbu" : "wb";  // gt_decompressor_new.hpp:439-447
+    htsFile* fout = hts_open(o.out.c_str(), flags);
+    if (!fout) { fprintf(stderr, "Could not open %s\n", o.out.c_str()); return 1; }
+    if (o.threads > 1) hts_set_threads(fout, o.threads);
+    if (bcf_hdr_write(fout, hout) < 0) { fprintf(stderr, "Could not write header to file %s\n", o.out.c_str()); return 1; }
+    const int gt_id = bcf_hdr_id2int(hout, BCF_DT_ID, "GT");
+    if (gt_id < 0) { fprintf(stderr, "no GT FORMAT in the header\n"); return 1; }
+
+    xsi_ctx* ctx = nullptr;
+    rc = xsi_create(o.device, &ctx);
+    if (rc != XSI_OK) { fprintf(stderr, "xsi_create failed (no CUDA device? there is no CPU fallback)\n"); return 1; }
+    const size_t N = (size_t)S * 2, stride8 = (N + 15) / 16 * 16;
+    const size_t win_rows = std::max<size_t>(1, o.window_bytes / stride8);
+    xsi_b200::Pinned win;
+    win.reserve(win_rows * stride8);
+    std::vector<bcf1_t*> recs(win_rows, nullptr);
+    for (auto& r : recs) r = bcf_init();
+    std::vector<uint32_t> blk(win_rows, 0), line(win_rows), nall(win_rows), filled(win_rows);
+    std::vector<int32_t> wide;  // only for records with more than 63 alleles
+    int32_t* bm = nullptr;
+    int n_bm = 0;
+    int64_t loaded = -1;
+    uint64_t records = 0, genotypes = 0;
+    bool eof = false, err = false;
+    bcf1_t* pending = bcf_init();  // a record of the NEXT block, read while filling a window, opens the next window
+    bool have_pending = false;
+    while (!err && (!eof || have_pending)) {
+        size_t n = 0;
+        int64_t want = -1;
+        while (n < win_rows) {
+            bcf1_t* rec = recs[n];
+            if (have_pending) { std::swap(recs[n], pending); rec = recs[n]; have_pending = false; }
+            else {
+                if (eof) break;
+                const int rr = bcf_read(vin, hin, rec);
+                if (rr < -1) { fprintf(stderr, "read error in %s\n", var_name.c_str()); err = true; break; }
+                if (rr < 0) { eof = true; break; }
+            }
+            // Accessor::position_from_bm_entry, accessor.hpp:37-46
+            if (bcf_unpack(rec, BCF_UN_ALL)) fprintf(stderr, "bcf_unpack error\n");
+            if (bcf_get_format_int32(hin, rec, "BM", &bm, &n_bm) < 1) { fprintf(stderr, "BM key value not found\n"); err = true; break; }
+            const uint32_t pos = (uint32_t)bm[0];
+            const int64_t b = pos >> 15;
+            if (want < 0) want = b;
+            if (b != want) { std::swap(recs[n], pending); have_pending = true; break; }
+            line[n] = pos & 0x7FFF;
+            nall[n] = rec->n_allele;
+            ++n;
+        }
+        if (err || n == 0) break;
+        if (want != loaded) {
+            const uint8_t* p = nullptr;
+            uint64_t sz = 0;
+            rc = xsi_reader_gt_block(rd, (uint32_t)want, &p, &sz);
+            if (rc == XSI_OK) rc = xsi_decode_load_blocks(ctx, 1, &p, &sz, S, (int32_t)aet);
+            if (rc != XSI_OK) { fprintf(stderr, "block %lld: %s (rc %d)\n", (long long)want, xsi_last_error(ctx), rc); err = true; break; }
+            loaded = want;
+        }
+        bool all_i8 = true;
+        for (size_t i = 0; i < n; ++i) all_i8 &= nall[i] >= 2 && nall[i] <= 63;
+        if (all_i8) {
+            rc = xsi_decode_records_i8(ctx, n, blk.data(), line.data(), nall.data(), win.as<int8_t>(), stride8, 0, filled.data(), nullptr, 0);
+            if (rc != XSI_OK) { fprintf(stderr, "decode: %s (rc %d)\n", xsi_last_error(ctx), rc); err = true; break; }
+        }
+        for (size_t i = 0; i < n && !err; ++i) {
+            bcf1_t* rec = recs[i];
+            if (all_i8) {
+                // the record leaves with ONE FORMAT field: [typed int key = GT][type: ploidy x int8][S * ploidy bytes], i.e. what
+                // bcf_update_format(BM, NULL) + bcf_update_genotypes + bcf1_sync build (gt_decompressor_new.hpp:275-320)
+                const uint32_t len = filled[i], pl = (uint32_t)(len / S);
+                if (pl == 0 || pl > 2) { fprintf(stderr, "PLOIDY ERROR\n"); err = true; break; }
+                rec->indiv.l = 0;
+                bcf_enc_int1(&rec->indiv, gt_id);
+                bcf_enc_size(&rec->indiv, (int)pl, BCF_BT_INT8);
+                if (ks_resize(&rec->indiv, rec->indiv.l + len) != 0) { err = true; break; }
+                memcpy(rec->indiv.s + rec->indiv.l, win.as<int8_t>() + i * stride8, len);
+                rec->indiv.l += len;
+                rec->n_fmt = 1;
+                rec->n_sample = (uint32_t)S;
+                rec->d.indiv_dirty = 0;
+                rec->unpacked &= ~BCF_UN_FMT;  // d.fmt[] described the BM field that is gone
+                genotypes += len;
+            } else {  // wide alleles: the reference's own way
+                wide.resize(N);
+                uint32_t f = 0;
+                rc = xsi_decode_records(ctx, 1, &blk[i], &line[i], &nall[i], wide.data(), N, 0, &f, nullptr, 0);
+                if (rc != XSI_OK) { fprintf(stderr, "decode: %s (rc %d)\n", xsi_last_error(ctx), rc); err = true; break; }
+                bcf_update_format(hin, rec, "BM", NULL, 0, BCF_HT_INT);
+                if (bcf_update_genotypes(hout, rec, wide.data(), (int)f)) { fprintf(stderr, "Failed to update genotypes\n"); err = true; break; }
+                genotypes += f;
+            }
+            if (bcf_write1(fout, hout, rec)) { fprintf(stderr, "Failed to write record\n"); err = true; break; }
+            ++records;
+        }
+    }
+    free(bm);
+    bcf_destroy(pending);
+    for (auto& r : recs) bcf_destroy(r);
+    xsi_destroy(ctx);
+    if (hts_close(fout) < 0) err = true;
+    hts_close(vin);
+    bcf_hdr_destroy(hin);
+    bcf_hdr_destroy(hout);
+    xsi_reader_close(rd);
+    if (err) { fprintf(stderr, "Failure occurred, exiting...\n"); return 1; }
+    printf("xsi_b200_bcf extract: records %llu genotypes %llu seconds %.6f threads %d\n", (unsigned long long)records,
+           (unsigned long long)genotypes, now() - t0, o.threads);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
-    if (argc < 4 || std::string(argv[1]) != "compress") {
+    const std::string cmd = argc > 1 ? argv[1] : "";
+    if (argc < 4 || (cmd != "compress" && cmd != "extract")) {
+        fprintf(stderr, "usage: %s extract in.xsi out.bcf [-O b|u] [--threads t] [--window-bytes n] [--device d]\n", argv[0]);
         fprintf(stderr, "usage: %s compress in.bcf out.xsi [--maf f] [--variant-block-length n] [--zstd] [--zstd-level l]\n"
                         "          [--wah-encode-missing] [--threads t] [--batch-blocks k] [--device d]\n", argv[0]);
         return 2;
@@ -264,11 +512,14 @@ int main(int argc, char** argv) {
         else if (a == "--threads") o.threads = atoi(val());
         else if (a == "--batch-blocks") o.batch_blocks = atoi(val());
         else if (a == "--device") o.device = atoi(val());
+        else if (a == "--reference-var") o.reference_var = true;
+        else if (a == "-O" || a == "--output-type") o.output_type = val();
+        else if (a == "--window-bytes") o.window_bytes = (size_t)atoll(val());
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     if (o.block_len == 0 || o.batch_blocks < 1) return 2;
     try {
-        return compress(o);
+        return cmd == "compress" ? compress(o) : extract(o);
     } catch (const char* e) {
         fprintf(stderr, "%s\nFailure occurred, exiting...\n", e);
         return 1;

@@ -85,6 +85,11 @@ def main():
             entry = {"input": src, "compress_argv": c_argv, "extract_argv": xopts, "xsi_size": os.path.getsize(xsi)}
             if "--zstd" not in copts:  # zstd frames depend on the libzstd build; compare by content there
                 entry["xsi_sha256"] = sha(open(xsi, "rb").read())
+            entry["var_sha256"] = sha(open(xsi + "_var.bcf", "rb").read())  # companion (holds ##XSI=<basename>: tests keep the name)
+            if not xopts:
+                bcf = os.path.join(tmp, name + "_x.bcf")
+                run([CLI, "-x", "-f", xsi, "-o", bcf])
+                entry["x_bcf_sha256"] = sha(open(bcf, "rb").read())
             if "x" in xopts:  # -Ox writes a new .xsi + _var.bcf pair: record that file and its decoded content
                 out = os.path.join(tmp, name + "_out.xsi")
                 run([CLI, "-x"] + xopts + ["-f", xsi, "-o", out])
