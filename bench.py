@@ -172,9 +172,9 @@ def ref_worker(args):
     torch.set_num_threads(1)
     import xsi_ref
     S, R = args.samples, args.ref_records
-    gt = torch.empty((R, 2 * S), dtype=torch.int32)
-    HrcSynth(S, 9000 + args.ref_worker, "cpu").fill(gt, chunk=64)
-    g = gt.numpy().reshape(-1)
+    # every worker maps the SAME rows (one full PBWT block by default), generated once by the parent into /dev/shm:
+    # identical, deterministic work per core without a private 2 GB copy each
+    g = np.memmap(args.ref_data, dtype=np.int32, mode="r", shape=(R * 2 * S,))
     ngt = np.full(R, 2 * S, np.int32)
     nal = np.full(R, 2, np.int32)
     off = (np.arange(R, dtype=np.uint64) * np.uint64(2 * S))
@@ -182,7 +182,8 @@ def ref_worker(args):
     tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
     path = os.path.join(tmpdir, "xsi_ref_bench_%d_%d.xsi" % (os.getpid(), args.ref_worker))
     out = np.empty(2 * S, np.int32)
-    pos = np.arange(R, dtype=np.uint64)  # one block (R <= block length): BM = line offset
+    rr = np.arange(R, dtype=np.uint64)
+    pos = ((rr // np.uint64(BLOCK_LEN)) << np.uint64(15)) | (rr % np.uint64(BLOCK_LEN))  # bi-allelic: BM = block<<15 | line
     print("ready", flush=True)
     for line in sys.stdin:
         if line.strip() != "go":
@@ -197,7 +198,7 @@ def ref_worker(args):
             chk += n
         acc.close()
         t2 = time.perf_counter()
-        ok = bool(chk == R * 2 * S and np.array_equal(out, g[(R - 1) * 2 * S:]))
+        ok = bool(chk == R * 2 * S and np.array_equal(out, np.asarray(g[(R - 1) * 2 * S:])))
         print(json.dumps({"enc_s": t1 - t0, "dec_s": t2 - t1, "ok": ok, "xsi_bytes": os.path.getsize(path)}), flush=True)
     try:
         os.unlink(path)
@@ -205,14 +206,34 @@ def ref_worker(args):
         pass
 
 
+def ref_sample_file(samples, records):
+    """One sample of the workload (HrcSynth, the generator of the GPU arm, seed 9000) as raw int32 rows in /dev/shm."""
+    import torch
+    tmpdir = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    path = os.path.join(tmpdir, "xsi_ref_rows_%d.i32" % os.getpid())
+    dev = "cuda" if torch.cuda.is_available() else "cpu"
+    gen = HrcSynth(samples, 9000, dev)
+    mm = np.memmap(path, dtype=np.int32, mode="w+", shape=(records, 2 * samples))
+    step = 512
+    buf = torch.empty((step, 2 * samples), dtype=torch.int32, device=dev)
+    for r0 in range(0, records, step):
+        n = min(step, records - r0)
+        gen.fill(buf[:n], chunk=256 if dev == "cuda" else 64)
+        mm[r0:r0 + n] = buf[:n].cpu().numpy()
+    mm.flush()
+    del mm
+    return path
+
+
 class RefPool:
     def __init__(self, samples, records, workers):
         self.samples, self.records = samples, records
         self.procs = []
+        self.data = ref_sample_file(samples, records)
         for w in range(workers):
             self.procs.append(subprocess.Popen(
                 [sys.executable, os.path.abspath(__file__), "--ref-worker", str(w), "--samples", str(samples),
-                 "--ref-records", str(records)], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1))
+                 "--ref-records", str(records), "--ref-data", self.data], stdin=subprocess.PIPE, stdout=subprocess.PIPE, text=True, bufsize=1))
         for p in self.procs:
             line = p.stdout.readline()
             if line.strip() != "ready":
@@ -238,6 +259,10 @@ class RefPool:
                 pass
         for p in self.procs:
             p.wait(timeout=60)
+        try:
+            os.unlink(self.data)
+        except OSError:
+            pass
 
 
 def usable_cores():
@@ -254,8 +279,8 @@ def run_reference(args, steps, warmup, label_impl=True):
         return None
     import psutil
     S, R = args.samples, args.ref_records
-    per_worker = R * 2 * S * 4 * 1.6 + 600e6
-    workers = int(max(1, min(usable_cores(), psutil.virtual_memory().available * 0.6 // per_worker)))
+    per_worker = 900e6  # the rows are shared (one mapping); a worker holds the reference's block state and one output row
+    workers = int(max(1, min(usable_cores(), (psutil.virtual_memory().available * 0.6 - R * 2 * S * 4) // per_worker)))
     if args.ref_workers:
         workers = args.ref_workers
     pool = RefPool(S, R, workers)
@@ -272,9 +297,116 @@ def run_reference(args, steps, warmup, label_impl=True):
     t = float(np.sum(walls))
     return {"value": 2 * G * steps / t / 1e9, "compress": G * steps / float(np.sum(encs)) / 1e9,
             "decompress": G * steps / float(np.sum(decs)) / 1e9, "ms_per_step": t / steps * 1e3, "cores": workers,
-            "ok": all(oks), "sample": "%d worker processes x %d HRC-shaped records (%d haplotypes, one partial PBWT block each), "
-            "reference XsiFactoryExt encode to /dev/shm + Accessor decode of every record" % (workers, R, 2 * S),
+            "ok": all(oks), "sample": "%d worker processes (one per host core) x %d HRC-shaped records (%d haplotypes, %s of %d records each; "
+            "every worker maps the same rows), unmodified reference XsiFactoryExt encode to /dev/shm + Accessor decode of every record"
+            % (workers, R, 2 * S, "%d full PBWT block(s)" % (R // BLOCK_LEN) if R % BLOCK_LEN == 0 else "a partial PBWT block", BLOCK_LEN),
             "genotypes_per_step": G}
+
+
+# ------------------------------------------------------------------------------------------------
+# BCF legs: one synthetic BCF written once with htslib, fed to both implementations
+# ------------------------------------------------------------------------------------------------
+BIND = os.path.join(ROOT, "bindings", "_out")
+REFBIN = os.path.join(ROOT, "oracle", "_ref")
+
+
+def _run_timed(argv, env=None):
+    t0 = time.perf_counter()
+    p = subprocess.run(argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    dt = time.perf_counter() - t0
+    if p.returncode != 0:
+        raise RuntimeError("%s failed (%d): %s" % (" ".join(argv), p.returncode, p.stderr.decode()[-400:]))
+    return dt, p.stdout.decode()
+
+
+def _sha(path):
+    import hashlib
+    h = hashlib.sha256()
+    with open(path, "rb") as f:
+        for chunk in iter(lambda: f.read(1 << 24), b""):
+            h.update(chunk)
+    return h.hexdigest()
+
+
+def bcf_legs(samples, records, which, threads):
+    """BCF file -> .xsi + _var.bcf -> rows / BCF, whole processes timed by wall clock (start-up, CUDA init, file I/O on
+    /dev/shm all inside).  which: 'b200', 'reference' or 'both'.  The reference programs are the unmodified reference
+    (oracle/_ref/xsqueezeit_ref; bindings/_out/capi_decode_ref = its c_api.h loop); the B200 programs are
+    bindings/_out/xsi_b200_bcf (ingest / egress around the C ABI), xsqueezeit_b200 (the reference CLI with the two
+    adapters) and capi_decode_b200 (c_api.h on the GPU Accessor)."""
+    need = [os.path.join(BIND, "synth_bcf")]
+    if which in ("b200", "both"):
+        need += [os.path.join(BIND, x) for x in ("xsi_b200_bcf", "xsqueezeit_b200", "capi_decode_b200")]
+    if which in ("reference", "both"):
+        need += [os.path.join(REFBIN, "xsqueezeit_ref"), os.path.join(BIND, "capi_decode_ref")]
+    missing = [x for x in need if not os.path.exists(x)]
+    if missing:
+        return {"unavailable": "not built: " + ", ".join(os.path.relpath(x, ROOT) for x in missing)}
+    import shutil
+    import tempfile
+    G = records * 2 * samples
+    tmp = tempfile.mkdtemp(prefix="xsi_bcf_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    out = {"workload": "HRC-shaped synthetic BCF: %d samples x %d records (%d PBWT blocks), bindings/synth_bcf.cpp seed 1002 "
+                       "(log-uniform allele frequency, haplotype-copying LD), bgzf-compressed, in /dev/shm" % (samples, records, -(-records // BLOCK_LEN)),
+           "genotypes": G, "unit": "Ggt/s", "timing": "wall clock of whole processes", "host_cores": usable_cores()}
+    try:
+        src = os.path.join(tmp, "in.bcf")
+        _run_timed([os.path.join(BIND, "synth_bcf"), src, "hrc", str(samples), str(records), "1002", str(threads)])
+        out["bcf_bytes"] = os.path.getsize(src)
+        env_nosum = dict(os.environ, XSI_CAPI_NO_CHECKSUM="1")
+
+        def ggts(t):
+            return G / t / 1e9
+
+        ref = None
+        if which in ("reference", "both"):
+            rx = os.path.join(tmp, "ref", "d.xsi")
+            os.makedirs(os.path.dirname(rx))
+            tc, _ = _run_timed([os.path.join(REFBIN, "xsqueezeit_ref"), "-c", "-f", src, "-o", rx])
+            td, so = _run_timed([os.path.join(BIND, "capi_decode_ref"), rx + "_var.bcf"], env=env_nosum)
+            tdl = float(so.split()[5])
+            _, so = _run_timed([os.path.join(BIND, "capi_decode_ref"), rx + "_var.bcf"])
+            ref_sum = so.split()[7]
+            tx, _ = _run_timed([os.path.join(REFBIN, "xsqueezeit_ref"), "-x", "-f", rx, "-o", os.path.join(tmp, "ref", "o.bcf")])
+            ref = {"compress": {"ggts": ggts(tc), "seconds": tc, "program": "xsqueezeit -c (as shipped: one encode thread + one _var.bcf thread)"},
+                   "decode_c_api": {"ggts": ggts(td), "seconds": td, "loop_seconds": tdl, "program": "c_xcf_get_genotypes per record (c_api.h), 1 thread"},
+                   "extract_bcf": {"ggts": ggts(tx), "seconds": tx, "program": "xsqueezeit -x to bgzf-compressed BCF, 1 thread"},
+                   "value": 2 * G / (tc + td) / 1e9}
+            out["reference"] = ref
+        if which in ("b200", "both"):
+            bx = os.path.join(tmp, "b200", "d.xsi")
+            os.makedirs(os.path.dirname(bx))
+            tc, so = _run_timed([os.path.join(BIND, "xsi_b200_bcf"), "compress", src, bx, "--threads", str(threads), "--batch-blocks", "1"])
+            td, so2 = _run_timed([os.path.join(BIND, "capi_decode_b200"), bx + "_var.bcf"], env=env_nosum)
+            tdl = float(so2.split()[5])
+            _, so3 = _run_timed([os.path.join(BIND, "capi_decode_b200"), bx + "_var.bcf"])
+            tx, _ = _run_timed([os.path.join(BIND, "xsi_b200_bcf"), "extract", bx, os.path.join(tmp, "b200", "o.bcf"), "--threads", str(threads)])
+            ax = os.path.join(tmp, "ada", "d.xsi")
+            os.makedirs(os.path.dirname(ax))
+            tac, _ = _run_timed([os.path.join(BIND, "xsqueezeit_b200"), "-c", "-f", src, "-o", ax])
+            out["compress"] = {"ggts": ggts(tc), "seconds": tc, "program": "xsi_b200_bcf compress: one pass, %d BGZF threads, raw int8 FORMAT/GT rows, encode thread" % threads}
+            out["decode_c_api"] = {"ggts": ggts(td), "seconds": td, "loop_seconds": tdl,
+                                   "program": "c_xcf_get_genotypes per record (c_api.h) on AccessorInternalsB200 (decode-ahead window), 1 thread"}
+            out["extract_bcf"] = {"ggts": ggts(tx), "seconds": tx, "program": "xsi_b200_bcf extract: int8 rows spliced into the records, %d BGZF threads" % threads}
+            out["compress_reference_cli_with_adapter"] = {"ggts": ggts(tac), "seconds": tac, "program": "xsqueezeit -c built with bindings/gt_block_b200.hpp"}
+            out["value"] = 2 * G / (tc + td) / 1e9
+            out["value_is"] = "2 * genotypes / (compress seconds + C API decode seconds)"
+            ident = {"adapter_cli_xsi_equals_ingest_xsi": _sha(ax) == _sha(bx)}
+            if ref is not None:
+                ident.update({"xsi": _sha(bx) == _sha(rx), "var_bcf": _sha(bx + "_var.bcf") == _sha(rx + "_var.bcf"),
+                              "extract_bcf": _sha(os.path.join(tmp, "b200", "o.bcf")) == _sha(os.path.join(tmp, "ref", "o.bcf")),
+                              "c_api_checksum": so3.split()[7] == ref_sum})
+            out["identical_to_reference"] = ident
+            if ref is not None:
+                out["speedup"] = {"compress": ref["compress"]["seconds"] / tc, "decode_c_api": ref["decode_c_api"]["seconds"] / td,
+                                  "extract_bcf": ref["extract_bcf"]["seconds"] / tx}
+        elif ref is not None:
+            out["value"] = ref["value"]
+    except Exception as ex:
+        out["error"] = repr(ex)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -309,13 +441,15 @@ def main():
     ap.add_argument("--block-len", type=int, default=BLOCK_LEN)
     ap.add_argument("--elem", type=int, default=4, choices=[1, 4],
                     help="bytes per genotype of the resident rows: 4 = int32 (the metric's boundary type), 1 = raw BCF int8")
-    ap.add_argument("--ref-records", type=int, default=1024)
+    ap.add_argument("--ref-records", type=int, default=BLOCK_LEN, help="records per reference worker and step (default: one full PBWT block)")
+    ap.add_argument("--ref-data", default="", help=argparse.SUPPRESS)
     ap.add_argument("--ref-workers", type=int, default=0)
     ap.add_argument("--ref-worker", type=int, default=-1, help=argparse.SUPPRESS)
     ap.add_argument("--resident-contexts", type=int, default=3,
                     help="also time the resident leg from this many host threads (one xsi_ctx each, blocks split between them)")
     ap.add_argument("--shape", default="hrc", choices=["hrc", "chrx"],
                     help="chrx: mixed ploidy, multi-allelic, missing and unphased genotypes (SURVEY 8(d) S4); resident one-context leg only")
+    ap.add_argument("--bcf-records", type=int, default=2 * BLOCK_LEN, help="records of the synthetic BCF of the e2e_bcf legs (0: skip them)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="one resident step, no e2e / cpu legs (for ncu)")
@@ -329,7 +463,16 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     steps, warmup = args.steps, max(args.warmup, 0)
     workload = "%s synthetic: %d haplotypes, PBWT blocks of %d records, maf %.3g" % (
-        "HRC-shaped" if args.shape == "hrc" else "chrX-shaped (mixed ploidy, multi-allelic, missing, unphased)", 2 * args.samples, args.block_len, MAF)
+        ("HRC-shaped" if args.samples == HRC_SAMPLES else "1KGP3-shaped" if args.samples == 2504 else "biobank-shaped" if args.samples >= 400000
+         else "custom-width") if args.shape == "hrc" else "chrX-shaped (mixed ploidy, multi-allelic, missing, unphased)", 2 * args.samples, args.block_len, MAF)
+
+    # the configuration both arms are run on (identical keys and values in both JSON lines; what a run measured on top
+    # of it -- payload bytes, line counts, contexts -- is reported under "stats")
+    G_cfg = args.blocks * args.block_len * 2 * args.samples
+    config = {"workload": workload, "blocks_per_gpu_per_step": args.blocks, "records_per_gpu_per_step": args.blocks * args.block_len,
+              "genotypes_per_gpu_per_step": G_cfg,
+              "input": "%s rows resident in HBM (%.1f GB, > L2; no flush needed)" % ("int32" if args.elem == 4 else "int8", G_cfg * args.elem / 1e9),
+              "parallelism": "blocks sharded over %d GPU(s)" % world}
 
     # ---------------- reference arm ----------------
     if args.impl == "reference":
@@ -342,12 +485,14 @@ def main():
         line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": "Ggt/s", "n_gpus": args.gpus,
                 "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
-                "config": {"workload": workload, "sample_records_per_core": args.ref_records},
+                "config": config, "stats": {"sample_records_per_core": args.ref_records, "genotypes_per_step": r["genotypes_per_step"]},
                 "compress_ggts": r["compress"], "decompress_ggts": r["decompress"], "verified": r["ok"],
                 "cpu_baseline": {"value": r["value"], "unit": "Ggt/s", "cores": r["cores"], "kind": "reference",
                                  "sample": r["sample"]},
                 "e2e": {"value": r["value"], "unit": "Ggt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
+        if args.bcf_records > 0 and world == 1:
+            line["e2e_bcf"] = bcf_legs(args.samples, args.bcf_records, "reference", min(16, usable_cores()))
         print(json.dumps(line))
         return
 
@@ -715,6 +860,11 @@ def main():
             cpu = {"value": r["value"], "unit": "Ggt/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"],
                    "compress_ggts": r["compress"], "decompress_ggts": r["decompress"], "verified": r["ok"]}
 
+    e2e_bcf = None
+    if rank == 0 and world == 1 and args.bcf_records > 0 and not args.profile_only and args.shape == "hrc":
+        ctx.sync()
+        e2e_bcf = bcf_legs(S, args.bcf_records, "both" if not args.no_cpu_baseline else "b200", min(16, usable_cores()))
+
     if rank == 0:
         # `value`: the better of the two resident legs (same batch, same calls, both verified); the per-kernel numbers
         # (`kernels`, `roofline`) always come from the one-context leg, where kernels do not overlap
@@ -724,13 +874,12 @@ def main():
                 "value_one_context": value, "ms_per_step_one_context": t_all / steps * 1e3,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32" if EL == 4 else "int8", "data": "synthetic",
-                "config": {"workload": workload, "blocks_per_gpu_per_step": B, "records_per_gpu_per_step": R,
-                           "genotypes_per_gpu_per_step": G, "input": "%s rows resident in HBM (%.1f GB, > L2; no flush needed)" % ("int32" if EL == 4 else "int8", G * EL / 1e9),
-                           "xsi_payload_bytes_per_step": res["payload"], "binary_lines": res["lines"][0], "wah_lines": res["lines"][1], "parallelism": "blocks sharded over %d GPU(s)" % world,
-                           "host_threads_per_gpu": resident_mt["contexts"] if use_mt else 1,
-                           "contexts_per_gpu": resident_mt["contexts"] if use_mt else 1},
+                "config": config,
+                "stats": {"xsi_payload_bytes_per_step": res["payload"], "binary_lines": res["lines"][0], "wah_lines": res["lines"][1],
+                          "host_threads_per_gpu": resident_mt["contexts"] if use_mt else 1,
+                          "contexts_per_gpu": resident_mt["contexts"] if use_mt else 1},
                 "compress_ggts": G * world * steps / t_enc / 1e9, "decompress_ggts": G * world * steps / t_dec / 1e9,
-                "verified": verified, "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8,
+                "verified": verified, "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8, "e2e_bcf": e2e_bcf,
                 "gpu_launches": resident_mt["gpu_launches"] if use_mt else res["launches"], "clocks": res["clocks"]}
         print(json.dumps(line))
     ctx.close()
