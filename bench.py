@@ -410,6 +410,44 @@ def bcf_legs(samples, records, which, threads):
 
 
 # ------------------------------------------------------------------------------------------------
+# the other shapes of BASELINE.json (configs[1], [3], [4]) as short sub-runs of this script
+# ------------------------------------------------------------------------------------------------
+SHAPES = {
+    # key: (BASELINE.json config, argv)
+    "s2_1kgp3": ("configs[1]: 1KGP3-shaped, 5,008 haplotypes x 1.8 M bi-allelic records (220 PBWT blocks)",
+                 ["--samples", "2504", "--blocks", "220"]),
+    "s4_chrx": ("configs[3]: chrX-shaped, 2,504 samples (every 2nd haploid), 200 k records, 5% multi-allelic, 0.5% missing, 1% unphased (24 PBWT blocks)",
+                ["--samples", "2504", "--blocks", "24", "--shape", "chrx"]),
+    "s5_biobank": ("configs[4]: biobank-shaped, 1,000,000 haplotypes (uint32 indices, grid-cooperative PBWT); 2 of the 25 PBWT blocks per GPU and step",
+                   ["--samples", "500000", "--blocks", "2"]),
+}
+
+
+def shape_subrun(key, device_index):
+    desc, argv = SHAPES[key]
+    env = dict(os.environ)
+    for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK", "LOCAL_WORLD_SIZE", "MASTER_ADDR", "MASTER_PORT"):
+        env.pop(k, None)
+    vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+    env["CUDA_VISIBLE_DEVICES"] = vis.split(",")[device_index] if vis else str(device_index)
+    try:
+        p = subprocess.run([sys.executable, os.path.abspath(__file__), "--sub", "--steps", "3", "--warmup", "2"] + argv,
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=600)
+        if p.returncode != 0:
+            return {"config": desc, "error": p.stderr.decode()[-300:]}
+        d = json.loads(p.stdout.decode().strip().splitlines()[-1])
+    except Exception as ex:  # a shape that fails must not take the headline line with it
+        return {"config": desc, "error": repr(ex)}
+    return {"config": desc, "workload": d["config"]["workload"], "blocks_per_step": d["config"]["blocks_per_gpu_per_step"],
+            "genotypes_per_step": d["config"]["genotypes_per_gpu_per_step"], "value": d["value"], "unit": "Ggt/s",
+            "compress_ggts": d["compress_ggts"], "decompress_ggts": d["decompress_ggts"], "ms_per_step": d["ms_per_step"],
+            "verified": d["verified"], "gpu_launches": d["gpu_launches"], "steps": d["steps"],
+            "xsi_payload_bytes_per_step": d["stats"]["xsi_payload_bytes_per_step"],
+            "kernels": {k: {"ms_per_step": v["ms_per_step"], "share": v["share"]} for k, v in d["kernels"].items() if v["share"] and v["share"] > 0.02},
+            "roofline_kernels": [{"kernel": r["kernel"], "frac": r["frac"], "achieved": r["achieved"], "unit": r["unit"]} for r in d["roofline_kernels"]]}
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def algorithmic_bytes(kernel, G, L_wah, L, WS, payload, elem=4):
@@ -450,6 +488,8 @@ def main():
     ap.add_argument("--shape", default="hrc", choices=["hrc", "chrx"],
                     help="chrx: mixed ploidy, multi-allelic, missing and unphased genotypes (SURVEY 8(d) S4); resident one-context leg only")
     ap.add_argument("--bcf-records", type=int, default=2 * BLOCK_LEN, help="records of the synthetic BCF of the e2e_bcf legs (0: skip them)")
+    ap.add_argument("--no-shapes", action="store_true", help="skip the other BASELINE.json shapes (1KGP3, chrX, biobank) of the default run")
+    ap.add_argument("--sub", action="store_true", help=argparse.SUPPRESS)  # a shape sub-run: resident one-context leg only
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-only", action="store_true", help="one resident step, no e2e / cpu legs (for ncu)")
@@ -457,6 +497,8 @@ def main():
 
     if args.ref_worker >= 0:
         return ref_worker(args)
+    if args.sub:
+        args.resident_contexts, args.no_e2e, args.no_cpu_baseline, args.bcf_records, args.no_shapes = 0, True, True, 0, True
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -865,6 +907,29 @@ def main():
         ctx.sync()
         e2e_bcf = bcf_legs(S, args.bcf_records, "both" if not args.no_cpu_baseline else "b200", min(16, usable_cores()))
 
+    # ---- the other shapes: short sub-runs once this process has let go of its device memory ----
+    shapes = None
+    if not args.no_shapes and not args.profile_only and args.shape == "hrc" and S == HRC_SAMPLES:
+        del gt
+        if "dec" in dir():
+            del dec
+        ctx.close()
+        ctx = None
+        torch.cuda.empty_cache()
+        if world == 1:
+            shapes = {k: shape_subrun(k, local_rank) for k in SHAPES}
+        else:
+            # N GPUs: the biobank decode sweep of configs[4] -- every rank runs its own blocks, the rates add up (weak scaling)
+            mine = shape_subrun("s5_biobank", local_rank)
+            allr = [None] * world
+            dist.all_gather_object(allr, mine)
+            if rank == 0:
+                ok = [r for r in allr if "value" in r]
+                shapes = {"s5_biobank": dict(allr[0], per_rank_values=[r.get("value") for r in allr],
+                                             value=sum(r["value"] for r in ok), compress_ggts=sum(r["compress_ggts"] for r in ok),
+                                             decompress_ggts=sum(r["decompress_ggts"] for r in ok), n_gpus=world,
+                                             verified=all(r.get("verified") for r in allr))}
+
     if rank == 0:
         # `value`: the better of the two resident legs (same batch, same calls, both verified); the per-kernel numbers
         # (`kernels`, `roofline`) always come from the one-context leg, where kernels do not overlap
@@ -879,10 +944,11 @@ def main():
                           "host_threads_per_gpu": resident_mt["contexts"] if use_mt else 1,
                           "contexts_per_gpu": resident_mt["contexts"] if use_mt else 1},
                 "compress_ggts": G * world * steps / t_enc / 1e9, "decompress_ggts": G * world * steps / t_dec / 1e9,
-                "verified": verified, "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8, "e2e_bcf": e2e_bcf,
+                "verified": verified, "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8, "e2e_bcf": e2e_bcf, "shapes": shapes,
                 "gpu_launches": resident_mt["gpu_launches"] if use_mt else res["launches"], "clocks": res["clocks"]}
         print(json.dumps(line))
-    ctx.close()
+    if ctx is not None:
+        ctx.close()
     if dist is not None:
         dist.destroy_process_group()
 

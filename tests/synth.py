@@ -64,3 +64,20 @@ def make_dataset(n_records, n_samples, seed, max_alt=1, multi_frac=0.0, missing=
     ngt = np.full(n_records, H, dtype=np.int32)
     return dict(gt=np.ascontiguousarray(gt.reshape(-1), dtype=np.int32), ngt=ngt, n_allele=n_allele,
                 n_samples=n_samples)
+
+
+def haploid_multiallelic_block(seed=77, ns=120, nrec=120):
+    """All-haploid records and multi-allelic records in the same PBWT block: the shape the reference writes but cannot read
+    back (gt_block.hpp:219-224,639-642 vs accessor_internals_new.hpp:116,165,265-271)."""
+    rng = np.random.default_rng(seed)
+    rows, ngt, nal = [], [], []
+    for r in range(nrec):
+        p = 1 if r % 7 == 3 else 2
+        k = 3 if r % 5 == 1 else 2
+        al = (rng.random(ns * p) < 0.3).astype(np.int8)
+        if k == 3:
+            al = np.where(al > 0, rng.integers(1, 3, size=al.size), 0).astype(np.int8)
+        rows.append(encode_gt(al, 1 if p == 2 else 0))
+        ngt.append(ns * p)
+        nal.append(k)
+    return dict(gt=np.concatenate(rows).astype(np.int32), ngt=np.array(ngt, np.int32), n_allele=np.array(nal, np.int32), n_samples=ns)

@@ -471,3 +471,132 @@ def test_sample_subset(ctx, tmp_path):
             assert filled[r] == want.size and np.array_equal(out[r, :filled[r]], want), r
             assert np.array_equal(ac[r, :int(ds["n_allele"][r]) - 1], want_ac), r
         acc.close()
+
+
+# ---- hygiene: orders, shared contexts, malformed input, the reference's own limits ----------------
+import ctypes  # noqa: E402
+
+
+def ctypes_block(acc, b):
+    p, s = ctypes.c_void_p(), ctypes.c_uint64()
+    assert acc._L.xsi_reader_gt_block(acc.r, b, ctypes.byref(p), ctypes.byref(s)) == 0
+    return p.value, s.value
+
+
+def test_positions_in_any_order(ctx, tmp_path):
+    """seek (accessor_internals_new.hpp:154-196) replays or resets the cursor; here any (block, line) is addressable:
+    shuffled, backward and repeated positions through fill_genotype_arrays, the one-record call and the subset call"""
+    import xsqueezeit_b200 as xb
+    ds = synth.make_dataset(700, 301, seed=61, max_alt=3, multi_frac=0.2, missing=0.01, unphased=0.02, haploid_samples=0.3)
+    bl = 128
+    p = gpu_encode(ctx, tmp_path, ds, bl, 0.01)
+    img = open(p, "rb").read()
+    nal, ns = ds["n_allele"], ds["n_samples"]
+    pos = xb.bm_positions(nal, bl)
+    rd = xo.Reader(img)
+    want = [rd.fill_genotype_array(int(nal[r]), int(pos[r])) for r in range(len(nal))]
+    want = [(row[:n].copy(), n) for row, n in want]
+    rng = np.random.default_rng(3)
+    orders = {"backward": np.arange(len(nal))[::-1], "shuffled": rng.permutation(len(nal)),
+              "repeated": rng.integers(0, len(nal), size=400), "ping_pong": np.array([0, len(nal) - 1] * 20 + [len(nal) // 2] * 3)}
+    for blocks_resident in (1, 3):
+        acc = xb.Accessor(p, ctx, blocks_resident=blocks_resident)
+        for name, order in orders.items():
+            out, filled, counts = acc.fill_genotype_arrays(nal[order], pos[order], want_counts=True)
+            for i, r in enumerate(order):
+                assert filled[i] == want[r][1] and np.array_equal(out[i, :filled[i]], want[r][0]), (name, i, r)
+            for r in order[:25]:  # one record per call, the reference's calling pattern
+                a, n = acc.fill_genotype_array(int(nal[r]), int(pos[r]))
+                assert n == want[r][1] and np.array_equal(a[:n], want[r][0]), (name, r)
+        acc.close()
+    # subset call in shuffled order
+    acc = xb.Accessor(p, ctx)
+    nb = (len(pos) + bl - 1) // bl
+    acc._load(0, nb)
+    order = orders["shuffled"]
+    sel = rng.permutation(ns)[:40].astype(np.uint32)
+    blk = (pos[order] >> np.uint64(15)).astype(np.uint32)
+    off = (pos[order] & np.uint64(0x7FFF)).astype(np.uint32)
+    out, filled, ac = ctx.decode_records_subset(blk, off, nal[order], sel)
+    for i, r in enumerate(order):
+        w, w_ac = xo.select_samples(want[r][0], want[r][1], ns, sel, int(nal[r]))
+        assert filled[i] == w.size and np.array_equal(out[i, :filled[i]], w), (i, r)
+        assert np.array_equal(ac[i, :int(nal[r]) - 1], w_ac), (i, r)
+    acc.close()
+
+
+def test_two_accessors_share_a_context(ctx, tmp_path):
+    """the loaded block set belongs to the context: an Accessor must notice that another one replaced it"""
+    import xsqueezeit_b200 as xb
+    d1 = synth.make_dataset(300, 200, seed=71)
+    d2 = synth.make_dataset(300, 200, seed=72, missing=0.01)
+    (tmp_path / "a").mkdir()
+    (tmp_path / "b").mkdir()
+    p1 = gpu_encode(ctx, tmp_path / "a", d1, 128, 0.01)
+    p2 = gpu_encode(ctx, tmp_path / "b", d2, 128, 0.01)
+    a1, a2 = xb.Accessor(p1, ctx), xb.Accessor(p2, ctx)
+    r1, r2 = xo.Reader(open(p1, "rb").read()), xo.Reader(open(p2, "rb").read())
+    pos = xb.bm_positions(d1["n_allele"], 128)
+    for r in (5, 200, 6, 201, 130, 7):
+        for acc, rd in ((a1, r1), (a2, r2), (a1, r1)):
+            a, n = acc.fill_genotype_array(2, int(pos[r]))
+            b, nb = rd.fill_genotype_array(2, int(pos[r]))
+            assert n == nb and np.array_equal(a[:n], b[:nb]), r
+    a1.close()
+    a2.close()
+
+
+def test_malformed_blocks_are_refused(ctx, tmp_path):
+    """truncated and corrupted GT blocks end in XSI_E_FORMAT (-6) / XSI_E_UNSUPPORTED (-5), never in a device fault:
+    the context must still work afterwards"""
+    import xsqueezeit_b200 as xb
+    ds = synth.make_dataset(300, 200, seed=81, max_alt=3, multi_frac=0.2, missing=0.02, haploid_samples=0.3)
+    p = gpu_encode(ctx, tmp_path, ds, 128, 0.3)  # maf 0.3: most lines are sparse index lists
+    acc = xb.Accessor(p, ctx)
+    ptr, size = ctypes_block(acc, 0)
+    good = bytes((ctypes.c_uint8 * size).from_address(ptr))
+    acc.close()
+    rng = np.random.default_rng(9)
+    refused = 0
+    trials = [good[:n] for n in (4, 12, 40, size // 3, size // 2, size - 7, size - 1)]
+    for _ in range(40):  # overwrite a few 16-bit words inside the sections with large counts / garbage
+        b = bytearray(good)
+        for _k in range(3):
+            at = int(rng.integers(100, size - 2)) & ~1
+            b[at:at + 2] = int(rng.choice([0x7FFF, 0xFFFF, 0x3FFF, int(rng.integers(0, 65536))])).to_bytes(2, "little")
+        trials.append(bytes(b))
+    for t in trials:
+        try:
+            ctx.decode_load_blocks([t], ds["n_samples"], 2)
+            # a corruption may leave a well-formed block: then every line must still decode without a fault
+            n = min(20, len(ds["n_allele"]))
+            ctx.decode_records(np.zeros(n, np.uint32), np.arange(n, dtype=np.uint32), np.full(n, 2, np.uint32))
+        except xb.XsiError as e:
+            assert e.code in (-6, -5, -2), e.code
+            refused += 1
+    assert refused >= 7
+    roundtrip(ctx, tmp_path, synth.make_dataset(100, 64, seed=82), 50, 0.01)  # the context survived
+
+
+def test_record_without_alt_is_refused(ctx):
+    import xsqueezeit_b200 as xb
+    gt = synth.encode_gt(np.zeros((3, 20), np.int8)).reshape(-1).copy()
+    for bad in (1, 255):
+        with pytest.raises(xb.XsiError) as e:
+            ctx.encode_launch(gt, [2, bad, 2], 10, 8192, 0, 1)
+        assert e.value.code == -5
+
+
+def test_haploid_and_multiallelic_block(ctx, tmp_path):
+    """A block holding an all-haploid record and a multi-allelic record: written byte for byte like the reference (the oracle
+    and the live reference agree on the bytes, tests/test_oracle_vs_reference.py), but the reference's reader corrupts its heap
+    on it (LINE_HAPLOID per BCF line vs per binary line) -- the decode call answers XSI_E_UNSUPPORTED."""
+    import xsqueezeit_b200 as xb
+    ds = synth.haploid_multiallelic_block()
+    p = gpu_encode(ctx, tmp_path, ds, 64, 0.01)
+    assert open(p, "rb").read() == oracle_image(ds, 64, 0.01)
+    acc = xb.Accessor(p, ctx)
+    with pytest.raises(xb.XsiError) as e:
+        acc.fill_genotype_array(2, 0)
+    assert e.value.code == -5
+    acc.close()

@@ -134,3 +134,19 @@ def test_wah_encode_missing():
                       xo.default_phased(ds["gt"], off, ds["ngt"], ds["n_samples"]))
     assert img != plain
     both_wah_missing(synth.make_dataset(60, 66000, seed=42, n_founders=16, fmin=0.001, missing=0.001), 20, 0.001)
+
+
+def test_haploid_and_multiallelic_block_bytes():
+    """The reference WRITES a block with all-haploid and multi-allelic records (and the oracle writes the same bytes) but its
+    reader corrupts the heap on it (probed in a child process: abort in munmap_chunk), so only the bytes are compared here;
+    the product refuses to decode such a block (tests/test_gpu_parity.py::test_haploid_and_multiallelic_block)."""
+    ds = synth.haploid_multiallelic_block()
+    gt, ngt, nal, ns = ds["gt"], ds["ngt"], ds["n_allele"], ds["n_samples"]
+    off = xo.row_offsets(ngt)
+    dp = xo.default_phased(gt, off, ngt, ns)
+    thr = xo.mac_threshold(ns, int(ngt[0]) // ns, 0.01)
+    img = xo.encode(gt, off, ngt, nal, ns, 64, thr, dp)
+    with tempfile.TemporaryDirectory() as tmp:
+        p = os.path.join(tmp, "r.xsi")
+        xsi_ref.encode_file(p, gt, off, ngt, nal, ns, 64, thr, dp)
+        assert img == open(p, "rb").read()

@@ -241,6 +241,8 @@ class Context:
                 a = np.frombuffer(b, dtype=np.uint8)
                 self._blk_keep.append(a)
                 ptrs[i], sizes[i] = a.ctypes.data, a.size
+        # the loaded set belongs to the context (a load replaces it): readers that cache "my block is resident" compare this
+        self.load_generation = getattr(self, "load_generation", 0) + 1
         self._check(self._L.xsi_decode_load_blocks(self.h, n, ptrs, sizes, int(num_samples), int(aet_bytes)))
         self._dec_hap = 2 * int(num_samples)
 
@@ -429,8 +431,9 @@ class Accessor:
         self.aet_bytes, self.n_blocks, self.block_len = aet.value, nb.value, bl.value
         self.xcf_entries, self.num_variants, self.zstd = ent.value, nv.value, bool(z.value)
         self.rare_threshold, self.default_phased = rt.value, dp.value
-        self._loaded = None  # (first block, count)
+        self._loaded = None  # (first block, count, load generation of the context)
         self._counts = None
+        self.blocks_resident = max(1, int(blocks_resident))  # blocks brought to the device per miss
 
     def get_sample_list(self):
         out = []
@@ -444,9 +447,16 @@ class Accessor:
     def get_number_of_samples(self):
         return len(self.get_sample_list())
 
-    def _load(self, b0, nb=1):
-        if self._loaded is not None and self._loaded[0] <= b0 and b0 + nb <= self._loaded[0] + self._loaded[1]:
+    def _load(self, b0, nb=None):
+        """Makes block b0 resident (with the blocks_resident - 1 that follow).  The context may be shared: another Accessor or
+        a direct decode_load_blocks call replaces the loaded set, which the generation check notices."""
+        if nb is None:
+            nb = min(self.blocks_resident, self.n_blocks - b0)
+        if (self._loaded is not None and self._loaded[2] == getattr(self.ctx, "load_generation", 0)
+                and self._loaded[0] <= b0 < self._loaded[0] + self._loaded[1]):
             return
+        if b0 < 0 or b0 >= self.n_blocks:
+            raise XsiError(-2, "block %d out of range (%d blocks)" % (b0, self.n_blocks))
         blocks = []
         for b in range(b0, b0 + nb):
             p, s = ctypes.c_void_p(), ctypes.c_uint64()
@@ -455,7 +465,7 @@ class Accessor:
                 raise XsiError(rc, "block error")
             blocks.append((p.value, s.value))
         self.ctx.decode_load_blocks(blocks, self.num_samples, self.aet_bytes)
-        self._loaded = (b0, nb)
+        self._loaded = (b0, nb, self.ctx.load_generation)
 
     def split_bm(self, position):
         position = int(position) & 0xFFFFFFFF
@@ -464,7 +474,7 @@ class Accessor:
     def fill_genotype_array(self, n_alleles, position, gt_arr=None):
         """Returns (gt_arr, n_filled) like AccessorInternals::fill_genotype_array."""
         b, off = self.split_bm(position)
-        self._load(b, 1)
+        self._load(b)
         stride = max(int(self.hap_samples), 2 * int(self.num_samples))
         out = np.empty((1, stride), dtype=np.int32)
         out, filled, counts = self.ctx.decode_records([b - self._loaded[0]], [off], [n_alleles], out=out,
@@ -482,7 +492,7 @@ class Accessor:
     def fill_allele_counts(self, n_alleles, position):
         """AccessorInternals::fill_allele_counts: counts without the genotype row; read with get_allele_counts()."""
         b, off = self.split_bm(position)
-        self._load(b, 1)
+        self._load(b)
         self._counts = self.ctx.decode_allele_counts([b - self._loaded[0]], [off], [n_alleles])[0, :n_alleles].copy()
 
     def fill_allele_counts_batch(self, n_alleles, positions):
@@ -495,11 +505,12 @@ class Accessor:
         counts = np.zeros((n, int(n_alleles.max()) if n else 2), dtype=np.uint64)
         i = 0
         while i < n:
+            self._load(int(blk[i]))
+            lo, hi = self._loaded[0], self._loaded[0] + self._loaded[1]
             j = i
-            while j < n and blk[j] == blk[i]:
+            while j < n and lo <= blk[j] < hi:
                 j += 1
-            self._load(int(blk[i]), 1)
-            c = self.ctx.decode_allele_counts(np.zeros(j - i, np.uint32), off[i:j], n_alleles[i:j])
+            c = self.ctx.decode_allele_counts((blk[i:j] - lo).astype(np.uint32), off[i:j], n_alleles[i:j])
             counts[i:j, :c.shape[1]] = c
             i = j
         return counts
@@ -519,12 +530,13 @@ class Accessor:
         counts = np.zeros((n, int(n_alleles.max()) if n else 2), dtype=np.uint64) if want_counts else None
         i = 0
         while i < n:
+            self._load(int(blk[i]))
+            lo, hi = self._loaded[0], self._loaded[0] + self._loaded[1]
             j = i
-            while j < n and blk[j] == blk[i]:
+            while j < n and lo <= blk[j] < hi:
                 j += 1
-            self._load(int(blk[i]), 1)
             sub_out = out[i:j] if not out_on_device else int(out) + i * stride * elem_bytes
-            o, f, c = self.ctx.decode_records(np.zeros(j - i, np.uint32), off[i:j], n_alleles[i:j], out=sub_out,
+            o, f, c = self.ctx.decode_records((blk[i:j] - lo).astype(np.uint32), off[i:j], n_alleles[i:j], out=sub_out,
                                               out_stride=stride, out_on_device=out_on_device, want_counts=want_counts,
                                               elem_bytes=elem_bytes)
             filled[i:j] = f

@@ -31,6 +31,7 @@ struct DecSeg {       // one WAH matrix (GT lines or phase lines) of one block
 struct DecBlock {
     uint64_t blob_off;
     uint64_t sparse_off, miss_off, eov_off;  // byte offsets in blob of the matrices (or ~0)
+    uint64_t sp_end, ms_end, ev_end;          // entries (aet bytes each) each matrix may hold: bound of the list walk
     uint32_t line0, n_lines;                  // binary lines (global index base)
     uint32_t wah0, n_wah;                     // GT WAH jobs
     uint32_t sp0, n_sp, ms0, n_ms, ev0, n_ev; // ordinals of sparse / missing / eov lists
@@ -857,17 +858,29 @@ __global__ void sparse_index_kernel(DecDev d) {
     uint64_t* off = kind == 0 ? d.sp_off + blk.sp0 : kind == 1 ? d.ms_off + blk.ms0 : d.ev_off + blk.ev0;
     if (!n) return;
     if (moff == ~0ull) { atomicOr(d.err, DERR_INDEX); return; }
+    // a truncated or corrupt file must end in XSI_E_FORMAT, not in a wild read: every list (count word + entries) has to
+    // lie inside its matrix; a list that does not raises DERR_INDEX (the load then fails and nothing reads the lists)
+    const uint64_t end = kind == 0 ? blk.sp_end : kind == 1 ? blk.ms_end : blk.ev_end;
     uint64_t e = 0;
     if (d.aet == 2) {
         const uint16_t* m = reinterpret_cast<const uint16_t*>(d.blob + moff);
-        for (uint32_t i = 0; i < n; ++i) { off[i] = e; e += 1 + (m[e] & 0x7FFFu); }
+        for (uint32_t i = 0; i < n; ++i) {
+            off[i] = 0;
+            if (e >= end) { atomicOr(d.err, DERR_INDEX); continue; }
+            const uint64_t nx = e + 1 + (m[e] & 0x7FFFu);
+            if (nx > end) { atomicOr(d.err, DERR_INDEX); e = end; continue; }
+            off[i] = e; e = nx;
+        }
     } else {
         const uint8_t* m = d.blob + moff;  // only 2-byte aligned in the file: assemble from halves
         for (uint32_t i = 0; i < n; ++i) {
-            off[i] = e;
+            off[i] = 0;
+            if (e >= end) { atomicOr(d.err, DERR_INDEX); continue; }
             const uint16_t* h = reinterpret_cast<const uint16_t*>(m + e * 4);
             const uint32_t c = (uint32_t)h[0] | ((uint32_t)h[1] << 16);
-            e += 1 + (c & 0x7FFFFFFFu);
+            const uint64_t nx = e + 1 + (c & 0x7FFFFFFFu);
+            if (nx > end) { atomicOr(d.err, DERR_INDEX); e = end; continue; }
+            off[i] = e; e = nx;
         }
     }
 }

@@ -706,7 +706,7 @@ int run_permute(xsi_ctx* ctx, const EncDev& p) {
 
 }  // namespace
 
-extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
+static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
     if (!ctx || !d) return XSI_E_ARG;
     auto& e = ctx->enc;
     e.launched = false; e.collected = false;
@@ -741,7 +741,10 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
             const uint32_t na = d->n_allele[r];
             if (pl > 2) { k.err = "Ploidy higher than 2 is not yet supported"; k.rc = XSI_E_PLOIDY; return; }
             if (pl == 0) { k.err = "record with ploidy 0"; k.rc = XSI_E_ARG; return; }
-            if (na < 1 || na > (uint32_t)E1_MAXALLELE) { k.err = "n_allele out of range (1..256)"; k.rc = XSI_E_UNSUPPORTED; return; }
+            // 2..254: what xsi_decode_records can read back.  A record without an ALT allele (n_allele 1) has no binary line;
+            // the reference then writes per-record flags that no longer line up with the per-line sections
+            // (gt_block.hpp:650-666) and cannot decode the block either, so it is refused here rather than written.
+            if (na < 2 || na > 254) { k.err = "n_allele out of range (2..254)"; k.rc = XSI_E_UNSUPPORTED; return; }
             if ((int)pl > k.max_pl) k.max_pl = (int)pl;
             if (pl == 1) k.hap = true;
             k.g += (uint64_t)S * pl;
@@ -1102,7 +1105,7 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
     return XSI_E_NOMEM;
 }
 
-extern "C" int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint8_t* const** blocks_out,
+static int xsi_encode_collect_impl(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint8_t* const** blocks_out,
                                   const uint64_t** sizes_out) {
     if (!ctx) return XSI_E_ARG;
     auto& e = ctx->enc;
@@ -1159,6 +1162,9 @@ int parse_block(std::string& err, const uint8_t* p, uint64_t size, ParsedBlock& 
     auto need = [&](uint32_t k, uint32_t& v) { auto it = pb.dict.find(k); if (it == pb.dict.end()) return false; v = it->second; return true; };
     uint32_t dp = 0, ws = 0;
     if (!need(KEY_BCF_LINES, pb.bcf_lines) || !need(KEY_BINARY_LINES, pb.bin_lines) || !need(KEY_DEFAULT_PHASING, dp)) { err = "GT block: required key missing"; return XSI_E_FORMAT; }
+    // BM addresses a binary line with 15 bits (accessor_internals.hpp:411) and every line costs at least a bit of the
+    // LINE_SELECT vector: anything else is not a GT block (and would size the flag vectors from unvalidated input)
+    if (pb.bin_lines >= 32768 || pb.bcf_lines > pb.bin_lines + 1 || (uint64_t)pb.bin_lines > size * 8) { err = "GT block: implausible line counts"; return XSI_E_FORMAT; }
     pb.default_phasing = dp == 1 ? 1 : 0;  // accessor_internals_new.hpp:77-81
     // WS_SPARSE is the writer's default, WS_WAH what --wah-encode-missing selects (gt_block.hpp:174-176); WS_PBWT_WAH (a
     // second PBWT over the weirdness lines, the v4 default) cannot be produced by the v5 command line
@@ -1181,6 +1187,15 @@ int parse_block(std::string& err, const uint8_t* p, uint64_t size, ParsedBlock& 
     vec(KEY_LINE_END_OF_VECTORS, pb.has_eov, pb.p_eov);
     vec(KEY_LINE_NON_UNIFORM_PHASING, pb.has_phase, pb.p_phase);
     vec(KEY_LINE_HAPLOID, pb.haploid, ph);  // read per BINARY line although written per BCF line (reference quirk)
+    // The writer emits LINE_HAPLOID with one bit per BCF line (gt_block.hpp:219-224,639-642), the reader takes one bit per
+    // BINARY line (accessor_internals_new.hpp:116,165,265-271).  With a multi-allelic record in the block the two disagree:
+    // the reference's Accessor then corrupts its heap on such a block (probed: "munmap_chunk(): invalid pointer").  The file
+    // is written byte for byte like the reference's, but it is not decoded: the caller gets XSI_E_UNSUPPORTED instead.
+    if (ph && pb.bcf_lines != pb.bin_lines) {
+        bool any = false;
+        for (uint8_t f : pb.haploid) any |= f != 0;
+        if (any) { err = "GT block holds all-haploid and multi-allelic records: the reference cannot decode it either (LINE_HAPLOID is per BCF line)"; return XSI_E_UNSUPPORTED; }
+    }
     if (!ph) pb.haploid.assign(pb.bin_lines, 0);
     if (!pb.p_missing) pb.has_missing.assign(pb.bin_lines, 0);
     if (!pb.p_eov) pb.has_eov.assign(pb.bin_lines, 0);
@@ -1198,7 +1213,7 @@ int launch_unpermute(xsi_ctx* ctx, const DecDev& dd, const uint8_t* job_hap, uin
 
 }  // namespace
 
-extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks,
+static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks,
                                       const uint64_t* sizes, uint64_t num_samples, int32_t aet_bytes) {
     if (!ctx || !gt_blocks || !sizes || n_blocks == 0) return XSI_E_ARG;
     if (aet_bytes != 2 && aet_bytes != 4) { ctx->err = "Unsupported access type"; return XSI_E_ARG; }
@@ -1327,6 +1342,13 @@ extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uin
                 return blob_off[b] + it->second;
             };
             bk.sparse_off = moff(KEY_MATRIX_SPARSE); bk.miss_off = moff(KEY_MATRIX_MISSING_SPARSE); bk.eov_off = moff(KEY_MATRIX_END_OF_VECTORS_SPARSE);
+            // entries each index-list matrix may hold (to the next section or the block end): the list walk is bounded by it
+            auto mend = [&](uint32_t key) -> uint64_t {
+                auto it = pb.dict.find(key);
+                if (it == pb.dict.end() || it->second == VAL_UNDEFINED || it->second >= sizes[b]) return 0;
+                return (section_end(pb, it->second, sizes[b]) - it->second) / d.aet;
+            };
+            bk.sp_end = mend(KEY_MATRIX_SPARSE); bk.ms_end = mend(KEY_MATRIX_MISSING_SPARSE); bk.ev_end = mend(KEY_MATRIX_END_OF_VECTORS_SPARSE);
             bk.wah0 = pl.wah0; bk.sp0 = pl.sp0; bk.ms0 = pl.ms0; bk.ev0 = pl.ev0;
             bk.n_wah = pl.n_wah; bk.n_sp = pl.n_sp; bk.n_ms = pl.n_ms; bk.n_ev = pl.n_ev;
             uint32_t jw = pl.wah0, jp = pl.ph0, sp = pl.sp0, ms = pl.ms0, ev = pl.ev0, gc = 0, gcp = 0;
@@ -1782,14 +1804,14 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
     return XSI_OK;
 }
 
-extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+static int xsi_decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                                   const uint32_t* n_alleles, int32_t* out, uint64_t out_stride, int32_t out_on_device,
                                   uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
     return decode_records_impl<int32_t>(ctx, n, block_index, line_offset, n_alleles, out, out_stride, out_on_device, n_filled,
                                         allele_counts, counts_stride);
 }
 
-extern "C" int xsi_decode_records_subset(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+static int xsi_decode_records_subset_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                                          const uint32_t* n_alleles, const uint32_t* samples_to_use, uint32_t n_sel,
                                          int32_t* out, uint64_t out_stride, int32_t out_on_device, uint32_t* n_filled,
                                          uint32_t* ac, uint32_t ac_stride) {
@@ -1843,7 +1865,7 @@ extern "C" int xsi_decode_records_subset(xsi_ctx* ctx, uint64_t n, const uint32_
     return XSI_OK;
 }
 
-extern "C" int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+static int xsi_decode_allele_counts_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                                         const uint32_t* n_alleles, uint64_t* allele_counts, uint32_t counts_stride) {
     if (!ctx || !block_index || !line_offset || !n_alleles || !allele_counts) return XSI_E_ARG;
     auto& d = ctx->dec;
@@ -1879,9 +1901,47 @@ extern "C" int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t
     return XSI_OK;
 }
 
-extern "C" int xsi_decode_records_i8(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+static int xsi_decode_records_i8_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                                      const uint32_t* n_alleles, int8_t* out, uint64_t out_stride, int32_t out_on_device,
                                      uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
     return decode_records_impl<int8_t>(ctx, n, block_index, line_offset, n_alleles, out, out_stride, out_on_device, n_filled,
                                        allele_counts, counts_stride);
+}
+
+// ---- the C ABI promises no exception across the boundary: host containers (std::vector, std::map) may throw ----
+template <typename F>
+static int guarded(xsi_ctx* ctx, F&& f) {
+    try {
+        return f();
+    } catch (const std::bad_alloc&) {
+        if (ctx) ctx->err = "out of host memory";
+        return XSI_E_NOMEM;
+    } catch (const std::exception& ex) {
+        if (ctx) ctx->err = std::string("internal error: ") + ex.what();
+        return XSI_E_ARG;
+    } catch (...) {
+        if (ctx) ctx->err = "internal error";
+        return XSI_E_ARG;
+    }
+}
+extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
+    return guarded(ctx, [&] { return xsi_encode_launch_impl(ctx, d); });
+}
+extern "C" int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint8_t* const** blocks_out, const uint64_t** sizes_out) {
+    return guarded(ctx, [&] { return xsi_encode_collect_impl(ctx, n_blocks_out, blocks_out, sizes_out); });
+}
+extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks, const uint64_t* sizes, uint64_t num_samples, int32_t aet_bytes) {
+    return guarded(ctx, [&] { return xsi_decode_load_blocks_impl(ctx, n_blocks, gt_blocks, sizes, num_samples, aet_bytes); });
+}
+extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset, const uint32_t* n_alleles, int32_t* out, uint64_t out_stride, int32_t out_on_device, uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
+    return guarded(ctx, [&] { return xsi_decode_records_impl(ctx, n, block_index, line_offset, n_alleles, out, out_stride, out_on_device, n_filled, allele_counts, counts_stride); });
+}
+extern "C" int xsi_decode_records_i8(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset, const uint32_t* n_alleles, int8_t* out, uint64_t out_stride, int32_t out_on_device, uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
+    return guarded(ctx, [&] { return xsi_decode_records_i8_impl(ctx, n, block_index, line_offset, n_alleles, out, out_stride, out_on_device, n_filled, allele_counts, counts_stride); });
+}
+extern "C" int xsi_decode_records_subset(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset, const uint32_t* n_alleles, const uint32_t* samples_to_use, uint32_t n_sel, int32_t* out, uint64_t out_stride, int32_t out_on_device, uint32_t* n_filled, uint32_t* ac, uint32_t ac_stride) {
+    return guarded(ctx, [&] { return xsi_decode_records_subset_impl(ctx, n, block_index, line_offset, n_alleles, samples_to_use, n_sel, out, out_stride, out_on_device, n_filled, ac, ac_stride); });
+}
+extern "C" int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset, const uint32_t* n_alleles, uint64_t* allele_counts, uint32_t counts_stride) {
+    return guarded(ctx, [&] { return xsi_decode_allele_counts_impl(ctx, n, block_index, line_offset, n_alleles, allele_counts, counts_stride); });
 }

@@ -30,16 +30,16 @@ struct Zstd {
     unsigned (*isError)(size_t) = nullptr;
     bool ok() const { return compress && decompress && isError; }
     static Zstd& get() {
-        static Zstd z;
-        static bool tried = false;
-        if (!tried) {
-            tried = true;
-            for (const char* n : {"libzstd.so.1", "libzstd.so"}) { z.h = dlopen(n, RTLD_NOW); if (z.h) break; }
-            if (z.h) {
-                z.compress = (decltype(z.compress))dlsym(z.h, "ZSTD_compress");
-                z.decompress = (decltype(z.decompress))dlsym(z.h, "ZSTD_decompress");
-                z.isError = (decltype(z.isError))dlsym(z.h, "ZSTD_isError");
-            }
+        static Zstd z = load();  // function-local static: initialised once, thread-safe
+        return z;
+    }
+    static Zstd load() {
+        Zstd z;
+        for (const char* n : {"libzstd.so.1", "libzstd.so"}) { z.h = dlopen(n, RTLD_NOW); if (z.h) break; }
+        if (z.h) {
+            z.compress = (decltype(z.compress))dlsym(z.h, "ZSTD_compress");
+            z.decompress = (decltype(z.decompress))dlsym(z.h, "ZSTD_decompress");
+            z.isError = (decltype(z.isError))dlsym(z.h, "ZSTD_isError");
         }
         return z;
     }
@@ -76,6 +76,7 @@ struct xsi_writer {
     std::vector<std::string> samples;
     std::vector<uint64_t> indices;
     uint64_t entries = 0, variants = 0;
+    bool failed = false;  // a block write failed: the file is not finalised (no index over a half-written block)
 };
 
 extern "C" int xsi_writer_open(const char* path, uint32_t n_samples, const char* sample_names, uint32_t block_len,
@@ -103,8 +104,12 @@ extern "C" int xsi_writer_open(const char* path, uint32_t n_samples, const char*
 extern "C" int xsi_writer_add_blocks(xsi_writer* w, uint32_t n_blocks, const uint8_t* const* blocks, const uint64_t* sizes,
                                      uint64_t n_records, uint64_t n_variants) {
     if (!w || !w->f || (n_blocks && (!blocks || !sizes))) return XSI_E_ARG;
+    if (w->failed) return XSI_E_IO;
+    struct Fail { xsi_writer* w; bool ok = false; ~Fail() { if (!ok) w->failed = true; } } guard{w};
     for (uint32_t b = 0; b < n_blocks; ++b) {
-        w->indices.push_back((uint64_t)ftello(w->f));  // xsi_factory.hpp:533
+        const off_t at = ftello(w->f);
+        if (at < 0) return XSI_E_IO;
+        w->indices.push_back((uint64_t)at);  // xsi_factory.hpp:533
         // outer dictionary: {KEY_GT_ENTRY: 16} (interfaces.hpp:187-221), then the GT block
         const uint32_t outer[4] = {0xFFFFFFFFu, 1u, KEY_GT_ENTRY, 16u};
         if (!w->zstd_on) {
@@ -120,20 +125,30 @@ extern "C" int xsi_writer_add_blocks(xsi_writer* w, uint32_t n_blocks, const uin
             const uint64_t cs = r, os = raw.size();
             if (fwrite(&cs, 8, 1, w->f) != 1 || fwrite(&os, 8, 1, w->f) != 1 || fwrite(comp.data(), 1, r, w->f) != r) return XSI_E_IO;
         }
-        const uint64_t pos = (uint64_t)ftello(w->f);  // interfaces.hpp:254-263
-        if (pos % 4) { const char z[4] = {0, 0, 0, 0}; fwrite(z, 1, 4 - pos % 4, w->f); }
+        const off_t end = ftello(w->f);  // interfaces.hpp:254-263
+        if (end < 0) return XSI_E_IO;
+        const uint64_t pos = (uint64_t)end;
+        if (pos % 4) { const char z[4] = {0, 0, 0, 0}; if (fwrite(z, 1, 4 - pos % 4, w->f) != 4 - pos % 4) return XSI_E_IO; }
     }
     w->entries += n_records;
     w->variants += n_variants;
+    guard.ok = true;
     return XSI_OK;
 }
 
 extern "C" int xsi_writer_close(xsi_writer* w, int32_t max_ploidy) {
     if (!w) return XSI_E_ARG;
     int rc = XSI_OK;
+    if (w->f && w->failed) {  // leave the placeholder header (no magic): readers refuse the file
+        fclose(w->f);
+        delete w;
+        return XSI_E_IO;
+    }
     if (w->f) {
-        uint64_t pos = (uint64_t)ftello(w->f);  // xsi_factory.hpp:558-565
-        if (pos % 8) { const char z[8] = {0}; fwrite(z, 1, 8 - pos % 8, w->f); pos += 8 - pos % 8; }
+        const off_t at = ftello(w->f);  // xsi_factory.hpp:558-565
+        if (at < 0) rc = XSI_E_IO;
+        uint64_t pos = at < 0 ? 0 : (uint64_t)at;
+        if (pos % 8) { const char z[8] = {0}; if (fwrite(z, 1, 8 - pos % 8, w->f) != 8 - pos % 8) rc = XSI_E_IO; pos += 8 - pos % 8; }
         Header h;
         memset(&h, 0, sizeof(h));
         h.endianness = ENDIANNESS; h.first_magic = MAGIC; h.last_magic = MAGIC;
@@ -152,14 +167,13 @@ extern "C" int xsi_writer_close(xsi_writer* w, int32_t max_ploidy) {
         h.indices_offset = pos;
         if (!w->indices.empty() && fwrite(w->indices.data(), 8, w->indices.size(), w->f) != w->indices.size()) rc = XSI_E_IO;
         h.samples_offset = pos + w->indices.size() * 8;
-        for (const std::string& s : w->samples) fwrite(s.c_str(), 1, s.size() + 1, w->f);
+        for (const std::string& s : w->samples) if (fwrite(s.c_str(), 1, s.size() + 1, w->f) != s.size() + 1) rc = XSI_E_IO;
         h.rearrangement_track_offset = 0xFFFFFFFFu; h.sparse_offset = 0xFFFFFFFFu;
         h.rare_threshold = (uint32_t)w->mac_threshold;
         h.xcf_entries = w->entries;
         h.num_samples = w->n_samples;
-        fflush(w->f);
-        fseeko(w->f, 0, SEEK_SET);
-        if (fwrite(&h, 1, sizeof(h), w->f) != sizeof(h)) rc = XSI_E_IO;
+        if (fflush(w->f) != 0 || fseeko(w->f, 0, SEEK_SET) != 0) rc = XSI_E_IO;
+        if (rc == XSI_OK && fwrite(&h, 1, sizeof(h), w->f) != sizeof(h)) rc = XSI_E_IO;  // a failed finalise keeps the magic-less placeholder
         if (fclose(w->f) != 0) rc = XSI_E_IO;
     }
     delete w;
