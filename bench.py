@@ -487,7 +487,7 @@ def main():
                     help="also time the resident leg from this many host threads (one xsi_ctx each, blocks split between them)")
     ap.add_argument("--shape", default="hrc", choices=["hrc", "chrx"],
                     help="chrx: mixed ploidy, multi-allelic, missing and unphased genotypes (SURVEY 8(d) S4); resident one-context leg only")
-    ap.add_argument("--bcf-records", type=int, default=2 * BLOCK_LEN, help="records of the synthetic BCF of the e2e_bcf legs (0: skip them)")
+    ap.add_argument("--bcf-records", type=int, default=4 * BLOCK_LEN, help="records of the synthetic BCF of the e2e_bcf legs (0: skip them)")
     ap.add_argument("--no-shapes", action="store_true", help="skip the other BASELINE.json shapes (1KGP3, chrX, biobank) of the default run")
     ap.add_argument("--sub", action="store_true", help=argparse.SUPPRESS)  # a shape sub-run: resident one-context leg only
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -539,6 +539,10 @@ def main():
         return
 
     # ---------------- B200 arm ----------------
+    # the BCF legs run whole programs (own CUDA contexts): before this process creates its own and fills the device
+    e2e_bcf = None
+    if rank == 0 and world == 1 and args.bcf_records > 0 and not args.profile_only and args.shape == "hrc" and not args.sub:
+        e2e_bcf = bcf_legs(args.samples, args.bcf_records, "both" if not args.no_cpu_baseline else "b200", min(16, usable_cores()))
     import torch
     import xsqueezeit_b200 as xb
     if not torch.cuda.is_available():
@@ -901,11 +905,6 @@ def main():
         if r is not None:
             cpu = {"value": r["value"], "unit": "Ggt/s", "cores": r["cores"], "kind": "reference", "sample": r["sample"],
                    "compress_ggts": r["compress"], "decompress_ggts": r["decompress"], "verified": r["ok"]}
-
-    e2e_bcf = None
-    if rank == 0 and world == 1 and args.bcf_records > 0 and not args.profile_only and args.shape == "hrc":
-        ctx.sync()
-        e2e_bcf = bcf_legs(S, args.bcf_records, "both" if not args.no_cpu_baseline else "b200", min(16, usable_cores()))
 
     # ---- the other shapes: short sub-runs once this process has let go of its device memory ----
     shapes = None

@@ -51,8 +51,28 @@ double now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+// Row staging of a batch.  Pageable on purpose: page-locking is slow on some hosts (2.5 s per GB measured on the B200 box,
+// i.e. longer than reading the records), while the H2D copy of a pageable batch through the driver's bounce buffers costs
+// tens of milliseconds and runs on the encoder thread beside the reader.
+struct Rows {
+    void* p = nullptr;
+    size_t cap = 0;
+    void reserve(size_t bytes, size_t keep = 0) {
+        if (bytes <= cap) return;
+        size_t want = cap ? cap : (size_t)1 << 20;
+        while (want < bytes) want *= 2;
+        void* q = malloc(want);
+        if (!q) throw "out of memory";
+        if (keep) memcpy(q, p, keep);
+        free(p);
+        p = q; cap = want;
+    }
+    ~Rows() { free(p); }
+    template <typename T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 struct Batch {
-    xsi_b200::Pinned rows;
+    Rows rows;
     std::vector<uint32_t> n_allele;
     std::vector<uint8_t> ploidy;
     size_t n_elems = 0;

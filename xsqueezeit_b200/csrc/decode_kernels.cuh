@@ -1141,7 +1141,6 @@ __global__ void __launch_bounds__(128) allele_counts_kernel(DecDev d, ReqDev q) 
 // listed carriers then patch (sparse lines) -- and hand every tile to the TMA engine
 // (cp.async.bulk shared->global), double buffered.  Needs 16-byte aligned output rows.
 // =============================================================================================
-constexpr int D5_TILE = 8192;
 __device__ __forceinline__ void bulk_s2g(void* dst_gmem, const void* src_smem, uint32_t bytes) {
     asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst_gmem), "r"(smem_u32(src_smem)), "r"(bytes) : "memory");
 }
@@ -1151,8 +1150,13 @@ __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.w
 template <int N_PENDING>
 __device__ __forceinline__ void bulk_wait() { asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N_PENDING) : "memory"); }
 
-template <typename OT>
-__global__ void __launch_bounds__(D4_THREADS, 2) compose_simple_kernel(DecDev d, ReqDev q) {
+// CTAs as wide as the rows are long in words (rounded up to a warp, at most 256 threads): at 5,008 haplotypes a 256-thread
+// CTA kept 157 threads busy; narrower CTAs also fit more per SM (two 20 KB tiles each), which covers the two barriers a
+// record costs.
+__host__ __device__ constexpr int d5_ctas_per_sm(int nt, int esize) { return nt >= 256 ? (esize == 1 ? 4 : 2) : (nt >= 192 ? 3 : 5); }
+template <typename OT, int NT>
+__global__ void __launch_bounds__(NT, d5_ctas_per_sm(NT, (int)sizeof(OT))) compose_simple_kernel(DecDev d, ReqDev q) {
+    constexpr uint32_t D5_TILE = NT * 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];  // 2 tiles of D5_TILE elements
     OT* tiles = reinterpret_cast<OT*>(smem_raw);
     const uint32_t tid = threadIdx.x;
@@ -1214,7 +1218,7 @@ __global__ void __launch_bounds__(D4_THREADS, 2) compose_simple_kernel(DecDev d,
             OT* tile = tiles + (size_t)buf * D5_TILE;
             const uint32_t elem0 = tt * D5_TILE;
             uint32_t w = 0;
-            if (wah) { const uint32_t wi = tt * 256 + tid; w = wi < d.WS ? row[wi] : 0u; }
+            if (wah) { const uint32_t wi = tt * NT + tid; w = wi < d.WS ? row[wi] : 0u; }
             const int32_t ce = base_even, co = base_even | ph;
             if (sizeof(OT) == 4) {
                 const uint32_t wr = __funnelshift_r(w, w, 4 * rot);  // chunk k of wr = chunk (k + rot) & 7 of w
@@ -1244,7 +1248,7 @@ __global__ void __launch_bounds__(D4_THREADS, 2) compose_simple_kernel(DecDev d,
             if (!wah && cnt) {
                 __syncthreads();
                 const int32_t spv = neg ? 2 : 4;
-                for (uint32_t k = tid; k < cnt; k += D4_THREADS) {
+                for (uint32_t k = tid; k < cnt; k += NT) {
                     const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet);
                     const uint32_t li = i - elem0;
                     if (li < (uint32_t)D5_TILE && i < n) tile[li] = (OT)(spv | ((int32_t)(i & 1u) & DP));

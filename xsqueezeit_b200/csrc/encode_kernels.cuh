@@ -72,7 +72,7 @@ __device__ __forceinline__ void emit_pred_row(const void* gt, uint64_t goff, uin
                                               uint32_t* __restrict__ dst) {
     const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
     const uint32_t nwords = (ngt + 31) >> 5, nchunks = (WS + 31) >> 5;
-    for (uint32_t c = warp; c < nchunks; c += E1_WARPS) {
+    for (uint32_t c = warp; c < nchunks; c += (blockDim.x >> 5)) {
         uint32_t keep = 0;
 #pragma unroll 4
         for (uint32_t s = 0; s < 32; ++s) {
@@ -108,7 +108,7 @@ __device__ __forceinline__ void emit_pred_row_vec(const void* gt, uint64_t goff,
         if (KIND == 2) return (uint32_t)(v == XSI_I32_VECTOR_END);
         return (uint32_t)((i & 1u) && ((v & 1) != key));
     };
-    for (uint32_t w = threadIdx.x; w < WS; w += E1_THREADS) {
+    for (uint32_t w = threadIdx.x; w < WS; w += blockDim.x) {
         const uint32_t i0 = w * 32;
         uint32_t word = 0;
         if (i0 < ngt) {
@@ -295,9 +295,14 @@ __global__ void __launch_bounds__(E1_THREADS) scan_rows_kernel(EncDev p) {
 // positions, one funnel shift to undo the rotation, coalesced 128-byte word stores.
 // Needs 16-byte aligned rows (host checks; otherwise scan_rows_kernel runs).
 // =============================================================================================
-constexpr int S2_TILE = 8192;   // genotypes per tile = 256 threads x 32
-// ring depth: ~64-96 KB of bulk copies in flight per CTA whatever the element size (8 KB int8 tiles need a deeper ring)
-__host__ __device__ constexpr int s2_stages(int elem) { return elem == 4 ? 3 : 8; }
+// genotypes per tile = NT threads x 32.  NT = 256 for long rows; rows of at most 224 words (7,168 genotypes: the 1KGP3 /
+// chrX widths) run with NT = the row's words rounded up to a warp, so that no thread idles through a tile (157 of 256
+// worked at 5,008 haplotypes) and more, smaller CTAs share an SM and cover each other's per-record bookkeeping.
+__host__ __device__ constexpr int s2_tile(int nt) { return nt * 32; }
+// ring depth: ~64-96 KB of bulk copies in flight per CTA for long rows whatever the element size (8 KB int8 tiles need a
+// deeper ring); short rows are one tile per record, two stages prefetch the next record
+__host__ __device__ constexpr int s2_stages(int elem, int nt = 256) { return elem == 4 ? (nt < 256 ? 2 : 3) : (nt < 256 ? 4 : 8); }
+__host__ __device__ constexpr int s2_ctas_per_sm(int nt) { return nt >= 256 ? 2 : (nt >= 192 ? 3 : (nt >= 160 ? 5 : 6)); }
 
 template <int ELEM>
 __device__ __forceinline__ int32_t tile_value(const unsigned char* base, uint32_t i) {
@@ -382,15 +387,16 @@ __device__ __forceinline__ void scan_words(const unsigned char* __restrict__ til
     }
 }
 
-template <int ELEM>
-__global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
+template <int ELEM, int NT>
+__global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(EncDev p) {
+    constexpr uint32_t S2_TILE = s2_tile(NT);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ uint32_t s_cnt[E1_MAXALLELE];
     __shared__ uint8_t s_lflag[E1_MAXALLELE];
     __shared__ uint32_t s_misc[4];
     __shared__ int32_t s_slot[3];
     constexpr uint32_t TILE_BYTES = S2_TILE * ELEM;
-    constexpr uint32_t S2_STAGES = s2_stages(ELEM);
+    constexpr uint32_t S2_STAGES = s2_stages(ELEM, NT);
     constexpr uint32_t TBYTES = 32 * ELEM;              // bytes of one thread's 32 genotypes
     constexpr uint32_t NCH = TBYTES / 16;               // 16-byte chunks per thread: 8 (int32) / 2 (int8)
     constexpr uint32_t EPC = 16 / ELEM;                 // genotypes per chunk: 4 / 16
@@ -398,11 +404,11 @@ __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
     uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + (size_t)S2_STAGES * TILE_BYTES);
     uint64_t* empty = full + S2_STAGES;
     const uint32_t tid = threadIdx.x, lane = lane_id();
-    const uint32_t tiles_per_rec = (p.WS + 255) / 256;
+    const uint32_t tiles_per_rec = (p.WS + NT - 1) / NT;
     const unsigned char* gbase = reinterpret_cast<const unsigned char*>(p.gt);
     const uint32_t rot = ELEM == 4 ? (tid & 7u) : ((tid >> 2) & 1u);  // chunk rotation of this thread
     if (tid == 0) {
-        for (uint32_t s = 0; s < S2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], E1_WARPS); }
+        for (uint32_t s = 0; s < S2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NT / 32); }
         fence_proxy_async();
     }
     __syncthreads();
@@ -433,7 +439,7 @@ __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
     uint32_t nx_ngt = 0, nx_nall = 0, nx_line0 = 0;
     uint64_t nx_goff = 0;
     if (blockIdx.x < p.R) { nx_ngt = p.rec_ngt[blockIdx.x]; nx_nall = p.rec_nallele[blockIdx.x]; nx_line0 = p.rec_line0[blockIdx.x]; nx_goff = p.rec_goff[blockIdx.x]; }
-    for (uint32_t i = tid; i < E1_MAXALLELE; i += E1_THREADS) { s_cnt[i] = 0; s_lflag[i] = 0; }
+    for (uint32_t i = tid; i < E1_MAXALLELE; i += NT) { s_cnt[i] = 0; s_lflag[i] = 0; }
     if (tid < 4) s_misc[tid] = 0;
     __syncthreads();
     for (uint32_t r = blockIdx.x; r < p.R; r += gridDim.x) {
@@ -447,7 +453,7 @@ __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
         const uint32_t ndt = (ngt + S2_TILE - 1) / S2_TILE;
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, nmiss = 0, neov = 0, phase = 0, err = 0;
         for (uint32_t tt = 0; tt < tiles_per_rec; ++tt) {
-            const uint32_t wi = tt * 256 + tid;
+            const uint32_t wi = tt * NT + tid;
             const uint32_t elem0 = tt * S2_TILE + tid * 32;
             const bool data = tt < ndt;
             uint32_t st = 0;
@@ -516,7 +522,7 @@ __global__ void __launch_bounds__(E1_THREADS, 2) scan_rows_v2_kernel(EncDev p) {
         // counters of the NEXT record (nobody reads these after the barrier inside finish_record): the barrier below then
         // serves both as the end of this record and as the start of the next one (one barrier less per record, which
         // is what short rows spend their time on: 39% barrier stalls at 5,008 haplotypes, ncu r01final)
-        for (uint32_t i = tid; i <= nx_nall && i < E1_MAXALLELE; i += E1_THREADS) s_cnt[i] = 0;
+        for (uint32_t i = tid; i <= nx_nall && i < E1_MAXALLELE; i += NT) s_cnt[i] = 0;
         if (tid < 4) s_misc[tid] = 0;
         __syncthreads();
     }

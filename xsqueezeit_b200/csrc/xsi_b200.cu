@@ -886,17 +886,35 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
 
         CK(cudaMemsetAsync(e.counters.p, 0, 16, ctx->stream));
         if (rows_aligned16 && !getenv("XSI_SCAN_V1")) {
-            // TMA-fed persistent scan: 2 CTAs per SM, each walks records blockIdx.x, +gridDim.x, ...
-            const uint32_t grid = (uint32_t)std::min<uint64_t>(R, (uint64_t)ctx->sm_count * 2);
-            const size_t stages = (size_t)s2_stages(elem);
-            const size_t smem = stages * S2_TILE * elem + 2 * stages * 8;
+            // TMA-fed persistent scan: CTAs walk records blockIdx.x, +gridDim.x, ...; the CTA is as wide as the rows are long
+            // (in words, rounded up to a warp) up to 256 threads, 2 to 6 CTAs per SM
+            const uint32_t words = (2 * e.n_samples + 31) / 32;
+            uint32_t nt = 256;
+            if (const char* s_ = getenv("XSI_SCAN_NT")) nt = (uint32_t)atoi(s_);
+            else if (words <= 128) nt = 128;
+            else if (words <= 160) nt = 160;
+            else if (words <= 192) nt = 192;
+            if (nt != 128 && nt != 160 && nt != 192) nt = 256;
+            const uint32_t grid = (uint32_t)std::min<uint64_t>(R, (uint64_t)ctx->sm_count * s2_ctas_per_sm((int)nt));
+            const size_t stages = (size_t)s2_stages(elem, (int)nt);
+            const size_t smem = stages * s2_tile((int)nt) * elem + 2 * stages * 8;
             PROF("scan_rows");
+            auto go = [&](auto kern) -> cudaError_t {
+                cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e_ != cudaSuccess) return e_;
+                kern<<<grid, nt, smem, ctx->stream>>>(p);
+                return cudaSuccess;
+            };
             if (elem == 4) {
-                CK(cudaFuncSetAttribute(scan_rows_v2_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                scan_rows_v2_kernel<4><<<grid, E1_THREADS, smem, ctx->stream>>>(p);
+                if (nt == 128) CK(go(scan_rows_v2_kernel<4, 128>));
+                else if (nt == 160) CK(go(scan_rows_v2_kernel<4, 160>));
+                else if (nt == 192) CK(go(scan_rows_v2_kernel<4, 192>));
+                else CK(go(scan_rows_v2_kernel<4, 256>));
             } else {
-                CK(cudaFuncSetAttribute(scan_rows_v2_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                scan_rows_v2_kernel<1><<<grid, E1_THREADS, smem, ctx->stream>>>(p);
+                if (nt == 128) CK(go(scan_rows_v2_kernel<1, 128>));
+                else if (nt == 160) CK(go(scan_rows_v2_kernel<1, 160>));
+                else if (nt == 192) CK(go(scan_rows_v2_kernel<1, 192>));
+                else CK(go(scan_rows_v2_kernel<1, 256>));
             }
         } else {
             PROF("scan_rows");
@@ -1674,10 +1692,26 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
         // (records whose own length is not, e.g. all-haploid rows of an odd sample count, stay with compose_records)
         const bool fast = !getenv("XSI_COMPOSE_V1") && (reinterpret_cast<uintptr_t>(q.out) % 16 == 0) && ((stride * sizeof(DT)) % 16 == 0);
         if (fast) {
-            const size_t smem = (size_t)2 * D5_TILE * sizeof(DT);
-            CK(cudaFuncSetAttribute(compose_simple_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            const uint32_t g2 = (uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * (sizeof(DT) == 1 ? 4 : 2));
-            { PROF("compose_simple"); compose_simple_kernel<DT><<<g2, D4_THREADS, smem, ctx->stream>>>(d.dev, q); }
+            const uint32_t words = (N + 31) / 32;
+            uint32_t nt = 256;
+            if (const char* s_ = getenv("XSI_COMPOSE_NT")) nt = (uint32_t)atoi(s_);
+            else if (words <= 160) nt = 160;
+            else if (words <= 192) nt = 192;
+            if (nt != 160 && nt != 192) nt = 256;
+            const size_t smem = (size_t)2 * nt * 32 * sizeof(DT);
+            const uint32_t g2 = (uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * d5_ctas_per_sm((int)nt, (int)sizeof(DT)));
+            auto go = [&](auto kern) -> cudaError_t {
+                cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+                if (e_ != cudaSuccess) return e_;
+                kern<<<g2, nt, smem, ctx->stream>>>(d.dev, q);
+                return cudaSuccess;
+            };
+            {
+                PROF("compose_simple");
+                if (nt == 160) CK(go(compose_simple_kernel<DT, 160>));
+                else if (nt == 192) CK(go(compose_simple_kernel<DT, 192>));
+                else CK(go(compose_simple_kernel<DT, 256>));
+            }
             CKL();
         }
         const size_t rec_smem = (size_t)2 * Npad <= (48u << 10) ? (size_t)2 * Npad : 0;
