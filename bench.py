@@ -656,7 +656,7 @@ def main():
         t_enc = sum(a.elapsed_time(b) for a, b in zip(e0, e1)) / 1e3
         t_dec = sum(b.elapsed_time(c) for b, c in zip(e1, e2)) / 1e3
         t_all = e0[0].elapsed_time(e2[-1]) / 1e3
-        return dict(t_enc=t_enc, t_dec=t_dec, t_all=t_all, payload=payload, clocks=clocks,
+        return dict(t_enc=t_enc, t_dec=t_dec, t_all=t_all, payload=payload, clocks=clocks, blocks=blocks,
                     launches=ctx.kernel_launches - launches0, prof=ctx.profile_read(), lines=lines,
                     host_ms={k: v / nsteps for k, v in host_ms.items()})
 
@@ -672,6 +672,41 @@ def main():
     verified = all(bool(torch.equal(gt[r0:r0 + BL], dec[r0:r0 + BL])) for r0 in range(0, R, BL))  # block-wise: no batch-sized temporary
     t_all, t_enc, t_dec = maxr(res["t_all"]), maxr(res["t_enc"]), maxr(res["t_dec"])
     value = 2.0 * G * world * steps / t_all / 1e9
+
+    # ---- N GPUs: ONE ordered file from the blocks the ranks encoded (outside the timed region) ----
+    # every rank writes its first blocks at the offsets of the all-gathered table (xsqueezeit_b200/sharded.py, finalised by
+    # xsi_writer_finalize_sharded); rank 0 also writes the same blocks through the single writer and compares the bytes
+    sharded_file = None
+    if dist is not None:
+        from xsqueezeit_b200 import sharded
+        nbw = min(2, B)
+        mine = [ctypes.string_at(p_, s_) for p_, s_ in res["blocks"][:nbw]]
+        tmpd = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+        tag = os.environ.get("MASTER_PORT", "0")
+        path_sh = os.path.join(tmpd, "xsi_bench_sharded_%s.xsi" % tag)
+        sharded.write_sharded(path_sh, rank, world, dist, dev, mine, nbw * world, S, None, BL, thr, 1, nbw * BL, nbw * BL, 2)
+        allb = [None] * world if rank == 0 else None
+        dist.gather_object(mine, allb, dst=0)
+        if rank == 0:
+            path_1w = os.path.join(tmpd, "xsi_bench_single_%s.xsi" % tag)
+            w = ctypes.c_void_p()
+            ok = L.xsi_writer_open(path_1w.encode(), S, None, BL, thr, 1, 0, 7, ctypes.byref(w)) == 0
+            for blks in allb:
+                for b_ in blks:
+                    buf_ = (ctypes.c_uint8 * len(b_)).from_buffer_copy(b_)
+                    ptr_ = (ctypes.c_void_p * 1)(ctypes.addressof(buf_))
+                    sz_ = (ctypes.c_uint64 * 1)(len(b_))
+                    ok = ok and L.xsi_writer_add_blocks(w, 1, ptr_, sz_, BL, BL) == 0
+            ok = ok and L.xsi_writer_close(w, 2) == 0
+            same = ok and open(path_sh, "rb").read() == open(path_1w, "rb").read()
+            sharded_file = {"ranks": world, "blocks": nbw * world, "bytes": os.path.getsize(path_sh),
+                            "equals_single_writer_file": bool(same)}
+            for f_ in (path_sh, path_1w):
+                try:
+                    os.unlink(f_)
+                except OSError:
+                    pass
+        dist.barrier()
 
     # ---- roofline of the dominant kernel (per-kernel CUDA-event times of the timed region) ----
     host_phases = {k: {"calls": n, "ms_per_step": ms / steps} for k, (n, ms) in res["prof"].items() if k.startswith("host:")}
@@ -943,7 +978,7 @@ def main():
                           "host_threads_per_gpu": resident_mt["contexts"] if use_mt else 1,
                           "contexts_per_gpu": resident_mt["contexts"] if use_mt else 1},
                 "compress_ggts": G * world * steps / t_enc / 1e9, "decompress_ggts": G * world * steps / t_dec / 1e9,
-                "verified": verified, "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8, "e2e_bcf": e2e_bcf, "shapes": shapes,
+                "verified": bool(verified and (sharded_file is None or sharded_file["equals_single_writer_file"])), "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8, "e2e_bcf": e2e_bcf, "shapes": shapes, "sharded_file": sharded_file,
                 "gpu_launches": resident_mt["gpu_launches"] if use_mt else res["launches"], "clocks": res["clocks"]}
         print(json.dumps(line))
     if ctx is not None:

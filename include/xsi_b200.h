@@ -182,6 +182,13 @@ int xsi_writer_add_blocks(xsi_writer* w, uint32_t n_blocks, const uint8_t* const
 /* finalize_file (xsi_factory.hpp:543-606): index, sample names, header rewrite. */
 int xsi_writer_close(xsi_writer* w, int32_t max_ploidy);
 
+/* One file written by several ranks (blocks shard across GPUs): after every rank has put its blocks at the
+ * offsets of the all-gathered table, ONE rank adds the index, the sample names and the header (the code of xsi_writer_close).
+ * indices[b]: absolute file offset of block b; end_of_blocks: first byte after the last block. */
+int xsi_writer_finalize_sharded(const char* path, uint32_t n_samples, const char* sample_names, uint32_t block_len,
+                                uint64_t mac_threshold, int32_t default_phasing, int32_t max_ploidy, uint32_t n_blocks,
+                                const uint64_t* indices, uint64_t end_of_blocks, uint64_t n_records, uint64_t n_variants);
+
 typedef struct xsi_reader xsi_reader;
 int  xsi_reader_open(const char* path, xsi_reader** out); /* mmap + header checks (accessor.cpp:26-82) */
 void xsi_reader_close(xsi_reader* r);

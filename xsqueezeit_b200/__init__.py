@@ -102,6 +102,14 @@ def lib():
     L.xsi_writer_add_blocks.argtypes = [vp, u32, P(vp), P(u64), u64, u64]
     L.xsi_writer_close.restype = i32
     L.xsi_writer_close.argtypes = [vp, i32]
+    L.xsi_writer_finalize_sharded.restype = i32
+    L.xsi_writer_finalize_sharded.argtypes = [ctypes.c_char_p, u32, ctypes.c_char_p, u32, u64, i32, i32, u32, P(u64), u64, u64, u64]
+    L.xsi_host_alloc.restype = i32
+    L.xsi_host_alloc.argtypes = [P(vp), u64]
+    L.xsi_host_free.restype = None
+    L.xsi_host_free.argtypes = [vp]
+    L.xsi_decode_block_info.restype = i32
+    L.xsi_decode_block_info.argtypes = [vp, u32, P(u32), P(u32)]
     L.xsi_reader_open.restype = i32
     L.xsi_reader_open.argtypes = [ctypes.c_char_p, P(vp)]
     L.xsi_reader_close.restype = None

@@ -136,6 +136,42 @@ extern "C" int xsi_writer_add_blocks(xsi_writer* w, uint32_t n_blocks, const uin
     return XSI_OK;
 }
 
+// finalize_file (xsi_factory.hpp:543-606) at the current position of `f` (just past the last block): padding to 8, the
+// u64 block index, the sample names, then the header at offset 0
+static int finalize_file(FILE* f, const xsi_writer& w, int32_t max_ploidy) {
+    int rc = XSI_OK;
+    const off_t at = ftello(f);  // xsi_factory.hpp:558-565
+    if (at < 0) return XSI_E_IO;
+    uint64_t pos = (uint64_t)at;
+    if (pos % 8) { const char z[8] = {0}; if (fwrite(z, 1, 8 - pos % 8, f) != 8 - pos % 8) rc = XSI_E_IO; pos += 8 - pos % 8; }
+    Header h;
+    memset(&h, 0, sizeof(h));
+    h.endianness = ENDIANNESS; h.first_magic = MAGIC; h.last_magic = MAGIC;
+    h.version = 5;  // xsi_factory.hpp:469
+    h.ploidy = (uint8_t)max_ploidy; h.ind_bytes = 4;
+    h.aet_bytes = ((uint64_t)w.n_samples * 2 <= 65535) ? 2 : 4;  // gt_compressor_new.hpp:182
+    h.wah_bytes = 2;
+    h.special_bitset = (uint8_t)(w.default_phasing << 2);
+    h.specific_bitset = (uint8_t)(0x01 | (w.zstd_on << 2));
+    h.hap_samples = (uint64_t)w.n_samples * (uint64_t)max_ploidy;
+    h.num_variants = w.variants;
+    h.block_size = 0; h.number_of_blocks = 1;
+    h.ss_rate = w.block_len;
+    h.number_of_ssas = (uint32_t)((w.entries + (uint32_t)w.block_len - 1) / (uint32_t)w.block_len);
+    h.wahs_offset = 256;
+    h.indices_offset = pos;
+    if (!w.indices.empty() && fwrite(w.indices.data(), 8, w.indices.size(), f) != w.indices.size()) rc = XSI_E_IO;
+    h.samples_offset = pos + w.indices.size() * 8;
+    for (const std::string& s : w.samples) if (fwrite(s.c_str(), 1, s.size() + 1, f) != s.size() + 1) rc = XSI_E_IO;
+    h.rearrangement_track_offset = 0xFFFFFFFFu; h.sparse_offset = 0xFFFFFFFFu;
+    h.rare_threshold = (uint32_t)w.mac_threshold;
+    h.xcf_entries = w.entries;
+    h.num_samples = w.n_samples;
+    if (fflush(f) != 0 || fseeko(f, 0, SEEK_SET) != 0) rc = XSI_E_IO;
+    if (rc == XSI_OK && fwrite(&h, 1, sizeof(h), f) != sizeof(h)) rc = XSI_E_IO;  // a failed finalise keeps the magic-less placeholder
+    return rc;
+}
+
 extern "C" int xsi_writer_close(xsi_writer* w, int32_t max_ploidy) {
     if (!w) return XSI_E_ARG;
     int rc = XSI_OK;
@@ -145,38 +181,35 @@ extern "C" int xsi_writer_close(xsi_writer* w, int32_t max_ploidy) {
         return XSI_E_IO;
     }
     if (w->f) {
-        const off_t at = ftello(w->f);  // xsi_factory.hpp:558-565
-        if (at < 0) rc = XSI_E_IO;
-        uint64_t pos = at < 0 ? 0 : (uint64_t)at;
-        if (pos % 8) { const char z[8] = {0}; if (fwrite(z, 1, 8 - pos % 8, w->f) != 8 - pos % 8) rc = XSI_E_IO; pos += 8 - pos % 8; }
-        Header h;
-        memset(&h, 0, sizeof(h));
-        h.endianness = ENDIANNESS; h.first_magic = MAGIC; h.last_magic = MAGIC;
-        h.version = 5;  // xsi_factory.hpp:469
-        h.ploidy = (uint8_t)max_ploidy; h.ind_bytes = 4;
-        h.aet_bytes = ((uint64_t)w->n_samples * 2 <= 65535) ? 2 : 4;  // gt_compressor_new.hpp:182
-        h.wah_bytes = 2;
-        h.special_bitset = (uint8_t)(w->default_phasing << 2);
-        h.specific_bitset = (uint8_t)(0x01 | (w->zstd_on << 2));
-        h.hap_samples = (uint64_t)w->n_samples * (uint64_t)max_ploidy;
-        h.num_variants = w->variants;
-        h.block_size = 0; h.number_of_blocks = 1;
-        h.ss_rate = w->block_len;
-        h.number_of_ssas = (uint32_t)((w->entries + (uint32_t)w->block_len - 1) / (uint32_t)w->block_len);
-        h.wahs_offset = 256;
-        h.indices_offset = pos;
-        if (!w->indices.empty() && fwrite(w->indices.data(), 8, w->indices.size(), w->f) != w->indices.size()) rc = XSI_E_IO;
-        h.samples_offset = pos + w->indices.size() * 8;
-        for (const std::string& s : w->samples) if (fwrite(s.c_str(), 1, s.size() + 1, w->f) != s.size() + 1) rc = XSI_E_IO;
-        h.rearrangement_track_offset = 0xFFFFFFFFu; h.sparse_offset = 0xFFFFFFFFu;
-        h.rare_threshold = (uint32_t)w->mac_threshold;
-        h.xcf_entries = w->entries;
-        h.num_samples = w->n_samples;
-        if (fflush(w->f) != 0 || fseeko(w->f, 0, SEEK_SET) != 0) rc = XSI_E_IO;
-        if (rc == XSI_OK && fwrite(&h, 1, sizeof(h), w->f) != sizeof(h)) rc = XSI_E_IO;  // a failed finalise keeps the magic-less placeholder
+        rc = finalize_file(w->f, *w, max_ploidy);
         if (fclose(w->f) != 0) rc = XSI_E_IO;
     }
     delete w;
+    return rc;
+}
+
+// Several writers, one file (one rank per GPU, xsqueezeit_b200/sharded.py): every rank has written its blocks at the offsets
+// of the global table (all-gather of the per-block byte counts); one rank then calls this to add what the single writer's
+// close adds -- same code, so the file is the single writer's byte for byte.  indices: absolute offset of every block;
+// end_of_blocks: first byte after the last block.
+extern "C" int xsi_writer_finalize_sharded(const char* path, uint32_t n_samples, const char* sample_names, uint32_t block_len,
+                                           uint64_t mac_threshold, int32_t default_phasing, int32_t max_ploidy, uint32_t n_blocks,
+                                           const uint64_t* indices, uint64_t end_of_blocks, uint64_t n_records, uint64_t n_variants) {
+    if (!path || block_len == 0 || (n_blocks && !indices)) return XSI_E_ARG;
+    xsi_writer w;
+    w.n_samples = n_samples; w.block_len = block_len; w.mac_threshold = mac_threshold;
+    w.default_phasing = default_phasing ? 1 : 0; w.zstd_on = 0;
+    const char* sn = sample_names;
+    for (uint32_t i = 0; i < n_samples; ++i) {
+        if (sn) { w.samples.emplace_back(sn); sn += w.samples.back().size() + 1; }
+        else w.samples.push_back("S" + std::to_string(i));
+    }
+    w.indices.assign(indices, indices + n_blocks);
+    w.entries = n_records; w.variants = n_variants;
+    FILE* f = fopen(path, "r+b");
+    if (!f) return XSI_E_IO;
+    int rc = fseeko(f, (off_t)end_of_blocks, SEEK_SET) == 0 ? finalize_file(f, w, max_ploidy) : XSI_E_IO;
+    if (fclose(f) != 0) rc = XSI_E_IO;
     return rc;
 }
 

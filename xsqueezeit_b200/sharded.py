@@ -80,25 +80,15 @@ def write_sharded(path, rank, world, dist, device, my_blocks, n_blocks_total, n_
         records = int(allv[:, per].sum())
         variants = int(allv[:, per + 1].sum())
         max_ploidy = int(allv[:, per + 2].max())
-        pos = (end + 7) // 8 * 8  # xsi_factory.hpp:558-565
-        names = sample_names if sample_names is not None else ["S%d" % i for i in range(n_samples)]
-        tail = b"\0" * (pos - end) + np.asarray(indices, dtype="<u8").tobytes() + b"".join(s.encode() + b"\0" for s in names)
-        h = bytearray(HEADER_BYTES)  # header_t, compression.hpp:40-104; fields as set by xsi_factory.hpp:468-495,544-603
-        struct.pack_into("<3I", h, 0, 0xaabbccdd, 0xfeed1767, 5)
-        aet = 2 if 2 * n_samples <= 65535 else 4
-        struct.pack_into("<6B", h, 12, max_ploidy, 4, aet, 2, (1 if default_phasing else 0) << 2, 0x01)
-        struct.pack_into("<2Q", h, 32, n_samples * max_ploidy, variants)
-        struct.pack_into("<4I", h, 48, 0, 1, block_len, (records + block_len - 1) // block_len)
-        struct.pack_into("<3Q", h, 64, 256, pos, pos + 8 * len(indices))
-        struct.pack_into("<3I", h, 88, 0xFFFFFFFF, 0xFFFFFFFF, int(mac_threshold) & 0xFFFFFFFF)
-        struct.pack_into("<Q", h, 100, records)
-        struct.pack_into("<Q", h, 112, n_samples)
-        struct.pack_into("<I", h, 252, 0xfeed1767)
-        with open(path, "r+b") as f:
-            f.seek(end)
-            f.write(tail)
-            f.seek(0)
-            f.write(bytes(h))
+        # index, sample names and header: the single writer's own finalize code (csrc/xsi_container.cpp)
+        import ctypes
+        from . import lib
+        blob = None if sample_names is None else b"".join(s.encode() + b"\0" for s in sample_names)
+        idx = np.ascontiguousarray(indices, dtype=np.uint64)
+        rc = lib().xsi_writer_finalize_sharded(path.encode(), int(n_samples), blob, int(block_len), int(mac_threshold), int(default_phasing),
+                                               max_ploidy, len(idx), idx.ctypes.data_as(ctypes.POINTER(ctypes.c_uint64)), int(end), records, variants)
+        if rc != 0:
+            raise RuntimeError("xsi_writer_finalize_sharded failed (%d)" % rc)
     if world > 1:
         dist.barrier()
     return indices
