@@ -265,6 +265,10 @@ class RefPool:
             pass
 
 
+def getenv_flag(name):
+    return os.environ.get(name, "") not in ("", "0")
+
+
 def usable_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -660,6 +664,39 @@ def main():
                     launches=ctx.kernel_launches - launches0, prof=ctx.profile_read(), lines=lines,
                     host_ms={k: v / nsteps for k, v in host_ms.items()})
 
+    def run_pipelined(nsteps, nwarm):
+        """ONE context, ONE host thread, software-pipelined through xsi_encode_async: in every step the encode of the batch is
+        handed to the library (its own thread and stream) and, while it runs, the blocks of the previous step are decoded on the
+        context stream; xsi_encode_collect then closes the step.  A step still encodes one batch and decodes one batch."""
+        def collect():
+            n = ctypes.c_uint32()
+            bp = ctypes.POINTER(ctypes.c_void_p)()
+            sz = ctypes.POINTER(ctypes.c_uint64)()
+            ctx._check(L.xsi_encode_collect(ctx.h, ctypes.byref(n), ctypes.byref(bp), ctypes.byref(sz)))
+            return [(bp[i], sz[i]) for i in range(n.value)]
+
+        ctx.encode_async(True)
+        try:
+            ctx.encode_launch(gt.data_ptr(), nal[:R], S, BL, thr, 1, gt_on_device=True, gt_elem_bytes=EL)
+            prev = collect()
+            l0 = 0
+            for it in range(nwarm + nsteps):
+                if it == nwarm:
+                    ctx.profile_read()
+                    l0 = ctx.kernel_launches
+                    barrier()
+                    a = ev()
+                    a.record(stream)
+                ctx.encode_launch(gt.data_ptr(), nal[:R], S, BL, thr, 1, gt_on_device=True, gt_elem_bytes=EL)
+                decode_step(prev, dec.data_ptr(), True, R, EL)
+                prev = collect()
+            z = ev()
+            z.record(stream)
+            barrier()
+            return a.elapsed_time(z) / 1e3, ctx.kernel_launches - l0, [zlib.crc32(ctypes.string_at(p_, s_)) for p_, s_ in prev]
+        finally:
+            ctx.encode_async(False)
+
     def maxr(x):
         if dist is None:
             return x
@@ -672,6 +709,18 @@ def main():
     verified = all(bool(torch.equal(gt[r0:r0 + BL], dec[r0:r0 + BL])) for r0 in range(0, R, BL))  # block-wise: no batch-sized temporary
     t_all, t_enc, t_dec = maxr(res["t_all"]), maxr(res["t_enc"]), maxr(res["t_dec"])
     value = 2.0 * G * world * steps / t_all / 1e9
+
+    # ---- the same context and host thread, encode and decode software-pipelined inside the library ----
+    pipelined = None
+    if not args.profile_only and not getenv_flag("XSI_BENCH_NO_PIPELINE"):
+        dec.zero_()
+        tp, lp, crc_p = run_pipelined(steps, max(1, warmup))
+        tp = maxr(tp)
+        okp = all(bool(torch.equal(gt[r0:r0 + BL], dec[r0:r0 + BL])) for r0 in range(0, R, BL)) and crc_p == crcs
+        verified = verified and okp
+        pipelined = {"value": 2.0 * G * world * steps / tp / 1e9, "unit": "Ggt/s", "ms_per_step": tp / steps * 1e3, "contexts": 1,
+                     "host_threads": 1, "gpu_launches": lp, "verified": okp,
+                     "how": "xsi_encode_async: batch i+1 encodes on the library's thread and stream while batch i is decoded by the caller"}
 
     # ---- N GPUs: ONE ordered file from the blocks the ranks encoded (outside the timed region) ----
     # every rank writes its first blocks at the offsets of the all-gathered table (xsqueezeit_b200/sharded.py, finalised by
@@ -968,9 +1017,15 @@ def main():
         # `value`: the better of the two resident legs (same batch, same calls, both verified); the per-kernel numbers
         # (`kernels`, `roofline`) always come from the one-context leg, where kernels do not overlap
         use_mt = resident_mt is not None and resident_mt["verified"] and resident_mt["value"] > value
-        line = {"metric": METRIC, "value": resident_mt["value"] if use_mt else value, "unit": "Ggt/s", "n_gpus": world, "steps": steps, "warmup": warmup,
-                "ms_per_step": resident_mt["ms_per_step"] if use_mt else t_all / steps * 1e3,
-                "value_one_context": value, "ms_per_step_one_context": t_all / steps * 1e3,
+        best, best_ms, mode = value, t_all / steps * 1e3, "one context, calls in sequence"
+        if pipelined is not None and pipelined["verified"] and pipelined["value"] > best:
+            best, best_ms, mode = pipelined["value"], pipelined["ms_per_step"], "one context, one host thread, xsi_encode_async pipeline"
+        if use_mt and resident_mt["value"] > best:
+            best, best_ms, mode = resident_mt["value"], resident_mt["ms_per_step"], "%d contexts on %d host threads" % (resident_mt["contexts"], resident_mt["contexts"])
+        use_mt = use_mt and mode.endswith("host threads")
+        line = {"metric": METRIC, "value": best, "unit": "Ggt/s", "n_gpus": world, "steps": steps, "warmup": warmup,
+                "ms_per_step": best_ms, "value_mode": mode,
+                "value_one_context": value, "ms_per_step_one_context": t_all / steps * 1e3, "one_context_pipelined": pipelined,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "int32" if EL == 4 else "int8", "data": "synthetic",
                 "config": config,
@@ -979,7 +1034,8 @@ def main():
                           "contexts_per_gpu": resident_mt["contexts"] if use_mt else 1},
                 "compress_ggts": G * world * steps / t_enc / 1e9, "decompress_ggts": G * world * steps / t_dec / 1e9,
                 "verified": bool(verified and (sharded_file is None or sharded_file["equals_single_writer_file"])), "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8, "e2e_bcf": e2e_bcf, "shapes": shapes, "sharded_file": sharded_file,
-                "gpu_launches": resident_mt["gpu_launches"] if use_mt else res["launches"], "clocks": res["clocks"]}
+                "gpu_launches": resident_mt["gpu_launches"] if use_mt else (pipelined["gpu_launches"] if mode.startswith("one context, one host") else res["launches"]),
+                "clocks": res["clocks"]}
         print(json.dumps(line))
     if ctx is not None:
         ctx.close()

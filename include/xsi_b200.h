@@ -79,9 +79,16 @@ typedef struct {
 
 /* Asynchronous part: uploads (if needed), runs every encode kernel on the context stream.  */
 int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* desc);
+/* on = 1: xsi_encode_launch of DEVICE rows returns at once; the batch is encoded by a thread of the library on a stream of
+ * its own and xsi_encode_collect waits for it (errors of the launch are reported there).  The caller may decode another batch
+ * on the same context meanwhile (xsi_decode_*): one host thread then keeps the PBWT chain of batch i+1 and the HBM-bound
+ * decode kernels of batch i on the device together, and the host-side work of either call overlaps the other's kernels.
+ * While a launch is in flight the descriptor's arrays and rows must stay valid, and no other xsi_encode_* call may be made
+ * before xsi_encode_collect.  The blocks a collect returned stay valid until the launch AFTER the next one.               */
+int xsi_encode_async(xsi_ctx* ctx, int on);
 /* Waits, brings the encoded sections back and assembles the byte-exact GT blocks.
  * n_blocks_out blocks; block b is blocks_out[b] .. +sizes_out[b] (memory owned by ctx, valid
- * until the next xsi_encode_launch on this ctx).  Each is exactly what the reference's
+ * until the next xsi_encode_collect on this ctx).  Each is exactly what the reference's
  * GtBlock::write_to_stream writes: [u32 -1][u32 n][dictionary][sections].                   */
 int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint8_t* const** blocks_out,
                        const uint64_t** sizes_out);

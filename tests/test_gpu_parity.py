@@ -600,3 +600,56 @@ def test_haploid_and_multiallelic_block(ctx, tmp_path):
         acc.fill_genotype_array(2, 0)
     assert e.value.code == -5
     acc.close()
+
+
+def test_async_encode_beside_decode(ctx, tmp_path):
+    """xsi_encode_async: a batch encodes on the library's thread and stream while the caller decodes the previous one on the
+    same context; blocks of a collect stay valid while the next launch runs.  Bytes and rows equal the synchronous path."""
+    import torch
+    import xsqueezeit_b200 as xb
+    dsA = synth.make_dataset(900, 1500, seed=91, max_alt=2, multi_frac=0.1, missing=0.003)
+    dsB = synth.make_dataset(900, 1500, seed=92)
+    bl, ns = 128, 1500
+    thr = xo.mac_threshold(ns, 2, 0.01)
+
+    def oracle_blocks(ds):
+        img = oracle_image(ds, bl, 0.01)
+        rd = xo.Reader(img)
+        pos = xb.bm_positions(ds["n_allele"], bl)
+        rows = [rd.fill_genotype_array(int(ds["n_allele"][r]), int(pos[r])) for r in range(len(pos))]
+        return pos, [(row[:n].copy(), n) for row, n in rows]
+
+    dev = {k: torch.as_tensor(d["gt"], device="cuda") for k, d in (("A", dsA), ("B", dsB))}
+    sync_blocks = {}
+    for k, d in (("A", dsA), ("B", dsB)):
+        ctx.encode_launch(dev[k].data_ptr(), d["n_allele"], ns, bl, thr, 1, gt_on_device=True)
+        sync_blocks[k] = ctx.encode_collect()
+    want = {k: oracle_blocks(d) for k, d in (("A", dsA), ("B", dsB))}
+    ctx.encode_async(True)
+    try:
+        ctx.encode_launch(dev["A"].data_ptr(), dsA["n_allele"], ns, bl, thr, 1, gt_on_device=True)
+        prev, prev_k = ctx.encode_collect(), "A"
+        for it in range(6):
+            k = "B" if it % 2 == 0 else "A"
+            d = dsB if k == "B" else dsA
+            ctx.encode_launch(dev[k].data_ptr(), d["n_allele"], ns, bl, thr, 1, gt_on_device=True)  # returns at once
+            assert prev == sync_blocks[prev_k]
+            dprev = dsA if prev_k == "A" else dsB
+            ctx.decode_load_blocks(prev, ns, 2)
+            pos, rows = want[prev_k]
+            out, filled, _ = ctx.decode_records((pos >> np.uint64(15)).astype(np.uint32), (pos & np.uint64(0x7FFF)).astype(np.uint32), dprev["n_allele"])
+            for r in range(0, len(pos), 7):
+                assert filled[r] == rows[r][1] and np.array_equal(out[r, :filled[r]], rows[r][0]), (it, r)
+            prev, prev_k = ctx.encode_collect(), k
+            assert prev == sync_blocks[k]
+        # an error inside an asynchronous launch is reported by the collect
+        bad = dsA["gt"].copy()
+        bad[5] = synth.encode_gt(np.array([7], np.int8))[0]
+        tb = torch.as_tensor(bad, device="cuda")
+        ctx.encode_launch(tb.data_ptr(), np.full(len(dsA["n_allele"]), 2, np.int32), ns, bl, thr, 1, gt_on_device=True)
+        with pytest.raises(xb.XsiError) as e:
+            ctx.encode_collect()
+        assert e.value.code == -3
+    finally:
+        ctx.encode_async(False)
+    roundtrip(ctx, tmp_path, synth.make_dataset(50, 40, seed=93), 16, 0.01)  # back in the synchronous mode

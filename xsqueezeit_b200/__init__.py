@@ -72,6 +72,8 @@ def lib():
     L.xsi_encode_launch.argtypes = [vp, P(_EncodeDesc)]
     L.xsi_encode_collect.restype = i32
     L.xsi_encode_collect.argtypes = [vp, P(u32), P(P(vp)), P(P(u64))]
+    L.xsi_encode_async.restype = i32
+    L.xsi_encode_async.argtypes = [vp, i32]
     L.xsi_encode_block_sizes.restype = i32
     L.xsi_encode_block_sizes.argtypes = [vp, P(u32), P(P(u64))]
     L.xsi_encode_max_ploidy.restype = i32
@@ -209,6 +211,11 @@ class Context:
         d.n_allele = self._na.ctypes.data
         d.ploidy = None if self._pl is None else self._pl.ctypes.data
         self._check(self._L.xsi_encode_launch(self.h, ctypes.byref(d)))
+
+    def encode_async(self, on=True):
+        """xsi_encode_async: launches of device rows return at once (a library thread encodes on its own stream) and
+        encode_collect waits; decode calls on this context may run meanwhile."""
+        self._check(self._L.xsi_encode_async(self.h, 1 if on else 0))
 
     def encode_collect(self):
         """Returns the byte-exact GT blocks (list of bytes) of the last launch."""

@@ -6,7 +6,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <map>
+#include <mutex>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -60,9 +63,19 @@ size_t vec_bytes(const std::vector<T>& v) { return v.size() * sizeof(T); }
 struct xsi_ctx {
     int device = 0;
     cudaStream_t stream = nullptr, stream2 = nullptr;
+    // encode stream: the context stream, or (xsi_encode_async) a stream of its own so that an encode running on the
+    // library's worker thread and a decode issued by the caller overlap on the device
+    cudaStream_t es = nullptr, stream_enc = nullptr;
     cudaEvent_t ev_side = nullptr;
     std::string err = "";
-    uint64_t launches = 0;
+    std::atomic<uint64_t> launches{0};
+    // asynchronous encode (xsi_encode_async): xsi_encode_launch hands the batch to this thread, xsi_encode_collect joins it
+    bool async_encode = false;
+    std::thread enc_thread;
+    int enc_rc = XSI_OK;
+    bool enc_pending = false;  // a launch was handed to enc_thread and its result not yet reported by xsi_encode_collect
+    xsi_encode_desc enc_desc;
+    std::mutex prof_m;
     int sm_count = 148;
     size_t smem_optin = 0;
     // optional per-kernel timing (CUDA events on the launching stream)
@@ -106,10 +119,13 @@ struct xsi_ctx {
         PinBuf h_small, h_offs, h_out, h_flags;
         uint64_t tot_sparse = 0, tot_miss = 0, tot_eov = 0, tot_wah = 0, tot_phase = 0, tot_missw = 0, tot_eovw = 0;
         bool wah_missing = false;  // --wah-encode-missing (WS_WAH)
-        PinBuf arena;                       // finished GT blocks, back to back (16-byte aligned starts)
+        // finished GT blocks, back to back (16-byte aligned starts).  Two arenas alternate from launch to launch: the blocks
+        // a collect returned stay valid while the NEXT launch runs (a caller that decodes batch i while batch i+1 encodes)
+        PinBuf arena[2];
+        int gen = 0;                        // arena / result set of the last launch
         std::vector<uint64_t> block_at;     // offset of every block in the arena
-        std::vector<const uint8_t*> block_ptrs;
-        std::vector<uint64_t> block_sizes;
+        std::vector<const uint8_t*> block_ptrs[2];
+        std::vector<uint64_t> block_sizes[2];
         bool collected = false;
         bool any_haploid = false;
         uint64_t n_wah_lines = 0;
@@ -139,19 +155,22 @@ struct xsi_ctx {
     } while (0)
 // PROF(name) { launch; }  brackets a launch with events when profiling is on
 struct ProfScope {
-    xsi_ctx* c; bool on; cudaEvent_t a = nullptr, b = nullptr; const char* name;
-    ProfScope(xsi_ctx* ctx, const char* n) : c(ctx), on(ctx->profile), name(n) {
-        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, c->stream); }
+    xsi_ctx* c; bool on; cudaEvent_t a = nullptr, b = nullptr; const char* name; cudaStream_t st;
+    ProfScope(xsi_ctx* ctx, const char* n, cudaStream_t s) : c(ctx), on(ctx->profile), name(n), st(s) {
+        if (on) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, st); }
     }
-    ~ProfScope() { if (on) { cudaEventRecord(b, c->stream); c->spans.push_back({name, a, b}); } }
+    ~ProfScope() { if (on) { cudaEventRecord(b, st); std::lock_guard<std::mutex> g(c->prof_m); c->spans.push_back({name, a, b}); } }
 };
-#define PROF(name) ProfScope prof_scope__(ctx, name)
+// XSI_STREAM names the stream of the code being compiled: the context stream for decode, ctx->es inside the encode path
+#define XSI_STREAM ctx->stream
+#define PROF(name) ProfScope prof_scope__(ctx, name, XSI_STREAM)
 // HOSTSPAN("host:parse");  wall-clock time of a host-side phase, to the end of the enclosing scope (profiling only)
 struct HostSpan {
     xsi_ctx* c; const char* name; std::chrono::steady_clock::time_point t0;
     HostSpan(xsi_ctx* ctx, const char* n) : c(ctx), name(n), t0(std::chrono::steady_clock::now()) {}
     ~HostSpan() {
         if (!c->profile) return;
+        std::lock_guard<std::mutex> g(c->prof_m);
         auto& s = c->host_spans[name];
         s.first++;
         s.second += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
@@ -166,7 +185,7 @@ static const bool g_debug_sync = getenv("XSI_DEBUG_SYNC") != nullptr;
     do {                                                                                           \
         ctx->launches++;                                                                           \
         cudaError_t e__ = cudaGetLastError();                                                      \
-        if (e__ == cudaSuccess && g_debug_sync) e__ = cudaStreamSynchronize(ctx->stream);          \
+        if (e__ == cudaSuccess && g_debug_sync) e__ = cudaStreamSynchronize(XSI_STREAM);           \
         if (e__ != cudaSuccess) {                                                                  \
             ctx->err = std::string("kernel launch (xsi_b200.cu:") + std::to_string(__LINE__) + "): " + cudaGetErrorString(e__); \
             return XSI_E_CUDA;                                                                     \
@@ -194,13 +213,16 @@ extern "C" int xsi_create(int device, xsi_ctx** out) {
         ctx->sm_count = prop.multiProcessorCount;
         ctx->smem_optin = prop.sharedMemPerBlockOptin;
     }
+    ctx->es = ctx->stream;
     *out = ctx;
     return XSI_OK;
 }
 
 extern "C" void xsi_destroy(xsi_ctx* ctx) {
     if (!ctx) return;
+    if (ctx->enc_thread.joinable()) ctx->enc_thread.join();
     cudaSetDevice(ctx->device);
+    if (ctx->stream_enc) { cudaStreamSynchronize(ctx->stream_enc); cudaStreamDestroy(ctx->stream_enc); }
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->stream2);
     auto& e = ctx->enc;
@@ -209,7 +231,7 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
                       &e.offs, &e.scanjobs, &e.out_wah, &e.out_sparse, &e.out_miss, &e.out_eov, &e.out_phase, &e.a_pool,
                       &e.auxslots, &e.out_missw, &e.out_eovw})
         b->release();
-    for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags, &e.arena}) b->release();
+    for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags, &e.arena[0], &e.arena[1]}) b->release();
     auto& d = ctx->dec;
     for (DevBuf* b : {&d.blob, &d.meta, &d.rows, &d.job_u32, &d.job_hap, &d.tile_u32, &d.dline, &d.lists, &d.err,
                       &d.a_pool, &d.x_pool, &d.req, &d.out, &d.scratch, &d.counts, &d.seg_total, &d.tabs})
@@ -239,7 +261,7 @@ extern "C" void xsi_host_free(void* p) { if (p) cudaFreeHost(p); }
 
 extern "C" const char* xsi_last_error(const xsi_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" void* xsi_stream(xsi_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
-extern "C" uint64_t xsi_kernel_launches(const xsi_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" uint64_t xsi_kernel_launches(const xsi_ctx* ctx) { return ctx ? ctx->launches.load() : (uint64_t)0; }
 extern "C" int xsi_profile(xsi_ctx* ctx, int on) {
     if (!ctx) return XSI_E_ARG;
     ctx->profile = on != 0;
@@ -248,8 +270,11 @@ extern "C" int xsi_profile(xsi_ctx* ctx, int on) {
 // "name count total_ms\n" per kernel since the last read; clears the record
 extern "C" const char* xsi_profile_read(xsi_ctx* ctx) {
     if (!ctx) return "";
+    if (ctx->enc_thread.joinable()) ctx->enc_thread.join();  // (its result is still reported by xsi_encode_collect)
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (ctx->es != ctx->stream) cudaStreamSynchronize(ctx->es);
+    std::lock_guard<std::mutex> g(ctx->prof_m);
     std::map<std::string, std::pair<int, double>> agg;
     std::vector<std::string> order;
     for (auto& sp : ctx->spans) {
@@ -417,6 +442,8 @@ namespace {
 
 // words-per-warp of the sequential PBWT kernels: smallest power of two that covers the row with
 // <= 32 warps; XSI_PBWT_WPW overrides it (tuning).  WPW 128 runs 512 threads with 128 registers.
+#undef XSI_STREAM
+#define XSI_STREAM ctx->es
 int choose_wpw(uint32_t W) {
     int wpw = 2;
     while ((W + wpw - 1) / wpw > 32) wpw *= 2;
@@ -430,7 +457,7 @@ int choose_wpw(uint32_t W) {
 template <int WPW, int MAXT>
 int launch_permute(xsi_ctx* ctx, const EncDev& p, uint32_t NW, size_t smem) {
     CK(cudaFuncSetAttribute(pbwt_permute_smem_kernel<WPW, MAXT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { PROF("pbwt_permute"); pbwt_permute_smem_kernel<WPW, MAXT><<<p.nb, NW * 32, smem, ctx->stream>>>(p); }
+    { PROF("pbwt_permute"); pbwt_permute_smem_kernel<WPW, MAXT><<<p.nb, NW * 32, smem, ctx->es>>>(p); }
     CKL();
     return XSI_OK;
 }
@@ -438,7 +465,7 @@ int launch_permute(xsi_ctx* ctx, const EncDev& p, uint32_t NW, size_t smem) {
 template <int WPW>
 int launch_permute_v2(xsi_ctx* ctx, const EncDev& p, uint32_t NW, size_t smem) {
     CK(cudaFuncSetAttribute(pbwt_permute_v2_kernel<WPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { PROF("pbwt_permute"); pbwt_permute_v2_kernel<WPW><<<p.nb, NW * 32, smem, ctx->stream>>>(p); }
+    { PROF("pbwt_permute"); pbwt_permute_v2_kernel<WPW><<<p.nb, NW * 32, smem, ctx->es>>>(p); }
     CKL();
     return XSI_OK;
 }
@@ -447,7 +474,7 @@ template <int C>
 int launch_permute_v3(xsi_ctx* ctx, const EncDev& p, const PermV3Cfg& cfg, size_t smem, bool probe_only, int* max_clusters) {
     CK(cudaFuncSetAttribute(pbwt_permute_v3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(p.nb * C); lc.blockDim = dim3(cfg.NW * 32); lc.dynamicSmemBytes = smem; lc.stream = ctx->stream;
+    lc.gridDim = dim3(p.nb * C); lc.blockDim = dim3(cfg.NW * 32); lc.dynamicSmemBytes = smem; lc.stream = ctx->es;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -510,7 +537,7 @@ template <int C, int KH>
 int launch_permute_v4(xsi_ctx* ctx, const EncDev& p, const PermV4Cfg& cfg, uint32_t NT, size_t smem, bool probe_only, int* max_clusters) {
     CK(cudaFuncSetAttribute(pbwt_permute_v4_kernel<C, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(p.nb * C); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = smem; lc.stream = ctx->stream;
+    lc.gridDim = dim3(p.nb * C); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = smem; lc.stream = ctx->es;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
@@ -589,7 +616,7 @@ int launch_permute_grid(xsi_ctx* ctx, const EncDev& p, const PermGridCfg& cfg, s
         return XSI_OK;
     }
     void* args[] = {const_cast<EncDev*>(&p), const_cast<PermGridCfg*>(&cfg)};
-    { PROF("pbwt_permute"); CK(cudaLaunchCooperativeKernel((const void*)pbwt_permute_grid_kernel<KH>, dim3(ctx->sm_count), dim3(1024), args, smem, ctx->stream)); }
+    { PROF("pbwt_permute"); CK(cudaLaunchCooperativeKernel((const void*)pbwt_permute_grid_kernel<KH>, dim3(ctx->sm_count), dim3(1024), args, smem, ctx->es)); }
     CKL();
     return XSI_OK;
 }
@@ -638,7 +665,7 @@ int run_permute_grid(xsi_ctx* ctx, const EncDev& p, bool* done) {
         int rc = launch_permute_grid_kh(ctx, KH, p, cfg, smem, true, &per_sm);
         if (rc) return rc;
         if (per_sm < 1) return XSI_OK;
-        CK(cudaMemsetAsync(base, 0, ((size_t)cfg.nbg * per_block + 4) * 4, ctx->stream));
+        CK(cudaMemsetAsync(base, 0, ((size_t)cfg.nbg * per_block + 4) * 4, ctx->es));
         rc = launch_permute_grid_kh(ctx, KH, p, cfg, smem, false, &per_sm);
         if (rc) return rc;
         b0 += cfg.nbg;
@@ -699,7 +726,7 @@ int run_permute(xsi_ctx* ctx, const EncDev& p) {
     // > 65536 haplotypes: a[] lives in global memory (two uint32 copies per block + y / even-mask words)
     auto& e = ctx->enc;
     CK(e.a_pool.ensure(((size_t)p.nb * 2 * N + (size_t)p.nb * 2 * p.WS) * 4));
-    { PROF("pbwt_permute"); pbwt_permute_gmem_kernel<<<p.nb, 1024, 0, ctx->stream>>>(p, e.a_pool.as<uint32_t>()); }
+    { PROF("pbwt_permute"); pbwt_permute_gmem_kernel<<<p.nb, 1024, 0, ctx->es>>>(p, e.a_pool.as<uint32_t>()); }
     CKL();
     return XSI_OK;
 }
@@ -796,6 +823,7 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
     const uint64_t Lp = L ? L : 1;
 
     if (ctx->profile) {
+        std::lock_guard<std::mutex> g_(ctx->prof_m);
         auto& sp = ctx->host_spans["host:encode_tables"];
         sp.first++;
         sp.second += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_tables).count();
@@ -815,7 +843,7 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
         if (!moved) {
             const size_t gt_bytes = goff * (size_t)elem;
             CK(e.gt.ensure(gt_bytes));
-            CK(cudaMemcpyAsync(e.gt.p, d->gt, gt_bytes, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(e.gt.p, d->gt, gt_bytes, cudaMemcpyHostToDevice, ctx->es));
         }
         dgt = e.gt.p;
     }
@@ -834,7 +862,7 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
         memcpy(h + t_l0, e.h_line0.data(), R * 4);
         memcpy(h + t_lr, e.h_line_rec.data(), Lp * 4);
         memcpy(h + t_bl, e.h_blk_line0.data(), (e.nb + 1) * 4);
-        CK(cudaMemcpyAsync(e.tables.p, h, t_end, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(e.tables.p, h, t_end, cudaMemcpyHostToDevice, ctx->es));
     }
     CK(e.bitrows.ensure(Lp * e.WS * 4));
     CK(e.wahslots.ensure(Lp * e.SLOTW * 2));
@@ -882,9 +910,9 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
         p.wah_missing = e.wah_missing ? 1u : 0u;
         p.auxslots = e.auxslots.as<uint16_t>();
         p.rec_missw_n = p.rec_phase_n + R; p.rec_eovw_n = p.rec_missw_n + R;
-        if (e.wah_missing) CK(cudaMemsetAsync(p.rec_missw_n, 0, R * 2 * 4, ctx->stream));
+        if (e.wah_missing) CK(cudaMemsetAsync(p.rec_missw_n, 0, R * 2 * 4, ctx->es));
 
-        CK(cudaMemsetAsync(e.counters.p, 0, 16, ctx->stream));
+        CK(cudaMemsetAsync(e.counters.p, 0, 16, ctx->es));
         if (rows_aligned16 && !getenv("XSI_SCAN_V1")) {
             // TMA-fed persistent scan: CTAs walk records blockIdx.x, +gridDim.x, ...; the CTA is as wide as the rows are long
             // (in words, rounded up to a warp) up to 256 threads, 2 to 6 CTAs per SM
@@ -902,7 +930,7 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
             auto go = [&](auto kern) -> cudaError_t {
                 cudaError_t e_ = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
                 if (e_ != cudaSuccess) return e_;
-                kern<<<grid, nt, smem, ctx->stream>>>(p);
+                kern<<<grid, nt, smem, ctx->es>>>(p);
                 return cudaSuccess;
             };
             if (elem == 4) {
@@ -918,19 +946,19 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
             }
         } else {
             PROF("scan_rows");
-            if (elem == 4) scan_rows_kernel<4><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
-            else scan_rows_kernel<1><<<(uint32_t)R, E1_THREADS, 0, ctx->stream>>>(p);
+            if (elem == 4) scan_rows_kernel<4><<<(uint32_t)R, E1_THREADS, 0, ctx->es>>>(p);
+            else scan_rows_kernel<1><<<(uint32_t)R, E1_THREADS, 0, ctx->es>>>(p);
         }
         CKL();
         if (L) {
-            { PROF("build_wah_lists"); build_wah_lists_kernel<<<e.nb, 32, 0, ctx->stream>>>(p); }
+            { PROF("build_wah_lists"); build_wah_lists_kernel<<<e.nb, 32, 0, ctx->es>>>(p); }
             CKL();
             int rc = run_permute(ctx, p);
             if (rc) return rc;
         }
         {
             const uint64_t jobs = L + (e.wah_missing ? 3 : 1) * R;
-            { PROF("wah_encode_rows"); wah_encode_rows_kernel<<<(uint32_t)((jobs + E4_WARPS - 1) / E4_WARPS), E4_WARPS * 32, 0, ctx->stream>>>(p); }
+            { PROF("wah_encode_rows"); wah_encode_rows_kernel<<<(uint32_t)((jobs + E4_WARPS - 1) / E4_WARPS), E4_WARPS * 32, 0, ctx->es>>>(p); }
             CKL();
         }
         uint8_t* ob = e.offs.as<uint8_t>();
@@ -942,18 +970,18 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
                            {p.rec_missw_n, reinterpret_cast<uint64_t*>(ob + o_mw), (uint32_t)R, 0},
                            {p.rec_eovw_n, reinterpret_cast<uint64_t*>(ob + o_ew), (uint32_t)R, 0}};
         const uint32_t n_scans = e.wah_missing ? 7 : 5;
-        CK(cudaMemcpyAsync(e.scanjobs.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice, ctx->stream));
-        { PROF("scan_u32"); scan_u32_kernel<<<n_scans, SCAN_THREADS, 0, ctx->stream>>>(e.scanjobs.as<ScanJob>()); }
+        CK(cudaMemcpyAsync(e.scanjobs.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice, ctx->es));
+        { PROF("scan_u32"); scan_u32_kernel<<<n_scans, SCAN_THREADS, 0, ctx->es>>>(e.scanjobs.as<ScanJob>()); }
         CKL();
         // totals + counters + flags back, then size the outputs and lay the blocks out
         CK(e.h_offs.ensure(o_end + 64));
         uint8_t* ho = e.h_offs.as<uint8_t>();
-        CK(cudaMemcpyAsync(ho, e.offs.p, o_end, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(ho + o_end, e.counters.p, 16, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(ho, e.offs.p, o_end, cudaMemcpyDeviceToHost, ctx->es));
+        CK(cudaMemcpyAsync(ho + o_end, e.counters.p, 16, cudaMemcpyDeviceToHost, ctx->es));
         CK(e.h_flags.ensure(Lp + R + 16));
-        CK(cudaMemcpyAsync(e.h_flags.p, e.line_flags.p, Lp, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(e.h_flags.as<uint8_t>() + Lp, e.rec_flags.p, R, cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaStreamSynchronize(ctx->stream));
+        CK(cudaMemcpyAsync(e.h_flags.p, e.line_flags.p, Lp, cudaMemcpyDeviceToHost, ctx->es));
+        CK(cudaMemcpyAsync(e.h_flags.as<uint8_t>() + Lp, e.rec_flags.p, R, cudaMemcpyDeviceToHost, ctx->es));
+        CK(cudaStreamSynchronize(ctx->es));
         const uint32_t* cnt = reinterpret_cast<const uint32_t*>(ho + o_end);
         if (cnt[2] & ERR_ALLELE) { ctx->err = "Unknown allele error !"; return XSI_E_ALLELE; }
         if (cnt[2] & (ERR_AUX_OVERFLOW | ERR_PHASE_OVERFLOW)) {
@@ -989,12 +1017,12 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
             const uint32_t grid = (uint32_t)((jobs5 + E5_WARPS - 1) / E5_WARPS);
             {
                 PROF("sparse_emit");
-                if (e.aet == 2) sparse_emit_kernel<uint16_t><<<grid, E5_WARPS * 32, 0, ctx->stream>>>(p, em);
-                else sparse_emit_kernel<uint32_t><<<grid, E5_WARPS * 32, 0, ctx->stream>>>(p, em);
+                if (e.aet == 2) sparse_emit_kernel<uint16_t><<<grid, E5_WARPS * 32, 0, ctx->es>>>(p, em);
+                else sparse_emit_kernel<uint32_t><<<grid, E5_WARPS * 32, 0, ctx->es>>>(p, em);
             }
             CKL();
             const uint64_t jobs6 = L + (e.wah_missing ? 3 : 1) * R;
-            { PROF("pack_wah"); pack_wah_kernel<<<(uint32_t)((jobs6 + E6_WARPS - 1) / E6_WARPS), E6_WARPS * 32, 0, ctx->stream>>>(p, em); }
+            { PROF("pack_wah"); pack_wah_kernel<<<(uint32_t)((jobs6 + E6_WARPS - 1) / E6_WARPS), E6_WARPS * 32, 0, ctx->es>>>(p, em); }
             CKL();
         }
         // ---- while those run: lay out every GT block (dictionary, per-line bool vectors, section offsets) in the
@@ -1095,25 +1123,27 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
                 }
                 ly.size = pos;
             });
+            const int gen = e.gen ^ 1;  // the other arena: what the previous collect handed out stays intact
             e.block_at.assign(e.nb, 0);
-            e.block_sizes.assign(e.nb, 0);
+            e.block_sizes[gen].assign(e.nb, 0);
             e.n_wah_lines = 0;
             uint64_t arena_size = 0;
             for (uint32_t b = 0; b < e.nb; ++b) {
                 e.block_at[b] = arena_size;
-                e.block_sizes[b] = lay[b].size;
+                e.block_sizes[gen][b] = lay[b].size;
                 e.n_wah_lines += lay[b].n_wah;
                 arena_size = (arena_size + lay[b].size + 15) / 16 * 16;
             }
-            CK(e.arena.ensure(arena_size + 16));
-            uint8_t* ar = e.arena.as<uint8_t>();
-            e.block_ptrs.assign(e.nb, nullptr);
+            CK(e.arena[gen].ensure(arena_size + 16));
+            uint8_t* ar = e.arena[gen].as<uint8_t>();
+            e.block_ptrs[gen].assign(e.nb, nullptr);
+            e.gen = gen;
             for (uint32_t b = 0; b < e.nb; ++b) {
                 uint8_t* at = ar + e.block_at[b];
-                e.block_ptrs[b] = at;
+                e.block_ptrs[gen][b] = at;
                 memcpy(at, lay[b].head.data(), lay[b].head.size());
                 for (const Tail& t : lay[b].tails) memcpy(at + t.at, t.bytes.data(), t.bytes.size());
-                for (const Copy& c : lay[b].copies) CK(cudaMemcpyAsync(at + c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->stream));
+                for (const Copy& c : lay[b].copies) CK(cudaMemcpyAsync(at + c.dst, c.src, c.bytes, cudaMemcpyDeviceToHost, ctx->es));
             }
         }
         e.launched = true;
@@ -1129,18 +1159,18 @@ static int xsi_encode_collect_impl(xsi_ctx* ctx, uint32_t* n_blocks_out, const u
     auto& e = ctx->enc;
     if (!e.launched) { ctx->err = "xsi_encode_collect without a successful xsi_encode_launch"; return XSI_E_ARG; }
     CK(cudaSetDevice(ctx->device));
-    CK(cudaStreamSynchronize(ctx->stream));  // the sections have landed in the arena (laid out in xsi_encode_launch)
+    CK(cudaStreamSynchronize(ctx->es));  // the sections have landed in the arena (laid out in xsi_encode_launch)
     e.collected = true;
     if (n_blocks_out) *n_blocks_out = e.nb;
-    if (blocks_out) *blocks_out = e.block_ptrs.data();
-    if (sizes_out) *sizes_out = e.block_sizes.data();
+    if (blocks_out) *blocks_out = e.block_ptrs[e.gen].data();
+    if (sizes_out) *sizes_out = e.block_sizes[e.gen].data();
     return XSI_OK;
 }
 
 extern "C" int xsi_encode_block_sizes(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint64_t** sizes_out) {
     if (!ctx || !ctx->enc.collected) return XSI_E_ARG;
     if (n_blocks_out) *n_blocks_out = ctx->enc.nb;
-    if (sizes_out) *sizes_out = ctx->enc.block_sizes.data();
+    if (sizes_out) *sizes_out = ctx->enc.block_sizes[ctx->enc.gen].data();
     return XSI_OK;
 }
 extern "C" int xsi_encode_max_ploidy(const xsi_ctx* ctx) { return ctx ? ctx->enc.max_ploidy : 0; }
@@ -1156,6 +1186,8 @@ extern "C" int xsi_encode_line_counts(const xsi_ctx* ctx, uint64_t* n_binary_lin
 // =================================================================================================
 namespace {
 
+#undef XSI_STREAM
+#define XSI_STREAM ctx->stream
 struct ParsedBlock {
     std::map<uint32_t, uint32_t> dict;
     uint32_t bcf_lines = 0, bin_lines = 0, default_phasing = 0;
@@ -1958,10 +1990,45 @@ static int guarded(xsi_ctx* ctx, F&& f) {
         return XSI_E_ARG;
     }
 }
+extern "C" int xsi_encode_async(xsi_ctx* ctx, int on) {
+    if (!ctx) return XSI_E_ARG;
+    if (ctx->enc_thread.joinable()) ctx->enc_thread.join();
+    if (on && !ctx->stream_enc) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream_enc, cudaStreamNonBlocking) != cudaSuccess) {
+            ctx->err = "cannot create the encode stream";
+            return XSI_E_CUDA;
+        }
+    }
+    if (ctx->es) cudaStreamSynchronize(ctx->es);
+    ctx->async_encode = on != 0;
+    ctx->es = on ? ctx->stream_enc : ctx->stream;
+    return XSI_OK;
+}
+
 extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
+    if (ctx && ctx->enc_thread.joinable()) ctx->enc_thread.join();  // a launch that was never collected
+    if (ctx) ctx->enc_pending = false;
+    // asynchronous mode: rows already on the device only (host rows share the context's transport rings with the decode side)
+    if (ctx && d && ctx->async_encode && d->gt_on_device) {
+        ctx->enc_desc = *d;
+        ctx->enc_rc = XSI_OK;
+        ctx->enc_pending = true;
+        try {
+            ctx->enc_thread = std::thread([ctx] { ctx->enc_rc = guarded(ctx, [&] { return xsi_encode_launch_impl(ctx, &ctx->enc_desc); }); });
+        } catch (...) {
+            ctx->err = "cannot start the encode thread";
+            return XSI_E_NOMEM;
+        }
+        return XSI_OK;
+    }
     return guarded(ctx, [&] { return xsi_encode_launch_impl(ctx, d); });
 }
 extern "C" int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint8_t* const** blocks_out, const uint64_t** sizes_out) {
+    if (ctx && ctx->enc_thread.joinable()) ctx->enc_thread.join();
+    if (ctx && ctx->enc_pending) {
+        ctx->enc_pending = false;
+        if (ctx->enc_rc != XSI_OK) return ctx->enc_rc;
+    }
     return guarded(ctx, [&] { return xsi_encode_collect_impl(ctx, n_blocks_out, blocks_out, sizes_out); });
 }
 extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks, const uint64_t* sizes, uint64_t num_samples, int32_t aet_bytes) {
