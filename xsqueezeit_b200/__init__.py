@@ -17,7 +17,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-SO_PATH = os.path.join(_HERE, "libxsi_b200.so")
+SO_PATH = os.environ.get("XSI_B200_SO") or os.path.join(_HERE, "libxsi_b200.so")  # the override is for A/B builds of the kernels
 
 XSI_OK = 0
 _ERRORS = {-1: "XSI_E_CUDA", -2: "XSI_E_ARG", -3: "XSI_E_ALLELE", -4: "XSI_E_PLOIDY", -5: "XSI_E_UNSUPPORTED",

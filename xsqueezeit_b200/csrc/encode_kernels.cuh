@@ -981,6 +981,8 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v3_kernel(EncDev p, Perm
 struct PermV4Cfg { uint32_t WSL, SH; };  // WSL = words per slice (power of 2, >= 32), SH = log2(WSL*32)
 
 template <int C, int KH>
+// (A register cap of 48 or 40, tried so that HBM-bound CTAs of another stream could share the SM, made the pipelined leg
+// SLOWER, 584 -> 502 / 483 Ggt/s: whatever shares the SM lengthens the chain, which is the critical path.  r02h.)
 __global__ void __launch_bounds__(1024, 1) pbwt_permute_v4_kernel(EncDev p, PermV4Cfg cfg) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int XW = KH == 64 ? 2 : 1;   // 32-bit words holding this thread's KH bits of a bit-row
@@ -1002,6 +1004,7 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v4_kernel(EncDev p, Perm
     const uint32_t* list = p.wah_list + p.blk_line0[b];
     const uint32_t sw0 = crank * WSL;         // first row word of this CTA's slice
     const uint32_t hb = sw0 * 32 + tid * KH;  // first haplotype of this thread
+    const bool wlive = sw0 * 32 + (tid & ~31u) * KH < N;  // this warp holds at least one real haplotype
     const uint32_t NP = WSL / WPT;            // threads taking part in step 2
     const uint32_t ypart_sa = smem_u32(ypart), ystage_sa = smem_u32(ystage), T_sa = smem_u32(T), zs_sa = smem_u32(zs), mb_sa = smem_u32(mb);
 
@@ -1120,6 +1123,9 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v4_kernel(EncDev p, Perm
 #pragma unroll
         for (int c = 0; c < C; ++c) { const uint32_t v = zs[c]; if (lane > (uint32_t)c) basev += v; Z += v; }
         Z -= pad_zeros;
+        // warps whose haplotypes all lie past N (row padding up to the power-of-two slice: 8192 positions for 5,008
+        // haplotypes) keep the barriers company but skip the update and the scatter: their positions are never read
+        if (wlive) {
 #pragma unroll
         for (int q = 0; q < KH; ++q) {
             const uint32_t j = PACK ? ((q & 1) ? (pk[q >> 1] >> 16) : (pk[q >> 1] & 0xFFFFu)) : pk[q];
@@ -1145,6 +1151,7 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v4_kernel(EncDev p, Perm
                 }
             }
         }
+        }  // wlive
 #pragma unroll
         for (int i = 0; i < XW; ++i) { x0[i] = x1[i]; x1[i] = extract_x(x2[i]); x2[i] = x3[i]; x3[i] = xf[i]; }
         e0 = e1; e1 = e2; e2 = e3; e3 = e4; e4 = e5;
