@@ -653,3 +653,21 @@ def test_async_encode_beside_decode(ctx, tmp_path):
     finally:
         ctx.encode_async(False)
     roundtrip(ctx, tmp_path, synth.make_dataset(50, 40, seed=93), 16, 0.01)  # back in the synchronous mode
+
+
+@pytest.mark.parametrize("env", [{"XSI_PBWT_V": "5"}, {"XSI_PBWT_V": "4"}, {"XSI_PBWT_V": "1"},
+                                 {"XSI_PBWT_V": "5", "XSI_PBWT_CLUSTER": "2"}, {"XSI_PBWT_V": "5", "XSI_PBWT_CLUSTER": "1", "XSI_PBWT_KH": "16"},
+                                 {"XSI_PBWT_V": "5", "XSI_PBWT_CLUSTER": "8"}, {"XSI_PBWT_V": "4", "XSI_PBWT_CLUSTER": "2"},
+                                 {"XSI_SCAN_V1": "1"}, {"XSI_SCAN_NT": "256", "XSI_COMPOSE_NT": "256"}, {"XSI_COMPOSE_V1": "1"}])
+def test_kernel_variants_are_byte_exact(ctx, tmp_path, monkeypatch, env):
+    """every kernel variant that ships (the two-line and the one-line cluster kernels at several cluster sizes, the general
+    shared-memory kernel, the ballot scan, the fixed-width CTAs) against the oracle: odd and even numbers of WAH lines per block,
+    rows of several widths, blocks that end on a sparse line"""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cases = [(synth.make_dataset(333, 2504, seed=101), 111, 0.001),            # 1KGP3 width, 3 blocks of 111 records
+             (synth.make_dataset(90, 20000, seed=102, n_founders=32), 45, 0.001),  # 40,000 haplotypes
+             (synth.make_dataset(64, 32488, seed=103, n_founders=32), 32, 0.001),  # HRC width
+             (synth.make_dataset(41, 700, seed=104, max_alt=3, multi_frac=0.3, missing=0.01), 41, 0.0)]  # every line WAH
+    for ds, bl, maf in cases:
+        roundtrip(ctx, tmp_path, ds, bl, maf)

@@ -676,283 +676,7 @@ __global__ void __launch_bounds__(MAXT, 1) pbwt_permute_smem_kernel(EncDev p) {
     }
 }
 
-// =============================================================================================
-// E3 v2: PBWT permute, diploid lines only (the launch falls back to the kernel above when the
-// batch holds an all-haploid record).  Same contract, ~4x fewer instructions per line:
-//   A  y[j] = row[a[j]] by ballot, the warp's y words stay in registers (lane q keeps word q)
-//   A' per-warp exclusive zero counts -> ytab[word] = {y, zeros before the word inside the warp}
-//   C  dest(j) = y[j] ? Z + j - zb(j) : zb(j),  zb(j) = zeros before j;  a[dest] = a[j]
-// Two block barriers per line.  Positions >= N of the last warp are treated as ones, so they
-// stay where they are; only that warp runs the checked variant of the loops.
-// dynamic smem (bytes): a[Npad*2] | row[2][WS*4] | ytab[RW*8] | zc[32*4] | mbar[2*8]
-// =============================================================================================
-template <int WPW, bool CHECK>
-__device__ __forceinline__ void permute_gather_v2(const uint16_t* __restrict__ a, const uint32_t* __restrict__ row,
-                                                  uint2* __restrict__ ytab, uint32_t* __restrict__ zc,
-                                                  uint32_t* __restrict__ grow, uint32_t (&av)[(WPW + 1) / 2], uint32_t N,
-                                                  uint32_t WS, uint32_t w0, uint32_t lane, uint32_t warp) {
-    constexpr int KQ = (WPW + 31) / 32;
-    uint32_t ykeep[KQ];
-#pragma unroll
-    for (int k = 0; k < KQ; ++k) ykeep[k] = 0;
-    // ---- A: gather ----
-#pragma unroll
-    for (int q = 0; q < WPW; ++q) {
-        const uint32_t j = (w0 + q) * 32 + lane;
-        const uint32_t aj = a[j];
-        if (q & 1) av[q >> 1] |= aj << 16; else av[q >> 1] = aj;
-        uint32_t bit;
-        if (CHECK) {
-            const bool valid = j < N;
-            const uint32_t gi = valid ? aj : 0u;
-            bit = valid ? ((row[gi >> 5] >> (gi & 31)) & 1u) : 1u;
-        } else {
-            bit = (row[aj >> 5] >> (aj & 31)) & 1u;
-        }
-        const uint32_t yk = __ballot_sync(XSI_FULL, bit);
-        if (lane == (uint32_t)(q & 31)) ykeep[q >> 5] = yk;
-    }
-    // ---- A': zero prefix per word inside the warp, permuted row to global ----
-    uint32_t carry = 0;
-#pragma unroll
-    for (int k = 0; k < KQ; ++k) {
-        const bool mine = (k * 32 + (int)lane) < WPW;
-        const uint32_t widx = w0 + k * 32 + lane;
-        const uint32_t nz = mine ? __popc(~ykeep[k]) : 0u;
-        uint32_t incl = nz;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, d); if (lane >= (uint32_t)d) incl += o; }
-        if (mine) {
-            ytab[widx] = make_uint2(ykeep[k], carry + incl - nz);
-            if (widx < WS) {
-                uint32_t yo = ykeep[k];
-                if (CHECK) {
-                    const uint32_t b0 = widx * 32;
-                    yo = b0 + 32 <= N ? yo : (b0 >= N ? 0u : (yo & ((1u << (N - b0)) - 1u)));
-                }
-                grow[widx] = yo;
-            }
-        }
-        carry += __shfl_sync(XSI_FULL, incl, 31);
-    }
-    if (lane == 0) zc[warp] = carry;
-}
-
-template <int WPW>
-__global__ void __launch_bounds__(1024, 1) pbwt_permute_v2_kernel(EncDev p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t N = 2 * p.n_samples;
-    const uint32_t WS = p.WS;
-    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, NW = blockDim.x >> 5;
-    const uint32_t RW = NW * WPW, Npad = RW * 32;
-    uint16_t* a = reinterpret_cast<uint16_t*>(smem_raw);
-    uint32_t* rowbuf = reinterpret_cast<uint32_t*>(smem_raw + (size_t)Npad * 2);
-    uint2* ytab = reinterpret_cast<uint2*>(rowbuf + 2 * WS);
-    uint32_t* zc = reinterpret_cast<uint32_t*>(ytab + RW);
-    uint64_t* mbar = reinterpret_cast<uint64_t*>(zc + 32);
-    const uint32_t b = blockIdx.x;
-    const uint32_t l0 = p.blk_line0[b], nwah = p.blk_nwah[b];
-    const uint32_t* list = p.wah_list + l0;
-    const uint32_t row_bytes = WS * 4;
-    for (uint32_t i = tid; i < Npad; i += blockDim.x) a[i] = (uint16_t)i;  // iota, gt_block.hpp:179
-    if (tid == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); fence_proxy_async(); }
-    __syncthreads();
-    if (nwah == 0) return;
-    if (tid == 0) {
-        mbar_expect_tx(&mbar[0], row_bytes);
-        bulk_g2s(rowbuf, p.bitrows + (size_t)(list[0] & 0x7FFFFFFFu) * WS, row_bytes, &mbar[0]);
-    }
-    const uint32_t w0 = warp * WPW, ltm = lanemask_lt(), lanebit = 1u << lane;
-    const bool checked = (w0 + WPW) * 32 > N;
-    uint32_t entry_cur = list[0], entry_next = nwah > 1 ? list[1] : 0;
-    uint32_t par0 = 0, par1 = 0;
-    for (uint32_t k = 0; k < nwah; ++k) {
-        const uint32_t cur = k & 1;
-        const uint32_t line = entry_cur & 0x7FFFFFFFu;
-        if (k + 1 < nwah && tid == 0) {
-            mbar_expect_tx(&mbar[cur ^ 1], row_bytes);
-            bulk_g2s(rowbuf + (cur ^ 1) * WS, p.bitrows + (size_t)(entry_next & 0x7FFFFFFFu) * WS, row_bytes, &mbar[cur ^ 1]);
-        }
-        entry_cur = entry_next;
-        entry_next = (k + 2 < nwah) ? list[k + 2] : 0;
-        if (cur == 0) { mbar_wait(&mbar[0], par0); par0 ^= 1; } else { mbar_wait(&mbar[1], par1); par1 ^= 1; }
-        const uint32_t* row = rowbuf + cur * WS;
-        uint32_t* grow = p.bitrows + (size_t)line * WS;
-        uint32_t av[(WPW + 1) / 2];
-        if (checked) permute_gather_v2<WPW, true>(a, row, ytab, zc, grow, av, N, WS, w0, lane, warp);
-        else permute_gather_v2<WPW, false>(a, row, ytab, zc, grow, av, N, WS, w0, lane, warp);
-        __syncthreads();  // #1: every read of a[] and row[] is done, zc complete
-        // ---- B: block offsets ----
-        const uint32_t zv = lane < NW ? zc[lane] : 0u;
-        const uint32_t Z = __reduce_add_sync(XSI_FULL, zv);
-        const uint32_t zbase = __reduce_add_sync(XSI_FULL, lane < warp ? zv : 0u);
-        const uint32_t ocst = Z + w0 * 32 + lane;
-        // ---- C: stable partition, dest(j) = y[j] ? Z + j - zb(j) : zb(j) ----
-#pragma unroll
-        for (int q = 0; q < WPW; ++q) {
-            const uint2 t = ytab[w0 + q];
-            const uint32_t zb = zbase + t.y + __popc(~t.x & ltm);
-            const uint32_t aj = (q & 1) ? (av[q >> 1] >> 16) : (av[q >> 1] & 0xFFFFu);
-            const uint32_t dest = (t.x & lanebit) ? (ocst + q * 32 - zb) : zb;
-            a[dest] = (uint16_t)aj;
-        }
-        __syncthreads();  // #2: a[] updated
-    }
-}
-
-// =============================================================================================
-// E3 v3: PBWT permute on a thread-block CLUSTER (diploid lines, <= 65534 haplotypes).
-// State is the inverse permutation pos[i] (current position of haplotype i), sliced over the C
-// CTAs of a cluster (distributed shared memory); one cluster per PBWT block.  Per WAH line:
-//   1  every CTA scatters the carriers of its haplotype slice: ypart[pos[i]] = 1   (local atomics)
-//   -- every CTA arrives on every CTA's "bitmaps ready" mbarrier (one release per CTA, not a cluster barrier) --
-//   2  CTA c ORs word slice c of all C partial bitmaps (DSMEM loads), writes the permuted row slice
-//      to global (in place), turns it into table entries  T[chunk] = zeros-before-in-slice<<16 | 16 bits
-//      and stores them, with the slice's zero total, into EVERY CTA's table (DSMEM stores)
-//   -- same with the "table ready" mbarrier --
-//   3  pos[i] <- y[j] ? Z + j - zb(j) : zb(j),  j = pos[i],  zb(j) = base[slice(j)] + T lookup
-// With C CTAs the per-line critical path shrinks ~C-fold (phases 1 and 3), which is what matters
-// when a batch has fewer blocks than the GPU has SMs.  C = 1 runs the same code without DSMEM.
-// dynamic smem: pos[NW*WPW*32] u16 | ypart[C*WSL] u32 | T[2*C*WSL] u32 | zs[8] | base[8] | sc[36] | mbar[2]
-// =============================================================================================
 namespace cgx = cooperative_groups;
-
-struct PermV3Cfg { uint32_t C, WSL, SH, NW, WPW; };  // WSL = words per slice (power of 2), SH = log2(WSL*32)
-
-template <int C>
-__global__ void __launch_bounds__(1024, 1) pbwt_permute_v3_kernel(EncDev p, PermV3Cfg cfg) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t N = 2 * p.n_samples, WS = p.WS;
-    const uint32_t WSL = cfg.WSL, WPW = cfg.WPW, NW = cfg.NW, SH = cfg.SH;
-    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, nthr = blockDim.x;
-    const uint32_t WT = C * WSL;  // words of the padded row
-    uint16_t* pos = reinterpret_cast<uint16_t*>(smem_raw);
-    const uint32_t WTa = (WT + 3) & ~3u;  // keep the table 16-byte aligned
-    uint32_t* ypart = reinterpret_cast<uint32_t*>(smem_raw + (((size_t)NW * WPW * 64 + 15) & ~(size_t)15));
-    uint32_t* T = ypart + WTa;
-    uint32_t* zs = T + 2 * WTa;
-    uint32_t* base = zs + 8;
-    uint32_t* sc = base + 8;  // [0..31] warp totals of the slice scan, [32] Z
-    uint64_t* mb = reinterpret_cast<uint64_t*>(sc + 36);  // [0] partial bitmaps ready, [1] table slices ready (C arrivals each)
-    uint32_t crank = 0;
-    if (C > 1) crank = cgx::this_cluster().block_rank();
-    const uint32_t b = blockIdx.x / C;
-    const uint32_t l0 = p.blk_line0[b], nwah = p.blk_nwah[b];
-    const uint32_t* list = p.wah_list + l0;
-    const uint32_t sw0 = crank * WSL;            // first row word of this CTA's slice
-    const uint32_t ww0 = sw0 + warp * WPW;       // first row word of this warp
-    uint16_t* mypos = pos + warp * WPW * 32 + lane;
-    for (uint32_t q = 0; q < WPW; ++q) mypos[q * 32] = (uint16_t)((ww0 + q) * 32 + lane);
-    for (uint32_t i = tid; i < WT; i += nthr) ypart[i] = 0;
-    const uint32_t ypart_sa = smem_u32(ypart), T_sa = smem_u32(T), zs_sa = smem_u32(zs);  // shared-window addresses
-    const uint32_t mb_sa = smem_u32(mb);
-    if (C > 1 && tid == 0) { mbar_init(&mb[0], C); mbar_init(&mb[1], C); }
-    if (C > 1) cgx::this_cluster().sync(); else __syncthreads();
-    // row words of this warp for the coming line: lane l keeps words l, l+32 (WPW <= 64)
-    auto load_words = [&](uint32_t line, uint32_t& a0, uint32_t& a1) {
-        const uint32_t* row = p.bitrows + (size_t)line * WS;
-        const uint32_t w_a = ww0 + lane, w_b = ww0 + 32 + lane;
-        a0 = (lane < WPW && w_a < WS) ? row[w_a] : 0u;
-        a1 = (lane + 32 < WPW && w_b < WS) ? row[w_b] : 0u;
-    };
-    uint32_t cur0 = 0, cur1 = 0, nxt0 = 0, nxt1 = 0;
-    if (nwah) load_words(list[0] & 0x7FFFFFFFu, cur0, cur1);
-    const uint32_t pad_zeros = WT * 32 - N;  // phantom zero positions past N (all in the last slices)
-    for (uint32_t k = 0; k < nwah; ++k) {
-        const uint32_t line = list[k] & 0x7FFFFFFFu;
-        if (k + 1 < nwah) load_words(list[k + 1] & 0x7FFFFFFFu, nxt0, nxt1);
-        // ---- 1: scatter the carriers of this slice ----
-        for (uint32_t q = 0; q < WPW; ++q) {
-            const uint32_t wq = __shfl_sync(XSI_FULL, q < 32 ? cur0 : cur1, q & 31);
-            if (wq == 0) continue;  // warp-uniform: no carrier among these 32 haplotypes
-            if ((wq >> lane) & 1u) {
-                const uint32_t j = mypos[q * 32];
-                atomicOr(&ypart[j >> 5], 1u << (j & 31));
-            }
-        }
-        __syncthreads();  // this CTA's partial bitmap is complete
-        if (C > 1) {
-            if (tid < C) mbar_arrive_cluster(mapa_u32(mb_sa, tid));  // tell every CTA of the cluster
-            mbar_wait_cluster(&mb[0], k & 1u);                        // ... and wait until all of theirs are
-        }
-        // ---- 2: combine word slice `crank`, zero-prefix inside the slice, publish table entries ----
-        uint32_t run = 0;  // zeros of this thread's words so far (threads own consecutive words: tid*K ..)
-        const uint32_t K = (WSL + nthr - 1) / nthr;  // words per thread
-        uint32_t yw[2] = {0, 0};
-        for (uint32_t kk = 0; kk < K; ++kk) {
-            const uint32_t w = tid * K + kk;
-            uint32_t y = 0;
-            if (w < WSL) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) y |= (C > 1) ? ld_cluster_u32(mapa_u32(ypart_sa + 4 * (sw0 + w), c)) : ypart[sw0 + w];
-            }
-            yw[kk & 1] = y;
-            run += (w < WSL) ? 32u - __popc(y) : 0u;
-        }
-        uint32_t incl = run;
-#pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, dd); if (lane >= (uint32_t)dd) incl += o; }
-        if (lane == 31) sc[warp] = incl;
-        __syncthreads();
-        {
-            const uint32_t wv = lane < (nthr >> 5) ? sc[lane] : 0u;
-            const uint32_t wbase = __reduce_add_sync(XSI_FULL, lane < warp ? wv : 0u);
-            const uint32_t total = __reduce_add_sync(XSI_FULL, wv);
-            uint32_t zp = wbase + incl - run;
-            for (uint32_t kk = 0; kk < K; ++kk) {
-                const uint32_t w = tid * K + kk;
-                if (w < WSL) {
-                    const uint32_t y = yw[kk & 1];
-                    const uint32_t e0 = (zp << 16) | (y & 0xFFFFu);
-                    const uint32_t zmid = zp + 16u - __popc(y & 0xFFFFu);
-                    const uint32_t e1 = (zmid << 16) | (y >> 16);
-#pragma unroll
-                    for (int c = 0; c < C; ++c) {
-                        if (C > 1) st_cluster_v2(mapa_u32(T_sa + 8 * (sw0 + w), c), e0, e1);
-                        else *reinterpret_cast<uint2*>(T + 2 * (sw0 + w)) = make_uint2(e0, e1);
-                    }
-                    const uint32_t gw = sw0 + w;
-                    if (gw < WS) p.bitrows[(size_t)line * WS + gw] = y;  // permuted row, in place
-                    zp += 32u - __popc(y);
-                }
-            }
-            if (tid == 0) {
-#pragma unroll
-                for (int c = 0; c < C; ++c) {
-                    if (C > 1) st_cluster_u32(mapa_u32(zs_sa + 4 * crank, c), total);
-                    else zs[crank] = total;
-                }
-            }
-        }
-        __syncthreads();  // this CTA's table slice is stored everywhere
-        if (C > 1) {
-            if (tid < C) mbar_arrive_cluster(mapa_u32(mb_sa + 8, tid));
-            mbar_wait_cluster(&mb[1], k & 1u);  // every slice of the table has landed here; my ypart is no longer read
-        }
-        // ---- slice bases, clear the partial bitmap for the next line ----
-        if (tid == 0) {
-            uint32_t acc = 0;
-#pragma unroll
-            for (int c = 0; c < C; ++c) { base[c] = acc; acc += zs[c]; }
-            sc[32] = acc - pad_zeros;  // Z: zeros among the N real positions
-        }
-        for (uint32_t i = tid; i < WT; i += nthr) ypart[i] = 0;
-        __syncthreads();
-        // ---- 3: pos[i] <- y[j] ? Z + j - zb(j) : zb(j) ----
-        const uint32_t Z = sc[32];
-#pragma unroll 4
-        for (uint32_t q = 0; q < WPW; ++q) {
-            const uint32_t j = mypos[q * 32];
-            const uint32_t e = T[j >> 4];
-            const uint32_t s = j & 15u;
-            uint32_t zb = (e >> 16) + __popc(~e & ((1u << s) - 1u));
-            if (C > 1) zb += base[j >> SH];
-            mypos[q * 32] = (uint16_t)(((e >> s) & 1u) ? Z + j - zb : zb);
-        }
-        cur0 = nxt0; cur1 = nxt1;
-    }
-    if (C > 1) cgx::this_cluster().sync();  // nobody exits while a peer may still touch its shared memory
-}
 
 // =============================================================================================
 // E3 v4: PBWT permute on a thread-block cluster with a fence-free exchange (diploid lines,
@@ -1155,6 +879,258 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v4_kernel(EncDev p, Perm
 #pragma unroll
         for (int i = 0; i < XW; ++i) { x0[i] = x1[i]; x1[i] = extract_x(x2[i]); x2[i] = x3[i]; x3[i] = xf[i]; }
         e0 = e1; e1 = e2; e2 = e3; e3 = e4; e4 = e5;
+    }
+    if (C > 1) cgx::this_cluster().sync();  // nobody exits while a peer may still push into its shared memory
+}
+
+// =============================================================================================
+// E3 v5: TWO WAH lines per exchange round (a 4-way stable partition).  v4 spends, per line, a fixed ~1.2 us
+// in its two DSMEM exchanges and ~2.6 us (C = 4) in the update itself, whose cost is the random table lookup
+// plus ~15 instructions per haplotype (r02d: 52.5 / 28.5 / 17.2 ms at C = 1 / 2 / 4, i.e. issue-bound per SM,
+// not latency-bound).  Taking lines k and k+1 together halves the exchange rounds AND the lookups:
+//   after both lines the order is: by bit of line k+1, then by bit of line k, then by the old order, so with
+//   the class c = x_k[i] | x_{k+1}[i] << 1 of haplotype i at old position j
+//       pos'[i] = (# positions of a class below c) + (# positions of class c before j)
+//   and the second term needs ONE lookup in a per-class table: per 16 positions and class, the count of that
+//   class before the chunk (inside the slice) << 16 | the 16-bit mask of the chunk's positions of that class.
+// Per pair and CTA (slice = WSL row words):
+//   0  (fused with step 4 of the previous pair) carriers of line k / k+1 set their bit in ypA / ypB at pos[i]
+//   -- __syncthreads --
+//   1  push the foreign word slices of ypA, ypB and ypO (see 5) to their owners (st.async -> ystage, mbY)
+//   2  owners (one thread per row word): y0, y1 = OR of the partial slices; row k -> global (in place); the four class
+//      masks, their counts packed 4 x 16 bit in one 64-bit word -> ONE block scan; table entries stored locally
+//      and pushed to every other CTA (two 16-byte st.async per word and destination) with the slice totals
+//   -- every thread arrives on mbT; wait: all tables here --
+//   3  per lane the base of (class, slice) = classes below + same class in lower slices (read by SHFL)
+//   4  pos[i] <- base(c, slice(j)) + count(c before j in the slice)          one LDS per haplotype and PAIR
+//   5  row k+1 has to come out in the order AFTER line k: the owner of a row word compresses its 32 bits of y1
+//      under ~y0 and under y0 (parallel-suffix compress) and ORs the two runs into ypO at the new positions of
+//      its zeros / ones of line k; ypO travels with the next round's exchange and is written one pair later.
+// Needs slices of at most 32768 positions (16-bit class counts), i.e. C >= 2 for more than 32768 haplotypes.
+// MEASURED (r02i / r02j, 32 HRC blocks, C = 4): byte-exact, but 21.6 ms against v4's 17.3 ms, so v4 stays the default and
+// this kernel is opt-in (XSI_PBWT_V=5).  The lookups did halve (16.9 instructions per haplotype and PAIR), but they are
+// only 24% of the 1,040 warp instructions a warp executes per pair: the owners' section (class masks, 64-bit scan, eight
+// table entries, six 16-byte remote stores, the two compress32 of step 5: 416 instructions on half of the warps) and the
+// exchange itself (48 KB of tables pushed per CTA and pair, twice v4's bytes per line) grew by as much as the lookups
+// shrank, and 30% of the stall samples sit in the two mbarrier waits while the owners work.  v4 itself executes 549 warp
+// instructions per warp and line of which the update is ~240: both kernels are bound by the exchange machinery around the
+// lookup, not by the lookup.
+// dynamic smem (u32): ypA[WT] ypB[WT] ypO[WT] | ystage[3][C][WSL] | T[2*WT][4] | zs[8][4] | sc64[32] (u64) | mbar[2] (u64)
+// =============================================================================================
+__device__ __forceinline__ uint32_t compress32(uint32_t x, uint32_t m) {  // bits of x under mask m, packed to the right
+    x &= m;
+    uint32_t mk = ~m << 1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        uint32_t mp = mk ^ (mk << 1);
+        mp ^= mp << 2; mp ^= mp << 4; mp ^= mp << 8; mp ^= mp << 16;
+        const uint32_t mv = mp & m;
+        m = (m ^ mv) | (mv >> (1 << i));
+        const uint32_t t = x & mv;
+        x = (x ^ t) | (t >> (1 << i));
+        mk &= ~mp;
+    }
+    return x;
+}
+
+template <int C, int KH>  // KH in {8, 16, 32}
+__global__ void __launch_bounds__(1024, 1) pbwt_permute_v5_kernel(EncDev p, PermV4Cfg cfg) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t N = 2 * p.n_samples, WS = p.WS;
+    const uint32_t WSL = cfg.WSL, SH = cfg.SH;
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, NT = blockDim.x;
+    const uint32_t WT = C * WSL;
+    uint32_t* yp = reinterpret_cast<uint32_t*>(smem_raw);  // ypA | ypB | ypO
+    uint32_t* ystage = yp + 3 * WT;                          // [3][C][WSL]
+    uint32_t* T = ystage + 3 * WT;                           // [2*WT chunks][4 classes]
+    uint32_t* zs = T + 8 * WT;                               // [C][4] class totals of every slice
+    uint64_t* sc64 = reinterpret_cast<uint64_t*>(zs + 32);   // [32] warp totals of the owners' scan
+    uint64_t* mb = sc64 + 32;                                // [0] mbY: partial slices landed, [1] mbT: tables complete
+    uint32_t crank = 0;
+    if (C > 1) crank = cgx::this_cluster().block_rank();
+    const uint32_t b = blockIdx.x / C;
+    const uint32_t nwah = p.blk_nwah[b];
+    const uint32_t* list = p.wah_list + p.blk_line0[b];
+    const uint32_t sw0 = crank * WSL;
+    const uint32_t hb = sw0 * 32 + tid * KH;
+    const bool wlive = sw0 * 32 + (tid & ~31u) * KH < N;
+    const uint32_t yp_sa = smem_u32(yp), ystage_sa = smem_u32(ystage), T_sa = smem_u32(T), zs_sa = smem_u32(zs), mb_sa = smem_u32(mb);
+
+    uint32_t pk[KH];
+#pragma unroll
+    for (int q = 0; q < KH; ++q) pk[q] = hb + q;
+    for (uint32_t i = tid; i < 3 * WT; i += NT) yp[i] = 0;
+    if (tid == 0) { mbar_init(&mb[0], 1); mbar_init(&mb[1], NT); }
+    if (C > 1) cgx::this_cluster().sync(); else __syncthreads();
+    if (nwah == 0) return;  // uniform over the cluster
+    const uint32_t npairs = (nwah + 1) / 2;
+
+    auto load_x = [&](uint32_t entry) -> uint32_t {  // the row word holding this thread's KH bits of a natural-order bit-row
+        const uint32_t* row = p.bitrows + (size_t)(entry & 0x7FFFFFFFu) * WS;
+        const uint32_t w = hb >> 5;
+        return w < WS ? row[w] : 0u;
+    };
+    auto extract_x = [&](uint32_t v) { return KH >= 32 ? v : ((v >> (hb & 31u)) & ((1u << (KH & 31)) - 1u)); };
+    auto entry_of = [&](uint32_t k) { return k < nwah ? list[k] : 0xFFFFFFFFu; };  // 0xFFFFFFFF: no such line
+    auto load_line = [&](uint32_t e) { return e == 0xFFFFFFFFu ? 0u : load_x(e); };
+    // lines of the current pair (x0, x1) and of the next one (x2, x3) as extracted bits; the pair after that as raw words
+    uint32_t e0 = entry_of(0), e1 = entry_of(1), e2 = entry_of(2), e3 = entry_of(3), e4 = entry_of(4), e5 = entry_of(5);
+    uint32_t x0 = extract_x(load_line(e0)), x1 = extract_x(load_line(e1));
+    uint32_t x2 = extract_x(load_line(e2)), x3 = extract_x(load_line(e3));
+    uint32_t r4 = load_line(e4), r5 = load_line(e5);
+    uint32_t eo = 0xFFFFFFFFu;  // the line whose permuted row sits in ypO (second line of the previous pair)
+    // step 0 of the first pair
+#pragma unroll
+    for (int q = 0; q < KH; ++q) {
+        red_or_shared_if(x0 & (1u << q), yp_sa + (((hb + q) >> 3) & ~3u), 1u << ((hb + q) & 31u));
+        red_or_shared_if(x1 & (1u << q), yp_sa + 4 * WT + (((hb + q) >> 3) & ~3u), 1u << ((hb + q) & 31u));
+    }
+    const uint32_t pad = WT * 32 - N;  // positions past N: always class 0, at the end of the position range
+
+    for (uint32_t t = 0; t <= npairs; ++t) {  // the last round only flushes ypO
+        const bool live = t < npairs;
+        const uint32_t par = t & 1u;
+        const uint32_t e6 = entry_of(2 * t + 6), e7 = entry_of(2 * t + 7);
+        const uint32_t r6 = live ? load_line(e6) : 0u, r7 = live ? load_line(e7) : 0u;
+        if (C > 1 && tid == 0) mbar_expect_tx(&mb[0], (C - 1) * WSL * 4 * 3);
+        __syncthreads();  // the three partial bitmaps of this CTA are complete
+        // ---- 1: push the foreign word slices, clear them ----
+        if (C > 1) {
+            for (uint32_t ch = tid; ch < 3 * (WT / 4); ch += NT) {
+                const uint32_t which = ch / (WT / 4), c4 = ch - which * (WT / 4);
+                const uint32_t w4 = c4 * 4, dest = w4 >> (SH - 5);
+                if (dest != crank) {
+                    uint4* src = reinterpret_cast<uint4*>(yp + which * WT) + c4;
+                    const uint4 v = *src;
+                    *src = make_uint4(0, 0, 0, 0);
+                    st_async_v4(mapa_u32(ystage_sa + 4 * ((which * C + crank) * WSL + (w4 & (WSL - 1))), dest), v, mapa_u32(mb_sa, dest));
+                }
+            }
+        }
+        // ---- 2: owners: combine my slice, write rows, publish the class tables ----
+        uint32_t y0 = 0, y1 = 0;
+        uint64_t before = 0;
+        if (tid < WSL) {
+            if (C > 1) mbar_wait(&mb[0], par);
+            const uint32_t gw = sw0 + tid;
+            uint32_t yo = yp[2 * WT + gw];
+            y0 = yp[gw]; y1 = yp[WT + gw];
+            yp[gw] = 0; yp[WT + gw] = 0; yp[2 * WT + gw] = 0;
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+                if (C > 1 && (uint32_t)c != crank) {
+                    y0 |= ystage[(0 * C + c) * WSL + tid];
+                    y1 |= ystage[(1 * C + c) * WSL + tid];
+                    yo |= ystage[(2 * C + c) * WSL + tid];
+                }
+            if (gw < WS) {
+                if (live) p.bitrows[(size_t)(e0 & 0x7FFFFFFFu) * WS + gw] = y0;                  // row k: order before line k
+                if (eo != 0xFFFFFFFFu) p.bitrows[(size_t)(eo & 0x7FFFFFFFu) * WS + gw] = yo;     // row k-1: order after line k-2
+            }
+            if (live) {
+                const uint32_t m0 = ~y0 & ~y1, m1 = y0 & ~y1, m2 = ~y0 & y1, m3 = y0 & y1;
+                const uint64_t P = (uint64_t)__popc(m0) | ((uint64_t)__popc(m1) << 16) | ((uint64_t)__popc(m2) << 32) | ((uint64_t)__popc(m3) << 48);
+                uint64_t incl = P;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) { const uint64_t o = __shfl_up_sync(XSI_FULL, incl, dd); if (lane >= (uint32_t)dd) incl += o; }
+                uint64_t wbase = 0, total = __shfl_sync(XSI_FULL, incl, 31);
+                if (WSL > 32) {
+                    if (lane == 31) sc64[warp] = incl;
+                    named_bar_sync1(WSL);
+                    const uint64_t wv = lane < (WSL >> 5) ? sc64[lane] : 0ull;
+                    const uint64_t lo = lane < warp ? wv : 0ull;
+                    // fields stay below 2^16 (slices of at most 32768 positions): the two halves can be summed separately
+                    wbase = (uint64_t)__reduce_add_sync(XSI_FULL, (uint32_t)lo) | ((uint64_t)__reduce_add_sync(XSI_FULL, (uint32_t)(lo >> 32)) << 32);
+                    total = (uint64_t)__reduce_add_sync(XSI_FULL, (uint32_t)wv) | ((uint64_t)__reduce_add_sync(XSI_FULL, (uint32_t)(wv >> 32)) << 32);
+                }
+                before = wbase + incl - P;
+                const uint32_t mm[4] = {m0, m1, m2, m3};
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    uint32_t ent[4];
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        uint32_t cnt = (uint32_t)(before >> (16 * c)) & 0xFFFFu;
+                        if (h) cnt += __popc(mm[c] & 0xFFFFu);
+                        ent[c] = (cnt << 16) | ((mm[c] >> (16 * h)) & 0xFFFFu);
+                    }
+                    const uint4 E = make_uint4(ent[0], ent[1], ent[2], ent[3]);
+                    const uint32_t chunk = 2 * gw + h;
+                    *reinterpret_cast<uint4*>(T + 4 * chunk) = E;
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        if (C > 1 && (uint32_t)c != crank) st_async_v4(mapa_u32(T_sa + 16 * chunk, c), E, mapa_u32(mb_sa + 8, c));
+                }
+                if (tid == 0) {
+                    const uint4 Z4 = make_uint4((uint32_t)total & 0xFFFFu, (uint32_t)(total >> 16) & 0xFFFFu,
+                                                (uint32_t)(total >> 32) & 0xFFFFu, (uint32_t)(total >> 48) & 0xFFFFu);
+                    *reinterpret_cast<uint4*>(zs + 4 * crank) = Z4;
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+                        if (C > 1 && (uint32_t)c != crank) st_async_v4(mapa_u32(zs_sa + 16 * crank, c), Z4, mapa_u32(mb_sa + 8, c));
+                }
+            }
+        }
+        if (!live) break;  // uniform: the flush round ends here
+        if (C > 1 && tid == 0) mbar_expect_tx(&mb[1], (C - 1) * (WSL * 32 + 16));  // counts as thread 0's arrival
+        else mbar_arrive(&mb[1]);
+        mbar_wait(&mb[1], par);
+        // ---- 3: bases.  lane c*C+s: positions of the classes below c, plus class c in the slices below s ----
+        uint32_t tot0 = 0, tot1 = 0, tot2 = 0, bs0 = 0, bs1 = 0, bs2 = 0, bs3 = 0, zb0base = 0;
+        const uint32_t myc = (lane / C) & 3u, mys = lane % C;
+#pragma unroll
+        for (int s = 0; s < C; ++s) {
+            const uint4 z = *reinterpret_cast<const uint4*>(zs + 4 * s);
+            if ((uint32_t)s < mys) { bs0 += z.x; bs1 += z.y; bs2 += z.z; bs3 += z.w; }
+            if ((uint32_t)s < crank) zb0base += z.x + z.z;  // zeros of line k in the slices below mine (step 5)
+            tot0 += z.x; tot1 += z.y; tot2 += z.z;
+        }
+        const uint32_t B1 = tot0 - pad, B2 = B1 + tot1, B3 = B2 + tot2;
+        const uint32_t cbv = myc == 0 ? bs0 : (myc == 1 ? B1 + bs1 : (myc == 2 ? B2 + bs2 : B3 + bs3));
+        // ---- 4: the update, one lookup per haplotype ----
+        if (wlive) {
+#pragma unroll
+            for (int q = 0; q < KH; ++q) {
+                const uint32_t j = pk[q];
+                const uint32_t c = ((x0 >> q) & 1u) | (((x1 >> q) & 1u) << 1);
+                const uint32_t e = lds_u32(T_sa + ((((j >> 4) << 2) | c) << 2));
+                const uint32_t r = (e >> 16) + __popc(e & ((1u << (j & 15u)) - 1u));
+                pk[q] = r + __shfl_sync(XSI_FULL, cbv, c * C + (j >> SH));
+            }
+            // step 0 of the next pair: carriers are the minority, so this is a separate, branchy pass
+            if (x2 | x3) {
+#pragma unroll
+                for (int q = 0; q < KH; ++q) {
+                    const uint32_t np = pk[q];
+                    if (x2 & (1u << q)) atomicOr(&yp[np >> 5], 1u << (np & 31u));
+                    if (x3 & (1u << q)) atomicOr(&yp[WT + (np >> 5)], 1u << (np & 31u));
+                }
+            }
+        }
+        // ---- 5: row k+1 in the order after line k, from the owner's side ----
+        if (tid < WSL && e1 != 0xFFFFFFFFu) {
+            const uint32_t gw = sw0 + tid;
+            // zeros of line k before this word (all slices): classes 0 and 2
+            const uint32_t zb = zb0base + ((uint32_t)before & 0xFFFFu) + ((uint32_t)(before >> 32) & 0xFFFFu);
+            const uint32_t Z0 = tot0 + tot2 - pad;
+            const uint32_t vz = compress32(y1, ~y0), vo = compress32(y1, y0);
+            uint32_t* out = yp + 2 * WT;
+            if (vz) {
+                const uint32_t d = zb, sh = d & 31u;
+                atomicOr(&out[d >> 5], vz << sh);
+                const uint32_t hi = sh ? vz >> (32u - sh) : 0u;  // the run may straddle two words
+                if (hi) atomicOr(&out[(d >> 5) + 1], hi);
+            }
+            if (vo) {
+                const uint32_t d = Z0 + gw * 32 - zb, sh = d & 31u;
+                atomicOr(&out[d >> 5], vo << sh);
+                const uint32_t hi = sh ? vo >> (32u - sh) : 0u;
+                if (hi) atomicOr(&out[(d >> 5) + 1], hi);
+            }
+        }
+        eo = e1;
+        x0 = x2; x1 = x3; x2 = extract_x(r4); x3 = extract_x(r5); r4 = r6; r5 = r7;
+        e0 = e2; e1 = e3; e2 = e4; e3 = e5; e4 = e6; e5 = e7;
     }
     if (C > 1) cgx::this_cluster().sync();  // nobody exits while a peer may still push into its shared memory
 }

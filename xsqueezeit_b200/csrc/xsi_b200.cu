@@ -462,77 +462,6 @@ int launch_permute(xsi_ctx* ctx, const EncDev& p, uint32_t NW, size_t smem) {
     return XSI_OK;
 }
 
-template <int WPW>
-int launch_permute_v2(xsi_ctx* ctx, const EncDev& p, uint32_t NW, size_t smem) {
-    CK(cudaFuncSetAttribute(pbwt_permute_v2_kernel<WPW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    { PROF("pbwt_permute"); pbwt_permute_v2_kernel<WPW><<<p.nb, NW * 32, smem, ctx->es>>>(p); }
-    CKL();
-    return XSI_OK;
-}
-
-template <int C>
-int launch_permute_v3(xsi_ctx* ctx, const EncDev& p, const PermV3Cfg& cfg, size_t smem, bool probe_only, int* max_clusters) {
-    CK(cudaFuncSetAttribute(pbwt_permute_v3_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t lc = {};
-    lc.gridDim = dim3(p.nb * C); lc.blockDim = dim3(cfg.NW * 32); lc.dynamicSmemBytes = smem; lc.stream = ctx->es;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    lc.attrs = at; lc.numAttrs = C > 1 ? 1 : 0;
-    if (probe_only) {
-        *max_clusters = 1 << 30;
-        if (C > 1) CK(cudaOccupancyMaxActiveClusters(max_clusters, pbwt_permute_v3_kernel<C>, &lc));
-        return XSI_OK;
-    }
-    { PROF("pbwt_permute"); CK(cudaLaunchKernelEx(&lc, pbwt_permute_v3_kernel<C>, p, cfg)); }
-    CKL();
-    return XSI_OK;
-}
-
-PermV3Cfg permute_v3_cfg(uint32_t W, uint32_t C, size_t* smem) {
-    PermV3Cfg c;
-    c.C = C;
-    uint32_t per = (W + C - 1) / C, wsl = 1, sh = 5;
-    while (wsl < per) { wsl *= 2; ++sh; }
-    c.WSL = wsl; c.SH = sh;
-    c.NW = std::min<uint32_t>(32, wsl);
-    c.WPW = wsl / c.NW;
-    const size_t WTa = ((size_t)C * wsl + 3) & ~(size_t)3;
-    *smem = (((size_t)c.NW * c.WPW * 64 + 15) & ~(size_t)15) + WTa * 4 + 2 * WTa * 4 + (8 + 8 + 36) * 4 + 16;
-    return c;
-}
-
-int run_permute_v3(xsi_ctx* ctx, const EncDev& p, uint32_t W, bool* done) {
-    *done = false;
-    int forced = 0;
-    if (const char* s = getenv("XSI_PBWT_CLUSTER")) forced = atoi(s);
-    for (uint32_t C : {8u, 4u, 2u, 1u}) {
-        if (forced && (uint32_t)forced != C) continue;
-        if (!forced && C > 1 && (uint64_t)p.nb * C > (uint64_t)ctx->sm_count) continue;
-        size_t smem = 0;
-        const PermV3Cfg cfg = permute_v3_cfg(W, C, &smem);
-        if (smem > ctx->smem_optin || cfg.WPW > 64 || (uint64_t)C * cfg.WSL * 32 > 65536) continue;
-        int maxc = 0, rc;
-        switch (C) {
-            case 8: rc = launch_permute_v3<8>(ctx, p, cfg, smem, true, &maxc); break;
-            case 4: rc = launch_permute_v3<4>(ctx, p, cfg, smem, true, &maxc); break;
-            case 2: rc = launch_permute_v3<2>(ctx, p, cfg, smem, true, &maxc); break;
-            default: rc = launch_permute_v3<1>(ctx, p, cfg, smem, true, &maxc); break;
-        }
-        if (rc) return rc;
-        if (!forced && C > 1 && (uint32_t)maxc < p.nb) continue;  // the clusters would not all be resident at once
-        switch (C) {
-            case 8: rc = launch_permute_v3<8>(ctx, p, cfg, smem, false, &maxc); break;
-            case 4: rc = launch_permute_v3<4>(ctx, p, cfg, smem, false, &maxc); break;
-            case 2: rc = launch_permute_v3<2>(ctx, p, cfg, smem, false, &maxc); break;
-            default: rc = launch_permute_v3<1>(ctx, p, cfg, smem, false, &maxc); break;
-        }
-        *done = rc == XSI_OK;
-        return rc;
-    }
-    return XSI_OK;
-}
-
 template <int C, int KH>
 int launch_permute_v4(xsi_ctx* ctx, const EncDev& p, const PermV4Cfg& cfg, uint32_t NT, size_t smem, bool probe_only, int* max_clusters) {
     CK(cudaFuncSetAttribute(pbwt_permute_v4_kernel<C, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -611,6 +540,78 @@ int run_permute_v4(xsi_ctx* ctx, const EncDev& p, uint32_t W, bool* done) {
     return XSI_OK;
 }
 
+// ---- v5: two WAH lines per exchange round ----
+template <int C, int KH>
+int launch_permute_v5(xsi_ctx* ctx, const EncDev& p, const PermV4Cfg& cfg, uint32_t NT, size_t smem, bool probe_only, int* max_clusters) {
+    CK(cudaFuncSetAttribute(pbwt_permute_v5_kernel<C, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t lc = {};
+    lc.gridDim = dim3(p.nb * C); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = smem; lc.stream = ctx->es;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    lc.attrs = at; lc.numAttrs = C > 1 ? 1 : 0;
+    if (probe_only) {
+        *max_clusters = 1 << 30;
+        if (C > 1) CK(cudaOccupancyMaxActiveClusters(max_clusters, pbwt_permute_v5_kernel<C, KH>, &lc));
+        return XSI_OK;
+    }
+    { PROF("pbwt_permute"); CK(cudaLaunchKernelEx(&lc, pbwt_permute_v5_kernel<C, KH>, p, cfg)); }
+    CKL();
+    return XSI_OK;
+}
+template <int C>
+int launch_permute_v5_kh(xsi_ctx* ctx, const EncDev& p, const PermV4Cfg& cfg, uint32_t KH, uint32_t NT, size_t smem, bool probe_only, int* maxc) {
+    switch (KH) {
+        case 8: return launch_permute_v5<C, 8>(ctx, p, cfg, NT, smem, probe_only, maxc);
+        case 16: return launch_permute_v5<C, 16>(ctx, p, cfg, NT, smem, probe_only, maxc);
+        default: return launch_permute_v5<C, 32>(ctx, p, cfg, NT, smem, probe_only, maxc);
+    }
+}
+int launch_permute_v5_c(xsi_ctx* ctx, const EncDev& p, uint32_t C, const PermV4Cfg& cfg, uint32_t KH, uint32_t NT, size_t smem, bool probe_only, int* maxc) {
+    switch (C) {
+        case 8: return launch_permute_v5_kh<8>(ctx, p, cfg, KH, NT, smem, probe_only, maxc);
+        case 4: return launch_permute_v5_kh<4>(ctx, p, cfg, KH, NT, smem, probe_only, maxc);
+        case 2: return launch_permute_v5_kh<2>(ctx, p, cfg, KH, NT, smem, probe_only, maxc);
+        default: return launch_permute_v5_kh<1>(ctx, p, cfg, KH, NT, smem, probe_only, maxc);
+    }
+}
+// Same cluster-size choice as v4 (the largest C whose clusters are all co-resident); additionally a slice may hold at most
+// 32768 positions (16-bit class counts) and the CTA needs one thread per row word of its slice (KH <= 32).
+int run_permute_v5(xsi_ctx* ctx, const EncDev& p, uint32_t W, bool* done) {
+    *done = false;
+    int forced = 0, forced_kh = 0;
+    if (const char* s = getenv("XSI_PBWT_CLUSTER")) forced = atoi(s);
+    if (const char* s = getenv("XSI_PBWT_KH")) forced_kh = atoi(s);
+    for (uint32_t C : {8u, 4u, 2u, 1u}) {
+        if (forced && (uint32_t)forced != C) continue;
+        PermV4Cfg cfg;
+        uint32_t per = (W + C - 1) / C, wsl = 32, sh = 10;
+        while (wsl < per) { wsl *= 2; ++sh; }
+        cfg.WSL = wsl; cfg.SH = sh;
+        const uint32_t HS = wsl * 32;
+        if ((uint64_t)C * HS > 65536 || HS > 32768) continue;
+        if (!forced && C > 1 && wsl * (C / 2) >= W) continue;
+        if (!forced && C > 1 && (uint64_t)p.nb * C > (uint64_t)ctx->sm_count) continue;
+        uint32_t KH = std::max<uint32_t>(8, HS / 1024);
+        if (C == 1 && KH == 8 && HS / KH > 512 && p.nb > (uint32_t)ctx->sm_count) KH = 16;
+        if (forced_kh == 8 || forced_kh == 16 || forced_kh == 32) KH = (uint32_t)forced_kh;
+        if (KH > 32) continue;
+        const uint32_t NT = HS / KH;
+        if (NT > 1024 || NT < 32 || NT < wsl) continue;
+        const size_t WT = (size_t)C * wsl;
+        const size_t smem = (14 * WT + 32) * 4 + 34 * 8;
+        if (smem > ctx->smem_optin) continue;
+        int maxc = 0;
+        int rc = launch_permute_v5_c(ctx, p, C, cfg, KH, NT, smem, true, &maxc);
+        if (rc) return rc;
+        if (!forced && C > 1 && (uint32_t)maxc < p.nb) continue;
+        rc = launch_permute_v5_c(ctx, p, C, cfg, KH, NT, smem, false, &maxc);
+        *done = rc == XSI_OK;
+        return rc;
+    }
+    return XSI_OK;
+}
+
 template <int KH>
 int launch_permute_grid(xsi_ctx* ctx, const EncDev& p, const PermGridCfg& cfg, size_t smem, bool probe_only, int* per_sm) {
     CK(cudaFuncSetAttribute(pbwt_permute_grid_kernel<KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -680,37 +681,25 @@ int run_permute_grid(xsi_ctx* ctx, const EncDev& p, bool* done) {
 int run_permute(xsi_ctx* ctx, const EncDev& p) {
     const uint32_t N = 2 * p.n_samples;
     const uint32_t W = (N + 31) / 32;
-    if (!ctx->enc.any_haploid && N > 65534 && !getenv("XSI_PBWT_V1")) {
+    // XSI_PBWT_V (tests, A/B runs): 4 = one WAH line per exchange round (default), 5 = two lines per round (measured slower:
+    // 21.6 vs 17.3 ms at 32 HRC blocks, see the note at pbwt_permute_v5_kernel), 1 = the general kernels (a[] in shared /
+    // global memory) that also serve blocks with an all-haploid record
+    int ver = 4;
+    if (const char* s = getenv("XSI_PBWT_V")) ver = atoi(s);
+    if (!ctx->enc.any_haploid && N > 65534 && ver != 1) {
         bool done = false;
         const int rc = run_permute_grid(ctx, p, &done);
         if (rc || done) return rc;
     }
-    if (!ctx->enc.any_haploid && N <= 65534 && !getenv("XSI_PBWT_V1") && !getenv("XSI_PBWT_V2") && !getenv("XSI_PBWT_V3")) {
+    if (!ctx->enc.any_haploid && N <= 65534 && ver >= 5) {
+        bool done = false;
+        const int rc = run_permute_v5(ctx, p, W, &done);
+        if (rc || done) return rc;
+    }
+    if (!ctx->enc.any_haploid && N <= 65534 && ver >= 4) {
         bool done = false;
         const int rc = run_permute_v4(ctx, p, W, &done);
         if (rc || done) return rc;
-    }
-    if (!ctx->enc.any_haploid && N <= 65534 && !getenv("XSI_PBWT_V1") && !getenv("XSI_PBWT_V2")) {
-        bool done = false;
-        const int rc = run_permute_v3(ctx, p, W, &done);
-        if (rc || done) return rc;
-    }
-    if (!ctx->enc.any_haploid && N <= 65534 && !getenv("XSI_PBWT_V1")) {
-        int wpw = 1;
-        while ((W + wpw - 1) / wpw > 32) wpw *= 2;
-        const uint32_t NW = (W + wpw - 1) / wpw, RW = NW * wpw;
-        const size_t smem2 = (size_t)RW * 32 * 2 + (size_t)2 * p.WS * 4 + (size_t)RW * 8 + 32 * 4 + 16;
-        if (wpw <= 64 && smem2 <= ctx->smem_optin) {
-            switch (wpw) {
-                case 1: return launch_permute_v2<1>(ctx, p, NW, smem2);
-                case 2: return launch_permute_v2<2>(ctx, p, NW, smem2);
-                case 4: return launch_permute_v2<4>(ctx, p, NW, smem2);
-                case 8: return launch_permute_v2<8>(ctx, p, NW, smem2);
-                case 16: return launch_permute_v2<16>(ctx, p, NW, smem2);
-                case 32: return launch_permute_v2<32>(ctx, p, NW, smem2);
-                default: return launch_permute_v2<64>(ctx, p, NW, smem2);
-            }
-        }
     }
     const size_t smem = ((size_t)N * 2 + 15) / 16 * 16 + (size_t)4 * p.WS * 4 + 64 * 4 + 16;
     if (N <= 65536 && smem <= ctx->smem_optin) {
