@@ -671,3 +671,20 @@ def test_kernel_variants_are_byte_exact(ctx, tmp_path, monkeypatch, env):
              (synth.make_dataset(41, 700, seed=104, max_alt=3, multi_frac=0.3, missing=0.01), 41, 0.0)]  # every line WAH
     for ds, bl, maf in cases:
         roundtrip(ctx, tmp_path, ds, bl, maf)
+
+
+def test_haploid_records_in_some_blocks_only(ctx, tmp_path):
+    """one batch, five blocks: all-haploid records only in blocks 1 and 3 -- those two take the general PBWT kernel, the other
+    three the cluster kernel, in the same launch (the haploid flag demotes a block, not the batch)"""
+    rng = np.random.default_rng(17)
+    ns, bl = 1300, 60
+    rows, ngt = [], []
+    for r in range(5 * bl - 7):
+        blk = r // bl
+        p = 1 if (blk in (1, 3) and r % 9 == 2) else 2
+        al = (rng.random(ns * p) < rng.uniform(0.02, 0.5)).astype(np.int8)
+        rows.append(synth.encode_gt(al, 1 if p == 2 else 0))
+        ngt.append(ns * p)
+    ds = dict(gt=np.concatenate(rows).astype(np.int32), ngt=np.array(ngt, np.int32), n_allele=np.full(len(ngt), 2, np.int32), n_samples=ns)
+    roundtrip(ctx, tmp_path, ds, bl, 0.01, blocks_per_batch=8)
+    roundtrip(ctx, tmp_path, ds, bl, 0.01, blocks_per_batch=2)

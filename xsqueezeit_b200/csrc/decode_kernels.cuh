@@ -523,93 +523,8 @@ __global__ void __launch_bounds__(MAXT, 1) pbwt_unpermute_smem_kernel(DecDev d, 
 }
 
 // =============================================================================================
-// D2 v2: undo the PBWT order without any block-wide barrier (diploid lines only; a batch with an
-// all-haploid line uses the kernel above).  State is the INVERSE permutation pos[i] = current
-// position of haplotype i, so every haplotype is independent given the line's table
-//   T[c] = (zeros in positions [0,16c)) << 16 | y bits of positions [16c, 16c+16)
-// (written by wah_expand):   j = pos[i];  x[i] = y[j];  pos[i] = y[j] ? Z + j - zb(j) : zb(j)
-// That makes the grid (block, haplotype slice): each CTA owns 32*warps words of haplotypes and
-// streams the tables through a TMA ring guarded by full/empty mbarriers.
-// dynamic smem: pos[nwarps*1024] u16 | ring[D][TW] u32 | full[D], empty[D] u64
-// =============================================================================================
-constexpr int D2_STAGES = 3;
-template <int WPW>  // natural-order words per warp: 32, 16 or 8 (fewer words = more warps in flight for small batches)
-__global__ void __launch_bounds__(1024) pbwt_unpermute_v2_kernel(DecDev d) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    const uint32_t N = 2 * d.n_samples, TW = d.TW, WS = d.WS;
-    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, NWARP = blockDim.x >> 5;
-    uint16_t* pos = reinterpret_cast<uint16_t*>(smem_raw);
-    uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw + (size_t)NWARP * WPW * 64);
-    uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)D2_STAGES * TW);
-    uint64_t* empty = full + D2_STAGES;
-    const DecBlock blk = d.blocks[blockIdx.x];
-    const uint32_t nwah = blk.n_wah;
-    const uint32_t word0 = (blockIdx.y * NWARP + warp) * WPW;  // first natural-order word of this warp
-    const uint32_t i0 = word0 * 32;
-    const uint32_t tab_bytes = TW * 4;
-    if (tid == 0) {
-        for (int s = 0; s < D2_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NWARP); }
-        fence_proxy_async();
-    }
-    uint16_t* mypos = pos + warp * WPW * 32 + lane;
-#pragma unroll
-    for (uint32_t q = 0; q < WPW; ++q) mypos[q * 32] = (uint16_t)(i0 + q * 32 + lane);
-    __syncthreads();
-    if (nwah == 0 || blockIdx.y * NWARP * WPW >= WS) return;
-    const uint32_t* tabs = d.tabs + (size_t)blk.wah0 * TW;
-    if (tid == 0) {
-        for (uint32_t k = 0; k < (uint32_t)(D2_STAGES - 1) && k < nwah; ++k) {
-            mbar_expect_tx(&full[k], tab_bytes);
-            bulk_g2s(ring + (size_t)k * TW, tabs + (size_t)k * TW, tab_bytes, &full[k]);
-        }
-    }
-    const bool checked = i0 + WPW * 32 > N;
-    for (uint32_t k = 0; k < nwah; ++k) {
-        const uint32_t st = k % D2_STAGES, use = k / D2_STAGES;
-        if (tid == 0 && k + D2_STAGES - 1 < nwah) {  // refill the stage line k-1 used
-            const uint32_t kn = k + D2_STAGES - 1, sn = kn % D2_STAGES, un = kn / D2_STAGES;
-            if (un > 0) mbar_wait(&empty[sn], (un - 1) & 1u);
-            mbar_expect_tx(&full[sn], tab_bytes);
-            bulk_g2s(ring + (size_t)sn * TW, tabs + (size_t)kn * TW, tab_bytes, &full[sn]);
-        }
-        mbar_wait(&full[st], use & 1u);
-        const uint32_t* T = ring + (size_t)st * TW;
-        const uint32_t job = blk.wah0 + k;
-        const uint32_t Z = T[2 * WS];
-        uint32_t xkeep = 0;
-        if (!checked) {
-#pragma unroll
-            for (uint32_t q = 0; q < WPW; ++q) {
-                const uint32_t j = mypos[q * 32];
-                const uint32_t e = T[j >> 4];
-                const uint32_t s = j & 15u;
-                const uint32_t zb = (e >> 16) + __popc(~e & ((1u << s) - 1u));
-                const uint32_t bit = (e >> s) & 1u;
-                mypos[q * 32] = (uint16_t)(bit ? Z + j - zb : zb);
-                const uint32_t xw = __ballot_sync(XSI_FULL, bit);
-                if (lane == q) xkeep = xw;
-            }
-        } else {
-            for (uint32_t q = 0; q < WPW; ++q) {
-                const bool valid = i0 + q * 32 + lane < N;
-                const uint32_t j = valid ? mypos[q * 32] : 0u;
-                const uint32_t e = T[j >> 4];
-                const uint32_t s = j & 15u;
-                const uint32_t zb = (e >> 16) + __popc(~e & ((1u << s) - 1u));
-                const uint32_t bit = valid ? ((e >> s) & 1u) : 0u;
-                if (valid) mypos[q * 32] = (uint16_t)(bit ? Z + j - zb : zb);
-                const uint32_t xw = __ballot_sync(XSI_FULL, bit);
-                if (lane == q) xkeep = xw;
-            }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
-        if (lane < WPW && word0 + lane < WS) d.rows[(size_t)job * WS + word0 + lane] = xkeep;  // natural-order row, in place
-    }
-}
-
-// =============================================================================================
-// D2 v3: same inverse-permutation formulation as v2, with the state in REGISTERS.  Thread t owns KH
+// D2 v3: inverse-permutation formulation (state = pos[i]; given the line's table every haplotype is independent:
+// j = pos[i]; x[i] = y[j]; pos[i] = y[j] ? Z + j - zb(j) : zb(j)), with the state in REGISTERS.  Thread t owns KH
 // consecutive haplotypes: their positions never touch shared memory (v2: one LDS + one STS per
 // haplotype and line), and the KH decoded bits of a line are assembled inside the thread (v2: one
 // ballot per 32 haplotypes), so the only shared-memory traffic left is the random table lookup

@@ -53,6 +53,9 @@ struct EncDev {
     uint16_t* auxslots;       // [aux_cap][SLOTW]
     uint32_t* rec_missw_n;    // [R] WAH words of the record's missing line (0 if none)
     uint32_t* rec_eovw_n;     // [R]
+    // PBWT kernels only: the blocks one launch works on (nb of them), or NULL for blocks 0..nb-1.  Blocks with an
+    // all-haploid record go to the general kernel, the others to the cluster kernel, in the same batch.
+    const uint32_t* blk_map;
 };
 
 #define ERR_ALLELE 1u
@@ -565,7 +568,7 @@ __global__ void __launch_bounds__(MAXT, 1) pbwt_permute_smem_kernel(EncDev p) {
     uint64_t* mbar = reinterpret_cast<uint64_t*>(zc + 64);
 
     const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5, NW = blockDim.x >> 5;
-    const uint32_t b = blockIdx.x;
+    const uint32_t b = p.blk_map ? p.blk_map[blockIdx.x] : blockIdx.x;
     const uint32_t l0 = p.blk_line0[b];
     const uint32_t nwah = p.blk_nwah[b];
     const uint32_t* list = p.wah_list + l0;
@@ -723,7 +726,7 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v4_kernel(EncDev p, Perm
     uint64_t* mb = reinterpret_cast<uint64_t*>(sc + 32);  // [0] mbY: partial slices landed, [1] mbT: table complete
     uint32_t crank = 0;
     if (C > 1) crank = cgx::this_cluster().block_rank();
-    const uint32_t b = blockIdx.x / C;
+    const uint32_t b = p.blk_map ? p.blk_map[blockIdx.x / C] : blockIdx.x / C;
     const uint32_t nwah = p.blk_nwah[b];
     const uint32_t* list = p.wah_list + p.blk_line0[b];
     const uint32_t sw0 = crank * WSL;         // first row word of this CTA's slice
@@ -948,7 +951,7 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v5_kernel(EncDev p, Perm
     uint64_t* mb = sc64 + 32;                                // [0] mbY: partial slices landed, [1] mbT: tables complete
     uint32_t crank = 0;
     if (C > 1) crank = cgx::this_cluster().block_rank();
-    const uint32_t b = blockIdx.x / C;
+    const uint32_t b = p.blk_map ? p.blk_map[blockIdx.x / C] : blockIdx.x / C;
     const uint32_t nwah = p.blk_nwah[b];
     const uint32_t* list = p.wah_list + p.blk_line0[b];
     const uint32_t sw0 = crank * WSL;

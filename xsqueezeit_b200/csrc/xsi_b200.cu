@@ -128,6 +128,9 @@ struct xsi_ctx {
         std::vector<uint64_t> block_sizes[2];
         bool collected = false;
         bool any_haploid = false;
+        std::vector<uint8_t> h_blk_hap;    // [nb] block holds an all-haploid record
+        std::vector<uint32_t> h_blk_map;   // diploid-only blocks, then the others (PBWT launch lists)
+        DevBuf blk_map;
         uint64_t n_wah_lines = 0;
     } enc;
 
@@ -229,7 +232,7 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
     for (DevBuf* b : {&e.gt, &e.tables, &e.bitrows, &e.auxrows, &e.phrows, &e.counters, &e.rec_aux, &e.line_u32,
                       &e.line_flags, &e.rec_u32, &e.rec_flags, &e.wah_list, &e.blk_nwah, &e.wahslots, &e.phslots,
                       &e.offs, &e.scanjobs, &e.out_wah, &e.out_sparse, &e.out_miss, &e.out_eov, &e.out_phase, &e.a_pool,
-                      &e.auxslots, &e.out_missw, &e.out_eovw})
+                      &e.auxslots, &e.out_missw, &e.out_eovw, &e.blk_map})
         b->release();
     for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags, &e.arena[0], &e.arena[1]}) b->release();
     auto& d = ctx->dec;
@@ -686,6 +689,27 @@ int run_permute(xsi_ctx* ctx, const EncDev& p) {
     // global memory) that also serve blocks with an all-haploid record
     int ver = 4;
     if (const char* s = getenv("XSI_PBWT_V")) ver = atoi(s);
+    // Mixed batch: blocks with an all-haploid record need the general kernel (haploid lines are encoded in the order of
+    // haploid_rearrangement_from_diploid, interfaces.hpp:318-333); the other blocks of the batch keep the cluster kernel.
+    if (ctx->enc.any_haploid && N <= 65534 && ver >= 4 && p.blk_map == nullptr) {
+        auto& e = ctx->enc;
+        uint32_t ndip = 0;
+        e.h_blk_map.clear();
+        for (uint32_t b = 0; b < p.nb; ++b) if (!e.h_blk_hap[b]) { e.h_blk_map.push_back(b); ++ndip; }
+        for (uint32_t b = 0; b < p.nb; ++b) if (e.h_blk_hap[b]) e.h_blk_map.push_back(b);
+        if (ndip > 0 && ndip < p.nb) {
+            CK(e.blk_map.ensure((size_t)p.nb * 4));
+            CK(cudaMemcpyAsync(e.blk_map.p, e.h_blk_map.data(), (size_t)p.nb * 4, cudaMemcpyHostToDevice, ctx->es));
+            EncDev q = p;
+            q.blk_map = e.blk_map.as<uint32_t>(); q.nb = ndip;
+            e.any_haploid = false;
+            int rc = run_permute(ctx, q);  // the diploid-only blocks
+            e.any_haploid = true;
+            if (rc) return rc;
+            q.blk_map = e.blk_map.as<uint32_t>() + ndip; q.nb = p.nb - ndip;
+            return run_permute(ctx, q);     // the blocks with an all-haploid record (general kernel)
+        }
+    }
     if (!ctx->enc.any_haploid && N > 65534 && ver != 1) {
         bool done = false;
         const int rc = run_permute_grid(ctx, p, &done);
@@ -748,6 +772,7 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
     // two passes over chunks of records on the worker pool: per-chunk sums, serial prefix, fill
     e.h_nallele.resize(R); e.h_ngt.resize(R); e.h_line0.resize(R); e.h_goff.resize(R);
     e.h_blk_line0.assign(e.nb + 1, 0); e.h_blk_rec0.assign(e.nb + 1, 0);
+    e.h_blk_hap.assign(e.nb, 0);
     constexpr uint64_t TCH = 1u << 16;
     const size_t nch = (size_t)((R + TCH - 1) / TCH);
     struct ChunkSum { uint64_t g = 0, l = 0; int rc = XSI_OK; const char* err = nullptr; int max_pl = 0; bool hap = false, al4 = true, al1 = true; };
@@ -765,7 +790,7 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
             // (gt_block.hpp:650-666) and cannot decode the block either, so it is refused here rather than written.
             if (na < 2 || na > 254) { k.err = "n_allele out of range (2..254)"; k.rc = XSI_E_UNSUPPORTED; return; }
             if ((int)pl > k.max_pl) k.max_pl = (int)pl;
-            if (pl == 1) k.hap = true;
+            if (pl == 1) { k.hap = true; e.h_blk_hap[r / d->block_len] = 1; }
             k.g += (uint64_t)S * pl;
             k.l += na - 1;
         }
@@ -900,6 +925,7 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
         p.wah_list = e.wah_list.as<uint32_t>(); p.blk_nwah = e.blk_nwah.as<uint32_t>();
         p.wahslots = e.wahslots.as<uint16_t>(); p.phslots = e.phslots.as<uint16_t>();
         p.wah_missing = e.wah_missing ? 1u : 0u;
+        p.blk_map = nullptr;
         p.auxslots = e.auxslots.as<uint16_t>();
         p.rec_missw_n = p.rec_phase_n + R; p.rec_eovw_n = p.rec_missw_n + R;
         if (e.wah_missing) CK(cudaMemsetAsync(p.rec_missw_n, 0, R * 2 * 4, ctx->es));
@@ -1496,26 +1522,13 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
     dd.err = d.err.as<uint32_t>();
     // D2 v2 (barrier-free, sliced over haplotypes) needs the per-line tables; all-haploid lines use v1
     const uint32_t TWv2 = 2 * d.WS + 4;
-    uint32_t un_warps = 0, un_slices = 0, un_wpw = 32;
-    size_t un_smem = 0;
-    const bool use_v2 = d.n_gt_jobs && !any_hap_job && N <= 65534 && !getenv("XSI_PBWT_V1");
-    if (use_v2) {
-        // words per warp: the largest of 32/16/8 that still puts ~24 warps on every SM
-        const uint32_t Wn = (N + 31) / 32;
-        const uint64_t want = (uint64_t)ctx->sm_count * 24;
-        un_wpw = 8;
-        for (uint32_t w : {32u, 16u}) if ((uint64_t)n_blocks * ((Wn + w - 1) / w) >= want) { un_wpw = w; break; }
-        if (const char* sw = getenv("XSI_UNPERM_WPW")) { const int v = atoi(sw); if (v == 8 || v == 16 || v == 32) un_wpw = (uint32_t)v; }
-        const uint32_t warps_total = (Wn + un_wpw - 1) / un_wpw;
-        un_warps = std::min<uint32_t>(16, warps_total);
-        if (const char* sw = getenv("XSI_UNPERM_WARPS")) { const int v = atoi(sw); if (v >= 1 && v <= 32) un_warps = std::min<uint32_t>(warps_total, (uint32_t)v); }
-        un_slices = (warps_total + un_warps - 1) / un_warps;
-        un_smem = (size_t)un_warps * un_wpw * 64 + (size_t)D2_STAGES * TWv2 * 4 + 2 * D2_STAGES * 8;
-    }
-    // D2 v3 (positions in registers) is the default; XSI_UNPERM_V2=1 keeps the shared-memory version
+    // XSI_PBWT_V=1 forces the general kernels (a[] in shared / global memory), which also serve blocks with haploid lines
+    const bool cluster_ok = d.n_gt_jobs && !any_hap_job && !(getenv("XSI_PBWT_V") && atoi(getenv("XSI_PBWT_V")) == 1);
+    const bool use_v2 = cluster_ok && N <= 65534;
+    // D2 v3: positions in registers, tables through a TMA ring
     uint32_t v3_kh = 0, v3_nc = 0, v3_slices = 0;
     const size_t v3_smem = (size_t)D3_STAGES * TWv2 * 4 + 2 * D3_STAGES * 8;
-    if (use_v2 && !getenv("XSI_UNPERM_V2") && v3_smem <= ctx->smem_optin) {
+    if (use_v2 && v3_smem <= ctx->smem_optin) {
         // haplotypes per thread: the largest of 32/16/8 that still gives every SM ~768 consumer threads
         const uint64_t want = (uint64_t)ctx->sm_count * 768;
         v3_kh = 8;
@@ -1526,9 +1539,9 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
         if (const char* sw = getenv("XSI_UNPERM_NC")) { const int v = atoi(sw); if (v >= 32 && v <= 512 && v % 32 == 0) v3_nc = std::min<uint32_t>(thr_total, (uint32_t)v); }
         v3_slices = (thr_total + v3_nc - 1) / v3_nc;
     }
-    const bool v2_ok = use_v2 && (v3_kh || un_smem <= ctx->smem_optin);
+    const bool v2_ok = v3_kh != 0;
     // D2 wide: more than 65,534 haplotypes (tables stay in global memory / L2)
-    const bool use_wide = d.n_gt_jobs && !any_hap_job && N > 65534 && !getenv("XSI_PBWT_V1");
+    const bool use_wide = cluster_ok && N > 65534;
     uint32_t wide_kh = 0, wide_slices = 0;
     if (use_wide) {
         // haplotypes per thread: the largest of 32/16/8 that still gives every SM ~1024 threads
@@ -1617,19 +1630,6 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
                 else pbwt_unpermute_wide_kernel<8><<<g, 256, 0, ctx->stream>>>(dd, k0, k1, ps);
                 CKL();
             }
-        } else if (v2_ok) {
-            const dim3 g(n_blocks, un_slices);
-            if (un_wpw == 32) {
-                CK(cudaFuncSetAttribute(pbwt_unpermute_v2_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)un_smem));
-                PROF("pbwt_unpermute"); pbwt_unpermute_v2_kernel<32><<<g, un_warps * 32, un_smem, ctx->stream>>>(dd);
-            } else if (un_wpw == 16) {
-                CK(cudaFuncSetAttribute(pbwt_unpermute_v2_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)un_smem));
-                PROF("pbwt_unpermute"); pbwt_unpermute_v2_kernel<16><<<g, un_warps * 32, un_smem, ctx->stream>>>(dd);
-            } else {
-                CK(cudaFuncSetAttribute(pbwt_unpermute_v2_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)un_smem));
-                PROF("pbwt_unpermute"); pbwt_unpermute_v2_kernel<8><<<g, un_warps * 32, un_smem, ctx->stream>>>(dd);
-            }
-            CKL();
         } else if (d.n_gt_jobs) {
             const uint32_t W = (N + 31) / 32;
             const size_t smem2 = ((size_t)N * 2 + 15) / 16 * 16 + (size_t)2 * d.WS * 4 + ((size_t)N + 32 + 15) / 16 * 16 + 64 * 4 + 16;
