@@ -116,8 +116,10 @@ private:
             const uint64_t end = block_id + 1 < this->header.number_of_ssas ? block_offset(block_id + 1) : (uint64_t)this->header.indices_offset;
             size = end - (uint64_t)(p - static_cast<const uint8_t*>(this->file_mmap_p));
         }
-        const int rc = xsi_decode_load_blocks(ctx, 1, &p, &size, this->header.num_samples, this->header.aet_bytes);
-        if (rc != XSI_OK) xsi_b200::raise(ctx, rc, "xsi_decode_load_blocks");
+        // lazy: every WAH line is expanded now, the sequential inverse-PBWT chain only runs as far as the records that are
+        // actually asked for (a region query near the start of a block does not pay for the whole block)
+        const int rc = xsi_decode_load_blocks_lazy(ctx, 1, &p, &size, this->header.num_samples, this->header.aet_bytes, 0);
+        if (rc != XSI_OK) xsi_b200::raise(ctx, rc, "xsi_decode_load_blocks_lazy");
         uint32_t bcf_lines = 0;
         if (xsi_decode_block_info(ctx, 0, &bcf_lines, &bin_lines) != XSI_OK) throw "xsi_decode_block_info";
         loaded = true;

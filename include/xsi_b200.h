@@ -112,6 +112,19 @@ int xsi_encode_line_counts(const xsi_ctx* ctx, uint64_t* n_binary_lines, uint64_
  * (include/compression.hpp:40-104).  Replaces any previously loaded set.                    */
 int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks,
                            const uint64_t* sizes, uint64_t num_samples, int32_t aet_bytes);
+/* The same load with a LAZY inverse-PBWT chain: every WAH line is expanded (parallel work), but the sequential chain that
+ * puts lines back into sample order stops after the WAH lines among the first `initial_lines` binary lines of each block (0:
+ * none at all).  xsi_decode_records* continue the chain on demand up to the last line they are asked for plus a window
+ * (XSI_LAZY_WINDOW, default 1024 lines), so a record near the start of a block no longer costs the whole block -- the
+ * reference's seek replays every line before the one it wants (accessor_internals_new.hpp:154-196), and so does this, but
+ * it never goes further than needed.  xsi_decode_allele_counts needs no chain at all.  Blocks that the continuing kernel
+ * does not serve (more than 65,534 haplotypes, all-haploid lines) are loaded in full.                                       */
+int xsi_decode_load_blocks_lazy(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks, const uint64_t* sizes,
+                                uint64_t num_samples, int32_t aet_bytes, uint32_t initial_lines);
+/* Continues the chain of loaded block `block_index` so that its binary lines [0, line_end) are final. */
+int xsi_decode_extend(xsi_ctx* ctx, uint32_t block_index, uint32_t line_end);
+/* Binary lines [0, *lines_ready) of the block are final (the whole block once its chain is complete). */
+int xsi_decode_lines_ready(const xsi_ctx* ctx, uint32_t block_index, uint32_t* lines_ready);
 /* Stage 2: materialise records. Record i is the one whose first binary line is line_offset[i]
  * (the low 15 bits of BM) in loaded block block_index[i] (index into the loaded set), with
  * n_alleles[i] alleles.  Row i is written at out + i*out_stride (int32 elements); entries

@@ -688,3 +688,50 @@ def test_haploid_records_in_some_blocks_only(ctx, tmp_path):
     ds = dict(gt=np.concatenate(rows).astype(np.int32), ngt=np.array(ngt, np.int32), n_allele=np.full(len(ngt), 2, np.int32), n_samples=ns)
     roundtrip(ctx, tmp_path, ds, bl, 0.01, blocks_per_batch=8)
     roundtrip(ctx, tmp_path, ds, bl, 0.01, blocks_per_batch=2)
+
+
+def test_lazy_chain(ctx, tmp_path):
+    """xsi_decode_load_blocks_lazy: the inverse-PBWT chain stops early and continues on demand; records before, at and after the
+    frontier, in any order, equal the oracle; allele counts need no chain at all"""
+    import xsqueezeit_b200 as xb
+    ds = synth.make_dataset(1500, 3000, seed=111, max_alt=2, multi_frac=0.1, missing=0.002)
+    bl = 700
+    p = gpu_encode(ctx, tmp_path, ds, bl, 0.002)
+    img = open(p, "rb").read()
+    nal = ds["n_allele"]
+    pos = xb.bm_positions(nal, bl)
+    rd = xo.Reader(img)
+    want = [rd.fill_genotype_array(int(nal[r]), int(pos[r])) for r in range(len(nal))]
+    want = [(row[:n].copy(), n) for row, n in want]
+    acc = xb.Accessor(p, ctx)
+    blocks = [ctypes_block(acc, b) for b in range(acc.n_blocks)]
+    os.environ["XSI_LAZY_WINDOW"] = "64"
+    try:
+        ctx.decode_load_blocks(blocks, ds["n_samples"], 2, lazy_lines=0)
+        assert ctx.decode_lines_ready(0) < 50 and ctx.decode_lines_ready(1) < 50  # nothing un-permuted yet (sparse lines are always final)
+        blk = (pos >> np.uint64(15)).astype(np.uint32)
+        off = (pos & np.uint64(0x7FFF)).astype(np.uint32)
+        # counts without any chain
+        rd2 = xo.Reader(img)
+        sel = np.arange(0, len(nal), 37)
+        ac = ctx.decode_allele_counts(blk[sel], off[sel], nal[sel])
+        for i, r in enumerate(sel):
+            assert np.array_equal(ac[i, :int(nal[r])], rd2.fill_allele_counts(int(nal[r]), int(pos[r]))), r
+        assert ctx.decode_lines_ready(0) < 50
+        rng = np.random.default_rng(5)
+        for r in [300, 301, 10, 650, 305, 1400, 1399, 699, 700, 0, len(nal) - 1]:
+            out, filled, _ = ctx.decode_records(blk[r:r + 1], off[r:r + 1], nal[r:r + 1])
+            assert filled[0] == want[r][1] and np.array_equal(out[0, :filled[0]], want[r][0]), r
+            assert ctx.decode_lines_ready(int(blk[r])) > off[r]
+        assert ctx.decode_lines_ready(0) >= off[650]
+        order = rng.permutation(len(nal))
+        out, filled, _ = ctx.decode_records(blk[order], off[order], nal[order])
+        for i, r in enumerate(order):
+            assert filled[i] == want[r][1] and np.array_equal(out[i, :filled[i]], want[r][0]), r
+        # explicit extension, then a full lazy load (initial_lines = everything) equals the eager one
+        ctx.decode_load_blocks(blocks, ds["n_samples"], 2, lazy_lines=0)
+        ctx.decode_extend(1, 400)
+        assert ctx.decode_lines_ready(1) >= 400 and ctx.decode_lines_ready(0) < 50
+    finally:
+        del os.environ["XSI_LAZY_WINDOW"]
+    acc.close()

@@ -110,6 +110,12 @@ def lib():
     L.xsi_host_alloc.argtypes = [P(vp), u64]
     L.xsi_host_free.restype = None
     L.xsi_host_free.argtypes = [vp]
+    L.xsi_decode_load_blocks_lazy.restype = i32
+    L.xsi_decode_load_blocks_lazy.argtypes = [vp, u32, P(vp), P(u64), u64, i32, u32]
+    L.xsi_decode_extend.restype = i32
+    L.xsi_decode_extend.argtypes = [vp, u32, u32]
+    L.xsi_decode_lines_ready.restype = i32
+    L.xsi_decode_lines_ready.argtypes = [vp, u32, P(u32)]
     L.xsi_decode_block_info.restype = i32
     L.xsi_decode_block_info.argtypes = [vp, u32, P(u32), P(u32)]
     L.xsi_reader_open.restype = i32
@@ -243,8 +249,9 @@ class Context:
         return int(a.value), int(b.value)
 
     # ---- decode --------------------------------------------------------------------------
-    def decode_load_blocks(self, blocks, num_samples, aet_bytes):
-        """blocks: list of bytes-like GT block payloads (or (address, size) tuples)."""
+    def decode_load_blocks(self, blocks, num_samples, aet_bytes, lazy_lines=None):
+        """blocks: list of bytes-like GT block payloads (or (address, size) tuples).  lazy_lines: stop the inverse-PBWT
+        chain after that many binary lines per block (xsi_decode_load_blocks_lazy); decode calls continue it on demand."""
         n = len(blocks)
         ptrs = (ctypes.c_void_p * n)()
         sizes = (ctypes.c_uint64 * n)()
@@ -258,8 +265,19 @@ class Context:
                 ptrs[i], sizes[i] = a.ctypes.data, a.size
         # the loaded set belongs to the context (a load replaces it): readers that cache "my block is resident" compare this
         self.load_generation = getattr(self, "load_generation", 0) + 1
-        self._check(self._L.xsi_decode_load_blocks(self.h, n, ptrs, sizes, int(num_samples), int(aet_bytes)))
+        if lazy_lines is None:
+            self._check(self._L.xsi_decode_load_blocks(self.h, n, ptrs, sizes, int(num_samples), int(aet_bytes)))
+        else:
+            self._check(self._L.xsi_decode_load_blocks_lazy(self.h, n, ptrs, sizes, int(num_samples), int(aet_bytes), int(lazy_lines)))
         self._dec_hap = 2 * int(num_samples)
+
+    def decode_lines_ready(self, block_index):
+        v = ctypes.c_uint32()
+        self._check(self._L.xsi_decode_lines_ready(self.h, int(block_index), ctypes.byref(v)))
+        return v.value
+
+    def decode_extend(self, block_index, line_end):
+        self._check(self._L.xsi_decode_extend(self.h, int(block_index), int(line_end)))
 
     def decode_records(self, block_index, line_offset, n_alleles, out=None, out_stride=None, out_on_device=False,
                        want_counts=False, elem_bytes=4):

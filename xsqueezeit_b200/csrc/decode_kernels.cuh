@@ -35,7 +35,10 @@ struct DecBlock {
     uint32_t line0, n_lines;                  // binary lines (global index base)
     uint32_t wah0, n_wah;                     // GT WAH jobs
     uint32_t sp0, n_sp, ms0, n_ms, ev0, n_ev; // ordinals of sparse / missing / eov lists
-    uint32_t default_phasing, pad;
+    uint32_t default_phasing;
+    // lazy chain (D2 v3): WAH lines [0, wah_done) of the block are back in sample order; a launch of the inverse-PBWT
+    // kernel processes [wah_done, wah_todo) and leaves its positions in pos_state for the next one
+    uint32_t wah_done, wah_todo, pad2;
 };
 
 struct DecDev {
@@ -534,8 +537,11 @@ __global__ void __launch_bounds__(MAXT, 1) pbwt_unpermute_smem_kernel(DecDev d, 
 // dynamic smem: ring[D][TW] u32 | full[D], empty[D] u64
 // =============================================================================================
 constexpr int D3_STAGES = 4;
+// The chain may stop early and be continued later (xsi_decode_load_blocks_lazy / xsi_decode_extend): a launch covers the
+// WAH lines [wah_done, wah_todo) of every block [b0, b0 + gridDim.x) and parks the positions in pos_state (uint16 per
+// haplotype slot) so that a record near the start of a block does not pay for the whole block (seek, :154-196, in reverse).
 template <int KH>  // haplotypes per thread: 8, 16 or 32 (one uint8 / uint16 / uint32 store per thread and line)
-__global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d) {
+__global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d, uint32_t b0, uint16_t* __restrict__ pos_state, uint32_t ps_stride) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t N = 2 * d.n_samples, TW = d.TW, WS = d.WS;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
@@ -543,20 +549,20 @@ __global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d) {
     uint32_t* ring = reinterpret_cast<uint32_t*>(smem_raw);
     uint64_t* full = reinterpret_cast<uint64_t*>(ring + (size_t)D3_STAGES * TW);
     uint64_t* empty = full + D3_STAGES;
-    const DecBlock blk = d.blocks[blockIdx.x];
-    const uint32_t nwah = blk.n_wah;
+    const DecBlock blk = d.blocks[blockIdx.x + b0];
+    const uint32_t k0 = blk.wah_done, k1 = min(blk.wah_todo, blk.n_wah);
     const uint32_t tab_bytes = TW * 4;
     if (tid == 0) {
         for (int s = 0; s < D3_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], NC >> 5); }
         fence_proxy_async();
     }
     __syncthreads();
-    if (nwah == 0 || blockIdx.y * NC * KH >= N) return;
+    if (k0 >= k1 || blockIdx.y * NC * KH >= N) return;
     const uint32_t* tabs = d.tabs + (size_t)blk.wah0 * TW;
     if (tid >= NC) {  // ---- producer warp ----
         if (lane == 0) {
-            for (uint32_t k = 0; k < nwah; ++k) {
-                const uint32_t st = k % D3_STAGES, use = k / D3_STAGES;
+            for (uint32_t k = k0; k < k1; ++k) {
+                const uint32_t st = (k - k0) % D3_STAGES, use = (k - k0) / D3_STAGES;
                 if (use > 0) mbar_wait(&empty[st], (use - 1) & 1u);
                 mbar_expect_tx(&full[st], tab_bytes);
                 bulk_g2s(ring + (size_t)st * TW, tabs + (size_t)k * TW, tab_bytes, &full[st]);
@@ -572,13 +578,19 @@ __global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d) {
     uint32_t pk[KH];
     // identity at block start (gt_block.hpp:179).  Haplotypes past N start at 0 and wander inside [0, N] (their
     // lookups stay inside the table); their bits are masked off before the store.
+    uint16_t* ps = pos_state ? pos_state + (size_t)(blockIdx.x + b0) * ps_stride + hb : nullptr;
+    if (k0 == 0 || !ps) {
 #pragma unroll
-    for (int q = 0; q < KH; ++q) pk[q] = (uint32_t)q < nvalid ? hb + q : 0u;
+        for (int q = 0; q < KH; ++q) pk[q] = (uint32_t)q < nvalid ? hb + q : 0u;
+    } else {  // continue the chain where the previous launch stopped
+#pragma unroll
+        for (int q = 0; q < KH; ++q) pk[q] = ps[q];
+    }
     const uint32_t vmask = nvalid >= 32 ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
     const bool store = hb < WS * 32;
     const uint32_t ring_sa = smem_u32(ring);
-    for (uint32_t k = 0; k < nwah; ++k) {
-        const uint32_t st = k % D3_STAGES, use = k / D3_STAGES;
+    for (uint32_t k = k0; k < k1; ++k) {
+        const uint32_t st = (k - k0) % D3_STAGES, use = (k - k0) / D3_STAGES;
         mbar_wait(&full[st], use & 1u);
         const uint32_t stw = st * TW;  // word offset of this stage in the ring
         uint32_t e[KH];
@@ -609,6 +621,10 @@ __global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d) {
         __threadfence_block();
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
+    }
+    if (ps && k1 < blk.n_wah) {
+#pragma unroll
+        for (int q = 0; q < KH; ++q) ps[q] = (uint16_t)pk[q];
     }
 }
 

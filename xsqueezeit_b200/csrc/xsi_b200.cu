@@ -141,6 +141,14 @@ struct xsi_ctx {
         uint64_t Lt = 0;
         std::vector<DecBlock> h_blocks;
         std::vector<uint32_t> h_bin_lines, h_bcf_lines;
+        // lazy inverse-PBWT chain (xsi_decode_load_blocks_lazy): WAH lines of block b in order, how many of them are back in
+        // sample order, and the launch shape of the chain kernel so that a continuation matches the first launch
+        std::vector<std::vector<uint16_t>> h_wah_lines;
+        std::vector<uint32_t> h_wah_done;
+        bool lazy_ok = false;
+        uint32_t v3_kh = 0, v3_nc = 0, v3_slices = 0, ps_stride = 0;
+        size_t v3_smem = 0, m_blk = 0;
+        DevBuf pos_state;
         DevBuf blob, meta, rows, job_u32, job_hap, tile_u32, dline, lists, err, a_pool, x_pool, req, out, scratch, counts,
             seg_total, tabs;
         PinBuf h_stage, h_meta;
@@ -237,7 +245,7 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
     for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags, &e.arena[0], &e.arena[1]}) b->release();
     auto& d = ctx->dec;
     for (DevBuf* b : {&d.blob, &d.meta, &d.rows, &d.job_u32, &d.job_hap, &d.tile_u32, &d.dline, &d.lists, &d.err,
-                      &d.a_pool, &d.x_pool, &d.req, &d.out, &d.scratch, &d.counts, &d.seg_total, &d.tabs})
+                      &d.a_pool, &d.x_pool, &d.req, &d.out, &d.scratch, &d.counts, &d.seg_total, &d.tabs, &d.pos_state})
         b->release();
     d.h_stage.release();
     d.h_meta.release();
@@ -1281,8 +1289,43 @@ int launch_unpermute(xsi_ctx* ctx, const DecDev& dd, const uint8_t* job_hap, uin
 
 }  // namespace
 
+// D2 v3 over blocks [b0, b0 + nb): the WAH lines [wah_done, wah_todo) the device block table names
+static int launch_unpermute_v3(xsi_ctx* ctx, const DecDev& dd, uint32_t b0, uint32_t nb) {
+    auto& d = ctx->dec;
+    const dim3 g(nb, d.v3_slices);
+    uint16_t* ps = d.pos_state.as<uint16_t>();
+    if (d.v3_kh == 32) {
+        CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.v3_smem));
+        PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<32><<<g, d.v3_nc + 32, d.v3_smem, ctx->stream>>>(dd, b0, ps, d.ps_stride);
+    } else if (d.v3_kh == 16) {
+        CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.v3_smem));
+        PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<16><<<g, d.v3_nc + 32, d.v3_smem, ctx->stream>>>(dd, b0, ps, d.ps_stride);
+    } else {
+        CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.v3_smem));
+        PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<8><<<g, d.v3_nc + 32, d.v3_smem, ctx->stream>>>(dd, b0, ps, d.ps_stride);
+    }
+    CKL();
+    return XSI_OK;
+}
+
+// Makes the binary lines [0, line_end) of loaded block b final (continues its inverse-PBWT chain as far as needed).
+static int extend_chain(xsi_ctx* ctx, uint32_t b, uint32_t line_end) {
+    auto& d = ctx->dec;
+    if (!d.lazy_ok || b >= d.nb) return XSI_OK;
+    const auto& wl = d.h_wah_lines[b];
+    const uint32_t todo = (uint32_t)(std::lower_bound(wl.begin(), wl.end(), (uint16_t)std::min<uint32_t>(line_end, 65535u)) - wl.begin());
+    if (todo <= d.h_wah_done[b]) return XSI_OK;
+    const uint32_t range[2] = {d.h_wah_done[b], todo};  // DecBlock::wah_done, wah_todo (adjacent)
+    uint8_t* dev_blk = d.meta.as<uint8_t>() + d.m_blk + (size_t)b * sizeof(DecBlock) + offsetof(DecBlock, wah_done);
+    CK(cudaMemcpyAsync(dev_blk, range, sizeof range, cudaMemcpyHostToDevice, ctx->stream));  // pageable source: staged before the call returns
+    const int rc = launch_unpermute_v3(ctx, d.dev, b, 1);
+    if (rc) return rc;
+    d.h_wah_done[b] = todo;
+    return XSI_OK;
+}
+
 static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks,
-                                      const uint64_t* sizes, uint64_t num_samples, int32_t aet_bytes) {
+                                      const uint64_t* sizes, uint64_t num_samples, int32_t aet_bytes, uint32_t lazy_lines = 0xFFFFFFFFu) {
     if (!ctx || !gt_blocks || !sizes || n_blocks == 0) return XSI_E_ARG;
     if (aet_bytes != 2 && aet_bytes != 4) { ctx->err = "Unsupported access type"; return XSI_E_ARG; }
     if (num_samples == 0 || num_samples >= (1ull << 30)) { ctx->err = "bad num_samples"; return XSI_E_ARG; }
@@ -1320,6 +1363,8 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
         uint32_t wah0 = 0, sp0 = 0, ms0 = 0, ev0 = 0, ph0 = 0, seg_w = 0, seg_p = 0, tile_w = 0, tile_p = 0;
     };
     std::vector<BlkPlan> plan(n_blocks);
+    d.h_wah_lines.resize(n_blocks);
+    d.h_wah_done.assign(n_blocks, 0);
     {
         HOSTSPAN("host:decode_parse");
         host_parallel_for(n_blocks, [&](size_t b) {
@@ -1327,8 +1372,9 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
             ParsedBlock& pb = pbs[b];
             pl.rc = parse_block(pl.err, gt_blocks[b], sizes[b], pb);
             if (pl.rc) return;
+            d.h_wah_lines[b].clear();
             for (uint32_t l = 0; l < pb.bin_lines; ++l) {
-                if (pb.is_wah[l]) { pl.n_wah++; if (pb.haploid[l]) pl.any_hap = true; } else pl.n_sp++;
+                if (pb.is_wah[l]) { pl.n_wah++; d.h_wah_lines[b].push_back((uint16_t)l); if (pb.haploid[l]) pl.any_hap = true; } else pl.n_sp++;
                 if (pb.ws == WS_WAH) { pl.n_msw += pb.has_missing[l] != 0; pl.n_evw += pb.has_eov[l] != 0; }
                 else { pl.n_ms += pb.has_missing[l] != 0; pl.n_ev += pb.has_eov[l] != 0; }
                 pl.n_ph += pb.has_phase[l] != 0;
@@ -1377,6 +1423,12 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
     }
     d.Lt = Lt;
     d.NJ = njobs;
+    // The chain kernel that can stop and continue is D2 v3 (positions in registers, <= 65534 haplotypes, no haploid lines);
+    // anything else undoes the PBWT order of whole blocks at once.
+    const bool chain_v3 = d.n_gt_jobs && !any_hap_job && 2 * S <= 65534 && !(getenv("XSI_PBWT_V") && atoi(getenv("XSI_PBWT_V")) == 1) &&
+                          (size_t)D3_STAGES * (2 * d.WS + 4) * 4 + 2 * D3_STAGES * 8 <= ctx->smem_optin;
+    d.lazy_ok = chain_v3;
+    const bool lazy = chain_v3 && lazy_lines != 0xFFFFFFFFu;
     // ---- one pinned staging area for everything the kernels index ----
     const uint32_t NJp = njobs ? njobs : 1, ntp = ntiles ? ntiles : 1;
     const uint64_t Ltp = Lt ? Lt : 1;
@@ -1419,6 +1471,13 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
             bk.sp_end = mend(KEY_MATRIX_SPARSE); bk.ms_end = mend(KEY_MATRIX_MISSING_SPARSE); bk.ev_end = mend(KEY_MATRIX_END_OF_VECTORS_SPARSE);
             bk.wah0 = pl.wah0; bk.sp0 = pl.sp0; bk.ms0 = pl.ms0; bk.ev0 = pl.ev0;
             bk.n_wah = pl.n_wah; bk.n_sp = pl.n_sp; bk.n_ms = pl.n_ms; bk.n_ev = pl.n_ev;
+            bk.wah_done = 0;
+            bk.wah_todo = pl.n_wah;
+            if (lazy) {  // WAH lines among the first lazy_lines binary lines
+                const auto& wl = d.h_wah_lines[b];
+                bk.wah_todo = (uint32_t)(std::lower_bound(wl.begin(), wl.end(), (uint16_t)std::min<uint32_t>(lazy_lines, 65535u)) - wl.begin());
+            }
+            d.h_wah_done[b] = bk.wah_todo;
             uint32_t jw = pl.wah0, jp = pl.ph0, sp = pl.sp0, ms = pl.ms0, ev = pl.ev0, gc = 0, gcp = 0;
             uint32_t jm = pl.msw0, je = pl.evw0, gcm = 0, gce = 0;
             const bool weird_wah = pb.ws == WS_WAH;
@@ -1484,6 +1543,7 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
     // ---- upload (from the pinned staging area: asynchronous) ----
     // meta: blocks | segs
     const size_t m_blk = 0, m_seg = m_blk + sizeof(DecBlock) * n_blocks, m_end = m_seg + sizeof(DecSeg) * (nseg ? nseg : 1);
+    d.m_blk = m_blk;
     CK(d.meta.ensure(m_end));
     CK(cudaMemcpyAsync(d.meta.as<uint8_t>() + m_blk, blocks, sizeof(DecBlock) * n_blocks, cudaMemcpyHostToDevice, ctx->stream));
     if (nseg) CK(cudaMemcpyAsync(d.meta.as<uint8_t>() + m_seg, segs, sizeof(DecSeg) * nseg, cudaMemcpyHostToDevice, ctx->stream));
@@ -1600,18 +1660,11 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
         CKL();
         }
         if (v3_kh) {
-            const dim3 g(n_blocks, v3_slices);
-            if (v3_kh == 32) {
-                CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem));
-                PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<32><<<g, v3_nc + 32, v3_smem, ctx->stream>>>(dd);
-            } else if (v3_kh == 16) {
-                CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem));
-                PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<16><<<g, v3_nc + 32, v3_smem, ctx->stream>>>(dd);
-            } else {
-                CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)v3_smem));
-                PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<8><<<g, v3_nc + 32, v3_smem, ctx->stream>>>(dd);
-            }
-            CKL();
+            d.v3_kh = v3_kh; d.v3_nc = v3_nc; d.v3_slices = v3_slices; d.v3_smem = v3_smem;
+            d.ps_stride = v3_slices * v3_nc * v3_kh;
+            CK(d.pos_state.ensure((size_t)n_blocks * d.ps_stride * 2));
+            int rc = launch_unpermute_v3(ctx, dd, 0, n_blocks);
+            if (rc) return rc;
         } else if (use_wide) {
             const dim3 g(n_blocks, wide_slices);
             uint32_t max_nwah = 0;
@@ -1694,6 +1747,17 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
     }
     const bool want_counts = allele_counts != nullptr;
     if (want_counts && counts_stride < max_all) { ctx->err = "counts_stride too small"; return XSI_E_ARG; }
+    if (d.lazy_ok) {  // blocks loaded lazily: continue their inverse-PBWT chains up to the last line asked for (plus a window)
+        uint32_t window = 1024;
+        if (const char* s_ = getenv("XSI_LAZY_WINDOW")) window = (uint32_t)std::max(0, atoi(s_));
+        std::vector<uint32_t> need(d.nb, 0);
+        for (uint64_t i = 0; i < n; ++i) need[block_index[i]] = std::max(need[block_index[i]], line_offset[i] + n_alleles[i] - 1);
+        for (uint32_t b = 0; b < d.nb; ++b) {
+            if (!need[b] || d.h_wah_done[b] >= d.h_wah_lines[b].size()) continue;
+            const int rc = extend_chain(ctx, b, std::min<uint32_t>(d.h_bin_lines[b], need[b] + window));
+            if (rc) return rc;
+        }
+    }
     const uint32_t Npad = (N + 63) / 64 * 64;
     // uploads the requests of records [c0, c0+cn) and composes their rows (element type DT) at dev_out, stride in elements
     auto compose_chunk = [&](auto* dev_out, uint64_t stride, uint64_t c0, uint64_t cn, ReqDev& q) -> int {
@@ -2025,6 +2089,24 @@ extern "C" int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const ui
 }
 extern "C" int xsi_decode_load_blocks(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks, const uint64_t* sizes, uint64_t num_samples, int32_t aet_bytes) {
     return guarded(ctx, [&] { return xsi_decode_load_blocks_impl(ctx, n_blocks, gt_blocks, sizes, num_samples, aet_bytes); });
+}
+extern "C" int xsi_decode_load_blocks_lazy(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks, const uint64_t* sizes, uint64_t num_samples,
+                                           int32_t aet_bytes, uint32_t initial_lines) {
+    return guarded(ctx, [&] { return xsi_decode_load_blocks_impl(ctx, n_blocks, gt_blocks, sizes, num_samples, aet_bytes, initial_lines == 0xFFFFFFFFu ? 0xFFFFFFFEu : initial_lines); });
+}
+extern "C" int xsi_decode_extend(xsi_ctx* ctx, uint32_t block_index, uint32_t line_end) {
+    if (!ctx || !ctx->dec.loaded || block_index >= ctx->dec.nb) return XSI_E_ARG;
+    return guarded(ctx, [&]() -> int {
+        CK(cudaSetDevice(ctx->device));
+        return extend_chain(ctx, block_index, std::min<uint32_t>(line_end, ctx->dec.h_bin_lines[block_index]));
+    });
+}
+extern "C" int xsi_decode_lines_ready(const xsi_ctx* ctx, uint32_t block_index, uint32_t* lines_ready) {
+    if (!ctx || !ctx->dec.loaded || block_index >= ctx->dec.nb || !lines_ready) return XSI_E_ARG;
+    const auto& d = ctx->dec;
+    const auto& wl = d.h_wah_lines[block_index];
+    *lines_ready = (!d.lazy_ok || d.h_wah_done[block_index] >= wl.size()) ? d.h_bin_lines[block_index] : wl[d.h_wah_done[block_index]];
+    return XSI_OK;
 }
 extern "C" int xsi_decode_records(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset, const uint32_t* n_alleles, int32_t* out, uint64_t out_stride, int32_t out_on_device, uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
     return guarded(ctx, [&] { return xsi_decode_records_impl(ctx, n, block_index, line_offset, n_alleles, out, out_stride, out_on_device, n_filled, allele_counts, counts_stride); });
