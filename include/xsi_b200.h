@@ -151,6 +151,14 @@ int xsi_decode_records_i8(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index,
  * (fill_genotype_array / xsi_decode_records does subtract them).                               */
 int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                              const uint32_t* n_alleles, uint64_t* allele_counts, uint32_t counts_stride);
+/* Dot products on the ENCODED lines: the compressive-access consumer of the reference (dot_prod/dot_prod.hpp:113-245 over
+ * InternalGtAccess, accessor_internals_new.hpp:444-471).  For record i and ALT allele a, out[i*out_stride + a-1] receives the
+ * sum of y[sample] over the entries of the record that carry allele a (y: num_samples doubles, host or device; out: host).
+ * WAH lines are read as 1-bit-per-genotype rows, sparse lines as their index lists; no genotype row is materialised except
+ * for lists of REF carriers, which the reference decompresses too (dot_prod.hpp:405-412).  Accumulation is in double, in a
+ * fixed but different order than a sequential loop: results agree with a CPU sum to rounding (tests use rel. 1e-10). */
+int xsi_decode_dot_products(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                            const uint32_t* n_alleles, const double* y, int32_t y_on_device, double* out, uint32_t out_stride);
 /* Sample subset: what the extractor's -s/-S does per record (fill_selected_genotypes,
  * include/gt_decompressor_new.hpp:208-238, sample list from enable_select_samples :324-365).  Row i of `out`
  * holds the entries of samples_to_use[0..n_sel) in that order (n_sel * ploidy values, ploidy 1 for an all-haploid

@@ -735,3 +735,46 @@ def test_lazy_chain(ctx, tmp_path):
     finally:
         del os.environ["XSI_LAZY_WINDOW"]
     acc.close()
+
+
+def test_dot_products_on_encoded_lines(ctx, tmp_path):
+    """xsi_decode_dot_products (the reference's dot_prod consumer of InternalGtAccess) against a float64 sum over the oracle's
+    decoded rows: WAH and sparse lines, multi-allelic records, missing, haploid samples, all-haploid records and negated sparse
+    lines (composed-row path).  Floating point: different summation order, tolerance 1e-10 relative (stated in include/xsi_b200.h)."""
+    import xsqueezeit_b200 as xb
+    rng = np.random.default_rng(23)
+    neg = synth.make_dataset(120, 100, seed=121)
+    g = neg["gt"].reshape(120, 200)
+    g[5, :] = synth.encode_gt(np.ones(200, np.int8))
+    g[6, :] = synth.encode_gt(np.ones(200, np.int8))
+    g[6, 17] = synth.encode_gt(np.zeros(1, np.int8))[0]
+    g[6, 40] = 0  # a missing entry on a negated line
+    neg["gt"] = np.ascontiguousarray(g.reshape(-1))
+    al = (rng.random((150, 90)) < rng.uniform(0.0, 0.6, size=(150, 1))).astype(np.int8)
+    haploid = dict(gt=np.ascontiguousarray(synth.encode_gt(al, 0).reshape(-1)), ngt=np.full(150, 90, np.int32),
+                   n_allele=np.full(150, 2, np.int32), n_samples=90)
+    for ds, bl, maf in ((synth.make_dataset(400, 1500, seed=122, max_alt=3, multi_frac=0.3, missing=0.01, haploid_samples=0.3), 128, 0.01),
+                        (neg, 64, 0.05), (haploid, 40, 0.05), (synth.make_dataset(64, 32488, seed=123, n_founders=32), 32, 0.001)):
+        ns = ds["n_samples"]
+        p = gpu_encode(ctx, tmp_path, ds, bl, maf)
+        img = open(p, "rb").read()
+        acc = xb.Accessor(p, ctx)
+        nal = ds["n_allele"]
+        pos = xb.bm_positions(nal, bl)
+        y = rng.normal(0, 10, ns)
+        rd = xo.Reader(img)
+        nb = (len(pos) + bl - 1) // bl
+        blocks = [ctypes_block(acc, b) for b in range(nb)]
+        ctx.decode_load_blocks(blocks, ns, 2 if 2 * ns <= 65535 else 4, lazy_lines=0)
+        blk = (pos >> np.uint64(15)).astype(np.uint32)
+        off = (pos & np.uint64(0x7FFF)).astype(np.uint32)
+        got = ctx.decode_dot_products(blk, off, nal, y)
+        for r in range(len(nal)):
+            row, n = rd.fill_genotype_array(int(nal[r]), int(pos[r]))
+            row = row[:n].astype(np.int64)
+            ys = y if n == ns else np.repeat(y, 2)
+            for a in range(1, int(nal[r])):
+                want = float(ys[(row >> 1) - 1 == a].sum()) if True else 0.0
+                # vector end (INT32_MIN + 1) and bcf_int32_missing shift to large negatives: never equal to an allele
+                assert abs(got[r, a - 1] - want) <= 1e-10 * max(1.0, abs(want)), (r, a, got[r, a - 1], want)
+        acc.close()

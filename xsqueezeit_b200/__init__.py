@@ -116,6 +116,8 @@ def lib():
     L.xsi_decode_extend.argtypes = [vp, u32, u32]
     L.xsi_decode_lines_ready.restype = i32
     L.xsi_decode_lines_ready.argtypes = [vp, u32, P(u32)]
+    L.xsi_decode_dot_products.restype = i32
+    L.xsi_decode_dot_products.argtypes = [vp, u64, vp, vp, vp, vp, i32, vp, u32]
     L.xsi_decode_block_info.restype = i32
     L.xsi_decode_block_info.argtypes = [vp, u32, P(u32), P(u32)]
     L.xsi_reader_open.restype = i32
@@ -270,6 +272,18 @@ class Context:
         else:
             self._check(self._L.xsi_decode_load_blocks_lazy(self.h, n, ptrs, sizes, int(num_samples), int(aet_bytes), int(lazy_lines)))
         self._dec_hap = 2 * int(num_samples)
+
+    def decode_dot_products(self, block_index, line_offset, n_alleles, y):
+        """xsi_decode_dot_products: float64 [n, max(n_alleles)-1], column a-1 = sum of y[sample] over the carriers of ALT a."""
+        bi = np.ascontiguousarray(block_index, dtype=np.uint32)
+        lo = np.ascontiguousarray(line_offset, dtype=np.uint32)
+        na = np.ascontiguousarray(n_alleles, dtype=np.uint32)
+        yy = np.ascontiguousarray(y, dtype=np.float64)
+        stride = max(1, int(na.max()) - 1) if na.size else 1
+        out = np.zeros((bi.size, stride), dtype=np.float64)
+        self._check(self._L.xsi_decode_dot_products(self.h, bi.size, bi.ctypes.data, lo.ctypes.data, na.ctypes.data, yy.ctypes.data, 0,
+                                                    out.ctypes.data, stride))
+        return out
 
     def decode_lines_ready(self, block_index):
         v = ctypes.c_uint32()

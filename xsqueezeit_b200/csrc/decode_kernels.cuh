@@ -1066,6 +1066,88 @@ __global__ void __launch_bounds__(128) allele_counts_kernel(DecDev d, ReqDev q) 
 }
 
 // =============================================================================================
+// D7: dot products on the encoded lines (the consumer of InternalGtAccess in the reference, dot_prod/dot_prod.hpp:113-245:
+// Sxy = sum of y[sample] over the carriers of an ALT allele).  One warp per record and ALT line: a WAH line is read as its
+// bit-row in sample order (1 bit per genotype instead of a 4-byte row), a sparse line as its index list.  Lists of REF
+// carriers (negated sparse, MSB of the count) are left to the composed-row path (dot_rows_kernel), like the reference, which
+// decompresses such lines (dot_prod.hpp:405-412).  Sums are accumulated in double, lane-strided then a shuffle tree.
+// =============================================================================================
+struct DotDev {
+    const double* y;        // [num_samples]
+    double* out;            // [n][out_stride], ALT allele a at column a-1
+    uint32_t out_stride;
+    uint32_t* fallback;     // [n] set to 1 when the record holds a line this kernel does not serve
+};
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(XSI_FULL, v, o);
+    return v;
+}
+__global__ void __launch_bounds__(128) dot_lines_kernel(DecDev d, ReqDev q, DotDev t) {
+    const uint32_t ri = blockIdx.x * 4 + (threadIdx.x >> 5), lane = lane_id();
+    if (ri >= q.n) return;
+    const DecBlock blk = d.blocks[q.blk[ri]];
+    const uint32_t nall = q.nall[ri];
+    const uint32_t gl0 = blk.line0 + q.line[ri];
+    const uint32_t S = d.n_samples;
+    const uint32_t msb = d.aet == 2 ? 0x8000u : 0x80000000u;
+    const bool hap = (d.dline_flags[gl0] & DL_HAPLOID) != 0;
+    const uint32_t n = hap ? S : 2 * S, sh = hap ? 0u : 1u;
+    const uint8_t* spm = d.blob + blk.sparse_off;
+    bool fb = false;
+    for (uint32_t alt = 1; alt < nall; ++alt) {
+        const uint32_t gl = gl0 + alt - 1;
+        const uint8_t fl = d.dline_flags[gl];
+        double acc = 0.0;
+        if (fl & DL_WAH) {
+            const uint32_t* row = d.rows + (size_t)d.dline_ord[gl] * d.WS;
+            const uint32_t nwords = (n + 31) >> 5;
+            for (uint32_t w = lane; w < nwords; w += 32) {
+                uint32_t x = row[w];
+                while (x) {
+                    const uint32_t b = __ffs(x) - 1;
+                    x &= x - 1;
+                    const uint32_t i = w * 32 + b;
+                    if (i < n) acc += t.y[i >> sh];
+                }
+            }
+        } else {
+            const uint64_t e0 = d.sp_off[d.dline_ord[gl]];
+            const uint32_t hdr = rd_entry(spm, e0, d.aet);
+            if (hdr & msb) fb = true;
+            else {
+                const uint32_t cnt = hdr & ~msb;
+                for (uint32_t k = lane; k < cnt; k += 32) {
+                    const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet);
+                    if (i < n) acc += t.y[i >> sh];
+                }
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) t.out[(size_t)ri * t.out_stride + alt - 1] = acc;
+    }
+    if (lane == 0) t.fallback[ri] = fb ? 1u : 0u;
+}
+// the same sums from composed int8 rows (records with a negated sparse line): row r of `rows` belongs to request idx[r]
+__global__ void __launch_bounds__(128) dot_rows_kernel(const int8_t* __restrict__ rows, uint64_t stride, const uint32_t* __restrict__ filled,
+                                                        const uint32_t* __restrict__ idx, const uint32_t* __restrict__ nall_all, uint32_t nrows,
+                                                        uint32_t n_samples, DotDev t) {
+    const uint32_t r = blockIdx.x * 4 + (threadIdx.x >> 5), lane = lane_id();
+    if (r >= nrows) return;
+    const uint32_t ri = idx[r], n = filled[r], sh = n == n_samples ? 0u : 1u;
+    const int8_t* row = rows + (size_t)r * stride;
+    for (uint32_t alt = 1; alt < nall_all[ri]; ++alt) {
+        double acc = 0.0;
+        for (uint32_t i = lane; i < n; i += 32) {
+            const int32_t v = row[i];
+            if ((v >> 1) - 1 == (int32_t)alt) acc += t.y[i >> sh];
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) t.out[(size_t)ri * t.out_stride + alt - 1] = acc;
+    }
+}
+
+// =============================================================================================
 // D4 fast path: records with one ALT line and no missing / end-of-vector / phase overlay (the bulk
 // of any file).  Persistent CTAs build 8192-genotype int32 tiles in shared memory -- a thread
 // expands its own 32-bit word of the bit-row (WAH lines) or writes the default pattern that the

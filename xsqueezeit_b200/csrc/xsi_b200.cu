@@ -1324,6 +1324,22 @@ static int extend_chain(xsi_ctx* ctx, uint32_t b, uint32_t line_end) {
     return XSI_OK;
 }
 
+// blocks loaded lazily: continue their inverse-PBWT chains up to the last line the requests need (plus a window)
+static int ensure_lines(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset, const uint32_t* n_alleles) {
+    auto& d = ctx->dec;
+    if (!d.lazy_ok) return XSI_OK;
+    uint32_t window = 1024;
+    if (const char* s_ = getenv("XSI_LAZY_WINDOW")) window = (uint32_t)std::max(0, atoi(s_));
+    std::vector<uint32_t> need(d.nb, 0);
+    for (uint64_t i = 0; i < n; ++i) need[block_index[i]] = std::max(need[block_index[i]], line_offset[i] + n_alleles[i] - 1);
+    for (uint32_t b = 0; b < d.nb; ++b) {
+        if (!need[b] || d.h_wah_done[b] >= d.h_wah_lines[b].size()) continue;
+        const int rc = extend_chain(ctx, b, std::min<uint32_t>(d.h_bin_lines[b], need[b] + window));
+        if (rc) return rc;
+    }
+    return XSI_OK;
+}
+
 static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const uint8_t* const* gt_blocks,
                                       const uint64_t* sizes, uint64_t num_samples, int32_t aet_bytes, uint32_t lazy_lines = 0xFFFFFFFFu) {
     if (!ctx || !gt_blocks || !sizes || n_blocks == 0) return XSI_E_ARG;
@@ -1747,17 +1763,7 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
     }
     const bool want_counts = allele_counts != nullptr;
     if (want_counts && counts_stride < max_all) { ctx->err = "counts_stride too small"; return XSI_E_ARG; }
-    if (d.lazy_ok) {  // blocks loaded lazily: continue their inverse-PBWT chains up to the last line asked for (plus a window)
-        uint32_t window = 1024;
-        if (const char* s_ = getenv("XSI_LAZY_WINDOW")) window = (uint32_t)std::max(0, atoi(s_));
-        std::vector<uint32_t> need(d.nb, 0);
-        for (uint64_t i = 0; i < n; ++i) need[block_index[i]] = std::max(need[block_index[i]], line_offset[i] + n_alleles[i] - 1);
-        for (uint32_t b = 0; b < d.nb; ++b) {
-            if (!need[b] || d.h_wah_done[b] >= d.h_wah_lines[b].size()) continue;
-            const int rc = extend_chain(ctx, b, std::min<uint32_t>(d.h_bin_lines[b], need[b] + window));
-            if (rc) return rc;
-        }
-    }
+    { const int rc_ = ensure_lines(ctx, n, block_index, line_offset, n_alleles); if (rc_) return rc_; }
     const uint32_t Npad = (N + 63) / 64 * 64;
     // uploads the requests of records [c0, c0+cn) and composes their rows (element type DT) at dev_out, stride in elements
     auto compose_chunk = [&](auto* dev_out, uint64_t stride, uint64_t c0, uint64_t cn, ReqDev& q) -> int {
@@ -2023,6 +2029,77 @@ static int xsi_decode_allele_counts_impl(xsi_ctx* ctx, uint64_t n, const uint32_
     return XSI_OK;
 }
 
+
+static int xsi_decode_dot_products_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
+                                        const uint32_t* n_alleles, const double* y, int32_t y_on_device, double* out, uint32_t out_stride) {
+    if (!ctx || !block_index || !line_offset || !n_alleles || !y || !out) return XSI_E_ARG;
+    auto& d = ctx->dec;
+    if (!d.loaded) { ctx->err = "xsi_decode_dot_products without loaded blocks"; return XSI_E_ARG; }
+    if (n == 0) return XSI_OK;
+    if (n >= (1ull << 31)) { ctx->err = "too many records in one call"; return XSI_E_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    uint32_t max_all = 2;
+    for (uint64_t i = 0; i < n; ++i) {
+        if (block_index[i] >= d.nb) { ctx->err = "block index out of range"; return XSI_E_ARG; }
+        if (n_alleles[i] < 2 || n_alleles[i] > 63) { ctx->err = "n_alleles out of range (2..63)"; return XSI_E_UNSUPPORTED; }
+        if ((uint64_t)line_offset[i] + n_alleles[i] - 1 > d.h_bin_lines[block_index[i]]) { ctx->err = "record runs past the end of its block"; return XSI_E_ARG; }
+        max_all = std::max(max_all, n_alleles[i]);
+    }
+    if (out_stride + 1 < max_all) { ctx->err = "out_stride too small"; return XSI_E_ARG; }
+    { const int rc_ = ensure_lines(ctx, n, block_index, line_offset, n_alleles); if (rc_) return rc_; }
+    const uint32_t S = d.n_samples;
+    // scratch: y[S] f64 | out[n*stride] f64 | fallback[n] u32   (d.counts is idle here)
+    const size_t o_y = 0, o_out = o_y + (size_t)S * 8, o_fb = o_out + (size_t)n * out_stride * 8, o_end = o_fb + (size_t)n * 4;
+    CK(d.counts.ensure(o_end));
+    uint8_t* sb = d.counts.as<uint8_t>();
+    DotDev t;
+    if (y_on_device) t.y = y;
+    else { CK(cudaMemcpyAsync(sb + o_y, y, (size_t)S * 8, cudaMemcpyHostToDevice, ctx->stream)); t.y = reinterpret_cast<const double*>(sb + o_y); }
+    t.out = reinterpret_cast<double*>(sb + o_out); t.out_stride = out_stride; t.fallback = reinterpret_cast<uint32_t*>(sb + o_fb);
+    CK(cudaMemsetAsync(t.out, 0, (size_t)n * out_stride * 8, ctx->stream));
+    CK(d.req.ensure(n * 4 * 4));
+    uint32_t* rq = d.req.as<uint32_t>();
+    CK(cudaMemcpyAsync(rq, block_index, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(rq + n, line_offset, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(rq + 2 * n, n_alleles, n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ReqDev q = {};
+    q.blk = rq; q.line = rq + n; q.nall = rq + 2 * n; q.n = (uint32_t)n;
+    { PROF("dot_lines"); dot_lines_kernel<<<(uint32_t)((n + 3) / 4), 128, 0, ctx->stream>>>(d.dev, q, t); }
+    CKL();
+    std::vector<uint32_t> fb(n);
+    CK(cudaMemcpyAsync(fb.data(), t.fallback, n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    std::vector<uint32_t> idx;
+    for (uint64_t i = 0; i < n; ++i) if (fb[i]) idx.push_back((uint32_t)i);
+    if (!idx.empty()) {  // records with a negated sparse line: from their composed rows, in chunks
+        const uint64_t stride8 = ((uint64_t)2 * S + 15) / 16 * 16;
+        const uint64_t chunk = std::max<uint64_t>(1, std::min<uint64_t>(idx.size(), (256ull << 20) / stride8));
+        std::vector<uint32_t> b2, l2, a2;
+        for (uint64_t c0 = 0; c0 < idx.size(); c0 += chunk) {
+            const uint64_t cn = std::min<uint64_t>(chunk, idx.size() - c0);
+            b2.resize(cn); l2.resize(cn); a2.resize(cn);
+            for (uint64_t k = 0; k < cn; ++k) { b2[k] = block_index[idx[c0 + k]]; l2[k] = line_offset[idx[c0 + k]]; a2[k] = n_alleles[idx[c0 + k]]; }
+            CK(d.x_pool.ensure(cn * stride8 + cn * 8 + (size_t)n * 4));
+            int8_t* rows8 = d.x_pool.as<int8_t>();
+            uint32_t* dfilled = reinterpret_cast<uint32_t*>(rows8 + cn * stride8);
+            uint32_t* didx = dfilled + cn;
+            uint32_t* dnall = didx + cn;
+            std::vector<uint32_t> filled(cn);
+            int rc = decode_records_impl<int8_t>(ctx, cn, b2.data(), l2.data(), a2.data(), rows8, stride8, 1, filled.data(), nullptr, 0);
+            if (rc) return rc;
+            CK(cudaMemcpyAsync(dfilled, filled.data(), cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(didx, idx.data() + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(dnall, n_alleles, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+            { PROF("dot_rows"); dot_rows_kernel<<<(uint32_t)((cn + 3) / 4), 128, 0, ctx->stream>>>(rows8, stride8, dfilled, didx, dnall, (uint32_t)cn, S, t); }
+            CKL();
+            CK(cudaStreamSynchronize(ctx->stream));  // filled / idx staging of this chunk is reused by the next
+        }
+    }
+    CK(cudaMemcpyAsync(out, t.out, (size_t)n * out_stride * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return XSI_OK;
+}
+
 static int xsi_decode_records_i8_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                                      const uint32_t* n_alleles, int8_t* out, uint64_t out_stride, int32_t out_on_device,
                                      uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
@@ -2119,4 +2196,8 @@ extern "C" int xsi_decode_records_subset(xsi_ctx* ctx, uint64_t n, const uint32_
 }
 extern "C" int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset, const uint32_t* n_alleles, uint64_t* allele_counts, uint32_t counts_stride) {
     return guarded(ctx, [&] { return xsi_decode_allele_counts_impl(ctx, n, block_index, line_offset, n_alleles, allele_counts, counts_stride); });
+}
+extern "C" int xsi_decode_dot_products(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset, const uint32_t* n_alleles,
+                                       const double* y, int32_t y_on_device, double* out, uint32_t out_stride) {
+    return guarded(ctx, [&] { return xsi_decode_dot_products_impl(ctx, n, block_index, line_offset, n_alleles, y, y_on_device, out, out_stride); });
 }
