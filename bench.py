@@ -269,6 +269,34 @@ def getenv_flag(name):
     return os.environ.get(name, "") not in ("", "0")
 
 
+def bind_to_gpu_numa_node(index):
+    """Restricts this process (and the library's worker pool, created later) to the cores of the NUMA node the GPU hangs off, so
+    that the pinned rings and the int8 <-> int32 conversion of a rank stay on the memory of that node.  Returns a short
+    description, or None when the topology is not exposed (single node, container without sysfs).  Round 1 measured the
+    host-buffer leg at 67 GB/s each way for 8 ranks together: one node's memory serving every rank."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bus = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(index)).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        dom, rest = bus.split(":", 1)
+        path = "/sys/bus/pci/devices/%s:%s/numa_node" % (dom[-4:].lower(), rest.lower())
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed or allowed == set(os.sched_getaffinity(0)):
+            return None
+        os.sched_setaffinity(0, allowed)
+        return {"numa_node": node, "cores": len(allowed)}
+    except Exception:
+        return None
+
+
 def usable_cores():
     try:
         return len(os.sched_getaffinity(0))
@@ -559,6 +587,11 @@ def main():
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 and not getenv_flag("XSI_BENCH_NO_NUMA") else None
+    if numa is not None and "XSI_HOST_THREADS" not in os.environ:
+        # the ranks whose GPUs share this node share its cores
+        per_node = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)) // max(1, len([n for n in os.listdir("/sys/devices/system/node") if n.startswith("node")])))
+        os.environ["XSI_HOST_THREADS"] = str(max(2, numa["cores"] // per_node))
     if world > 1 and "XSI_HOST_THREADS" not in os.environ:
         # the ranks of one box share its cores: size each rank's conversion pool accordingly (read once by the library)
         os.environ["XSI_HOST_THREADS"] = str(max(2, len(os.sched_getaffinity(0)) // int(os.environ.get("LOCAL_WORLD_SIZE", world))))
@@ -1033,7 +1066,7 @@ def main():
                           "host_threads_per_gpu": resident_mt["contexts"] if use_mt else 1,
                           "contexts_per_gpu": resident_mt["contexts"] if use_mt else 1},
                 "compress_ggts": G * world * steps / t_enc / 1e9, "decompress_ggts": G * world * steps / t_dec / 1e9,
-                "verified": bool(verified and (sharded_file is None or sharded_file["equals_single_writer_file"])), "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8, "e2e_bcf": e2e_bcf, "shapes": shapes, "sharded_file": sharded_file,
+                "verified": bool(verified and (sharded_file is None or sharded_file["equals_single_writer_file"])), "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8, "e2e_bcf": e2e_bcf, "shapes": shapes, "sharded_file": sharded_file, "numa_binding": numa,
                 "gpu_launches": resident_mt["gpu_launches"] if use_mt else (pipelined["gpu_launches"] if mode.startswith("one context, one host") else res["launches"]),
                 "clocks": res["clocks"]}
         print(json.dumps(line))
