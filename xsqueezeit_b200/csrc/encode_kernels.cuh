@@ -155,7 +155,7 @@ __device__ __forceinline__ void emit_pred_row_vec(const void* gt, uint64_t goff,
 template <int ELEM>
 __device__ __forceinline__ void finish_record(const EncDev& p, uint32_t r, uint32_t ngt, uint32_t n_allele, uint32_t line0,
                                               uint64_t goff, uint32_t P, uint32_t* s_cnt, uint8_t* s_lflag,
-                                              uint32_t* s_misc, int32_t* s_slot, bool aligned16 = false) {
+                                              uint32_t* s_misc, int32_t* s_slot, bool aligned16 = false, bool aux_done = false) {
     // ---- per-record decisions (gt_block.hpp:292-338) ----
     if (threadIdx.x == 0) {
         const uint32_t nmiss = s_misc[0], neov = s_misc[1];
@@ -200,6 +200,7 @@ __device__ __forceinline__ void finish_record(const EncDev& p, uint32_t r, uint3
     for (uint32_t a = 1; a < n_allele; ++a)
         if (s_lflag[a] & LF_NEGATED)  // negated sparse lists REF carriers (block.hpp:59-65 with sparse_allele 0)
             emit_pred_row<ELEM, 0>(p.gt, goff, ngt, p.WS, 0, p.bitrows + (size_t)(line0 + a - 1) * p.WS);
+    if (aux_done) return;  // the caller holds the missing / end-of-vector / phase words of a one-tile row in registers
     if (aligned16) {
         if (s_slot[0] >= 0) emit_pred_row_vec<ELEM, 1>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[0] * p.WS);
         if (s_slot[1] >= 0) emit_pred_row_vec<ELEM, 2>(p.gt, goff, ngt, p.WS, 0, p.auxrows + (size_t)s_slot[1] * p.WS);
@@ -390,6 +391,41 @@ __device__ __forceinline__ void scan_words(const unsigned char* __restrict__ til
     }
 }
 
+// The missing / end-of-vector / non-default-phase words of a thread's 32 genotypes, from the tile that is still in shared
+// memory (same predicates as emit_pred_row_vec).  Rows of one tile (1KGP3 / chrX widths) use this instead of three more passes
+// over the row: a chrX-shaped file has end-of-vector entries, missing alleles and unphased genotypes in EVERY record.
+template <int ELEM>
+__device__ __forceinline__ void aux_words(const unsigned char* __restrict__ tile, uint32_t nvalid, uint32_t rot, int32_t dpx,
+                                          uint32_t& wm, uint32_t& we, uint32_t& wp) {
+    constexpr uint32_t NCH = 32 * ELEM / 16, EPC = 16 / ELEM;
+    wm = 0; we = 0; wp = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < NCH; ++k) {
+        const uint32_t c = (k + rot) & (NCH - 1);
+        const int4 q = *reinterpret_cast<const int4*>(tile + c * 16);
+        int32_t v[EPC];
+        if (ELEM == 4) { v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w; }
+        else {
+            const uint32_t qq[4] = {(uint32_t)q.x, (uint32_t)q.y, (uint32_t)q.z, (uint32_t)q.w};
+#pragma unroll
+            for (uint32_t e = 0; e < EPC; ++e) {
+                const int32_t sb = (int32_t)(int8_t)(qq[e >> 2] >> (8 * (e & 3)));
+                v[e] = sb == -128 ? XSI_I32_MISSING : (sb == -127 ? XSI_I32_VECTOR_END : sb);
+            }
+        }
+#pragma unroll
+        for (uint32_t e = 0; e < EPC; ++e) {
+            const uint32_t idx = c * EPC + e;
+            if (idx < nvalid) {
+                const uint32_t bitv = 1u << idx;
+                if (gt_is_missing(v[e])) wm |= bitv;
+                if (v[e] == XSI_I32_VECTOR_END) we |= bitv;
+                if ((e & 1u) && ((v[e] & 1) != dpx)) wp |= bitv;
+            }
+        }
+    }
+}
+
 template <int ELEM, int NT>
 __global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(EncDev p) {
     constexpr uint32_t S2_TILE = s2_tile(NT);
@@ -455,6 +491,8 @@ __global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(En
         const uint32_t P = p.n_samples ? ngt / p.n_samples : 0;
         const uint32_t ndt = (ngt + S2_TILE - 1) / S2_TILE;
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, nmiss = 0, neov = 0, phase = 0, err = 0;
+        uint32_t am = 0, ae = 0, ap = 0;  // one-tile rows: this thread's missing / end-of-vector / phase words
+        const bool fuse_aux = tiles_per_rec == 1;
         for (uint32_t tt = 0; tt < tiles_per_rec; ++tt) {
             const uint32_t wi = tt * NT + tid;
             const uint32_t elem0 = tt * S2_TILE + tid * 32;
@@ -478,6 +516,7 @@ __global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(En
                 } else {
                     scan_words<ELEM, 4, false>(tile, nvalid, rot, (int32_t)alt0 + 1, n_allele, dpx, w, acc);
                 }
+                if (fuse_aux && alt0 == 1 && ((acc.nmiss | acc.neov | (acc.phase & 1u)) != 0u)) aux_words<ELEM>(tile, nvalid, rot, dpx, am, ae, ap);
                 nmiss = acc.nmiss; neov = acc.neov; phase = acc.phase; err = acc.err;
                 const uint32_t w0 = w[0], w1 = nal > 1 ? w[1] : 0u, w2 = nal > 2 ? w[2] : 0u, w3 = nal > 3 ? w[3] : 0u;
                 if (wi < p.WS) {
@@ -506,10 +545,13 @@ __global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(En
             }
         }
         // ---- block totals ----
-        c0 = __reduce_add_sync(XSI_FULL, c0); c1 = __reduce_add_sync(XSI_FULL, c1);
-        c2 = __reduce_add_sync(XSI_FULL, c2); c3 = __reduce_add_sync(XSI_FULL, c3);
-        nmiss = __reduce_add_sync(XSI_FULL, nmiss); neov = __reduce_add_sync(XSI_FULL, neov);
-        phase = __reduce_or_sync(XSI_FULL, phase & 1u); err = __reduce_or_sync(XSI_FULL, err);
+        // the common record (one ALT, nothing missing, default phase) needs one sum and one "anything odd?" vote
+        c0 = __reduce_add_sync(XSI_FULL, c0);
+        if (n_allele > 2) { c1 = __reduce_add_sync(XSI_FULL, c1); c2 = __reduce_add_sync(XSI_FULL, c2); c3 = __reduce_add_sync(XSI_FULL, c3); }
+        if (__reduce_or_sync(XSI_FULL, nmiss | neov | (phase & 1u) | err)) {
+            nmiss = __reduce_add_sync(XSI_FULL, nmiss); neov = __reduce_add_sync(XSI_FULL, neov);
+            phase = __reduce_or_sync(XSI_FULL, phase & 1u); err = __reduce_or_sync(XSI_FULL, err);
+        } else { nmiss = 0; neov = 0; phase = 0; err = 0; }
         if (lane == 0) {
             if (n_allele > 1) atomicAdd(&s_cnt[1], c0);
             if (n_allele > 2) atomicAdd(&s_cnt[2], c1);
@@ -521,7 +563,12 @@ __global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(En
             if (err) atomicOr(&s_misc[3], 1u);
         }
         __syncthreads();
-        finish_record<ELEM>(p, r, ngt, n_allele, line0, goff, P, s_cnt, s_lflag, s_misc, s_slot, true);
+        finish_record<ELEM>(p, r, ngt, n_allele, line0, goff, P, s_cnt, s_lflag, s_misc, s_slot, true, fuse_aux);
+        if (fuse_aux && tid < p.WS) {  // slots were handed out by thread 0 inside finish_record (barrier there)
+            if (s_slot[0] >= 0) p.auxrows[(size_t)s_slot[0] * p.WS + tid] = am;
+            if (s_slot[1] >= 0) p.auxrows[(size_t)s_slot[1] * p.WS + tid] = ae;
+            if (s_slot[2] >= 0) p.phrows[(size_t)s_slot[2] * p.WS + tid] = ap;
+        }
         // counters of the NEXT record (nobody reads these after the barrier inside finish_record): the barrier below then
         // serves both as the end of this record and as the start of the next one (one barrier less per record, which
         // is what short rows spend their time on: 39% barrier stalls at 5,008 haplotypes, ncu r01final)
