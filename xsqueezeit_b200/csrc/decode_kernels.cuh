@@ -190,9 +190,11 @@ __global__ void wah_expand_kernel(DecDev d, uint32_t warps_per_cta, uint32_t Gpa
     for (uint32_t i = lane; i < Tpad; i += 32) tog[i] = 0;
     __syncwarp();
     uint32_t gbase = 0;
+    uint32_t wpre = ws + lane < we ? w[ws + lane] : 0u;  // the next 32 WAH words are in flight while these are placed
     for (uint32_t b = ws; b < we; b += 32) {
         const uint32_t i = b + lane;
-        const uint32_t word = i < we ? w[i] : 0u;
+        const uint32_t word = wpre;
+        wpre = i + 32 < we ? w[i + 32] : 0u;
         const uint32_t ng = i < we ? wah_word_groups(word) : 0u;
         uint32_t incl = ng;
 #pragma unroll

@@ -492,7 +492,9 @@ __global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(En
         const uint32_t ndt = (ngt + S2_TILE - 1) / S2_TILE;
         uint32_t c0 = 0, c1 = 0, c2 = 0, c3 = 0, nmiss = 0, neov = 0, phase = 0, err = 0;
         uint32_t am = 0, ae = 0, ap = 0;  // one-tile rows: this thread's missing / end-of-vector / phase words
-        const bool fuse_aux = tiles_per_rec == 1;
+        // rows of the narrow CTAs are one tile long by construction (the host picks NT >= words of the row); the 256-thread
+        // kernel streams long rows and keeps the second passes (and its register count: fusing cost it 15% at the HRC width)
+        constexpr bool fuse_aux = NT < 256;
         for (uint32_t tt = 0; tt < tiles_per_rec; ++tt) {
             const uint32_t wi = tt * NT + tid;
             const uint32_t elem0 = tt * S2_TILE + tid * 32;
@@ -1449,9 +1451,15 @@ __device__ __forceinline__ uint32_t wah_encode_row_warp(const uint32_t* __restri
     const uint32_t iters = (G + 31) >> 5;
     uint32_t heads_base = 0, carry_type = 3, carry_len = 0;
     const uint32_t le = lanemask_lt() | (1u << lane);
+    // the 16 row words of an iteration are loaded two iterations ahead: the loop is a chain of shuffles and ballots, and an
+    // exposed global load per iteration (a line is 136 iterations at 64,976 haplotypes) was most of its time
+    uint32_t wnext = (lane < 16 && lane < WS) ? row[lane] : 0u;
+    uint32_t wnext2 = (lane < 16 && 15 + lane < WS && iters > 1) ? row[15 + lane] : 0u;
     for (uint32_t it = 0; it < iters; ++it) {
-        const uint32_t wi = it * 15 + lane;
-        const uint32_t wv = (lane < 16 && wi < WS) ? row[wi] : 0u;
+        const uint32_t wv = wnext;
+        wnext = wnext2;
+        const uint32_t wi2 = (it + 2) * 15 + lane;
+        wnext2 = (lane < 16 && wi2 < WS && it + 2 < iters) ? row[wi2] : 0u;
         const uint32_t bitpos = 15 * lane;
         const uint32_t lo = __shfl_sync(XSI_FULL, wv, bitpos >> 5);
         const uint32_t hi = __shfl_sync(XSI_FULL, wv, (bitpos >> 5) + 1);
