@@ -90,10 +90,39 @@ public:
     // the base returns its cursor's vector (accessor_internals_new.hpp:755-757); there is no cursor here
     inline const std::vector<size_t>& get_allele_counts() const override { return this->allele_counts; }
 
-    inline InternalGtAccess get_internal_access(size_t, size_t) override {
-        // pointers into the encoded block plus the cursor's live permutation `a` (accessor_internals_new.hpp:444-471):
-        // the device path keeps no host cursor.  Use xsi_decode_records / xsi_decode_allele_counts instead.
-        throw "get_internal_access is not available on the B200 path";
+    // accessor_internals_new.hpp:444-471: pointers to the record's encoded lines inside the mapped block, and the PBWT
+    // arrangement `a` in force at the record.  The device has located every line when the block was loaded; the arrangement is
+    // what the lazy chain has parked after the WAH lines before the record (the chain is continued up to there; a request behind
+    // the chain reloads the block, like the reference's backward seek resets its cursor, :178-186).
+    inline InternalGtAccess get_internal_access(size_t n_alleles, size_t new_position) override {
+        uint32_t line;
+        locate(new_position, line);
+        InternalGtAccess ia;
+        ia.position = line;
+        ia.n_alleles = n_alleles;
+        ia.sparse_bytes = sizeof(A_T);
+        ia.wah_bytes = sizeof(WAH_T);
+        ia.a_bytes = sizeof(A_T);
+        if (n_alleles == 0) return ia;
+        if (n_alleles < 2) throw "get_internal_access: fewer than 2 alleles";
+        std::vector<xsi_line_access> la(n_alleles - 1);
+        a_host.resize(N);
+        int32_t dflt = 0;
+        int rc = xsi_decode_internal_access(ctx, 0, line, (uint32_t)n_alleles, la.data(), &dflt, a_host.data());
+        if (rc == XSI_E_UNSUPPORTED) {  // the chain is already past this line: start the block again
+            loaded = false;
+            locate(new_position, line);
+            rc = xsi_decode_internal_access(ctx, 0, line, (uint32_t)n_alleles, la.data(), &dflt, a_host.data());
+        }
+        if (rc != XSI_OK) xsi_b200::raise(ctx, rc, "xsi_decode_internal_access");
+        ia.default_allele = dflt;
+        ia.a = a_host.data();
+        char* base = static_cast<char*>(this->gt_block_p);
+        for (const auto& l : la) {
+            ia.sparse.push_back(l.is_sparse != 0);
+            ia.pointers.push_back(base + l.byte_offset);
+        }
+        return ia;
     }
 
 private:
@@ -157,6 +186,7 @@ private:
     uint32_t win_line0 = 0, win_n = 0;
     std::vector<uint32_t> win_filled, req_blk, req_line, req_na;
     std::vector<uint64_t> win_counts, counts_tmp;
+    std::vector<A_T> a_host;  // the arrangement handed out by get_internal_access
 };
 
 // from here on, every mention of AccessorInternalsNewTemplate in this translation unit (accessor.cpp:64,71) is the adapter

@@ -159,6 +159,22 @@ int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t* block_ind
  * fixed but different order than a sequential loop: results agree with a CPU sum to rounding (tests use rel. 1e-10). */
 int xsi_decode_dot_products(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                             const uint32_t* n_alleles, const double* y, int32_t y_on_device, double* out, uint32_t out_stride);
+/* InternalGtAccess (include/accessor_internals.hpp:374-397, filled by DecompressPointerGTBlock::get_internal_access,
+ * accessor_internals_new.hpp:444-471): for the record at (block_index, line_offset), where each of its n_alleles-1 encoded
+ * lines lies inside the GT block the caller loaded (byte_offset from the block start; a WAH line of n_entries 16-bit words, or
+ * a sparse list whose first A_T word is its count with the MSB meaning "lists REF carriers"), the default allele of the first
+ * line, and -- when `a` is not NULL -- the PBWT arrangement in force at the record's last line (what the reference's live `a`
+ * holds when it returns): a[j] = haplotype at position j, the order
+ * WAH lines are written in (aet_bytes per entry, 2*num_samples entries, host).  The arrangement needs a block loaded with
+ * xsi_decode_load_blocks_lazy whose chain has not yet passed the record (XSI_E_UNSUPPORTED otherwise: load it again). */
+typedef struct {
+    uint32_t is_sparse;
+    uint32_t reserved;
+    uint64_t byte_offset;
+    uint64_t n_entries;
+} xsi_line_access;
+int xsi_decode_internal_access(xsi_ctx* ctx, uint32_t block_index, uint32_t line_offset, uint32_t n_alleles, xsi_line_access* lines,
+                               int32_t* default_allele, void* a);
 /* Sample subset: what the extractor's -s/-S does per record (fill_selected_genotypes,
  * include/gt_decompressor_new.hpp:208-238, sample list from enable_select_samples :324-365).  Row i of `out`
  * holds the entries of samples_to_use[0..n_sel) in that order (n_sel * ploidy values, ploidy 1 for an all-haploid

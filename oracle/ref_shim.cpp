@@ -125,6 +125,32 @@ uint64_t xsi_ref_allele_counts(void* h, uint64_t* out, uint64_t cap) {
     return ac.size();
 }
 
+// InternalGtAccess of a record (Accessor::get_internal_access, accessor.hpp:69-72 -> accessor_internals_new.hpp:444-471): per
+// line the sparse flag and the first `nbytes` bytes at its pointer, the default allele, and the arrangement widened to uint32.
+namespace {
+struct Peek : public Accessor {
+    static AccessorInternals* internals_of(Accessor* a) { return (a->*(&Peek::internals)).get(); }
+};
+}
+int xsi_ref_internal_access(void* h, uint64_t n_alleles, uint64_t position, uint32_t* a_out, uint64_t a_n, int a_bytes,
+                            uint8_t* sparse_out, uint8_t* bytes_out, uint32_t nbytes, int32_t* default_allele) {
+    try {
+        InternalGtAccess ia = Peek::internals_of(static_cast<Accessor*>(h))->get_internal_access(n_alleles, position);
+        if ((int)ia.a_bytes != a_bytes) return -2;
+        for (uint64_t i = 0; i < a_n; ++i)
+            a_out[i] = a_bytes == 2 ? static_cast<const uint16_t*>(ia.a)[i] : static_cast<const uint32_t*>(ia.a)[i];
+        for (size_t k = 0; k < ia.pointers.size(); ++k) {
+            sparse_out[k] = ia.sparse[k] ? 1 : 0;
+            memcpy(bytes_out + k * nbytes, ia.pointers[k], nbytes);
+        }
+        if (default_allele) *default_allele = ia.default_allele;
+        return (int)ia.pointers.size();
+    } catch (const char* e) {
+        fprintf(stderr, "xsi_ref_internal_access: threw: %s\n", e);
+        return -1;
+    }
+}
+
 void xsi_ref_accessor_close(void* h) { delete static_cast<Accessor*>(h); }
 
 }  // extern "C"

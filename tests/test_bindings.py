@@ -204,3 +204,86 @@ def test_bcf_ingest_tool(tmp_path, name):
         assert sha(open(bcf, "rb").read()) == case["x_bcf_sha256"], "xsi_b200_bcf extract: BCF differs from the reference's -x output"
     line = run([CAPI, out + "_var.bcf"]).stdout.decode().split()
     assert {"records": int(line[1]), "genotypes": int(line[3]), "checksum": line[7]} == case["capi_decode"]
+
+
+# ---- the in-memory door (oracle/ref_shim.cpp: XsiFactoryExt + Accessor fed from arrays) built twice: CPU reference vs both adapters ----
+SHIM = os.path.join(OUT, "libxsi_shim_b200.so")
+
+
+def _plugin_cases():
+    import numpy as np
+    import synth
+    rng = np.random.default_rng(7)
+    ns = 120
+    rows, ngt = [], []
+    for r in range(200):
+        p = 1 if r % 7 == 3 else 2
+        al = (rng.random(ns * p) < 0.3).astype(np.int8)
+        rows.append(synth.encode_gt(al, 1 if p == 2 else 0))
+        ngt.append(ns * p)
+    mixed = dict(gt=np.concatenate(rows).astype(np.int32), ngt=np.array(ngt, np.int32), n_allele=np.full(200, 2, np.int32), n_samples=ns)
+    return [("biallelic", synth.make_dataset(700, 301, seed=1), 256, 0.01),
+            ("multiallelic_missing_eov", synth.make_dataset(600, 257, seed=2, max_alt=4, multi_frac=0.2, missing=0.01, unphased=0.02, haploid_samples=0.4), 128, 0.02),
+            ("all_sparse", synth.make_dataset(300, 257, seed=3, max_alt=3, multi_frac=0.2, missing=0.01), 8192, 0.3),
+            ("mixed_ploidy_records", mixed, 64, 0.01),
+            ("uint32_indices", synth.make_dataset(12, 66000, seed=5, n_founders=16, fmin=0.001), 5, 0.001)]
+
+
+@pytest.mark.gpu
+@needs_bindings
+@pytest.mark.skipif(not os.path.exists(SHIM), reason="bindings/_out/libxsi_shim_b200.so not built")
+@pytest.mark.parametrize("case", range(5))
+def test_plugin_interfaces_against_the_live_reference(tmp_path, case):
+    """The reference's writer (XsiFactoryExt) with GtBlockB200 and its reader (Accessor) with AccessorInternalsB200, fed from
+    memory exactly like the CPU reference in tests/test_oracle_vs_reference.py: same file bytes; fill_genotype_array /
+    get_allele_counts / fill_allele_counts / get_internal_access equal record by record, forward, backward and shuffled."""
+    import numpy as np
+    import xsi_oracle as xo
+    import xsi_ref
+    if not xsi_ref.available():
+        pytest.skip("oracle/_ref/libxsi_ref.so not built")
+    name, ds, bl, maf = _plugin_cases()[case]
+    gt, ngt, nal, ns = ds["gt"], ds["ngt"], ds["n_allele"], ds["n_samples"]
+    off = xo.row_offsets(ngt)
+    dp = xo.default_phased(gt, off, ngt, ns)
+    thr = xo.mac_threshold(ns, int(ngt[0]) // ns, maf)
+    B = xsi_ref.open_lib(SHIM)
+    pr, pb = str(tmp_path / "ref.xsi"), str(tmp_path / "b200.xsi")
+    xsi_ref.encode_file(pr, gt, off, ngt, nal, ns, bl, thr, dp)
+    xsi_ref.encode_file(pb, gt, off, ngt, nal, ns, bl, thr, dp, L=B)
+    assert open(pr, "rb").read() == open(pb, "rb").read(), "XsiFactoryExt + GtBlockB200 wrote different bytes"
+    pos = xo.bm_positions(nal, bl)
+    R = len(nal)
+    ref = xsi_ref.RefAccessor(pr)
+    want = []
+    for r in range(R):
+        row, n = ref.fill_genotype_array(int(nal[r]), int(pos[r]))
+        want.append((row[:n].copy(), n, ref.allele_counts()))
+    ref.close()
+    acc = xsi_ref.RefAccessor(pb, L=B)
+    rng = np.random.default_rng(case)
+    for order in (range(R), range(R - 1, -1, -1), rng.permutation(R)[:150]):
+        for r in order:
+            row, n = acc.fill_genotype_array(int(nal[r]), int(pos[r]))
+            assert n == want[r][1] and np.array_equal(row[:n], want[r][0]), (name, r)
+            assert np.array_equal(acc.allele_counts(), want[r][2]), (name, r)
+    acc.close()
+    # counts only: fresh cursors on both sides, file order (the reference's own call pattern)
+    ref, acc = xsi_ref.RefAccessor(pr), xsi_ref.RefAccessor(pb, L=B)
+    for r in range(R):
+        assert np.array_equal(acc.fill_allele_counts(int(nal[r]), int(pos[r])), ref.fill_allele_counts(int(nal[r]), int(pos[r]))), (name, r)
+    ref.close()
+    acc.close()
+    # InternalGtAccess: sparse flags, the bytes the pointers point at, the default allele, the arrangement a[]
+    if name != "mixed_ploidy_records":  # haploid lines: the arrangement is only kept by the lazy chain kernel (diploid lines)
+        a_bytes = 2 if 2 * ns <= 65535 else 4
+        ref, acc = xsi_ref.RefAccessor(pr), xsi_ref.RefAccessor(pb, L=B)
+        if a_bytes == 2:
+            seq = list(range(0, R, 3)) + [R // 2, 1, R - 1]  # forward, then requests behind the chain (block reload)
+            for r in seq:
+                ra = ref.internal_access(int(nal[r]), int(pos[r]), a_bytes)
+                ba = acc.internal_access(int(nal[r]), int(pos[r]), a_bytes)
+                assert np.array_equal(ra[1], ba[1]) and np.array_equal(ra[2], ba[2]) and ra[3] == ba[3], (name, r)
+                assert np.array_equal(ra[0], ba[0]), (name, r, "arrangement")
+        ref.close()
+        acc.close()

@@ -624,7 +624,7 @@ __global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d, uint32
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[st]);
     }
-    if (ps && k1 < blk.n_wah) {
+    if (ps) {  // also after the last line: xsi_decode_internal_access reads the arrangement from here
 #pragma unroll
         for (int q = 0; q < KH; ++q) ps[q] = (uint16_t)pk[q];
     }

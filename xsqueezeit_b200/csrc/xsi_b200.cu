@@ -149,6 +149,10 @@ struct xsi_ctx {
         uint32_t v3_kh = 0, v3_nc = 0, v3_slices = 0, ps_stride = 0;
         size_t v3_smem = 0, m_blk = 0;
         DevBuf pos_state;
+        // host views of the tables of the loaded set (inside h_meta, valid until the next load): for xsi_decode_internal_access
+        const DecBlock* hv_blocks = nullptr; const DecSeg* hv_segs = nullptr; const uint32_t* hv_job_seg = nullptr;
+        const uint32_t* hv_dl_ord = nullptr; const uint8_t* hv_dl_flags = nullptr;
+        std::vector<uint64_t> h_blob_off, h_blk_size;
         DevBuf blob, meta, rows, job_u32, job_hap, tile_u32, dline, lists, err, a_pool, x_pool, req, out, scratch, counts,
             seg_total, tabs;
         PinBuf h_stage, h_meta;
@@ -1461,6 +1465,8 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
     uint32_t* tile_seg = reinterpret_cast<uint32_t*>(hm + s_tile), *tile_word0 = tile_seg + ntp;
     uint32_t* dl_ord = reinterpret_cast<uint32_t*>(hm + s_dl), *dl_mord = dl_ord + Ltp, *dl_eord = dl_mord + Ltp, *dl_pord = dl_eord + Ltp;
     uint8_t* dl_flags = reinterpret_cast<uint8_t*>(dl_pord + Ltp);
+    d.hv_blocks = blocks; d.hv_segs = segs; d.hv_job_seg = job_seg; d.hv_dl_ord = dl_ord; d.hv_dl_flags = dl_flags;
+    d.h_blob_off = blob_off; d.h_blk_size.assign(sizes, sizes + n_blocks);
     // ---- pass B (worker pool): every block fills its own slices ----
     {
         HOSTSPAN("host:decode_tables");
@@ -2100,6 +2106,84 @@ static int xsi_decode_dot_products_impl(xsi_ctx* ctx, uint64_t n, const uint32_t
     return XSI_OK;
 }
 
+// InternalGtAccess (accessor_internals.hpp:374-397; filled by DecompressPointerGTBlock::get_internal_access,
+// accessor_internals_new.hpp:444-471): where the encoded lines of a record lie inside its GT block, the default allele of its
+// first line, and the PBWT arrangement in force at the record (a[j] = haplotype at position j, the order WAH lines are in).
+static int xsi_decode_internal_access_impl(xsi_ctx* ctx, uint32_t b, uint32_t line, uint32_t n_alleles, xsi_line_access* lines,
+                                           int32_t* default_allele, void* a_out) {
+    if (!ctx || !lines) return XSI_E_ARG;
+    auto& d = ctx->dec;
+    if (!d.loaded || b >= d.nb) { ctx->err = "xsi_decode_internal_access: block not loaded"; return XSI_E_ARG; }
+    if (n_alleles < 2 || (uint64_t)line + n_alleles - 1 > d.h_bin_lines[b]) { ctx->err = "record runs past the end of its block"; return XSI_E_ARG; }
+    CK(cudaSetDevice(ctx->device));
+    const DecBlock& bk = d.hv_blocks[b];
+    const uint32_t msb = d.aet == 2 ? 0x8000u : 0x80000000u;
+    const uint32_t nl = n_alleles - 1;
+    // what the device located: first word of every WAH line inside its matrix, first entry of every sparse list
+    std::vector<uint32_t> w0(nl + 1, 0);
+    std::vector<uint64_t> e0(nl, 0);
+    for (uint32_t k = 0; k < nl; ++k) {
+        const uint32_t gl = bk.line0 + line + k;
+        const uint32_t ord = d.hv_dl_ord[gl];
+        if (d.hv_dl_flags[gl] & DL_WAH) {
+            CK(cudaMemcpyAsync(&w0[k], d.dev.job_word0 + ord, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        } else {
+            CK(cudaMemcpyAsync(&e0[k], d.dev.sp_off + ord, 8, cudaMemcpyDeviceToHost, ctx->stream));
+        }
+    }
+    std::vector<uint32_t> w1(nl, 0);  // word after the line: the next WAH job of the block's matrix, or its end
+    for (uint32_t k = 0; k < nl; ++k) {
+        const uint32_t gl = bk.line0 + line + k;
+        if (!(d.hv_dl_flags[gl] & DL_WAH)) continue;
+        const uint32_t ord = d.hv_dl_ord[gl];
+        const DecSeg& sg = d.hv_segs[d.hv_job_seg[ord]];
+        if (ord + 1 < sg.job0 + sg.njobs) CK(cudaMemcpyAsync(&w1[k], d.dev.job_word0 + ord + 1, 4, cudaMemcpyDeviceToHost, ctx->stream));
+        else w1[k] = sg.n_words;
+    }
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (uint32_t k = 0; k < nl; ++k) {
+        const uint32_t gl = bk.line0 + line + k;
+        const uint32_t ord = d.hv_dl_ord[gl];
+        if (d.hv_dl_flags[gl] & DL_WAH) {
+            const DecSeg& sg = d.hv_segs[d.hv_job_seg[ord]];
+            lines[k].is_sparse = 0;
+            lines[k].byte_offset = (sg.byte_off - bk.blob_off) + (uint64_t)w0[k] * 2;
+            lines[k].n_entries = w1[k] - w0[k];
+        } else {
+            lines[k].is_sparse = 1;
+            lines[k].byte_offset = (bk.sparse_off - bk.blob_off) + e0[k] * d.aet;
+            lines[k].n_entries = 0;  // the list's own header word says (count, MSB = lists REF carriers)
+        }
+    }
+    if (default_allele) {  // accessor_internals_new.hpp:456-463
+        *default_allele = 0;
+        if (lines[0].is_sparse) {
+            uint32_t hdr = 0;
+            CK(cudaMemcpy(&hdr, d.blob.as<uint8_t>() + bk.blob_off + lines[0].byte_offset, d.aet, cudaMemcpyDeviceToHost));
+            *default_allele = (hdr & msb) ? 1 : 0;
+        }
+    }
+    if (a_out) {
+        if (!d.lazy_ok) { ctx->err = "the arrangement is only kept by the lazy chain (at most 65534 haplotypes, no all-haploid lines)"; return XSI_E_UNSUPPORTED; }
+        const auto& wl = d.h_wah_lines[b];
+        // the reference hands out its live `a` after seeking to the record's LAST line (the loop at :456-468 seeks line by line)
+        const uint32_t at = line + nl - 1;
+        const uint32_t k = (uint32_t)(std::lower_bound(wl.begin(), wl.end(), (uint16_t)at) - wl.begin());  // WAH lines before it
+        if (d.h_wah_done[b] > k) { ctx->err = "the chain of this block is already past that line: load it lazily again"; return XSI_E_UNSUPPORTED; }
+        if (d.h_wah_done[b] < k) { const int rc = extend_chain(ctx, b, at); if (rc) return rc; }
+        const uint32_t N = 2 * d.n_samples;
+        std::vector<uint16_t> pos(N);
+        if (k == 0) for (uint32_t i = 0; i < N; ++i) pos[i] = (uint16_t)i;  // identity at block start (gt_block.hpp:179)
+        else {
+            CK(cudaMemcpyAsync(pos.data(), d.pos_state.as<uint16_t>() + (size_t)b * d.ps_stride, (size_t)N * 2, cudaMemcpyDeviceToHost, ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream));
+        }
+        if (d.aet == 2) { uint16_t* a = static_cast<uint16_t*>(a_out); for (uint32_t i = 0; i < N; ++i) a[pos[i]] = (uint16_t)i; }
+        else { uint32_t* a = static_cast<uint32_t*>(a_out); for (uint32_t i = 0; i < N; ++i) a[pos[i]] = i; }
+    }
+    return XSI_OK;
+}
+
 static int xsi_decode_records_i8_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset,
                                      const uint32_t* n_alleles, int8_t* out, uint64_t out_stride, int32_t out_on_device,
                                      uint32_t* n_filled, uint64_t* allele_counts, uint32_t counts_stride) {
@@ -2200,4 +2284,8 @@ extern "C" int xsi_decode_allele_counts(xsi_ctx* ctx, uint64_t n, const uint32_t
 extern "C" int xsi_decode_dot_products(xsi_ctx* ctx, uint64_t n, const uint32_t* block_index, const uint32_t* line_offset, const uint32_t* n_alleles,
                                        const double* y, int32_t y_on_device, double* out, uint32_t out_stride) {
     return guarded(ctx, [&] { return xsi_decode_dot_products_impl(ctx, n, block_index, line_offset, n_alleles, y, y_on_device, out, out_stride); });
+}
+extern "C" int xsi_decode_internal_access(xsi_ctx* ctx, uint32_t block_index, uint32_t line_offset, uint32_t n_alleles, xsi_line_access* lines,
+                                          int32_t* default_allele, void* a) {
+    return guarded(ctx, [&] { return xsi_decode_internal_access_impl(ctx, block_index, line_offset, n_alleles, lines, default_allele, a); });
 }
