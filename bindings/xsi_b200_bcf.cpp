@@ -27,6 +27,16 @@
 // their rows decoded on the device as raw BCF int8 FORMAT/GT payload (xsi_decode_records_i8) in windows, and spliced into
 // the records as the typed vector bcf_update_genotypes would have built, so the CPU neither widens to int32 nor narrows
 // back (bcf_enc_vint); BGZF deflate of the output runs on the thread pool.  The output equals the reference's byte for byte.
+//
+//   xsi_b200_bcf subset <in.xsi> <out.xsi> [--samples a,b,c | --samples ^a,b | --samples-file f] [--maf 0.001] [--zstd] [--zstd-level 7]
+//                [--batch-blocks K] [--threads T] [--device D]
+// is `xsqueezeit -x -O x [-s/-S]` (gt_decompressor_new.hpp:130-143,241-273: decode every record, keep the selected samples,
+// append the row to a new XsiFactoryExt, write the companion with the new BM and, under -s/-S, AC / AN recomputed) with the
+// rows never leaving the device: whole blocks are decoded and gathered by xsi_decode_records_subset into device rows, and
+// xsi_encode_launch_strided encodes them from there; only the selected carriers' counts (ac_s) and the encoded blocks come back.
+// Whole files only (the reference's -r/-t with -Ox goes through bindings/_out/xsqueezeit_b200).  Both output files equal the
+// reference's byte for byte.
+#include <algorithm>
 #include <atomic>
 #include <chrono>
 #include <condition_variable>
@@ -99,6 +109,7 @@ struct Options {
     int zstd_level = 7, threads = 8, batch_blocks = 2, device = 0;
     std::string output_type = "b";
     size_t window_bytes = (size_t)64 << 20;
+    std::string samples, samples_file;
 };
 
 void widen_batch(Batch& b) {  // a record without an int8 GT payload arrived: the batch moves int32 from here on
@@ -508,11 +519,222 @@ int extract(const Options& o) {
     return 0;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// subset: `xsqueezeit -x -O x [-s list | -S file]` (gt_decompressor_new.hpp:130-143,241-273) with device-resident rows
+// ------------------------------------------------------------------------------------------------------------------
+int subset(const Options& o) {
+    const double t0 = now();
+    xsi_reader* rd = nullptr;
+    int rc = xsi_reader_open(o.in.c_str(), &rd);
+    if (rc != XSI_OK) { fprintf(stderr, "Failed to open file %s (rc %d)\n", o.in.c_str(), rc); return 1; }
+    uint64_t S = 0, hap = 0, entries = 0, nvar = 0, rare = 0;
+    uint32_t ploidy = 0, aet = 0, nblocks = 0, block_len = 0;
+    int32_t zstd = 0, dph = 0;
+    xsi_reader_info(rd, &S, &hap, &ploidy, &aet, &nblocks, &block_len, &entries, &nvar, &zstd, &rare, &dph);
+    std::vector<std::string> sample_list;
+    for (uint64_t i = 0; i < S; ++i) sample_list.push_back(xsi_reader_sample_name(rd, i));
+    // enable_select_samples, gt_decompressor_new.hpp:324-365 (and the -S file form, :391-421)
+    std::vector<uint32_t> use;
+    bool select = false;
+    std::string opt = o.samples;
+    if (opt.empty() && !o.samples_file.empty()) {
+        std::string file = o.samples_file;
+        bool exclude = false;
+        if (file[0] == '^') { exclude = true; file.erase(0, 1); }
+        FILE* f = fopen(file.c_str(), "r");
+        if (!f) { fprintf(stderr, "Could not open file %s\n", file.c_str()); return 1; }
+        if (exclude) opt = "^";
+        char buf[4096];
+        while (fgets(buf, sizeof buf, f)) {
+            std::string l(buf);
+            while (!l.empty() && (l.back() == '\n' || l.back() == '\r')) l.pop_back();
+            opt += l.substr(0, l.find('\t')) + ",";
+        }
+        fclose(f);
+    }
+    if (!opt.empty()) {
+        select = true;
+        bool inverse = opt[0] == '^';
+        std::vector<std::string> named;
+        size_t p = inverse ? 1 : 0;
+        while (p <= opt.size()) {
+            const size_t q = std::min(opt.find(',', p), opt.size());
+            if (q > p) named.push_back(opt.substr(p, q - p));
+            p = q + 1;
+        }
+        if (inverse) {
+            for (uint32_t i = 0; i < S; ++i)
+                if (std::find(named.begin(), named.end(), sample_list[i]) == named.end()) use.push_back(i);
+        } else {  // bcftools has samples in order of option
+            for (const auto& n : named) {
+                auto it = std::find(sample_list.begin(), sample_list.end(), n);
+                if (it != sample_list.end()) use.push_back((uint32_t)(it - sample_list.begin()));
+            }
+        }
+    } else {
+        for (uint32_t i = 0; i < S; ++i) use.push_back(i);
+    }
+    if (use.empty()) { fprintf(stderr, "No samples to extract\nNo samples found\n"); return 1; }
+    const uint32_t n_sel = (uint32_t)use.size();
+    // the new file's sample list: the selected names only when FEWER samples are kept (create_output_file, :483-490)
+    std::string names;
+    if (use.size() < sample_list.size()) for (uint32_t i : use) { names += sample_list[i]; names.push_back('\0'); }
+    else for (const auto& n : sample_list) { names += n; names.push_back('\0'); }
+    const uint64_t n_haps = (uint64_t)n_sel * ploidy;               // :491
+    const uint64_t mac = (uint64_t)((double)n_haps * o.maf);        // :492
+
+    const std::string var_name = o.in + "_var.bcf";
+    htsFile* vin = hts_open(var_name.c_str(), "r");
+    if (!vin) { fprintf(stderr, "Failed to open file %s\n", var_name.c_str()); return 1; }
+    if (o.threads > 1) hts_set_threads(vin, 2);
+    bcf_hdr_t* hin = bcf_hdr_read(vin);
+    if (!hin) { fprintf(stderr, "Failed to read the header of %s\n", var_name.c_str()); return 1; }
+    bcf_hdr_t* hout = bcf_hdr_dup(hin);
+    bcf_hdr_remove(hout, BCF_HL_GEN, "XSI");
+    {
+        std::string tmp(o.out);
+        bcf_hdr_append(hout, std::string("##XSI=").append(std::string(basename((char*)tmp.c_str()))).c_str());
+    }
+    bcf_hdr_add_sample(hout, NULL);
+    if (bcf_hdr_sync(hout) < 0) fprintf(stderr, "bcf_hdr_sync() failed ...\n");
+    const std::string var_out = o.out + "_var.bcf";
+    htsFile* fout = hts_open(var_out.c_str(), "wb");
+    if (!fout) { fprintf(stderr, "Could not open %s\n", var_out.c_str()); return 1; }
+    if (o.threads > 1) hts_set_threads(fout, o.threads);
+    if (bcf_hdr_write(fout, hout) < 0) { fprintf(stderr, "Could not write header to file %s\n", var_out.c_str()); return 1; }
+
+    xsi_ctx* ctx = nullptr;
+    rc = xsi_create(o.device, &ctx);
+    if (rc != XSI_OK) { fprintf(stderr, "xsi_create failed (no CUDA device? there is no CPU fallback)\n"); return 1; }
+    xsi_writer* w = nullptr;
+    rc = xsi_writer_open(o.out.c_str(), n_sel, names.data(), block_len, mac, dph ? 1 : 0, (o.zstd || zstd) ? 1 : 0, o.zstd_level, &w);
+    if (rc != XSI_OK) { fprintf(stderr, "Failed to open file %s (rc %d)\n", o.out.c_str(), rc); return 1; }
+
+    const size_t batch_records = (size_t)block_len * (size_t)o.batch_blocks;
+    const uint64_t stride = 2ull * n_sel;
+    void* d_rows = nullptr;
+    rc = xsi_device_alloc(ctx, &d_rows, batch_records * stride * 4);
+    if (rc != XSI_OK) { fprintf(stderr, "device allocation failed\n"); return 1; }
+    std::vector<bcf1_t*> recs(batch_records, nullptr);
+    for (auto& r : recs) r = bcf_init();
+    std::vector<uint32_t> blk(batch_records), line(batch_records), nall(batch_records), filled(batch_records);
+    std::vector<uint8_t> pl(batch_records);
+    std::vector<uint32_t> ac;
+    std::vector<int32_t> ac_s;
+    std::vector<std::vector<uint8_t>> held;  // copies of the GT blocks of a batch (a zstd reader reuses its buffer)
+    int32_t* bm = nullptr;
+    int n_bm = 0;
+    uint64_t records = 0, genotypes = 0, out_block = 0;
+    int max_ploidy = 0;
+    bool eof = false, err = false;
+    while (!eof && !err) {
+        size_t n = 0;
+        int64_t first_block = -1, last_block = -1;
+        uint32_t max_all = 2;
+        uint64_t variants = 0;
+        while (n < batch_records) {
+            bcf1_t* rec = recs[n];
+            const int rr = bcf_read(vin, hin, rec);
+            if (rr < -1) { fprintf(stderr, "read error in %s\n", var_name.c_str()); err = true; break; }
+            if (rr < 0) { eof = true; break; }
+            if (bcf_unpack(rec, BCF_UN_ALL)) fprintf(stderr, "bcf_unpack error\n");
+            if (bcf_get_format_int32(hin, rec, "BM", &bm, &n_bm) < 1) { fprintf(stderr, "BM key value not found\n"); err = true; break; }
+            const uint32_t pos = (uint32_t)bm[0];  // Accessor::position_from_bm_entry, accessor.hpp:37-46
+            const int64_t b = pos >> 15;
+            if (first_block < 0) first_block = b;
+            if (b < last_block || b >= first_block + o.batch_blocks) { fprintf(stderr, "records of %s are not in block order\n", var_name.c_str()); err = true; break; }
+            last_block = b;
+            blk[n] = (uint32_t)(b - first_block);
+            line[n] = pos & 0x7FFF;
+            nall[n] = rec->n_allele;
+            max_all = std::max(max_all, nall[n]);
+            variants += rec->n_allele ? rec->n_allele - 1 : 0;
+            ++n;
+        }
+        if (err || n == 0) break;
+        // the blocks of this batch -> device, decoded and gathered there
+        const uint32_t nb = (uint32_t)(last_block - first_block + 1);
+        held.resize(nb);
+        std::vector<const uint8_t*> ptrs(nb);
+        std::vector<uint64_t> sizes(nb);
+        for (uint32_t b = 0; b < nb && rc == XSI_OK; ++b) {
+            const uint8_t* p = nullptr;
+            uint64_t sz = 0;
+            rc = xsi_reader_gt_block(rd, (uint32_t)first_block + b, &p, &sz);
+            if (rc == XSI_OK) { held[b].assign(p, p + sz); ptrs[b] = held[b].data(); sizes[b] = sz; }
+        }
+        if (rc == XSI_OK) rc = xsi_decode_load_blocks(ctx, nb, ptrs.data(), sizes.data(), S, (int32_t)aet);
+        const uint32_t ac_stride = max_all - 1;
+        ac.assign(n * (size_t)ac_stride, 0);
+        if (rc == XSI_OK)
+            rc = xsi_decode_records_subset(ctx, n, blk.data(), line.data(), nall.data(), use.data(), n_sel, static_cast<int32_t*>(d_rows),
+                                           stride, 1, filled.data(), ac.data(), ac_stride);
+        if (rc != XSI_OK) { fprintf(stderr, "decode: %s (rc %d)\n", xsi_last_error(ctx), rc); err = true; break; }
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t p = filled[i] / n_sel;  // CURRENT_LINE_PLOIDY of the selected row, :209-220
+            if (p == 0 || p > 2) { fprintf(stderr, "PLOIDY ERROR\n"); err = true; break; }
+            pl[i] = (uint8_t)p;
+            genotypes += filled[i];
+        }
+        if (err) break;
+        // ... and encoded from there as the next blocks of the new file
+        xsi_encode_desc d;
+        memset(&d, 0, sizeof d);
+        d.n_records = n; d.n_samples = n_sel; d.block_len = block_len; d.mac_threshold = mac; d.default_phasing = dph ? 1 : 0;
+        d.gt_elem_bytes = 4; d.gt_on_device = 1; d.gt = d_rows; d.n_allele = nall.data(); d.ploidy = pl.data();
+        uint32_t nbo = 0;
+        const uint8_t* const* bo = nullptr;
+        const uint64_t* so = nullptr;
+        rc = xsi_encode_launch_strided(ctx, &d, stride);
+        if (rc == XSI_OK) rc = xsi_encode_collect(ctx, &nbo, &bo, &so);
+        if (rc == XSI_OK) rc = xsi_writer_add_blocks(w, nbo, bo, so, n, variants);
+        if (rc != XSI_OK) { fprintf(stderr, "encode: %s (rc %d)\n", xsi_last_error(ctx), rc); err = true; break; }
+        max_ploidy = std::max(max_ploidy, xsi_encode_max_ploidy(ctx));
+        // the companion: new BM, AC / AN as bcftools view -s recomputes them (update_and_write_xsi, :241-273)
+        for (size_t i = 0; i < n && !err; ++i) {
+            bcf1_t* rec = recs[i];
+            const uint64_t r = records + i;
+            const uint64_t nblk = r / block_len;
+            if (nblk != out_block) out_block = nblk;
+            // block_id << 15 | offset of the NEW file (:169-180); records are not filtered here, so the offset inside the block is the old one
+            int32_t v = (int32_t)((uint32_t)nblk << 15 | line[i]);
+            bcf_update_format(hin, rec, "BM", &v, 1, BCF_HT_INT);
+            if (select) {
+                ac_s.assign(nall[i] - 1, 0);
+                for (uint32_t a = 0; a + 1 < nall[i]; ++a) ac_s[a] = (int32_t)ac[i * (size_t)ac_stride + a];
+                int32_t an = (int32_t)filled[i];
+                bcf_update_info_int32(hout, rec, "AC", ac_s.data(), (int)(nall[i] - 1));
+                bcf_update_info_int32(hout, rec, "AN", &an, 1);
+            }
+            if (bcf_write1(fout, hout, rec)) { fprintf(stderr, "Failed to write record\n"); err = true; break; }
+        }
+        records += n;
+    }
+    free(bm);
+    for (auto& r : recs) bcf_destroy(r);
+    xsi_device_free(ctx, d_rows);
+    xsi_destroy(ctx);
+    if (w) {
+        rc = xsi_writer_close(w, max_ploidy);
+        if (rc != XSI_OK) { fprintf(stderr, "finalize failed (rc %d)\n", rc); err = true; }
+    }
+    if (hts_close(fout) < 0) err = true;
+    hts_close(vin);
+    bcf_hdr_destroy(hin);
+    bcf_hdr_destroy(hout);
+    xsi_reader_close(rd);
+    if (err) { fprintf(stderr, "Failure occurred, exiting...\n"); return 1; }
+    printf("xsi_b200_bcf subset: records %llu selected_samples %u genotypes %llu seconds %.6f\n", (unsigned long long)records, n_sel,
+           (unsigned long long)genotypes, now() - t0);
+    return 0;
+}
+
 }  // namespace
 
 int main(int argc, char** argv) {
     const std::string cmd = argc > 1 ? argv[1] : "";
-    if (argc < 4 || (cmd != "compress" && cmd != "extract")) {
+    if (argc < 4 || (cmd != "compress" && cmd != "extract" && cmd != "subset")) {
+        fprintf(stderr, "usage: %s subset in.xsi out.xsi [--samples a,b|^a,b] [--samples-file f] [--maf f] [--zstd] [--batch-blocks k]\n", argv[0]);
         fprintf(stderr, "usage: %s extract in.xsi out.bcf [-O b|u] [--threads t] [--window-bytes n] [--device d]\n", argv[0]);
         fprintf(stderr, "usage: %s compress in.bcf out.xsi [--maf f] [--variant-block-length n] [--zstd] [--zstd-level l]\n"
                         "          [--wah-encode-missing] [--threads t] [--batch-blocks k] [--device d]\n", argv[0]);
@@ -535,11 +757,13 @@ int main(int argc, char** argv) {
         else if (a == "--reference-var") o.reference_var = true;
         else if (a == "-O" || a == "--output-type") o.output_type = val();
         else if (a == "--window-bytes") o.window_bytes = (size_t)atoll(val());
+        else if (a == "--samples" || a == "-s") o.samples = val();
+        else if (a == "--samples-file" || a == "-S") o.samples_file = val();
         else { fprintf(stderr, "unknown option %s\n", a.c_str()); return 2; }
     }
     if (o.block_len == 0 || o.batch_blocks < 1) return 2;
     try {
-        return cmd == "compress" ? compress(o) : extract(o);
+        return cmd == "compress" ? compress(o) : cmd == "extract" ? extract(o) : subset(o);
     } catch (const char* e) {
         fprintf(stderr, "%s\nFailure occurred, exiting...\n", e);
         return 1;

@@ -55,6 +55,10 @@ const char* xsi_profile_read(xsi_ctx* ctx);
  * receive rows from xsi_decode_records*: pinned buffers cross PCIe by DMA without a bounce copy. */
 int  xsi_host_alloc(void** p, uint64_t bytes);
 void xsi_host_free(void* p);
+/* Device memory on the context's GPU for callers without a CUDA runtime of their own (rows handed from xsi_decode_records*
+ * with out_on_device = 1 to xsi_encode_launch[_strided] with gt_on_device = 1). */
+int  xsi_device_alloc(xsi_ctx* ctx, void** p, uint64_t bytes);
+void xsi_device_free(xsi_ctx* ctx, void* p);
 
 /* ------------------------------------------------------------------------------------------
  * ENCODE  -- replaces GtBlock<A_T,uint16_t>::encode_line + write_to_stream
@@ -79,6 +83,11 @@ typedef struct {
 
 /* Asynchronous part: uploads (if needed), runs every encode kernel on the context stream.  */
 int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* desc);
+/* The same launch for DEVICE rows that are not back to back: row r starts at element r * row_stride (row_stride >= 2 * n_samples;
+ * a haploid row uses the first n_samples elements).  This is the layout xsi_decode_records* write with out_on_device = 1, so the
+ * extractor's XSI -> XSI path (-Ox with -s/-S: decode, select samples, encode again; XsiFactoryExt::append of the selected row,
+ * include/gt_decompressor_new.hpp:241-273) runs without the rows leaving the device.                                        */
+int xsi_encode_launch_strided(xsi_ctx* ctx, const xsi_encode_desc* desc, uint64_t row_stride);
 /* on = 1: xsi_encode_launch of DEVICE rows returns at once; the batch is encoded by a thread of the library on a stream of
  * its own and xsi_encode_collect waits for it (errors of the launch are reported there).  The caller may decode another batch
  * on the same context meanwhile (xsi_decode_*): one host thread then keeps the PBWT chain of batch i+1 and the HBM-bound

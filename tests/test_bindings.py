@@ -206,6 +206,30 @@ def test_bcf_ingest_tool(tmp_path, name):
     assert {"records": int(line[1]), "genotypes": int(line[3]), "checksum": line[7]} == case["capi_decode"]
 
 
+SUBMAN = json.load(open(os.path.join(G, "subset_manifest.json")))
+
+
+@pytest.mark.gpu
+@needs_bindings
+@pytest.mark.parametrize("name", sorted(SUBMAN["cases"]))
+def test_subset_tool_matches_reference_Ox(tmp_path, name):
+    """`xsi_b200_bcf subset` = `xsqueezeit -x -O x [-s/-S]` (gt_decompressor_new.hpp:241-273) with the rows kept on the device between
+    xsi_decode_records_subset and xsi_encode_launch_strided: the new .xsi AND its companion (new BM, AC / AN of the selected
+    samples) equal the unmodified reference's, byte for byte (tests/golden/make_subset_golden.py)"""
+    case = SUBMAN["cases"][name]
+    xsi = str(tmp_path / "in.xsi")
+    run([CLI, "-c", "--maf", "0.002", "-f", os.path.join(INP, case["input"]), "-o", xsi])
+    lst = str(tmp_path / "samples.txt")
+    open(lst, "w").write(SUBMAN["sample_file"])
+    out = str(tmp_path / "sub.xsi")
+    for batch in ("1", "3"):
+        run([os.path.join(OUT, "xsi_b200_bcf"), "subset", xsi, out, "--batch-blocks", batch] + [lst if a == "@LIST" else a for a in case["subset_argv"]])
+        data = open(out, "rb").read()
+        assert len(data) == case["xsi_size"]
+        assert sha(data) == case["xsi_sha256"], "subset: .xsi differs from the reference's -Ox output"
+        assert sha(open(out + "_var.bcf", "rb").read()) == case["var_sha256"], "subset: companion differs from the reference's"
+
+
 # ---- the in-memory door (oracle/ref_shim.cpp: XsiFactoryExt + Accessor fed from arrays) built twice: CPU reference vs both adapters ----
 SHIM = os.path.join(OUT, "libxsi_shim_b200.so")
 

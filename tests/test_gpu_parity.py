@@ -483,6 +483,57 @@ def ctypes_block(acc, b):
     return p.value, s.value
 
 
+def test_subset_reencode_on_device(ctx, tmp_path):
+    """The extractor's XSI -> XSI path with a sample subset (-s ... -Ox, gt_decompressor_new.hpp:241-273) without the rows leaving the
+    device: xsi_decode_records_subset into device rows, xsi_encode_launch_strided from them.  The GT blocks equal the oracle's
+    encoding of the rows fill_selected_genotypes would have handed to XsiFactoryExt::append (mixed ploidy, all-haploid records)."""
+    import xsqueezeit_b200 as xb
+    rng = np.random.default_rng(15)
+    al = (rng.random((150, 90)) < rng.uniform(0.0, 0.6, size=(150, 1))).astype(np.int8)
+    haploid = dict(gt=np.ascontiguousarray(synth.encode_gt(al, 0).reshape(-1)), ngt=np.full(150, 90, np.int32),
+                   n_allele=np.full(150, 2, np.int32), n_samples=90)
+    for k, (ds, bl) in enumerate(((synth.make_dataset(300, 257, seed=61, max_alt=4, multi_frac=0.3, missing=0.02, unphased=0.02, haploid_samples=0.4), 128),
+                                  (synth.make_dataset(200, 1000, seed=62), 64), (haploid, 40))):
+        ns, nal = ds["n_samples"], ds["n_allele"]
+        p = gpu_encode(ctx, tmp_path, ds, bl, 0.01)
+        acc = xb.Accessor(p, ctx)
+        rd = xo.Reader(open(p, "rb").read())
+        pos = xb.bm_positions(nal, bl)
+        sel = rng.permutation(ns)[: max(5, ns // 3)].astype(np.uint32)
+        R, n_sel = len(pos), len(sel)
+        acc._load(0, (R + bl - 1) // bl)
+        blk = (pos >> np.uint64(15)).astype(np.uint32)
+        off = (pos & np.uint64(0x7FFF)).astype(np.uint32)
+        dev = ctx.device_alloc(R * 2 * n_sel * 4)
+        try:
+            _, filled, _ = ctx.decode_records_subset(blk, off, nal, sel, out_device=dev)
+            rows = []
+            for r in range(R):
+                row, n = rd.fill_genotype_array(int(nal[r]), int(pos[r]))
+                rows.append(xo.select_samples(row, n, ns, sel, int(nal[r]))[0])
+            ngt = np.array([x.size for x in rows], dtype=np.int32)
+            assert np.array_equal(filled, ngt)
+            gt = np.ascontiguousarray(np.concatenate(rows), dtype=np.int32)
+            o = xo.row_offsets(ngt)
+            dp = xo.default_phased(gt, o, ngt, n_sel)
+            thr = xo.mac_threshold(n_sel, int(ngt[0]) // n_sel, 0.01)
+            want = str(tmp_path / ("want%d.xsi" % k))
+            open(want, "wb").write(xo.encode(gt, o, ngt, nal, n_sel, bl, thr, dp, None))
+            ctx.encode_launch(dev, nal, n_sel, bl, thr, dp, ploidy=(ngt // n_sel).astype(np.uint8), gt_on_device=True, row_stride=2 * n_sel)
+            blocks = ctx.encode_collect()
+        finally:
+            ctx.device_free(dev)
+        acc.close()
+        ref = xb.Accessor(want, ctx)
+        assert len(blocks) == ref.n_blocks
+        for b, got in enumerate(blocks):
+            a, n = ctypes_block(ref, b)
+            assert got == ctypes.string_at(a, n), (k, b)
+        ref.close()
+        with pytest.raises(xb.XsiError):  # strided rows are device rows
+            ctx.encode_launch(gt, nal, n_sel, bl, thr, dp, ploidy=(ngt // n_sel).astype(np.uint8), row_stride=2 * n_sel)
+
+
 def test_positions_in_any_order(ctx, tmp_path):
     """seek (accessor_internals_new.hpp:154-196) replays or resets the cursor; here any (block, line) is addressable:
     shuffled, backward and repeated positions through fill_genotype_arrays, the one-record call and the subset call"""

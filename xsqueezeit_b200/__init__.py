@@ -110,6 +110,12 @@ def lib():
     L.xsi_host_alloc.argtypes = [P(vp), u64]
     L.xsi_host_free.restype = None
     L.xsi_host_free.argtypes = [vp]
+    L.xsi_device_alloc.restype = i32
+    L.xsi_device_alloc.argtypes = [vp, P(vp), u64]
+    L.xsi_device_free.restype = None
+    L.xsi_device_free.argtypes = [vp, vp]
+    L.xsi_encode_launch_strided.restype = i32
+    L.xsi_encode_launch_strided.argtypes = [vp, vp, u64]
     L.xsi_decode_load_blocks_lazy.restype = i32
     L.xsi_decode_load_blocks_lazy.argtypes = [vp, u32, P(vp), P(u64), u64, i32, u32]
     L.xsi_decode_extend.restype = i32
@@ -201,8 +207,9 @@ class Context:
 
     # ---- encode --------------------------------------------------------------------------
     def encode_launch(self, gt, n_allele, n_samples, block_len, mac_threshold, default_phasing, ploidy=None,
-                      gt_elem_bytes=4, gt_on_device=False, wah_encode_missing=False):
-        """gt: numpy array (host) or an integer device address when gt_on_device."""
+                      gt_elem_bytes=4, gt_on_device=False, wah_encode_missing=False, row_stride=0):
+        """gt: numpy array (host) or an integer device address when gt_on_device.  row_stride (elements, device rows only):
+        rows r * row_stride apart instead of back to back (xsi_encode_launch_strided)."""
         self._na = np.ascontiguousarray(n_allele, dtype=np.uint32)
         self._pl = None if ploidy is None else np.ascontiguousarray(ploidy, dtype=np.uint8)
         self._gt_keep = gt
@@ -218,7 +225,19 @@ class Context:
         d.gt = _ptr(gt)
         d.n_allele = self._na.ctypes.data
         d.ploidy = None if self._pl is None else self._pl.ctypes.data
-        self._check(self._L.xsi_encode_launch(self.h, ctypes.byref(d)))
+        if row_stride:
+            self._check(self._L.xsi_encode_launch_strided(self.h, ctypes.byref(d), int(row_stride)))
+        else:
+            self._check(self._L.xsi_encode_launch(self.h, ctypes.byref(d)))
+
+    def device_alloc(self, nbytes):
+        """xsi_device_alloc: a device address on this context's GPU (free with device_free)."""
+        p = ctypes.c_void_p()
+        self._check(self._L.xsi_device_alloc(self.h, ctypes.byref(p), int(nbytes)))
+        return p.value
+
+    def device_free(self, addr):
+        self._L.xsi_device_free(self.h, ctypes.c_void_p(addr))
 
     def encode_async(self, on=True):
         """xsi_encode_async: launches of device rows return at once (a library thread encodes on its own stream) and
@@ -315,21 +334,23 @@ class Context:
         return out, filled, counts
 
 
-    def decode_records_subset(self, block_index, line_offset, n_alleles, samples_to_use, want_ac=True):
+    def decode_records_subset(self, block_index, line_offset, n_alleles, samples_to_use, want_ac=True, out_device=None):
         """Rows of the selected samples only, in the order given (the extractor's -s/-S, gt_decompressor_new.hpp:208-238),
-        their lengths, and the selected carriers per ALT allele (ac_s)."""
+        their lengths, and the selected carriers per ALT allele (ac_s).  out_device: a device address that receives the rows
+        (2 * len(samples_to_use) int32 apart) instead of a host array."""
         bi = np.ascontiguousarray(block_index, dtype=np.uint32)
         lo = np.ascontiguousarray(line_offset, dtype=np.uint32)
         na = np.ascontiguousarray(n_alleles, dtype=np.uint32)
         sel = np.ascontiguousarray(samples_to_use, dtype=np.uint32)
         n = bi.size
         stride = 2 * sel.size
-        out = np.zeros((n, stride), dtype=np.int32)
+        out = None if out_device else np.zeros((n, stride), dtype=np.int32)
         filled = np.zeros(n, dtype=np.uint32)
         acs = max(1, int(na.max()) - 1) if n else 1
         ac = np.zeros((n, acs), dtype=np.uint32) if want_ac else None
         self._check(self._L.xsi_decode_records_subset(self.h, n, bi.ctypes.data, lo.ctypes.data, na.ctypes.data, sel.ctypes.data,
-                                                      sel.size, out.ctypes.data, stride, 0, filled.ctypes.data,
+                                                      sel.size, out_device if out_device else out.ctypes.data, stride,
+                                                      1 if out_device else 0, filled.ctypes.data,
                                                       None if ac is None else ac.ctypes.data, acs))
         return out, filled, ac
 

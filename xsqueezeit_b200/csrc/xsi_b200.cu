@@ -75,6 +75,7 @@ struct xsi_ctx {
     int enc_rc = XSI_OK;
     bool enc_pending = false;  // a launch was handed to enc_thread and its result not yet reported by xsi_encode_collect
     xsi_encode_desc enc_desc;
+    uint64_t enc_row_stride = 0;   // xsi_encode_launch_strided: element distance between rows of the launch being set up (0: back to back)
     std::mutex prof_m;
     int sm_count = 148;
     size_t smem_optin = 0;
@@ -273,6 +274,21 @@ extern "C" int xsi_host_alloc(void** p, uint64_t bytes) {
     return XSI_OK;
 }
 extern "C" void xsi_host_free(void* p) { if (p) cudaFreeHost(p); }
+// device rows for C / C++ callers that keep a decode -> encode hand-over on the device (bindings/xsi_b200_bcf.cpp `subset`)
+extern "C" int xsi_device_alloc(xsi_ctx* ctx, void** p, uint64_t bytes) {
+    if (!ctx || !p) return XSI_E_ARG;
+    *p = nullptr;
+    if (bytes == 0) return XSI_OK;
+    if (cudaSetDevice(ctx->device) != cudaSuccess) { cudaGetLastError(); return XSI_E_CUDA; }
+    const cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) { cudaGetLastError(); *p = nullptr; ctx->err = "device allocation failed"; return e == cudaErrorMemoryAllocation ? XSI_E_NOMEM : XSI_E_CUDA; }
+    return XSI_OK;
+}
+extern "C" void xsi_device_free(xsi_ctx* ctx, void* p) {
+    if (!ctx || !p) return;
+    cudaSetDevice(ctx->device);
+    cudaFree(p);
+}
 
 extern "C" const char* xsi_last_error(const xsi_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
 extern "C" void* xsi_stream(xsi_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
@@ -761,9 +777,13 @@ int run_permute(xsi_ctx* ctx, const EncDev& p) {
 
 }  // namespace
 
-static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
+static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d, uint64_t row_stride = 0) {
     if (!ctx || !d) return XSI_E_ARG;
     auto& e = ctx->enc;
+    if (row_stride) {
+        if (!d->gt_on_device) { ctx->err = "strided rows must be device rows"; return XSI_E_ARG; }
+        if (row_stride < 2ull * d->n_samples) { ctx->err = "row_stride smaller than 2*n_samples"; return XSI_E_ARG; }
+    }
     e.launched = false; e.collected = false;
     if (!d->gt || !d->n_allele || d->n_records == 0 || d->n_samples == 0 || d->block_len == 0) { ctx->err = "bad encode descriptor"; return XSI_E_ARG; }
     if (d->gt_elem_bytes != 4 && d->gt_elem_bytes != 1) { ctx->err = "gt_elem_bytes must be 1 or 4"; return XSI_E_ARG; }
@@ -817,6 +837,7 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
         const uint64_t g = k.g, l = k.l;
         k.g = goff; k.l = L;  // now: the chunk's first element / line
         goff += g; L += l;
+        if (row_stride) k.g = (uint64_t)c * TCH * row_stride;
         if (L >= (1ull << 31)) { ctx->err = "too many binary lines in batch"; return XSI_E_ARG; }
         e.max_ploidy = std::max(e.max_ploidy, k.max_pl);
         e.any_haploid |= k.hap;
@@ -838,7 +859,7 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d) {
             if (g % 16 || ((uint64_t)S * pl) % 16) k.al1 = false;
             e.h_line0[r] = (uint32_t)l;
             for (uint32_t a = 1; a < na; ++a) e.h_line_rec[l + a - 1] = (uint32_t)r;
-            g += (uint64_t)S * pl;
+            g += row_stride ? row_stride : (uint64_t)S * pl;
             l += na - 1;
         }
     });
@@ -2230,15 +2251,25 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         ctx->enc_desc = *d;
         ctx->enc_rc = XSI_OK;
         ctx->enc_pending = true;
+        const uint64_t stride = ctx->enc_row_stride;
         try {
-            ctx->enc_thread = std::thread([ctx] { ctx->enc_rc = guarded(ctx, [&] { return xsi_encode_launch_impl(ctx, &ctx->enc_desc); }); });
+            ctx->enc_thread = std::thread([ctx, stride] { ctx->enc_rc = guarded(ctx, [&] { return xsi_encode_launch_impl(ctx, &ctx->enc_desc, stride); }); });
         } catch (...) {
             ctx->err = "cannot start the encode thread";
             return XSI_E_NOMEM;
         }
         return XSI_OK;
     }
-    return guarded(ctx, [&] { return xsi_encode_launch_impl(ctx, d); });
+    const uint64_t stride = ctx ? ctx->enc_row_stride : 0;
+    return guarded(ctx, [&] { return xsi_encode_launch_impl(ctx, d, stride); });
+}
+extern "C" int xsi_encode_launch_strided(xsi_ctx* ctx, const xsi_encode_desc* d, uint64_t row_stride) {
+    if (!ctx) return XSI_E_ARG;
+    if (ctx->enc_thread.joinable()) ctx->enc_thread.join();
+    ctx->enc_row_stride = row_stride;
+    const int rc = xsi_encode_launch(ctx, d);
+    ctx->enc_row_stride = 0;
+    return rc;
 }
 extern "C" int xsi_encode_collect(xsi_ctx* ctx, uint32_t* n_blocks_out, const uint8_t* const** blocks_out, const uint64_t** sizes_out) {
     if (ctx && ctx->enc_thread.joinable()) ctx->enc_thread.join();
