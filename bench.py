@@ -411,13 +411,16 @@ def bcf_legs(samples, records, which, threads):
             tc, so = _run_timed([os.path.join(BIND, "xsi_b200_bcf"), "compress", src, bx, "--threads", str(threads), "--batch-blocks", "1"])
             td, so2 = _run_timed([os.path.join(BIND, "capi_decode_b200"), bx + "_var.bcf"], env=env_nosum)
             tdl = float(so2.split()[5])
-            _, so3 = _run_timed([os.path.join(BIND, "capi_decode_b200"), bx + "_var.bcf"])
+            td2, so3 = _run_timed([os.path.join(BIND, "capi_decode_b200"), bx + "_var.bcf"])
             tx, _ = _run_timed([os.path.join(BIND, "xsi_b200_bcf"), "extract", bx, os.path.join(tmp, "b200", "o.bcf"), "--threads", str(threads)])
             ax = os.path.join(tmp, "ada", "d.xsi")
             os.makedirs(os.path.dirname(ax))
             tac, _ = _run_timed([os.path.join(BIND, "xsqueezeit_b200"), "-c", "-f", src, "-o", ax])
             out["compress"] = {"ggts": ggts(tc), "seconds": tc, "program": "xsi_b200_bcf compress: one pass, %d BGZF threads, raw int8 FORMAT/GT rows, encode thread" % threads}
+            tok = so2.split()
             out["decode_c_api"] = {"ggts": ggts(td), "seconds": td, "loop_seconds": tdl,
+                                   "setup_seconds": float(tok[9]) if len(tok) > 11 else None, "teardown_seconds": float(tok[11]) if len(tok) > 11 else None,
+                                   "seconds_second_run_with_checksum": td2,
                                    "program": "c_xcf_get_genotypes per record (c_api.h) on AccessorInternalsB200 (decode-ahead window), 1 thread"}
             out["extract_bcf"] = {"ggts": ggts(tx), "seconds": tx, "program": "xsi_b200_bcf extract: int8 rows spliced into the records, %d BGZF threads" % threads}
             out["compress_reference_cli_with_adapter"] = {"ggts": ggts(tac), "seconds": tac, "program": "xsqueezeit -c built with bindings/gt_block_b200.hpp"}

@@ -2,7 +2,7 @@
  * as SHAPEIT4 or the reference's own c_api_test/main.c uses it: one c_xcf_get_genotypes call per record of the
  * `_var.bcf` companion.  Linked twice by bindings/Makefile: with the reference's accessor.o (CPU) and with
  * accessor_b200.o (the adapter, GPU).  Prints one line:
- *     records <R> genotypes <G> seconds <T> checksum <C>
+ *     records <R> genotypes <G> seconds <T> checksum <C> setup <seconds before the loop> teardown <seconds in c_xcf_delete>
  * where the checksum (four multiply-add lanes over every returned int32; XSI_CAPI_NO_CHECKSUM=1 skips it) lets the two builds be compared without storing rows.
  * usage: capi_decode <file.xsi_var.bcf | file.bcf> [max_records]
  */
@@ -24,6 +24,7 @@ static double now(void) {
 int main(int argc, char** argv) {
     if (argc < 2) { fprintf(stderr, "usage: %s file [max_records]\n", argv[0]); return 2; }
     const long max_records = argc > 2 ? atol(argv[2]) : -1;
+    const double ts = now();
     c_xcf* x = c_xcf_new();
     bcf_srs_t* sr = bcf_sr_init();
     if (!bcf_sr_add_reader(sr, argv[1])) { fprintf(stderr, "could not load %s\n", argv[1]); return 1; }
@@ -58,7 +59,8 @@ int main(int argc, char** argv) {
     }
     const double t1 = now();
     c_xcf_delete(x);
-    printf("records %ld genotypes %llu seconds %.6f checksum %016llx\n", records, (unsigned long long)genotypes, t1 - t0,
-           (unsigned long long)(h0 ^ (h1 * 3) ^ (h2 * 5) ^ (h3 * 7)));
+    const double t2 = now();
+    printf("records %ld genotypes %llu seconds %.6f checksum %016llx setup %.6f teardown %.6f\n", records, (unsigned long long)genotypes, t1 - t0,
+           (unsigned long long)(h0 ^ (h1 * 3) ^ (h2 * 5) ^ (h3 * 7)), t0 - ts, t2 - t1);
     return 0;
 }

@@ -709,7 +709,9 @@ def test_async_encode_beside_decode(ctx, tmp_path):
 @pytest.mark.parametrize("env", [{"XSI_PBWT_V": "5"}, {"XSI_PBWT_V": "4"}, {"XSI_PBWT_V": "1"},
                                  {"XSI_PBWT_V": "5", "XSI_PBWT_CLUSTER": "2"}, {"XSI_PBWT_V": "5", "XSI_PBWT_CLUSTER": "1", "XSI_PBWT_KH": "16"},
                                  {"XSI_PBWT_V": "5", "XSI_PBWT_CLUSTER": "8"}, {"XSI_PBWT_V": "4", "XSI_PBWT_CLUSTER": "2"},
-                                 {"XSI_SCAN_V1": "1"}, {"XSI_SCAN_NT": "256", "XSI_COMPOSE_NT": "256"}, {"XSI_COMPOSE_V1": "1"}])
+                                 {"XSI_SCAN_V1": "1"}, {"XSI_SCAN_NT": "256", "XSI_COMPOSE_NT": "256"}, {"XSI_COMPOSE_V1": "1"},
+                                 {"XSI_PBWT_SMALL": "0"}, {"XSI_UNPERM_FENCE": "1"}, {"XSI_UNPERM_KH": "32", "XSI_UNPERM_NC": "160"},
+                                 {"XSI_UNPERM_KH": "16", "XSI_UNPERM_NC": "320"}])
 def test_kernel_variants_are_byte_exact(ctx, tmp_path, monkeypatch, env):
     """every kernel variant that ships (the two-line and the one-line cluster kernels at several cluster sizes, the general
     shared-memory kernel, the ballot scan, the fixed-width CTAs) against the oracle: odd and even numbers of WAH lines per block,
@@ -717,6 +719,8 @@ def test_kernel_variants_are_byte_exact(ctx, tmp_path, monkeypatch, env):
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     cases = [(synth.make_dataset(333, 2504, seed=101), 111, 0.001),            # 1KGP3 width, 3 blocks of 111 records
+             (synth.make_dataset(150, 4096, seed=105), 50, 0.001),             # 8192 haplotypes: the widest row of the small-row kernel
+             (synth.make_dataset(150, 4097, seed=106), 75, 0.001),             # ... and the first one past it
              (synth.make_dataset(90, 20000, seed=102, n_founders=32), 45, 0.001),  # 40,000 haplotypes
              (synth.make_dataset(64, 32488, seed=103, n_founders=32), 32, 0.001),  # HRC width
              (synth.make_dataset(41, 700, seed=104, max_alt=3, multi_frac=0.3, missing=0.01), 41, 0.0)]  # every line WAH

@@ -543,7 +543,7 @@ constexpr int D3_STAGES = 4;
 // WAH lines [wah_done, wah_todo) of every block [b0, b0 + gridDim.x) and parks the positions in pos_state (uint16 per
 // haplotype slot) so that a record near the start of a block does not pay for the whole block (seek, :154-196, in reverse).
 template <int KH>  // haplotypes per thread: 8, 16 or 32 (one uint8 / uint16 / uint32 store per thread and line)
-__global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d, uint32_t b0, uint16_t* __restrict__ pos_state, uint32_t ps_stride) {
+__global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d, uint32_t b0, uint16_t* __restrict__ pos_state, uint32_t ps_stride, int fence) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t N = 2 * d.n_samples, TW = d.TW, WS = d.WS;
     const uint32_t tid = threadIdx.x, lane = tid & 31u;
@@ -608,6 +608,22 @@ __global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d, uint32
             pk[q] = ((int32_t)w < 0) ? zb : Z + j - zb;
             xinv = __funnelshift_l(w, xinv, 1);  // (xinv << 1) | sign(w)
         }
+        // Release the stage only when this warp's table reads have PERFORMED, not merely issued: ptxas would otherwise put
+        // the arrive right after the LDS issue (their results are consumed later), and with consumers that were starved on
+        // `full` all waking at once the shared-memory pipe is backed up far enough for the producer's next TMA fill of the
+        // stage to overtake reads still queued (seen as wrong rows / wild positions when several contexts decode
+        // concurrently; XSI_UNPERM_NC=128 made it near-certain).  The update chain above has CONSUMED every loaded entry by
+        // the time xinv and pk[] are complete, so tying the arrive to those registers orders it behind the reads without a
+        // memory fence (round 1 used __threadfence_block here, which also waited for the row store of the previous line:
+        // `fence` keeps that variant selectable, XSI_UNPERM_FENCE=1).
+        if (fence) __threadfence_block();
+        else {
+#pragma unroll
+            for (int q = 0; q < KH; ++q) asm volatile("" ::"r"(pk[q]) : "memory");
+            asm volatile("" ::"r"(xinv) : "memory");
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[st]);
         if (store) {  // natural-order row, in place
             const uint32_t x = ~xinv & vmask;
             const size_t row = (size_t)(blk.wah0 + k) * WS;
@@ -615,14 +631,6 @@ __global__ void __launch_bounds__(544) pbwt_unpermute_v3_kernel(DecDev d, uint32
             else if (KH == 16) reinterpret_cast<uint16_t*>(d.rows + row)[hb >> 4] = (uint16_t)x;
             else reinterpret_cast<uint8_t*>(d.rows + row)[hb >> 3] = (uint8_t)x;
         }
-        // Release the stage only when this warp's table reads have PERFORMED, not merely issued.  Without the fence
-        // ptxas schedules the arrive right after the LDS issue (their results are consumed later); with consumers
-        // that were starved on `full` all waking at once, the shared-memory pipe is backed up far enough for the
-        // producer's next TMA fill of the stage to overtake reads still queued (seen as wrong rows / wild positions
-        // when several contexts decode concurrently; XSI_UNPERM_NC=128 made it near-certain).
-        __threadfence_block();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[st]);
     }
     if (ps) {  // also after the last line: xsi_decode_internal_access reads the arrangement from here
 #pragma unroll

@@ -748,6 +748,14 @@ int run_permute(xsi_ctx* ctx, const EncDev& p) {
         const int rc = run_permute_v5(ctx, p, W, &done);
         if (rc || done) return rc;
     }
+    // short rows (<= 8192 haplotypes): one small CTA per block, one row word per thread (XSI_PBWT_SMALL=0: the cluster kernel)
+    if (!ctx->enc.any_haploid && N <= 8192 && ver == 4 && !getenv("XSI_PBWT_CLUSTER") && !getenv("XSI_PBWT_KH") &&
+        !(getenv("XSI_PBWT_SMALL") && atoi(getenv("XSI_PBWT_SMALL")) == 0)) {
+        const uint32_t NT = (W + 31) / 32 * 32;
+        { PROF("pbwt_permute"); pbwt_permute_small_kernel<<<p.nb, NT, 0, ctx->es>>>(p); }
+        CKL();
+        return XSI_OK;
+    }
     if (!ctx->enc.any_haploid && N <= 65534 && ver >= 4) {
         bool done = false;
         const int rc = run_permute_v4(ctx, p, W, &done);
@@ -1319,15 +1327,16 @@ static int launch_unpermute_v3(xsi_ctx* ctx, const DecDev& dd, uint32_t b0, uint
     auto& d = ctx->dec;
     const dim3 g(nb, d.v3_slices);
     uint16_t* ps = d.pos_state.as<uint16_t>();
+    const int fence = getenv("XSI_UNPERM_FENCE") ? atoi(getenv("XSI_UNPERM_FENCE")) : 0;
     if (d.v3_kh == 32) {
         CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.v3_smem));
-        PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<32><<<g, d.v3_nc + 32, d.v3_smem, ctx->stream>>>(dd, b0, ps, d.ps_stride);
+        PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<32><<<g, d.v3_nc + 32, d.v3_smem, ctx->stream>>>(dd, b0, ps, d.ps_stride, fence);
     } else if (d.v3_kh == 16) {
         CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.v3_smem));
-        PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<16><<<g, d.v3_nc + 32, d.v3_smem, ctx->stream>>>(dd, b0, ps, d.ps_stride);
+        PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<16><<<g, d.v3_nc + 32, d.v3_smem, ctx->stream>>>(dd, b0, ps, d.ps_stride, fence);
     } else {
         CK(cudaFuncSetAttribute(pbwt_unpermute_v3_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)d.v3_smem));
-        PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<8><<<g, d.v3_nc + 32, d.v3_smem, ctx->stream>>>(dd, b0, ps, d.ps_stride);
+        PROF("pbwt_unpermute"); pbwt_unpermute_v3_kernel<8><<<g, d.v3_nc + 32, d.v3_smem, ctx->stream>>>(dd, b0, ps, d.ps_stride, fence);
     }
     CKL();
     return XSI_OK;
