@@ -922,25 +922,44 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
 
         // -------- general path (accessor_internals_new.hpp:207-384) --------
         // allele code / phase-by-index flag per genotype: shared memory when the row fits (a chrX-shaped file sends every
-        // record through here: 36 us per record with the scratch in global memory), else the per-CTA global scratch
+        // record through here: 36 us per record with the scratch in global memory), else the per-CTA global scratch.
+        // The passes that cover the whole row (the first ALT line, WAH lines, the final compose) work on QUADS: four
+        // genotypes = one 32-bit word of codes and one of flags, four row bits spread with one multiply, 16-byte stores of
+        // the result; only the index lists (sparse / missing / end-of-vector) write single bytes.
         uint8_t* val = scratch_in_smem ? smem_raw : q.scratch + (size_t)blockIdx.x * 2 * q.Npad;
         uint8_t* pf = val + q.Npad;
+        uint32_t* val4 = reinterpret_cast<uint32_t*>(val);
+        uint32_t* pf4 = reinterpret_cast<uint32_t*>(pf);
+        const uint32_t nq = (n + 3) >> 2;
+        auto spread4 = [](uint32_t bits) { return ((bits & 0xFu) * 0x00204081u) & 0x01010101u; };  // bit k -> byte k
         uint32_t total_alt = 0;
         for (uint32_t alt = 1; alt < nall; ++alt) {
             const uint32_t gl = gl0 + alt - 1;
             const uint8_t fl = d.dline_flags[gl];
             const bool hapl = (fl & DL_HAPLOID) != 0;
+            const uint32_t pfw = hapl ? 0u : 0x01010101u;
             uint32_t ones;
             if (fl & DL_WAH) {
                 const uint32_t job = d.dline_ord[gl];
-                const uint32_t* row = d.rows + (size_t)job * d.WS;
+                const uint32_t* __restrict__ row = d.rows + (size_t)job * d.WS;
                 ones = d.job_ones[job];
                 if (alt == 1) {
-                    for (uint32_t i = tid; i < n; i += D4_THREADS) { val[i] = (uint8_t)((row[i >> 5] >> (i & 31)) & 1u); pf[i] = hapl ? 0 : 1; }
+                    for (uint32_t iq = tid; iq < nq; iq += D4_THREADS) {
+                        const uint32_t i = iq << 2;
+                        val4[iq] = spread4(__ldg(row + (i >> 5)) >> (i & 31u));
+                        pf4[iq] = pfw;
+                    }
                 } else {
-                    const uint8_t code = hapl ? (uint8_t)1 : (uint8_t)alt;  // sic: haploid WAH ALT>=2 writes allele 1 (:269)
-                    for (uint32_t i = tid; i < n; i += D4_THREADS)
-                        if ((row[i >> 5] >> (i & 31)) & 1u) { val[i] = code; pf[i] = hapl ? 0 : 1; }
+                    const uint32_t code = hapl ? 1u : alt;  // sic: haploid WAH ALT>=2 writes allele 1 (:269)
+                    for (uint32_t iq = tid; iq < nq; iq += D4_THREADS) {
+                        const uint32_t i = iq << 2;
+                        const uint32_t m = spread4(__ldg(row + (i >> 5)) >> (i & 31u));
+                        if (m) {
+                            const uint32_t mask = m * 0xFFu;
+                            val4[iq] = (val4[iq] & ~mask) | (m * code);
+                            pf4[iq] = (pf4[iq] & ~mask) | (m & pfw);
+                        }
+                    }
                 }
             } else {
                 const uint64_t e0 = d.sp_off[d.dline_ord[gl]];
@@ -949,11 +968,15 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
                 const uint32_t cnt = hdr & ~msb;
                 ones = neg ? n - cnt : cnt;
                 if (alt == 1) {
-                    for (uint32_t i = tid; i < n; i += D4_THREADS) { val[i] = neg ? 1 : 0; pf[i] = 1; }
+                    for (uint32_t iq = tid; iq < nq; iq += D4_THREADS) { val4[iq] = neg ? 0x01010101u : 0u; pf4[iq] = 0x01010101u; }
                     __syncthreads();
                     for (uint32_t k = tid; k < cnt; k += D4_THREADS) { const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet); if (i < q.Npad) { val[i] = neg ? 0 : 1; pf[i] = 1; } }
                 } else if (neg) {
-                    for (uint32_t i = tid; i < n; i += D4_THREADS) if (val[i] == 0) { val[i] = (uint8_t)alt; pf[i] = 1; }
+                    for (uint32_t iq = tid; iq < nq; iq += D4_THREADS) {
+                        const uint32_t v = val4[iq];
+                        const uint32_t m = __vcmpeq4(v, 0u) & 0x01010101u;  // the genotypes that still carry REF
+                        if (m) { val4[iq] = v | (m * alt); pf4[iq] |= m; }
+                    }
                     __syncthreads();
                     for (uint32_t k = tid; k < cnt; k += D4_THREADS) { const uint32_t i = rd_entry(spm, e0 + 1 + k, d.aet); if (i < q.Npad && val[i] == (uint8_t)alt) { val[i] = 0; pf[i] = 1; } }
                 } else {
@@ -969,9 +992,13 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
             // --wah-encode-missing files (accessor_internals_new.hpp:307-321): the line was expanded like any WAH row,
             // natural order (a_weird is the identity under WS_WAH)
             const uint32_t job = d.dline_mord[gl0];
-            const uint32_t* mrow = d.rows + (size_t)job * d.WS;
+            const uint32_t* __restrict__ mrow = d.rows + (size_t)job * d.WS;
             n_missing = d.job_ones[job];
-            for (uint32_t i = tid; i < n; i += D4_THREADS) if ((mrow[i >> 5] >> (i & 31)) & 1u) { val[i] = CODE_MISSING; pf[i] = 1; }
+            for (uint32_t iq = tid; iq < nq; iq += D4_THREADS) {
+                const uint32_t i = iq << 2;
+                const uint32_t m = spread4(__ldg(mrow + (i >> 5)) >> (i & 31u));
+                if (m) { val4[iq] = (val4[iq] & ~(m * 0xFFu)) | (m * CODE_MISSING); pf4[iq] |= m; }
+            }
             __syncthreads();
         } else if (f0 & DL_MISSING) {
             const uint8_t* mm = d.blob + blk.miss_off;
@@ -982,9 +1009,13 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
         }
         if ((f0 & DL_EOV) && (f0 & DL_WEIRD_WAH)) {
             const uint32_t job = d.dline_eord[gl0];
-            const uint32_t* erow = d.rows + (size_t)job * d.WS;
+            const uint32_t* __restrict__ erow = d.rows + (size_t)job * d.WS;
             n_eov = d.job_ones[job];
-            for (uint32_t i = tid; i < n; i += D4_THREADS) if ((erow[i >> 5] >> (i & 31)) & 1u) val[i] = CODE_EOV;
+            for (uint32_t iq = tid; iq < nq; iq += D4_THREADS) {
+                const uint32_t i = iq << 2;
+                const uint32_t m = spread4(__ldg(erow + (i >> 5)) >> (i & 31u));
+                if (m) val4[iq] |= m * 0xFFu;  // CODE_EOV = 255
+            }
             __syncthreads();
         } else if (f0 & DL_EOV) {
             const uint8_t* mm = d.blob + blk.eov_off;
@@ -993,16 +1024,23 @@ __global__ void __launch_bounds__(D4_THREADS) compose_records_kernel(DecDev d, R
             for (uint32_t k = tid; k < n_eov; k += D4_THREADS) { const uint32_t i = rd_entry(mm, e0 + 1 + k, d.aet); if (i < q.Npad) val[i] = CODE_EOV; }
             __syncthreads();
         }
-        const uint32_t* prow = (f0 & DL_PHASE) ? d.rows + (size_t)d.dline_pord[gl0] * d.WS : nullptr;
-        for (uint32_t i = tid; i < n; i += D4_THREADS) {
-            const uint8_t c = val[i];
-            int32_t v;
-            if (c == CODE_EOV) v = XSI_I32_VECTOR_END;
-            else {
-                v = (c == CODE_MISSING ? 0 : (int32_t)(((uint32_t)c + 1u) << 1)) | ((int32_t)(pf[i] & i & 1u) & DP);
-                if (prow && ((prow[i >> 5] >> (i & 31)) & 1u)) v ^= (int32_t)(i & 1u);
+        const uint32_t* __restrict__ prow = (f0 & DL_PHASE) ? d.rows + (size_t)d.dline_pord[gl0] * d.WS : nullptr;
+        const bool vec_ok = (reinterpret_cast<uintptr_t>(out) & (4 * sizeof(OT) - 1)) == 0;
+        for (uint32_t iq = tid; iq < nq; iq += D4_THREADS) {
+            const uint32_t i = iq << 2;
+            const uint32_t c4 = val4[iq], p4 = pf4[iq];
+            const uint32_t tog = prow ? (__ldg(prow + (i >> 5)) >> (i & 31u)) & 0xFu : 0u;
+            int32_t v[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint32_t c = (c4 >> (8 * k)) & 0xFFu;
+                const uint32_t odd = (uint32_t)k & 1u;  // i is a multiple of 4: the parity of i + k is that of k
+                int32_t x = (c == CODE_MISSING ? 0 : (int32_t)((c + 1u) << 1)) | ((int32_t)((p4 >> (8 * k)) & odd) & DP);
+                x ^= (int32_t)((tog >> k) & odd);
+                v[k] = c == CODE_EOV ? XSI_I32_VECTOR_END : x;
             }
-            out[i] = gt_out<OT>(v);
+            if (vec_ok && i + 3 < n) store4<OT>(out + i, gt_out<OT>(v[0]), gt_out<OT>(v[1]), gt_out<OT>(v[2]), gt_out<OT>(v[3]));
+            else for (int k = 0; k < 4; ++k) if (i + k < n) out[i + k] = gt_out<OT>(v[k]);
         }
         if (cnts && tid == 0) cnts[0] = n - (total_alt + n_missing + n_eov);
         __syncthreads();
