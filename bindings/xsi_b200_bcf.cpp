@@ -715,7 +715,11 @@ int subset(const Options& o) {
     xsi_device_free(ctx, d_rows);
     xsi_destroy(ctx);
     if (w) {
-        rc = xsi_writer_close(w, max_ploidy);
+        // sic: the extractor finalises its factory WITHOUT the ploidy it has seen (gt_decompressor_new.hpp:138), so the interface's
+        // default applies (finalize_file(max_ploidy = 2), xsi_factory.hpp:43): header.ploidy = 2 and hap_samples = 2 * samples even
+        // when every record of the new file is haploid
+        (void)max_ploidy;
+        rc = xsi_writer_close(w, 2);
         if (rc != XSI_OK) { fprintf(stderr, "finalize failed (rc %d)\n", rc); err = true; }
     }
     if (hts_close(fout) < 0) err = true;

@@ -528,7 +528,8 @@ def test_subset_reencode_on_device(ctx, tmp_path):
         assert len(blocks) == ref.n_blocks
         for b, got in enumerate(blocks):
             a, n = ctypes_block(ref, b)
-            assert got == ctypes.string_at(a, n), (k, b)
+            want_b = ctypes.string_at(a, n)  # the reader's view runs to the next block: up to 3 bytes of file padding follow
+            assert n - len(got) in (0, 1, 2, 3) and got == want_b[:len(got)] and not any(want_b[len(got):]), (k, b)
         ref.close()
         with pytest.raises(xb.XsiError):  # strided rows are device rows
             ctx.encode_launch(gt, nal, n_sel, bl, thr, dp, ploidy=(ngt // n_sel).astype(np.uint8), row_stride=2 * n_sel)

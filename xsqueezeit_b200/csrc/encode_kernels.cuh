@@ -972,7 +972,6 @@ __global__ void __launch_bounds__(256, 2) pbwt_permute_small_kernel(EncDev p) {
     uint32_t e0 = list[0], e4 = nwah > 4 ? list[4] : 0u;
     uint32_t e1 = nwah > 1 ? list[1] : 0u, e2 = nwah > 2 ? list[2] : 0u, e3 = nwah > 3 ? list[3] : 0u;
     __syncthreads();
-    const uint32_t yp_sa = smem_u32(&yp[0][0]), T_sa = smem_u32(T);
     // carriers of the first line at their identity positions
     if (x0) atomicOr(&yp[0][tid], x0);
     const uint32_t pad_zeros = NT * 32 - N;
@@ -1001,15 +1000,22 @@ __global__ void __launch_bounds__(256, 2) pbwt_permute_small_kernel(EncDev p) {
         yp[par][tid] = 0;  // next written after barrier A of line k+1
         if (live) {
             const uint32_t Z = zs - pad_zeros;
-            const uint32_t nx_sa = yp_sa + (par ^ 1u) * 1024u;
+            // all 32 table reads first (plain loads: independent, in flight together), then the arithmetic, then the carriers of
+            // line k+1 as a separate pass -- a volatile asm inside the update loop would serialise the lookups
+            uint32_t e[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) e[q] = T[pk[q] >> 4];
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
                 const uint32_t j = pk[q];
-                const uint32_t e = lds_u32(T_sa + ((j >> 4) << 2));
-                const uint32_t zb = (e >> 16) + __popc(e & ~(0xFFFFFFFFu << (j & 15u)));
-                const uint32_t np = (x0 & (1u << q)) ? Z + j - zb : zb;
-                pk[q] = np;
-                red_or_shared_if(x1 & (1u << q), nx_sa + ((np >> 3) & ~3u), 1u << (np & 31u));
+                const uint32_t zb = (e[q] >> 16) + __popc(e[q] & ~(0xFFFFFFFFu << (j & 15u)));
+                pk[q] = (x0 & (1u << q)) ? Z + j - zb : zb;
+            }
+            if (x1) {
+                uint32_t* nx = yp[par ^ 1u];
+#pragma unroll
+                for (int q = 0; q < 32; ++q)
+                    if (x1 & (1u << q)) atomicOr(&nx[pk[q] >> 5], 1u << (pk[q] & 31u));
             }
         }
         x0 = x1; x1 = x2; x2 = x3; x3 = xf;
