@@ -7,7 +7,7 @@ show='import json,sys
 d=json.loads(sys.stdin.read().strip().splitlines()[-1])
 print("value %.1f enc %.1f dec %.1f ms/step %.2f verified %s" % (d["value"], d["compress_ggts"], d["decompress_ggts"], d["ms_per_step"], d["verified"]))
 print("  " + "  ".join("%s %.2f" % (k, v["ms_per_step"]) for k, v in sorted(d["kernels"].items(), key=lambda kv: -kv[1]["ms_per_step"])[:9]))'
-run() { echo "== $1 | $2"; env $1 timeout 600 python bench.py --sub --steps 4 --warmup 2 $2 2>/dev/null | python -c "$show"; }
+run() { echo "== $1 | $2"; env $1 timeout 600 python bench.py --sub --warmup 2 --steps 4 $2 2>/dev/null | python -c "$show"; }
 {
 run "XSI_X=0" "--samples 2504 --blocks 220"
 run "XSI_PBWT_SMALL=0" "--samples 2504 --blocks 220"
@@ -34,3 +34,13 @@ t=time.time(); L.xsi_create(0,ctypes.byref(c)); print('create',time.time()-t)
 t=time.time(); L.xsi_destroy(c); print('destroy',time.time()-t)"
 rm -rf $D
 } 2>&1 | tee gpurun_out/${T}_capi.txt
+# priorities: who gets the SMs that free up when batch i+1 encodes beside the decode of batch i (pipelined leg = `value` here)
+{
+for rep in 1 2; do
+run "XSI_X=0" "--blocks 32 --steps 8"
+run "XSI_PERMUTE_PRIORITY=1" "--blocks 32 --steps 8"
+run "XSI_ENC_STREAM_PRIORITY=1" "--blocks 32 --steps 8"
+run "XSI_DEC_STREAM_PRIORITY=1" "--blocks 32 --steps 8"
+run "XSI_PERMUTE_PRIORITY=1 XSI_UNPERM_KH=32" "--blocks 32 --steps 8"
+done
+} 2>&1 | tee gpurun_out/${T}_priority.txt

@@ -75,6 +75,8 @@ struct xsi_ctx {
     int enc_rc = XSI_OK;
     bool enc_pending = false;  // a launch was handed to enc_thread and its result not yet reported by xsi_encode_collect
     xsi_encode_desc enc_desc;
+    int prio_hi = 0;          // greatest stream / launch priority of the device
+    bool perm_priority = false;  // launch the PBWT cluster kernel at prio_hi (XSI_PERMUTE_PRIORITY=1)
     uint64_t enc_row_stride = 0;   // xsi_encode_launch_strided: element distance between rows of the launch being set up (0: back to back)
     std::mutex prof_m;
     int sm_count = 148;
@@ -218,7 +220,13 @@ extern "C" int xsi_create(int device, xsi_ctx** out) {
     xsi_ctx* ctx = new xsi_ctx();
     ctx->device = device;
     if (cudaSetDevice(device) != cudaSuccess) { delete ctx; return XSI_E_CUDA; }
-    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+    {
+        int lo = 0, hi = 0;
+        if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess) ctx->prio_hi = hi;
+        if (const char* s_ = getenv("XSI_PERMUTE_PRIORITY")) ctx->perm_priority = atoi(s_) != 0;
+    }
+    const bool dec_hi = getenv("XSI_DEC_STREAM_PRIORITY") && atoi(getenv("XSI_DEC_STREAM_PRIORITY")) != 0;
+    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, dec_hi ? ctx->prio_hi : 0) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
@@ -498,7 +506,7 @@ int launch_permute_v4(xsi_ctx* ctx, const EncDev& p, const PermV4Cfg& cfg, uint3
     CK(cudaFuncSetAttribute(pbwt_permute_v4_kernel<C, KH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t lc = {};
     lc.gridDim = dim3(p.nb * C); lc.blockDim = dim3(NT); lc.dynamicSmemBytes = smem; lc.stream = ctx->es;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = C; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     lc.attrs = at; lc.numAttrs = C > 1 ? 1 : 0;
@@ -506,6 +514,14 @@ int launch_permute_v4(xsi_ctx* ctx, const EncDev& p, const PermV4Cfg& cfg, uint3
         *max_clusters = 1 << 30;
         if (C > 1) CK(cudaOccupancyMaxActiveClusters(max_clusters, pbwt_permute_v4_kernel<C, KH>, &lc));
         return XSI_OK;
+    }
+    // The chain kernel owns whole SMs (1024 threads, all registers) and is the critical path of a batch: when a decode of
+    // the previous batch runs beside it (xsi_encode_async, several contexts), its clusters should get the SMs that free up
+    // before the HBM-bound kernels' CTAs do, which then fill the SMs the clusters cannot use (148 - 4 * 32 = 20).
+    if (ctx->perm_priority && C > 1) {
+        at[1].id = cudaLaunchAttributePriority;
+        at[1].val.priority = ctx->prio_hi;
+        lc.numAttrs = 2;
     }
     { PROF("pbwt_permute"); CK(cudaLaunchKernelEx(&lc, pbwt_permute_v4_kernel<C, KH>, p, cfg)); }
     CKL();
@@ -2241,7 +2257,9 @@ extern "C" int xsi_encode_async(xsi_ctx* ctx, int on) {
     if (!ctx) return XSI_E_ARG;
     if (ctx->enc_thread.joinable()) ctx->enc_thread.join();
     if (on && !ctx->stream_enc) {
-        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream_enc, cudaStreamNonBlocking) != cudaSuccess) {
+        const bool enc_hi = getenv("XSI_ENC_STREAM_PRIORITY") && atoi(getenv("XSI_ENC_STREAM_PRIORITY")) != 0;
+        if (cudaSetDevice(ctx->device) != cudaSuccess ||
+            cudaStreamCreateWithPriority(&ctx->stream_enc, cudaStreamNonBlocking, enc_hi ? ctx->prio_hi : 0) != cudaSuccess) {
             ctx->err = "cannot create the encode stream";
             return XSI_E_CUDA;
         }
