@@ -936,94 +936,6 @@ __global__ void __launch_bounds__(1024, 1) pbwt_permute_v4_kernel(EncDev p, Perm
 }
 
 // =============================================================================================
-// E3 small: the v4 formulation for SHORT rows (at most 8192 haplotypes: the 1KGP3 and chrX shapes), one CTA per PBWT block
-// and one row word (32 haplotypes, positions in 32 registers) per thread, so a 5,008-haplotype block is a 160-thread
-// CTA and a batch of hundreds of blocks is resident at once, several CTAs per SM covering each other's barriers.
-// v4 at C = 1 spends 512 threads (16 haplotypes each, 8192 slots for 5,008 haplotypes), three CTA-wide synchronisations
-// and a cross-warp scan per line on such a row: 2.45 us per line and CTA (10.8 ms for 220 blocks).  Here a line is
-//   A  __syncthreads: the carriers' bits of line k are complete in yp[k & 1]
-//   B  every thread: zeros in the words of the warps below its own (<= 7 LDS + popc, one redux) + a warp scan of its own
-//      word -> its two table entries (zeros before << 16 | zero positions of the 16 positions); row k -> global, in place
-//   C  __syncthreads: table complete
-//   D  32 lookups (one LDS each) -> new positions; carriers of line k+1 set their bit in yp[(k + 1) & 1] on the way
-// i.e. two barriers and no cross-warp exchange.  Positions past N are zeros that never carry (pad_zeros as in v4).
-// =============================================================================================
-__global__ void __launch_bounds__(256, 2) pbwt_permute_small_kernel(EncDev p) {
-    __shared__ uint32_t yp[2][256];
-    __shared__ __align__(8) uint32_t T[512];
-    __shared__ uint32_t zs;
-    const uint32_t N = 2 * p.n_samples, WS = p.WS;
-    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5, NT = blockDim.x;
-    const uint32_t b = p.blk_map ? p.blk_map[blockIdx.x] : blockIdx.x;
-    const uint32_t nwah = p.blk_nwah[b];
-    if (nwah == 0) return;
-    const uint32_t* list = p.wah_list + p.blk_line0[b];
-    const uint32_t hb = tid * 32;
-    const bool live = hb < N;
-    uint32_t pk[32];
-#pragma unroll
-    for (int q = 0; q < 32; ++q) pk[q] = hb + q;  // identity at block start (gt_block.hpp:179)
-    yp[0][tid] = 0; yp[1][tid] = 0;
-    auto load_x = [&](uint32_t entry) -> uint32_t {
-        return tid < WS ? p.bitrows[(size_t)(entry & 0x7FFFFFFFu) * WS + tid] : 0u;
-    };
-    uint32_t x0 = load_x(list[0]);
-    uint32_t x1 = nwah > 1 ? load_x(list[1]) : 0u, x2 = nwah > 2 ? load_x(list[2]) : 0u, x3 = nwah > 3 ? load_x(list[3]) : 0u;
-    uint32_t e0 = list[0], e4 = nwah > 4 ? list[4] : 0u;
-    uint32_t e1 = nwah > 1 ? list[1] : 0u, e2 = nwah > 2 ? list[2] : 0u, e3 = nwah > 3 ? list[3] : 0u;
-    __syncthreads();
-    // carriers of the first line at their identity positions
-    if (x0) atomicOr(&yp[0][tid], x0);
-    const uint32_t pad_zeros = NT * 32 - N;
-    for (uint32_t k = 0; k < nwah; ++k) {
-        const uint32_t par = k & 1u;
-        const uint32_t xf = k + 4 < nwah ? load_x(e4) : 0u;
-        const uint32_t e5 = k + 5 < nwah ? list[k + 5] : 0u;
-        __syncthreads();  // A
-        const uint32_t* Y = yp[par];
-        uint32_t below = 0;
-        for (uint32_t g = 0; g < warp; ++g) below += 32u - __popc(Y[g * 32 + lane]);
-        const uint32_t wbase = __reduce_add_sync(XSI_FULL, below);
-        const uint32_t y = Y[tid];
-        const uint32_t zeros = 32u - __popc(y);
-        uint32_t incl = zeros;
-#pragma unroll
-        for (int dd = 1; dd < 32; dd <<= 1) { const uint32_t o = __shfl_up_sync(XSI_FULL, incl, dd); if (lane >= (uint32_t)dd) incl += o; }
-        const uint32_t zp = wbase + incl - zeros;
-        const uint32_t ny = ~y;  // the table keeps the ZERO positions as set bits
-        const uint32_t t0 = (zp << 16) | (ny & 0xFFFFu);
-        const uint32_t t1 = ((zp + __popc(ny & 0xFFFFu)) << 16) | (ny >> 16);
-        *reinterpret_cast<uint2*>(T + 2 * tid) = make_uint2(t0, t1);
-        if (tid < WS) p.bitrows[(size_t)(e0 & 0x7FFFFFFFu) * WS + tid] = y;  // permuted row, in place
-        if (tid == NT - 1) zs = zp + zeros;
-        __syncthreads();  // C
-        yp[par][tid] = 0;  // next written after barrier A of line k+1
-        if (live) {
-            const uint32_t Z = zs - pad_zeros;
-            // all 32 table reads first (plain loads: independent, in flight together), then the arithmetic, then the carriers of
-            // line k+1 as a separate pass -- a volatile asm inside the update loop would serialise the lookups
-            uint32_t e[32];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) e[q] = T[pk[q] >> 4];
-#pragma unroll
-            for (int q = 0; q < 32; ++q) {
-                const uint32_t j = pk[q];
-                const uint32_t zb = (e[q] >> 16) + __popc(e[q] & ~(0xFFFFFFFFu << (j & 15u)));
-                pk[q] = (x0 & (1u << q)) ? Z + j - zb : zb;
-            }
-            if (x1) {
-                uint32_t* nx = yp[par ^ 1u];
-#pragma unroll
-                for (int q = 0; q < 32; ++q)
-                    if (x1 & (1u << q)) atomicOr(&nx[pk[q] >> 5], 1u << (pk[q] & 31u));
-            }
-        }
-        x0 = x1; x1 = x2; x2 = x3; x3 = xf;
-        e0 = e1; e1 = e2; e2 = e3; e3 = e4; e4 = e5;
-    }
-}
-
-// =============================================================================================
 // E3 v5: TWO WAH lines per exchange round (a 4-way stable partition).  v4 spends, per line, a fixed ~1.2 us
 // in its two DSMEM exchanges and ~2.6 us (C = 4) in the update itself, whose cost is the random table lookup
 // plus ~15 instructions per haplotype (r02d: 52.5 / 28.5 / 17.2 ms at C = 1 / 2 / 4, i.e. issue-bound per SM,

@@ -76,7 +76,15 @@ struct xsi_ctx {
     bool enc_pending = false;  // a launch was handed to enc_thread and its result not yet reported by xsi_encode_collect
     xsi_encode_desc enc_desc;
     int prio_hi = 0;          // greatest stream / launch priority of the device
-    bool perm_priority = false;  // launch the PBWT cluster kernel at prio_hi (XSI_PERMUTE_PRIORITY=1)
+    bool perm_priority = false;  // launch the PBWT cluster kernel at prio_hi (XSI_PERMUTE_PRIORITY=1, or the ordered overlap below)
+    // Ordered overlap inside one context (xsi_encode_async; XSI_OVERLAP_ORDER=0 turns it off): the decode of batch i and the
+    // encode of batch i+1 are on the device together.  The PBWT cluster kernel of the encode owns 128 whole SMs for most of
+    // the batch's time and leaves 20 idle, while the HBM-bound compose kernels of the decode need few SMs to move their bytes:
+    // so the compose kernels wait for the encode's scan (both want every SM and all of HBM) and start WITH the cluster kernel,
+    // which is launched at the greatest priority and takes its SMs first; the compose CTAs fill what is left.
+    bool overlap_order = true;
+    cudaEvent_t ev_scan = nullptr;                 // recorded on the encode stream right after the scan kernel of an asynchronous launch
+    std::atomic<uint64_t> enc_seq{0}, scan_seq{0};  // launches handed to the encode thread / launches whose scan is enqueued (or that ended)
     uint64_t enc_row_stride = 0;   // xsi_encode_launch_strided: element distance between rows of the launch being set up (0: back to back)
     std::mutex prof_m;
     int sm_count = 148;
@@ -224,6 +232,7 @@ extern "C" int xsi_create(int device, xsi_ctx** out) {
         int lo = 0, hi = 0;
         if (cudaDeviceGetStreamPriorityRange(&lo, &hi) == cudaSuccess) ctx->prio_hi = hi;
         if (const char* s_ = getenv("XSI_PERMUTE_PRIORITY")) ctx->perm_priority = atoi(s_) != 0;
+        if (const char* s_ = getenv("XSI_OVERLAP_ORDER")) ctx->overlap_order = atoi(s_) != 0;
     }
     const bool dec_hi = getenv("XSI_DEC_STREAM_PRIORITY") && atoi(getenv("XSI_DEC_STREAM_PRIORITY")) != 0;
     if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, dec_hi ? ctx->prio_hi : 0) != cudaSuccess ||
@@ -267,6 +276,7 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
     for (cudaEvent_t ev : ctx->ring_ev) if (ev) cudaEventDestroy(ev);
     for (cudaEvent_t ev : ctx->dma_ev) if (ev) cudaEventDestroy(ev);
     cudaEventDestroy(ctx->ev_side);
+    if (ctx->ev_scan) cudaEventDestroy(ctx->ev_scan);
     cudaStreamDestroy(ctx->stream);
     cudaStreamDestroy(ctx->stream2);
     delete ctx;
@@ -518,7 +528,7 @@ int launch_permute_v4(xsi_ctx* ctx, const EncDev& p, const PermV4Cfg& cfg, uint3
     // The chain kernel owns whole SMs (1024 threads, all registers) and is the critical path of a batch: when a decode of
     // the previous batch runs beside it (xsi_encode_async, several contexts), its clusters should get the SMs that free up
     // before the HBM-bound kernels' CTAs do, which then fill the SMs the clusters cannot use (148 - 4 * 32 = 20).
-    if (ctx->perm_priority && C > 1) {
+    if ((ctx->perm_priority || (ctx->async_encode && ctx->overlap_order)) && C > 1) {
         at[1].id = cudaLaunchAttributePriority;
         at[1].val.priority = ctx->prio_hi;
         lc.numAttrs = 2;
@@ -763,14 +773,6 @@ int run_permute(xsi_ctx* ctx, const EncDev& p) {
         bool done = false;
         const int rc = run_permute_v5(ctx, p, W, &done);
         if (rc || done) return rc;
-    }
-    // short rows (<= 8192 haplotypes): one small CTA per block, one row word per thread (XSI_PBWT_SMALL=0: the cluster kernel)
-    if (!ctx->enc.any_haploid && N <= 8192 && ver == 4 && !getenv("XSI_PBWT_CLUSTER") && !getenv("XSI_PBWT_KH") &&
-        !(getenv("XSI_PBWT_SMALL") && atoi(getenv("XSI_PBWT_SMALL")) == 0)) {
-        const uint32_t NT = (W + 31) / 32 * 32;
-        { PROF("pbwt_permute"); pbwt_permute_small_kernel<<<p.nb, NT, 0, ctx->es>>>(p); }
-        CKL();
-        return XSI_OK;
     }
     if (!ctx->enc.any_haploid && N <= 65534 && ver >= 4) {
         bool done = false;
@@ -1025,6 +1027,10 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d, uint64
             else scan_rows_kernel<1><<<(uint32_t)R, E1_THREADS, 0, ctx->es>>>(p);
         }
         CKL();
+        if (ctx->async_encode && ctx->overlap_order && ctx->ev_scan && ctx->es == ctx->stream_enc) {
+            CK(cudaEventRecord(ctx->ev_scan, ctx->es));
+            ctx->scan_seq.store(ctx->enc_seq.load());
+        }
         if (L) {
             { PROF("build_wah_lists"); build_wah_lists_kernel<<<e.nb, 32, 0, ctx->es>>>(p); }
             CKL();
@@ -1664,6 +1670,9 @@ static int xsi_decode_load_blocks_impl(xsi_ctx* ctx, uint32_t n_blocks, const ui
         if (const char* sw = getenv("XSI_UNPERM_KH")) { const int v = atoi(sw); if (v == 8 || v == 16 || v == 32) v3_kh = (uint32_t)v; }
         const uint32_t thr_total = ((N + v3_kh - 1) / v3_kh + 31) / 32 * 32;
         v3_nc = std::min<uint32_t>(512, thr_total);
+        // short rows (1KGP3 / chrX shapes: 5,008 haplotypes = 640 threads at KH = 8): four CTAs of a quarter of the row each
+        // instead of one wide and one nearly empty CTA per block (r02o: 6.8 -> 5.7 ms at 220 blocks, 2.3 -> 1.3 ms at 24)
+        if (v3_kh == 8 && thr_total <= 1024) v3_nc = std::max<uint32_t>(128, (thr_total / 4 + 31) / 32 * 32);
         if (const char* sw = getenv("XSI_UNPERM_NC")) { const int v = atoi(sw); if (v >= 32 && v <= 512 && v % 32 == 0) v3_nc = std::min<uint32_t>(thr_total, (uint32_t)v); }
         v3_slices = (thr_total + v3_nc - 1) / v3_nc;
     }
@@ -1820,6 +1829,12 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
     // uploads the requests of records [c0, c0+cn) and composes their rows (element type DT) at dev_out, stride in elements
     auto compose_chunk = [&](auto* dev_out, uint64_t stride, uint64_t c0, uint64_t cn, ReqDev& q) -> int {
         using DT = std::remove_pointer_t<decltype(dev_out)>;
+        if (ctx->async_encode && ctx->overlap_order && ctx->enc_pending && ctx->ev_scan) {
+            // ordered overlap (see xsi_ctx::overlap_order): compose after the scan of the batch that is being encoded beside us
+            const uint64_t want = ctx->enc_seq.load();
+            for (int spin = 0; ctx->scan_seq.load() < want && spin < 100000; ++spin) std::this_thread::sleep_for(std::chrono::microseconds(20));
+            if (ctx->scan_seq.load() >= want) CK(cudaStreamWaitEvent(ctx->stream, ctx->ev_scan, 0));
+        }
         CK(d.req.ensure(cn * 4 * 4));
         uint32_t* rq = d.req.as<uint32_t>();
         CK(cudaMemcpyAsync(rq, block_index + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -2264,6 +2279,11 @@ extern "C" int xsi_encode_async(xsi_ctx* ctx, int on) {
             return XSI_E_CUDA;
         }
     }
+    if (on && !ctx->ev_scan && cudaEventCreateWithFlags(&ctx->ev_scan, cudaEventDisableTiming) != cudaSuccess) {
+        ctx->ev_scan = nullptr;
+        ctx->err = "cannot create the scan event";
+        return XSI_E_CUDA;
+    }
     if (ctx->es) cudaStreamSynchronize(ctx->es);
     ctx->async_encode = on != 0;
     ctx->es = on ? ctx->stream_enc : ctx->stream;
@@ -2279,8 +2299,12 @@ extern "C" int xsi_encode_launch(xsi_ctx* ctx, const xsi_encode_desc* d) {
         ctx->enc_rc = XSI_OK;
         ctx->enc_pending = true;
         const uint64_t stride = ctx->enc_row_stride;
+        const uint64_t seq = ctx->enc_seq.fetch_add(1) + 1;
         try {
-            ctx->enc_thread = std::thread([ctx, stride] { ctx->enc_rc = guarded(ctx, [&] { return xsi_encode_launch_impl(ctx, &ctx->enc_desc, stride); }); });
+            ctx->enc_thread = std::thread([ctx, stride, seq] {
+                ctx->enc_rc = guarded(ctx, [&] { return xsi_encode_launch_impl(ctx, &ctx->enc_desc, stride); });
+                if (ctx->scan_seq.load() < seq) ctx->scan_seq.store(seq);  // a launch that failed before its scan: nobody waits for it
+            });
         } catch (...) {
             ctx->err = "cannot start the encode thread";
             return XSI_E_NOMEM;
