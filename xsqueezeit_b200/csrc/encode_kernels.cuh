@@ -434,6 +434,9 @@ __global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(En
     __shared__ uint8_t s_lflag[E1_MAXALLELE];
     __shared__ uint32_t s_misc[4];
     __shared__ int32_t s_slot[3];
+    // narrow CTAs (one tile per record): totals of the record, triple buffered so that a common record costs ONE barrier
+    // ([0..3] carriers of ALT 1..4, [4] missing, [5] end of vector, [6] non-default phase seen, [7] unknown allele seen)
+    __shared__ uint32_t s_tot[3][8];
     constexpr uint32_t TILE_BYTES = S2_TILE * ELEM;
     constexpr uint32_t S2_STAGES = s2_stages(ELEM, NT);
     constexpr uint32_t TBYTES = 32 * ELEM;              // bytes of one thread's 32 genotypes
@@ -480,8 +483,10 @@ __global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(En
     if (blockIdx.x < p.R) { nx_ngt = p.rec_ngt[blockIdx.x]; nx_nall = p.rec_nallele[blockIdx.x]; nx_line0 = p.rec_line0[blockIdx.x]; nx_goff = p.rec_goff[blockIdx.x]; }
     for (uint32_t i = tid; i < E1_MAXALLELE; i += NT) { s_cnt[i] = 0; s_lflag[i] = 0; }
     if (tid < 4) s_misc[tid] = 0;
+    if (tid < 24) (&s_tot[0][0])[tid] = 0;
     __syncthreads();
-    for (uint32_t r = blockIdx.x; r < p.R; r += gridDim.x) {
+    uint32_t it = 0;  // records this CTA has taken
+    for (uint32_t r = blockIdx.x; r < p.R; r += gridDim.x, ++it) {
         const uint32_t ngt = nx_ngt, n_allele = nx_nall, line0 = nx_line0;
         const uint64_t goff = nx_goff;
         if (r + gridDim.x < p.R) {
@@ -495,6 +500,14 @@ __global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(En
         // rows of the narrow CTAs are one tile long by construction (the host picks NT >= words of the row); the 256-thread
         // kernel streams long rows and keeps the second passes (and its register count: fusing cost it 15% at the HRC width)
         constexpr bool fuse_aux = NT < 256;
+        if (fuse_aux && n_allele > 5) {
+            // a narrow CTA on a record with more than 4 ALT alleles takes the general epilogue below; the records before it may
+            // have taken the one-barrier path, which does not touch s_cnt / s_misc: clear them here
+            for (uint32_t i = tid; i <= n_allele && i < E1_MAXALLELE; i += NT) s_cnt[i] = 0;
+            if (tid < 4) s_misc[tid] = 0;
+            __syncthreads();
+            if (tid < 8) s_tot[(it + 2u) % 3u][tid] = 0;  // what the one-barrier path would have cleared during this record
+        }
         for (uint32_t tt = 0; tt < tiles_per_rec; ++tt) {
             const uint32_t wi = tt * NT + tid;
             const uint32_t elem0 = tt * S2_TILE + tid * 32;
@@ -554,6 +567,87 @@ __global__ void __launch_bounds__(NT, s2_ctas_per_sm(NT)) scan_rows_v2_kernel(En
             nmiss = __reduce_add_sync(XSI_FULL, nmiss); neov = __reduce_add_sync(XSI_FULL, neov);
             phase = __reduce_or_sync(XSI_FULL, phase & 1u); err = __reduce_or_sync(XSI_FULL, err);
         } else { nmiss = 0; neov = 0; phase = 0; err = 0; }
+        // ---- narrow CTAs, at most 4 ALT alleles: one barrier per record ----
+        // Short rows spend their time on the record epilogue (25% barrier stalls at 5,008 haplotypes, ncu r02e): three CTA
+        // barriers and thread 0's decisions between two of them.  Here the totals go to s_tot[it % 3]; after the one barrier
+        // EVERY thread derives the (cheap) per-line decisions from them, thread 0 alone writes them out while the other warps
+        // are already in the next record, and the buffer of the record after next is cleared (its last readers passed this
+        // barrier, its next writers come after the next one).  Negated lines and missing / end-of-vector / phase rows are
+        // rare and pay their own barrier.
+        const uint32_t kb = it % 3u;
+        if (fuse_aux && n_allele <= 5) {
+            uint32_t* tot = s_tot[kb];
+            if (lane == 0) {
+                if (c0) atomicAdd(&tot[0], c0);
+                if (n_allele > 2) { if (c1) atomicAdd(&tot[1], c1); if (c2) atomicAdd(&tot[2], c2); if (c3) atomicAdd(&tot[3], c3); }
+                if (nmiss) atomicAdd(&tot[4], nmiss);
+                if (neov) atomicAdd(&tot[5], neov);
+                if (phase && P == 2) atomicOr(&tot[6], 1u);
+                if (err) atomicOr(&tot[7], 1u);
+            }
+            __syncthreads();
+            const uint32_t T[4] = {tot[0], tot[1], tot[2], tot[3]};
+            const uint32_t tm = tot[4], te = tot[5], tp = tot[6], terr = tot[7];
+            if (tid < 8) s_tot[(kb + 2u) % 3u][tid] = 0;
+            const uint32_t cnt0 = ngt - (T[0] + T[1] + T[2] + T[3]) - tm - te;
+            uint32_t negmask = 0;
+#pragma unroll
+            for (uint32_t a = 1; a < 5; ++a) {
+                if (a < n_allele) {
+                    const uint32_t c = T[a - 1], mac = min(c, ngt - c);
+                    if (!((uint64_t)mac > p.mac_thr) && c != mac) negmask |= 1u << a;
+                }
+            }
+            const bool aux = (tm | te | tp) != 0;
+            if (tid == 0) {  // per-record decisions (gt_block.hpp:292-338), same values as finish_record
+                uint8_t rf = 0;
+                if (tm) rf |= RF_MISSING;
+                if (te) rf |= RF_EOV;
+                if (tp) rf |= RF_PHASE;
+                if (P == 1) rf |= RF_HAPLOID;
+                if (terr) atomicOr(&p.counters[2], ERR_ALLELE);
+#pragma unroll
+                for (uint32_t a = 1; a < 5; ++a) {
+                    if (a >= n_allele) break;
+                    const uint32_t c = T[a - 1], mac = min(c, ngt - c), line = line0 + a - 1;
+                    uint8_t lf = (P == 1) ? LF_HAPLOID : 0;
+                    uint32_t sn = 0;
+                    if ((uint64_t)mac > p.mac_thr) lf |= LF_WAH;
+                    else if (c == mac) sn = c + 1;
+                    else { lf |= LF_NEGATED; sn = cnt0 + 1; }
+                    p.line_cnt[line] = c;
+                    p.line_flags[line] = lf;
+                    p.line_sparse_n[line] = sn;
+                    p.line_wah_n[line] = 0;
+                }
+                p.rec_flags[r] = rf;
+                p.rec_miss_n[r] = tm ? tm + 1 : 0;
+                p.rec_eov_n[r] = te ? te + 1 : 0;
+                p.rec_phase_n[r] = 0;
+                int32_t sl[3] = {-1, -1, -1};
+                if (tm) { const uint32_t q = atomicAdd(&p.counters[0], 1u); if (q < p.aux_cap) sl[0] = (int32_t)q; else atomicOr(&p.counters[2], ERR_AUX_OVERFLOW); }
+                if (te) { const uint32_t q = atomicAdd(&p.counters[0], 1u); if (q < p.aux_cap) sl[1] = (int32_t)q; else atomicOr(&p.counters[2], ERR_AUX_OVERFLOW); }
+                if (tp) { const uint32_t q = atomicAdd(&p.counters[1], 1u); if (q < p.phase_cap) sl[2] = (int32_t)q; else atomicOr(&p.counters[2], ERR_PHASE_OVERFLOW); }
+                p.rec_aux[r * 3 + 0] = sl[0];
+                p.rec_aux[r * 3 + 1] = sl[1];
+                p.rec_aux[r * 3 + 2] = sl[2];
+                if (aux) { s_slot[0] = sl[0]; s_slot[1] = sl[1]; s_slot[2] = sl[2]; }
+            }
+            if (negmask) {  // rare: negated sparse lists REF carriers (block.hpp:59-65 with sparse_allele 0); second pass over the L2-hot row
+                __syncthreads();
+                for (uint32_t a = 1; a < n_allele; ++a)
+                    if (negmask & (1u << a)) emit_pred_row<ELEM, 0>(p.gt, goff, ngt, p.WS, 0, p.bitrows + (size_t)(line0 + a - 1) * p.WS);
+            }
+            if (aux) {  // the slots were handed out by thread 0
+                __syncthreads();
+                if (tid < p.WS) {
+                    if (s_slot[0] >= 0) p.auxrows[(size_t)s_slot[0] * p.WS + tid] = am;
+                    if (s_slot[1] >= 0) p.auxrows[(size_t)s_slot[1] * p.WS + tid] = ae;
+                    if (s_slot[2] >= 0) p.phrows[(size_t)s_slot[2] * p.WS + tid] = ap;
+                }
+            }
+            continue;
+        }
         if (lane == 0) {
             if (n_allele > 1) atomicAdd(&s_cnt[1], c0);
             if (n_allele > 2) atomicAdd(&s_cnt[2], c1);
