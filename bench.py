@@ -711,6 +711,8 @@ def main():
             ctx._check(L.xsi_encode_collect(ctx.h, ctypes.byref(n), ctypes.byref(bp), ctypes.byref(sz)))
             return [(bp[i], sz[i]) for i in range(n.value)]
 
+        # measured (profiles/r02r_*): launch first 651-672 Ggt/s, load first 628 -- the scan then waits 2 ms for the load's host work
+        launch_first = os.environ.get("XSI_BENCH_PIPE_ORDER", "launch_first") == "launch_first"
         ctx.encode_async(True)
         try:
             ctx.encode_launch(gt.data_ptr(), nal[:R], S, BL, thr, 1, gt_on_device=True, gt_elem_bytes=EL)
@@ -723,12 +725,23 @@ def main():
                     barrier()
                     a = ev()
                     a.record(stream)
-                ctx.encode_launch(gt.data_ptr(), nal[:R], S, BL, thr, 1, gt_on_device=True, gt_elem_bytes=EL)
-                decode_step(prev, dec.data_ptr(), True, R, EL)
+                if launch_first:
+                    ctx.encode_launch(gt.data_ptr(), nal[:R], S, BL, thr, 1, gt_on_device=True, gt_elem_bytes=EL)
+                    decode_step(prev, dec.data_ptr(), True, R, EL)
+                else:
+                    # A/B (XSI_BENCH_PIPE_ORDER=load_first): the SM-bound half of the decode (expand + inverse PBWT of batch i) enqueued
+                    # BEFORE the encode of batch i+1, so that it does not fight the scan for SMs; the scan follows, and the compose kernels
+                    # (which the library orders behind the scan) run beside the cluster kernel (device timeline: profiles/r02r_*)
+                    ctx.decode_load_blocks(prev, S, AET)
+                    ctx.encode_launch(gt.data_ptr(), nal[:R], S, BL, thr, 1, gt_on_device=True, gt_elem_bytes=EL)
+                    fn = L.xsi_decode_records if EL == 4 else L.xsi_decode_records_i8
+                    ctx._check(fn(ctx.h, R, blk[:R].ctypes.data, off[:R].ctypes.data, nal[:R].ctypes.data, dec.data_ptr(), H, 1, None, None, 0))
+                    ctx.sync()
                 prev = collect()
             z = ev()
             z.record(stream)
             barrier()
+            ctx.profile_read()  # (XSI_TIMELINE: the kernels of this leg, both streams, on one time axis)
             return a.elapsed_time(z) / 1e3, ctx.kernel_launches - l0, [zlib.crc32(ctypes.string_at(p_, s_)) for p_, s_ in prev]
         finally:
             ctx.encode_async(False)

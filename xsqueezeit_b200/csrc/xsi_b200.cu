@@ -326,15 +326,28 @@ extern "C" const char* xsi_profile_read(xsi_ctx* ctx) {
     std::lock_guard<std::mutex> g(ctx->prof_m);
     std::map<std::string, std::pair<int, double>> agg;
     std::vector<std::string> order;
+    // XSI_TIMELINE=<file>: start / end of every profiled kernel relative to the first one of this read, on whichever stream it ran
+    // (how the encode of one batch and the decode of another actually interleave on the device)
+    FILE* tl = nullptr;
+    if (const char* tf = getenv("XSI_TIMELINE")) if (!ctx->spans.empty()) tl = fopen(tf, "a");
+    if (tl) fprintf(tl, "# read\n");
+    const cudaEvent_t first = ctx->spans.empty() ? nullptr : ctx->spans.front().a;  // destroyed after the loop: every span is measured against it
     for (auto& sp : ctx->spans) {
         float ms = 0;
         cudaEventElapsedTime(&ms, sp.a, sp.b);
+        if (tl) {
+            float t0 = 0;
+            cudaEventElapsedTime(&t0, first, sp.a);
+            fprintf(tl, "%-18s %10.3f %10.3f\n", sp.name, t0, t0 + ms);
+        }
         if (!agg.count(sp.name)) order.push_back(sp.name);
         agg[sp.name].first++;
         agg[sp.name].second += ms;
-        cudaEventDestroy(sp.a);
+        if (sp.a != first) cudaEventDestroy(sp.a);
         cudaEventDestroy(sp.b);
     }
+    if (tl) fclose(tl);
+    if (first) cudaEventDestroy(first);
     ctx->spans.clear();
     ctx->profile_text.clear();
     char line[256];
