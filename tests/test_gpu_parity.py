@@ -483,6 +483,43 @@ def ctypes_block(acc, b):
     return p.value, s.value
 
 
+def test_device_resident_reencode_is_idempotent(ctx, tmp_path):
+    """decode every record of a file into DEVICE rows (raw BCF int8 and int32, rows a stride apart) and encode those rows again with
+    xsi_encode_launch_strided: the GT blocks are the file's own blocks, byte for byte (mixed ploidy, missing, multi-allelic)"""
+    import xsqueezeit_b200 as xb
+    ds = synth.make_dataset(330, 413, seed=71, max_alt=4, multi_frac=0.25, missing=0.02, unphased=0.03, haploid_samples=0.3)
+    bl, maf = 100, 0.01
+    ns, nal = ds["n_samples"], ds["n_allele"]
+    p = gpu_encode(ctx, tmp_path, ds, bl, maf)
+    acc = xb.Accessor(p, ctx)
+    pos = xb.bm_positions(nal, bl)
+    R = len(pos)
+    nb = (R + bl - 1) // bl
+    acc._load(0, nb)
+    blk = (pos >> np.uint64(15)).astype(np.uint32)
+    off = (pos & np.uint64(0x7FFF)).astype(np.uint32)
+    na = np.ascontiguousarray(nal, dtype=np.uint32)
+    o = xo.row_offsets(ds["ngt"])
+    dp = xo.default_phased(ds["gt"], o, ds["ngt"], ns)
+    thr = xo.mac_threshold(ns, int(ds["ngt"][0]) // ns, maf)
+    want = [ctypes.string_at(*ctypes_block(acc, b)) for b in range(nb)]
+    for elem, stride in ((4, 2 * ns + 6), (1, (2 * ns + 15) // 16 * 16)):
+        dev = ctx.device_alloc(R * stride * elem)
+        try:
+            filled = np.zeros(R, dtype=np.uint32)
+            fn = ctx._L.xsi_decode_records if elem == 4 else ctx._L.xsi_decode_records_i8
+            ctx._check(fn(ctx.h, R, blk.ctypes.data, off.ctypes.data, na.ctypes.data, ctypes.c_void_p(dev), stride, 1, filled.ctypes.data, None, 0))
+            assert np.array_equal(filled, ds["ngt"].astype(np.uint32))
+            ctx.encode_launch(dev, nal, ns, bl, thr, dp, ploidy=(ds["ngt"] // ns).astype(np.uint8), gt_elem_bytes=elem, gt_on_device=True, row_stride=stride)
+            blocks = ctx.encode_collect()
+        finally:
+            ctx.device_free(dev)
+        assert len(blocks) == nb
+        for b, got in enumerate(blocks):
+            assert 0 <= len(want[b]) - len(got) < 16 and got == want[b][:len(got)] and not any(want[b][len(got):]), (elem, b)
+    acc.close()
+
+
 def test_subset_reencode_on_device(ctx, tmp_path):
     """The extractor's XSI -> XSI path with a sample subset (-s ... -Ox, gt_decompressor_new.hpp:241-273) without the rows leaving the
     device: xsi_decode_records_subset into device rows, xsi_encode_launch_strided from them.  The GT blocks equal the oracle's

@@ -234,8 +234,7 @@ extern "C" int xsi_create(int device, xsi_ctx** out) {
         if (const char* s_ = getenv("XSI_PERMUTE_PRIORITY")) ctx->perm_priority = atoi(s_) != 0;
         if (const char* s_ = getenv("XSI_OVERLAP_ORDER")) ctx->overlap_order = atoi(s_) != 0;
     }
-    const bool dec_hi = getenv("XSI_DEC_STREAM_PRIORITY") && atoi(getenv("XSI_DEC_STREAM_PRIORITY")) != 0;
-    if (cudaStreamCreateWithPriority(&ctx->stream, cudaStreamNonBlocking, dec_hi ? ctx->prio_hi : 0) != cudaSuccess ||
+    if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_side, cudaEventDisableTiming) != cudaSuccess) {
         delete ctx;
@@ -2285,9 +2284,7 @@ extern "C" int xsi_encode_async(xsi_ctx* ctx, int on) {
     if (!ctx) return XSI_E_ARG;
     if (ctx->enc_thread.joinable()) ctx->enc_thread.join();
     if (on && !ctx->stream_enc) {
-        const bool enc_hi = getenv("XSI_ENC_STREAM_PRIORITY") && atoi(getenv("XSI_ENC_STREAM_PRIORITY")) != 0;
-        if (cudaSetDevice(ctx->device) != cudaSuccess ||
-            cudaStreamCreateWithPriority(&ctx->stream_enc, cudaStreamNonBlocking, enc_hi ? ctx->prio_hi : 0) != cudaSuccess) {
+        if (cudaSetDevice(ctx->device) != cudaSuccess || cudaStreamCreateWithFlags(&ctx->stream_enc, cudaStreamNonBlocking) != cudaSuccess) {
             ctx->err = "cannot create the encode stream";
             return XSI_E_CUDA;
         }
