@@ -1625,43 +1625,73 @@ __global__ void __launch_bounds__(E4_WARPS * 32) wah_encode_rows_kernel(EncDev p
 }
 
 // =============================================================================================
-// exclusive scan of u32 -> u64 (single CTA per array; arrays are at most a few million entries)
+// exclusive scan of u32 -> u64 over several arrays at once: tiles of 4096 entries, one CTA per (tile, array); pass 1 sums
+// the tiles, pass 2 adds up the sums of the tiles before its own (at most a few hundred) and scans its tile.  (One CTA per
+// array walked 1.8 M entries in 440 dependent iterations: 1.4 ms per batch on the 1KGP3 shape.)
 // =============================================================================================
 struct ScanJob { const uint32_t* in; uint64_t* out; uint32_t n; uint32_t pad; };  // out has n+1 entries
 constexpr int SCAN_THREADS = 1024;
-__global__ void __launch_bounds__(SCAN_THREADS) scan_u32_kernel(const ScanJob* jobs) {
-    __shared__ uint64_t s_warp[32];
-    __shared__ uint64_t s_carry;
-    const ScanJob j = jobs[blockIdx.x];
-    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
-    if (tid == 0) s_carry = 0;
+constexpr uint32_t SCAN_TILE = SCAN_THREADS * 4;
+__host__ __device__ inline uint32_t scan_tiles(uint32_t n) { return n ? (n + SCAN_TILE - 1) / SCAN_TILE : 1u; }
+
+__device__ __forceinline__ uint64_t scan_block_sum(uint64_t v, uint64_t* s_warp) {  // sum over the CTA, returned to every thread
+    const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(XSI_FULL, v, d);
+    __syncthreads();  // s_warp may still be read by the previous use
+    if (lane == 0) s_warp[warp] = v;
     __syncthreads();
-    for (uint32_t base = 0; base < j.n; base += SCAN_THREADS * 4) {
-        const uint32_t i0 = base + tid * 4;
-        uint32_t v[4];
+    uint64_t t = s_warp[lane];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) v[q] = (i0 + q < j.n) ? j.in[i0 + q] : 0u;
-        uint64_t t = (uint64_t)v[0] + v[1] + v[2] + v[3];
-        uint64_t incl = t;
+    for (int d = 16; d > 0; d >>= 1) t += __shfl_xor_sync(XSI_FULL, t, d);
+    return t;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_u32_sums_kernel(const ScanJob* jobs, uint64_t* sums, uint32_t max_tiles) {
+    __shared__ uint64_t s_warp[32];
+    const ScanJob j = jobs[blockIdx.y];
+    const uint32_t tile = blockIdx.x;
+    if (tile >= scan_tiles(j.n)) return;
+    const uint32_t i0 = tile * SCAN_TILE + threadIdx.x * 4;
+    uint64_t t = 0;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(XSI_FULL, incl, d); if (lane >= (uint32_t)d) incl += o; }
-        if (lane == 31) s_warp[warp] = incl;
-        __syncthreads();
-        if (warp == 0) {
-            uint64_t w = s_warp[lane], wi = w;
+    for (int q = 0; q < 4; ++q) t += (i0 + q < j.n) ? j.in[i0 + q] : 0u;
+    t = scan_block_sum(t, s_warp);
+    if (threadIdx.x == 0) sums[(size_t)blockIdx.y * max_tiles + tile] = t;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) scan_u32_kernel(const ScanJob* jobs, const uint64_t* sums, uint32_t max_tiles) {
+    __shared__ uint64_t s_warp[32];
+    const ScanJob j = jobs[blockIdx.y];
+    const uint32_t tile = blockIdx.x, ntiles = scan_tiles(j.n);
+    if (tile >= ntiles) return;
+    const uint32_t tid = threadIdx.x, lane = lane_id(), warp = tid >> 5;
+    // entries of the tiles before this one
+    uint64_t before = 0;
+    for (uint32_t t = tid; t < tile; t += SCAN_THREADS) before += sums[(size_t)blockIdx.y * max_tiles + t];
+    before = scan_block_sum(before, s_warp);
+    const uint32_t i0 = tile * SCAN_TILE + tid * 4;
+    uint32_t v[4];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(XSI_FULL, wi, d); if (lane >= (uint32_t)d) wi += o; }
-            s_warp[lane] = wi - w;  // exclusive
-        }
-        __syncthreads();
-        uint64_t ex = s_carry + s_warp[warp] + (incl - t);
+    for (int q = 0; q < 4; ++q) v[q] = (i0 + q < j.n) ? j.in[i0 + q] : 0u;
+    const uint64_t t = (uint64_t)v[0] + v[1] + v[2] + v[3];
+    uint64_t incl = t;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) { if (i0 + q < j.n) j.out[i0 + q] = ex; ex += v[q]; }
-        __syncthreads();
-        if (tid == SCAN_THREADS - 1) s_carry = ex;
-        __syncthreads();
+    for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(XSI_FULL, incl, d); if (lane >= (uint32_t)d) incl += o; }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint64_t w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) { const uint64_t o = __shfl_up_sync(XSI_FULL, wi, d); if (lane >= (uint32_t)d) wi += o; }
+        s_warp[lane] = wi - w;  // exclusive
     }
-    if (tid == 0) j.out[j.n] = s_carry;
+    __syncthreads();
+    uint64_t ex = before + s_warp[warp] + (incl - t);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) { if (i0 + q < j.n) j.out[i0 + q] = ex; ex += v[q]; }
+    if (tile == ntiles - 1 && tid == SCAN_THREADS - 1) j.out[j.n] = ex;  // the last thread's running total covers the whole array
 }
 
 // =============================================================================================

@@ -124,7 +124,7 @@ struct xsi_ctx {
         std::vector<uint32_t> h_nallele, h_ngt, h_line0, h_line_rec, h_blk_line0, h_blk_rec0;
         std::vector<uint64_t> h_goff;
         DevBuf gt, tables, bitrows, auxrows, phrows, counters, rec_aux, line_u32, line_flags, rec_u32, rec_flags,
-            wah_list, blk_nwah, wahslots, phslots, offs, scanjobs, out_wah, out_sparse, out_miss, out_eov, out_phase,
+            wah_list, blk_nwah, wahslots, phslots, offs, scanjobs, scansums, out_wah, out_sparse, out_miss, out_eov, out_phase,
             auxslots, out_missw, out_eovw,
             a_pool;
         PinBuf h_small, h_offs, h_out, h_flags;
@@ -261,7 +261,7 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
     for (DevBuf* b : {&e.gt, &e.tables, &e.bitrows, &e.auxrows, &e.phrows, &e.counters, &e.rec_aux, &e.line_u32,
                       &e.line_flags, &e.rec_u32, &e.rec_flags, &e.wah_list, &e.blk_nwah, &e.wahslots, &e.phslots,
                       &e.offs, &e.scanjobs, &e.out_wah, &e.out_sparse, &e.out_miss, &e.out_eov, &e.out_phase, &e.a_pool,
-                      &e.auxslots, &e.out_missw, &e.out_eovw, &e.blk_map})
+                      &e.auxslots, &e.out_missw, &e.out_eovw, &e.blk_map, &e.scansums})
         b->release();
     for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags, &e.arena[0], &e.arena[1]}) b->release();
     auto& d = ctx->dec;
@@ -1064,7 +1064,13 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d, uint64
                            {p.rec_eovw_n, reinterpret_cast<uint64_t*>(ob + o_ew), (uint32_t)R, 0}};
         const uint32_t n_scans = e.wah_missing ? 7 : 5;
         CK(cudaMemcpyAsync(e.scanjobs.p, jobs, sizeof(jobs), cudaMemcpyHostToDevice, ctx->es));
-        { PROF("scan_u32"); scan_u32_kernel<<<n_scans, SCAN_THREADS, 0, ctx->es>>>(e.scanjobs.as<ScanJob>()); }
+        {
+            const uint32_t max_tiles = scan_tiles((uint32_t)std::max<uint64_t>(L, R));
+            CK(e.scansums.ensure((size_t)n_scans * max_tiles * 8));
+            PROF("scan_u32");
+            scan_u32_sums_kernel<<<dim3(max_tiles, n_scans), SCAN_THREADS, 0, ctx->es>>>(e.scanjobs.as<ScanJob>(), e.scansums.as<uint64_t>(), max_tiles);
+            scan_u32_kernel<<<dim3(max_tiles, n_scans), SCAN_THREADS, 0, ctx->es>>>(e.scanjobs.as<ScanJob>(), e.scansums.as<uint64_t>(), max_tiles);
+        }
         CKL();
         // totals + counters + flags back, then size the outputs and lay the blocks out
         CK(e.h_offs.ensure(o_end + 64));
