@@ -1,6 +1,6 @@
 # round 2: multi-CTA two-pass scan_u32
 mkdir -p gpurun_out
-T=${T:-r02w}
+T=${T:-r02x}
 timeout 1500 python -m pytest tests/test_gpu_parity.py -m gpu -q -x > gpurun_out/${T}_pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/${T}_pytest.log; tail -3 gpurun_out/${T}_pytest.log
 timeout 900 python -m pytest tests/test_bindings.py -m gpu -q -x -k "cli_on_gpu or small_fixtures or chr20_options" > gpurun_out/${T}_bind.log 2>&1; echo "bind rc=$?" >> gpurun_out/${T}_bind.log; tail -3 gpurun_out/${T}_bind.log
 show='import json,sys

@@ -124,7 +124,7 @@ struct xsi_ctx {
         std::vector<uint32_t> h_nallele, h_ngt, h_line0, h_line_rec, h_blk_line0, h_blk_rec0;
         std::vector<uint64_t> h_goff;
         DevBuf gt, tables, bitrows, auxrows, phrows, counters, rec_aux, line_u32, line_flags, rec_u32, rec_flags,
-            wah_list, blk_nwah, wahslots, phslots, offs, scanjobs, scansums, out_wah, out_sparse, out_miss, out_eov, out_phase,
+            wah_list, blk_nwah, wahslots, phslots, offs, blkoffs, scanjobs, scansums, out_wah, out_sparse, out_miss, out_eov, out_phase,
             auxslots, out_missw, out_eovw,
             a_pool;
         PinBuf h_small, h_offs, h_out, h_flags;
@@ -261,7 +261,7 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
     for (DevBuf* b : {&e.gt, &e.tables, &e.bitrows, &e.auxrows, &e.phrows, &e.counters, &e.rec_aux, &e.line_u32,
                       &e.line_flags, &e.rec_u32, &e.rec_flags, &e.wah_list, &e.blk_nwah, &e.wahslots, &e.phslots,
                       &e.offs, &e.scanjobs, &e.out_wah, &e.out_sparse, &e.out_miss, &e.out_eov, &e.out_phase, &e.a_pool,
-                      &e.auxslots, &e.out_missw, &e.out_eovw, &e.blk_map, &e.scansums})
+                      &e.auxslots, &e.out_missw, &e.out_eovw, &e.blk_map, &e.scansums, &e.blkoffs})
         b->release();
     for (PinBuf* b : {&e.h_small, &e.h_offs, &e.h_out, &e.h_flags, &e.arena[0], &e.arena[1]}) b->release();
     auto& d = ctx->dec;
@@ -1072,29 +1072,44 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d, uint64
             scan_u32_kernel<<<dim3(max_tiles, n_scans), SCAN_THREADS, 0, ctx->es>>>(e.scanjobs.as<ScanJob>(), e.scansums.as<uint64_t>(), max_tiles);
         }
         CKL();
-        // totals + counters + flags back, then size the outputs and lay the blocks out
-        CK(e.h_offs.ensure(o_end + 64));
+        // section offsets at the block boundaries + counters + flags back, then size the outputs and lay the blocks out
+        const size_t nbp = (size_t)e.nb + 1, c_end = 7 * nbp * 8;
+        CK(e.blkoffs.ensure(c_end));
+        {
+            GatherOffs g;
+            const size_t at[7] = {o_sp, o_ms, o_ev, o_wh, o_ph, o_mw, o_ew};
+            const uint32_t by_line[7] = {1, 0, 0, 1, 0, 0, 0};
+            for (int a = 0; a < 7; ++a) { g.src[a] = reinterpret_cast<const uint64_t*>(ob + at[a]); g.by_line[a] = by_line[a]; }
+            g.n_arrays = n_scans; g.nb = e.nb; g.block_len = e.block_len; g.R = (uint32_t)R;
+            g.blk_line0 = p.blk_line0; g.dst = e.blkoffs.as<uint64_t>();
+            gather_block_offsets_kernel<<<(uint32_t)((n_scans * nbp + 255) / 256), 256, 0, ctx->es>>>(g);
+            CKL();
+        }
+        CK(e.h_offs.ensure(c_end + 64));
         uint8_t* ho = e.h_offs.as<uint8_t>();
-        CK(cudaMemcpyAsync(ho, e.offs.p, o_end, cudaMemcpyDeviceToHost, ctx->es));
-        CK(cudaMemcpyAsync(ho + o_end, e.counters.p, 16, cudaMemcpyDeviceToHost, ctx->es));
+        memset(ho, 0, c_end);
+        CK(cudaMemcpyAsync(ho, e.blkoffs.p, n_scans * nbp * 8, cudaMemcpyDeviceToHost, ctx->es));
+        CK(cudaMemcpyAsync(ho + c_end, e.counters.p, 16, cudaMemcpyDeviceToHost, ctx->es));
         CK(e.h_flags.ensure(Lp + R + 16));
         CK(cudaMemcpyAsync(e.h_flags.p, e.line_flags.p, Lp, cudaMemcpyDeviceToHost, ctx->es));
         CK(cudaMemcpyAsync(e.h_flags.as<uint8_t>() + Lp, e.rec_flags.p, R, cudaMemcpyDeviceToHost, ctx->es));
         CK(cudaStreamSynchronize(ctx->es));
-        const uint32_t* cnt = reinterpret_cast<const uint32_t*>(ho + o_end);
+        const uint32_t* cnt = reinterpret_cast<const uint32_t*>(ho + c_end);
         if (cnt[2] & ERR_ALLELE) { ctx->err = "Unknown allele error !"; return XSI_E_ALLELE; }
         if (cnt[2] & (ERR_AUX_OVERFLOW | ERR_PHASE_OVERFLOW)) {
             e.aux_cap = std::max(e.aux_cap, cnt[0] + cnt[0] / 8 + 16);
             e.phase_cap = std::max(e.phase_cap, cnt[1] + cnt[1] / 8 + 16);
             continue;  // rerun the batch with big enough row pools
         }
-        e.tot_sparse = reinterpret_cast<const uint64_t*>(ho + o_sp)[L];
-        e.tot_miss = reinterpret_cast<const uint64_t*>(ho + o_ms)[R];
-        e.tot_eov = reinterpret_cast<const uint64_t*>(ho + o_ev)[R];
-        e.tot_wah = reinterpret_cast<const uint64_t*>(ho + o_wh)[L];
-        e.tot_phase = reinterpret_cast<const uint64_t*>(ho + o_ph)[R];
-        e.tot_missw = e.wah_missing ? reinterpret_cast<const uint64_t*>(ho + o_mw)[R] : 0;
-        e.tot_eovw = e.wah_missing ? reinterpret_cast<const uint64_t*>(ho + o_ew)[R] : 0;
+        // compact offsets: array a (sparse, missing, eov, wah, phase, missing-wah, eov-wah) at block b = hoff[a * (nb+1) + b]
+        const uint64_t* hoff = reinterpret_cast<const uint64_t*>(ho);
+        e.tot_sparse = hoff[0 * nbp + e.nb];
+        e.tot_miss = hoff[1 * nbp + e.nb];
+        e.tot_eov = hoff[2 * nbp + e.nb];
+        e.tot_wah = hoff[3 * nbp + e.nb];
+        e.tot_phase = hoff[4 * nbp + e.nb];
+        e.tot_missw = e.wah_missing ? hoff[5 * nbp + e.nb] : 0;
+        e.tot_eovw = e.wah_missing ? hoff[6 * nbp + e.nb] : 0;
         CK(e.out_sparse.ensure(e.tot_sparse * e.aet + 16));
         CK(e.out_miss.ensure(e.tot_miss * e.aet + 16));
         CK(e.out_eov.ensure(e.tot_eov * e.aet + 16));
@@ -1127,13 +1142,8 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d, uint64
         // ---- while those run: lay out every GT block (dictionary, per-line bool vectors, section offsets) in the
         //      pinned arena, then queue the device->host copies of the sections straight into their final place ----
         {
-            const uint64_t* off_sp = reinterpret_cast<const uint64_t*>(ho + o_sp);
-            const uint64_t* off_ms = reinterpret_cast<const uint64_t*>(ho + o_ms);
-            const uint64_t* off_ev = reinterpret_cast<const uint64_t*>(ho + o_ev);
-            const uint64_t* off_wh = reinterpret_cast<const uint64_t*>(ho + o_wh);
-            const uint64_t* off_ph = reinterpret_cast<const uint64_t*>(ho + o_ph);
-            const uint64_t* off_mw = reinterpret_cast<const uint64_t*>(ho + o_mw);
-            const uint64_t* off_ew = reinterpret_cast<const uint64_t*>(ho + o_ew);
+            const uint64_t *off_sp = hoff, *off_ms = hoff + nbp, *off_ev = hoff + 2 * nbp, *off_wh = hoff + 3 * nbp, *off_ph = hoff + 4 * nbp,
+                           *off_mw = hoff + 5 * nbp, *off_ew = hoff + 6 * nbp;  // indexed by BLOCK: [b] first entry of block b, [b+1] its end
             const uint8_t* lflags = e.h_flags.as<uint8_t>();
             const uint8_t* rflags = lflags + Lp;
             HOSTSPAN("host:encode_layout");
@@ -1201,19 +1211,19 @@ static int xsi_encode_launch_impl(xsi_ctx* ctx, const xsi_encode_desc* d, uint64
                     pos += t.bytes.size();
                     ly.tails.push_back(std::move(t));
                 };
-                section(KEY_MATRIX_WAH, e.out_wah.p, off_wh[l0], off_wh[l1], 2);
-                section(KEY_MATRIX_SPARSE, e.out_sparse.p, off_sp[l0], off_sp[l1], e.aet);
+                section(KEY_MATRIX_WAH, e.out_wah.p, off_wh[b], off_wh[b + 1], 2);
+                section(KEY_MATRIX_SPARSE, e.out_sparse.p, off_sp[b], off_sp[b + 1], e.aet);
                 if (any_missing) {
                     boolvec(KEY_LINE_MISSING, v_miss);
-                    if (e.wah_missing) section(KEY_MATRIX_MISSING, e.out_missw.p, off_mw[r0], off_mw[r1], 2);  // gt_block.hpp:574-576
-                    else section(KEY_MATRIX_MISSING_SPARSE, e.out_miss.p, off_ms[r0], off_ms[r1], e.aet);
+                    if (e.wah_missing) section(KEY_MATRIX_MISSING, e.out_missw.p, off_mw[b], off_mw[b + 1], 2);  // gt_block.hpp:574-576
+                    else section(KEY_MATRIX_MISSING_SPARSE, e.out_miss.p, off_ms[b], off_ms[b + 1], e.aet);
                 }
                 if (any_eov) {
                     boolvec(KEY_LINE_END_OF_VECTORS, v_eov);
-                    if (e.wah_missing) section(KEY_MATRIX_END_OF_VECTORS, e.out_eovw.p, off_ew[r0], off_ew[r1], 2);  // :596-598
-                    else section(KEY_MATRIX_END_OF_VECTORS_SPARSE, e.out_eov.p, off_ev[r0], off_ev[r1], e.aet);
+                    if (e.wah_missing) section(KEY_MATRIX_END_OF_VECTORS, e.out_eovw.p, off_ew[b], off_ew[b + 1], 2);  // :596-598
+                    else section(KEY_MATRIX_END_OF_VECTORS_SPARSE, e.out_eov.p, off_ev[b], off_ev[b + 1], e.aet);
                 }
-                if (any_phase) { boolvec(KEY_LINE_NON_UNIFORM_PHASING, v_phase); section(KEY_MATRIX_NON_UNIFORM_PHASING, e.out_phase.p, off_ph[r0], off_ph[r1], 2); }
+                if (any_phase) { boolvec(KEY_LINE_NON_UNIFORM_PHASING, v_phase); section(KEY_MATRIX_NON_UNIFORM_PHASING, e.out_phase.p, off_ph[b], off_ph[b + 1], 2); }
                 if (any_hap) boolvec(KEY_LINE_HAPLOID, v_hap);  // one bit per BCF line, gt_block.hpp:219-224,639-642
                 for (size_t i = 0; i < order.size(); ++i) {
                     memcpy(head.data() + dict_at + 8 * i, &order[i], 4);
