@@ -166,7 +166,8 @@ struct xsi_ctx {
         std::vector<uint64_t> h_blob_off, h_blk_size;
         DevBuf blob, meta, rows, job_u32, job_hap, tile_u32, dline, lists, err, a_pool, x_pool, req, out, scratch, counts,
             seg_total, tabs;
-        PinBuf h_stage, h_meta;
+        PinBuf h_stage, h_meta, h_req;
+        cudaEvent_t ev_req = nullptr;  // the last copy out of h_req
         DecDev dev;
     } dec;
 };
@@ -270,6 +271,8 @@ extern "C" void xsi_destroy(xsi_ctx* ctx) {
         b->release();
     d.h_stage.release();
     d.h_meta.release();
+    d.h_req.release();
+    if (d.ev_req) cudaEventDestroy(d.ev_req);
     ctx->ring.release();
     ctx->dma_stage.release(); ctx->dma_flag.release(); ctx->dma_flag_host.release();
     for (cudaEvent_t ev : ctx->ring_ev) if (ev) cudaEventDestroy(ev);
@@ -1842,13 +1845,30 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
     const uint32_t N = 2 * d.n_samples;
     if (out_stride < N) { ctx->err = "out_stride smaller than 2*num_samples"; return XSI_E_ARG; }
     uint32_t max_all = 2;
-    for (uint64_t i = 0; i < n; ++i) {
-        if (block_index[i] >= d.nb) { ctx->err = "block index out of range"; return XSI_E_ARG; }
-        if (n_alleles[i] < 2 || n_alleles[i] > 254) { ctx->err = "n_alleles out of range (2..254)"; return XSI_E_UNSUPPORTED; }
-        // BCF keeps FORMAT/GT as int8 only while (allele+1)<<1|1 <= 127 (htslib vcf.c bcf_update_format: wider types above)
-        if (sizeof(OT) == 1 && n_alleles[i] > 63) { ctx->err = "int8 genotype rows need n_alleles <= 63"; return XSI_E_UNSUPPORTED; }
-        if ((uint64_t)line_offset[i] + n_alleles[i] - 1 > d.h_bin_lines[block_index[i]]) { ctx->err = "record runs past the end of its block"; return XSI_E_ARG; }
-        max_all = std::max(max_all, n_alleles[i]);
+    {   // argument checks, in chunks on the worker pool (millions of records per call on short-row files)
+        constexpr uint64_t VCH = 1u << 16;
+        const size_t nvc = (size_t)((n + VCH - 1) / VCH);
+        struct Chk { int bad = 0; uint32_t max_all = 2; };
+        std::vector<Chk> chk(nvc);
+        host_parallel_for(nvc, [&](size_t c) {
+            Chk& k = chk[c];
+            const uint64_t i1 = std::min<uint64_t>(n, (c + 1) * VCH);
+            for (uint64_t i = c * VCH; i < i1; ++i) {
+                if (block_index[i] >= d.nb) { k.bad = 1; return; }
+                if (n_alleles[i] < 2 || n_alleles[i] > 254) { k.bad = 2; return; }
+                // BCF keeps FORMAT/GT as int8 only while (allele+1)<<1|1 <= 127 (htslib vcf.c bcf_update_format: wider types above)
+                if (sizeof(OT) == 1 && n_alleles[i] > 63) { k.bad = 3; return; }
+                if ((uint64_t)line_offset[i] + n_alleles[i] - 1 > d.h_bin_lines[block_index[i]]) { k.bad = 4; return; }
+                k.max_all = std::max(k.max_all, n_alleles[i]);
+            }
+        });
+        for (const Chk& k : chk) {
+            if (k.bad == 1) { ctx->err = "block index out of range"; return XSI_E_ARG; }
+            if (k.bad == 2) { ctx->err = "n_alleles out of range (2..254)"; return XSI_E_UNSUPPORTED; }
+            if (k.bad == 3) { ctx->err = "int8 genotype rows need n_alleles <= 63"; return XSI_E_UNSUPPORTED; }
+            if (k.bad == 4) { ctx->err = "record runs past the end of its block"; return XSI_E_ARG; }
+            max_all = std::max(max_all, k.max_all);
+        }
     }
     const bool want_counts = allele_counts != nullptr;
     if (want_counts && counts_stride < max_all) { ctx->err = "counts_stride too small"; return XSI_E_ARG; }
@@ -1865,9 +1885,27 @@ static int decode_records_impl(xsi_ctx* ctx, uint64_t n, const uint32_t* block_i
         }
         CK(d.req.ensure(cn * 4 * 4));
         uint32_t* rq = d.req.as<uint32_t>();
-        CK(cudaMemcpyAsync(rq, block_index + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(rq + cn, line_offset + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
-        CK(cudaMemcpyAsync(rq + 2 * cn, n_alleles + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        if (cn >= (1u << 16)) {
+            // the three request arrays are the caller's pageable memory: packed into one pinned buffer by the worker pool and sent
+            // as ONE asynchronous copy (three staged pageable copies of 7 MB each cost several ms per call at 1.8 M records)
+            if (!d.ev_req) CK(cudaEventCreateWithFlags(&d.ev_req, cudaEventDisableTiming));
+            else CK(cudaEventSynchronize(d.ev_req));  // the previous copy out of h_req has finished
+            CK(d.h_req.ensure(cn * 3 * 4));
+            uint32_t* hq = d.h_req.as<uint32_t>();
+            constexpr uint64_t PCH = 1u << 17;
+            host_parallel_for((size_t)((cn + PCH - 1) / PCH), [&](size_t c) {
+                const uint64_t i0 = c * PCH, m = std::min<uint64_t>(PCH, cn - i0);
+                memcpy(hq + i0, block_index + c0 + i0, m * 4);
+                memcpy(hq + cn + i0, line_offset + c0 + i0, m * 4);
+                memcpy(hq + 2 * cn + i0, n_alleles + c0 + i0, m * 4);
+            });
+            CK(cudaMemcpyAsync(rq, hq, cn * 3 * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaEventRecord(d.ev_req, ctx->stream));
+        } else {
+            CK(cudaMemcpyAsync(rq, block_index + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(rq + cn, line_offset + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+            CK(cudaMemcpyAsync(rq + 2 * cn, n_alleles + c0, cn * 4, cudaMemcpyHostToDevice, ctx->stream));
+        }
         const uint32_t grid = (uint32_t)std::min<uint64_t>(cn, (uint64_t)ctx->sm_count * 8);
         CK(d.scratch.ensure((size_t)grid * 2 * Npad));
         q.blk = rq; q.line = rq + cn; q.nall = rq + 2 * cn; q.n = (uint32_t)cn;
