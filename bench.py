@@ -1085,6 +1085,16 @@ def main():
                 "verified": bool(verified and (sharded_file is None or sharded_file["equals_single_writer_file"])), "roofline": roof, "roofline_kernels": roof_all, "kernels": kernels, "call_wall_ms_per_step": res["host_ms"], "host_phases": host_phases, "resident_multi_context": resident_mt, "cpu_baseline": cpu, "e2e": e2e, "e2e_bcf_int8": e2e_i8, "e2e_bcf": e2e_bcf, "shapes": shapes, "sharded_file": sharded_file, "numa_binding": numa,
                 "gpu_launches": resident_mt["gpu_launches"] if use_mt else (pipelined["gpu_launches"] if mode.startswith("one context, one host") else res["launches"]),
                 "clocks": res["clocks"]}
+        # the whole path against the HBM roofline: the boundary rows alone (EL bytes per genotype read by the encode, written by the
+        # decode) over the step of `value`, per GPU -- the per-kernel fractions above say where the rest of the time goes
+        try:
+            hbm = float(roof["peak"]) if roof else None
+            if hbm:
+                gbs = 2.0 * G * EL / (best_ms * 1e-3) / 1e9
+                line["whole_path"] = {"bound": "hbm", "achieved": gbs, "peak": hbm, "unit": "GB/s", "frac": gbs / hbm,
+                                      "bytes_per_step_per_gpu": 2 * G * EL, "what": "boundary rows only: %d B per genotype in, %d B out" % (EL, EL)}
+        except Exception:  # never lose the line over a derived number
+            pass
         print(json.dumps(line))
     if ctx is not None:
         ctx.close()
